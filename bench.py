@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- event-frames/sec of the OpenESS voxelisation hot path at DSEC 640x480 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode ordered|atomic]
+
+Unit of work: one event-frame = one [5,480,640] float32 voxel grid built from one 50 ms window
+of N = 100 000 events = one call of VoxelGrid.convert (DSEC/dataset/representations.py:15-55).
+One step = one batch of F = 160 event-frames (8 DSEC samples x 20 frames, config `batch_size_b: 8`,
+`nr_events_data: 20`) through ONE batched C-ABI call (oess_voxel_trilinear).
+
+ value : frames/s, inputs resident in HBM, CUDA-event timed over exactly K steps, max over ranks.
+ e2e   : same metric from PINNED HOST event arrays: per step H2D of the four float32 event arrays,
+         voxelisation, and a D2H read of one grid row per frame (the grids stay on the device because
+         the consumer, the event encoder, runs there).  `e2e_host_output` additionally copies every
+         grid back to pinned host memory (what VoxelGrid.convert returns for CPU inputs; PCIe-bound).
+ roofline : dominant kernel, algorithmic bytes (16 N + 4 C H W per frame) / its CUDA-event duration.
+ cpu_baseline : the C oracle port of the reference algorithm on the host cores (bounded sample).
+ --impl reference : the CPU arm alone (the reference is pure Python and cannot travel to the GPU box; the
+         oracle port restates it in C and is a *stronger* baseline than the reference's numpy/torch code).
+Multi-GPU: frames are sharded over ranks (independent units, no data-path collective) -> weak scaling.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+C, H, W = 5, 480, 640
+N_EVENTS = 100_000
+WINDOW_US = 50_000
+METRIC = "event-frames/sec at DSEC 640x480 50 ms window"
+UNIT = "frames/s"
+
+
+def synth_frames(rng, F, n=N_EVENTS, clustered_every=2):
+    """raw pixels + identity rectify map with +-0.75 px jitter, t over 50 ms, and every
+    second frame edge-clustered (80 % of the events on line segments)."""
+    xs, ys, ps, ts = [], [], [], []
+    for f in range(F):
+        if clustered_every and f % clustered_every == 1:
+            k = int(0.8 * n)
+            seg = rng.integers(0, 16, k)
+            a = rng.random(k)
+            x0, y0, x1, y1 = (rng.uniform(0, s, 16) for s in (W, H, W, H))
+            x = np.concatenate([x0[seg] + a * (x1[seg] - x0[seg]) + rng.normal(0, 0.7, k), rng.uniform(0, W, n - k)])
+            y = np.concatenate([y0[seg] + a * (y1[seg] - y0[seg]) + rng.normal(0, 0.7, k), rng.uniform(0, H, n - k)])
+            perm = rng.permutation(n)
+            x, y = x[perm], y[perm]
+        else:
+            x = rng.integers(0, W, n) + rng.uniform(-0.75, 0.75, n)
+            y = rng.integers(0, H, n) + rng.uniform(-0.75, 0.75, n)
+        t = np.sort(rng.integers(0, WINDOW_US, n)).astype(np.float64)
+        t = (t - t[0]).astype(np.float32)
+        t = t / t[-1]                                     # sequence_ov.py:155-156
+        xs.append(x.astype(np.float32)); ys.append(y.astype(np.float32))
+        ps.append(rng.integers(0, 2, n).astype(np.float32)); ts.append(t)
+    return [np.concatenate(a) for a in (xs, ys, ps, ts)]
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_throughput(frames_total, budget_s, threads=None, seed=1205):
+    """Oracle C port of VoxelGrid.convert on `threads` host threads (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as orc
+    orc.build()
+    threads = threads or os.cpu_count() or 1
+    rng = np.random.default_rng(seed)
+    base = synth_frames(rng, min(frames_total, 8))
+    nb = min(frames_total, 8)
+    frames = [tuple(a[i * N_EVENTS:(i + 1) * N_EVENTS] for a in base) for i in range(nb)]
+
+    tls = threading.local()
+
+    def work(i):
+        x, y, p, t = frames[i % nb]
+        if not hasattr(tls, "out"):
+            tls.out = np.empty((C, H, W), np.float32)     # one reusable grid per worker thread
+        return float(orc.voxel_trilinear(x, y, p, t, C, H, W, out=tls.out)[0, 0, 0])
+
+    work(0)  # warm-up (page-in, library load)
+    done = 0
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        while done < frames_total:
+            batch = min(threads * 2, frames_total - done)
+            list(ex.map(work, range(done, done + batch)))
+            done += batch
+            if time.perf_counter() - t0 > budget_s:
+                break
+    dt = time.perf_counter() - t0
+    return done / dt, done, dt, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    per_step = max(threads * 2, 8)
+    for _ in range(args.warmup):
+        cpu_port_throughput(min(per_step, threads), 5.0, threads)
+    t0 = time.perf_counter()
+    frames = 0
+    for _ in range(args.steps):
+        _, done, _, _ = cpu_port_throughput(per_step, 20.0, threads)
+        frames += done
+    dt = time.perf_counter() - t0
+    val = frames / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DSEC 640x480, {N_EVENTS} events per 50 ms frame, VoxelGrid.convert trilinear splat, "
+                               f"C={C}; reference arm = C oracle port on host threads, {per_step} frames per step"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{frames} frames of {N_EVENTS} events over {args.steps} steps"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from openess_b200 import _lib, voxel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (openess_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    F, K, Wm = args.frames, args.steps, args.warmup
+    mode = args.mode
+    rng = np.random.default_rng(1205 + rank)
+    # two input sets (each 16 B x F x N = 256 MB at F=160 > 126 MB L2), alternated between steps
+    host_sets = [[torch.from_numpy(a).pin_memory() for a in synth_frames(rng, F)] for _ in range(2)]
+    dev_sets = [[a.to(dev) for a in hs] for hs in host_sets]
+    fo = (torch.arange(F + 1, dtype=torch.int64) * N_EVENTS).to(dev)
+    out = torch.empty((F, C, H, W), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, m=mode):
+        x, y, p, t = dev_sets[i & 1]
+        voxel.voxel_trilinear(x, y, p, t, C, H, W, frame_offsets=fo, mode=m, out=out)
+
+    def timed(fn, steps, profile=False):
+        for i in range(Wm):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = _lib.launch_count()
+        prof = _lib.profile() if profile else None
+        if prof:
+            prof.__enter__()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        if prof:
+            prof.__exit__(None, None, None)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), _lib.launch_count() - launches0, (prof.kernels if prof else {})
+
+    # ---- device-resident throughput (the `value`), clocks sampled during the timed region
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, launches, kernels = timed(step, K, profile=True)
+    clocks = sampler.stop()
+    value = world * F * K / (ms * 1e-3)
+
+    # ---- the other mode, for the record
+    other = "atomic" if mode == "ordered" else "ordered"
+    ms_o, _, _ = timed(lambda i: step(i, other), K)
+    value_other = world * F * K / (ms_o * 1e-3)
+
+    # ---- end to end from pinned host buffers: H2D per step + voxelise + D2H of one grid row per frame
+    sub = args.e2e_sub
+    streams = [torch.cuda.Stream(dev) for _ in range(2)]
+    stage = [[torch.empty(sub * N_EVENTS, dtype=torch.float32, device=dev) for _ in range(4)] for _ in range(2)]
+    fo_sub = (torch.arange(sub + 1, dtype=torch.int64) * N_EVENTS).to(dev)
+    rows_host = torch.empty((F, C, W), dtype=torch.float32).pin_memory()
+    full_host = torch.empty((F, C, H, W), dtype=torch.float32).pin_memory() if args.host_output else None
+
+    def e2e_step(i, full=False):
+        hs = host_sets[i & 1]
+        for s, f0 in enumerate(range(0, F, sub)):
+            st = streams[s & 1]
+            with torch.cuda.stream(st):
+                for k in range(4):
+                    stage[s & 1][k].copy_(hs[k][f0 * N_EVENTS:(f0 + sub) * N_EVENTS], non_blocking=True)
+                voxel.voxel_trilinear(*stage[s & 1], C, H, W, frame_offsets=fo_sub, mode=mode, out=out[f0:f0 + sub])
+                if full:
+                    full_host[f0:f0 + sub].copy_(out[f0:f0 + sub], non_blocking=True)
+                else:
+                    rows_host[f0:f0 + sub].copy_(out[f0:f0 + sub, :, 0, :], non_blocking=True)
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+
+    assert F % sub == 0
+    ms_e, _, _ = timed(e2e_step, K)
+    e2e_value = world * F * K / (ms_e * 1e-3)
+    h2d = 16 * F * N_EVENTS
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * F * C * W,
+           "ms_per_step": ms_e / K}
+    e2e_host = None
+    if args.host_output:
+        ms_h, _, _ = timed(lambda i: e2e_step(i, True), max(2, K // 4))
+        e2e_host = {"value": world * F * max(2, K // 4) / (ms_h * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4 * F * C * H * W}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes_frame = 16 * N_EVENTS + 4 * C * H * W
+    dom = max(kernels.items(), key=lambda kv: kv[1][1]) if kernels else (None, (0, 0.0))
+    dom_name, (dom_cnt, dom_ms) = dom
+    per_launch_ms = dom_ms / max(dom_cnt, 1)
+    launches_per_step = max(dom_cnt // max(K, 1), 1)
+    achieved = alg_bytes_frame * F / launches_per_step / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0.0
+    path_gbs = alg_bytes_frame * F / (ms / K * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")   # per-launch dram bytes from the committed ncu capture
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom_name)
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes_frame * F // launches_per_step,
+                "path_achieved": path_gbs, "path_frac": path_gbs / peak,
+                "kernel_share_of_step": {k: round(v[1] / (ms if ms else 1), 4) for k, v in kernels.items()}}
+
+    # ---- CPU baseline (oracle port, all host threads, bounded sample)
+    cpu_val, cpu_frames, cpu_dt, cpu_threads = cpu_port_throughput(args.cpu_frames, args.cpu_budget)
+    cpu1_val, cpu1_frames, _, _ = cpu_port_throughput(8, 10.0, threads=1)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"DSEC 640x480, {N_EVENTS} events per 50 ms frame, VoxelGrid.convert trilinear splat C={C}, "
+                               f"F={F} frames per step per GPU (8 samples x 20 frames), every 2nd frame edge-clustered",
+                   "mode": mode, "bit_exact_vs_reference": mode == "ordered",
+                   "l2": f"inputs {16 * F * N_EVENTS / 1e6:.0f} MB + outputs {4 * F * C * H * W / 1e6:.0f} MB per step > 126 MB L2; "
+                         "two input sets alternated",
+                   "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+        "value_other_mode": {"mode": other, "value": value_other, "unit": UNIT},
+        "e2e": e2e, "e2e_host_output": e2e_host,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                         "sample": f"{cpu_frames} frames of {N_EVENTS} events in {cpu_dt:.1f} s (C oracle port of "
+                                   "VoxelGrid.convert, one frame per thread)",
+                         "single_thread_value": cpu1_val},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="ordered", choices=["ordered", "atomic"])
+    ap.add_argument("--frames", type=int, default=160, help="event-frames per step per GPU")
+    ap.add_argument("--e2e-sub", type=int, default=40, help="frames per pipelined H2D/compute sub-batch")
+    ap.add_argument("--host-output", type=int, default=1, help="also measure e2e with full D2H of the grids")
+    ap.add_argument("--cpu-frames", type=int, default=2000)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

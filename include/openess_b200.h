@@ -1,0 +1,163 @@
+/*
+ * openess_b200.h -- C ABI of libopeness_b200.so: the B200-native (sm_100a) implementation of the
+ * OpenESS per-step hot path.
+ *
+ * The reference (ldkong1205/OpenESS) is pure Python: it has no FFI and no operator registry, the
+ * "plugin boundary" is a set of Python callables.  Every entry point below names the
+ * reference callable it replaces (file:line into the reference tree); openess_b200/_lib.py is the
+ * ctypes binding and INTEGRATION.md shows the stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch types.
+ *  - Every data pointer is a DEVICE pointer owned by the caller (e.g. the PyTorch allocator).
+ *  - No hidden allocation: scratch space is a caller-provided workspace (`ws`, `ws_bytes`) whose size
+ *    comes from the matching *_ws_bytes() query (host-side arithmetic only, no CUDA call).
+ *  - No global mutable state, no host synchronisation: every call only enqueues work on `stream`
+ *    and is safe to call concurrently from several host threads on different streams.
+ *  - Return value: 0 = OK, <0 = argument error (OESS_E_*), >0 = cudaError_t of a failed launch.
+ *  - Batched: one call voxelises F event-frames.  Events of all frames are concatenated;
+ *    frame_offsets[F+1] (int64, device) delimits frame f as [frame_offsets[f], frame_offsets[f+1]).
+ *    A frame with zero events yields an all-zero grid (the single-frame reference raises IndexError;
+ *    the Python mirror raises the same before calling in).
+ */
+#ifndef OPENESS_B200_H
+#define OPENESS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* oess_stream_t; /* == cudaStream_t */
+
+#define OESS_OK 0
+#define OESS_E_ARG (-1)       /* bad shape / null pointer / unsupported value            */
+#define OESS_E_WORKSPACE (-2) /* workspace missing or too small                           */
+#define OESS_E_RANGE (-3)     /* size exceeds what the kernels index (per-frame n >= 2^31) */
+
+/* Accumulation mode of the voxelisers.
+ *  ORDERED: replays the reference's sequential accumulation order per voxel (stable radix sort by
+ *           pixel + per-pixel gather) -> bit-exact with the reference's single-thread CPU result,
+ *           deterministic.
+ *  ATOMIC : float atomics (red.global.add.f32) in event order of arrival -> fastest path for dense
+ *           reuse of one grid, result within ~1e-6 of ORDERED (same noise class as the reference's
+ *           own multi-threaded put_), not run-to-run deterministic.            */
+#define OESS_MODE_ORDERED 0
+#define OESS_MODE_ATOMIC 1
+
+/* Which voxeliser a workspace query is for. */
+#define OESS_KIND_TRILINEAR 0
+#define OESS_KIND_TBILINEAR 1
+
+int oess_abi_version(void);
+const char* oess_error_string(int code);
+
+/* Measurement hooks (bench.py): number of kernels this library has launched so far in the process, and
+ * an optional per-host-thread recorder that brackets every kernel with CUDA events on its stream.
+ * oess_profile_end synchronises the recorded events and writes "kernel,launches,total_ms\n" lines. */
+unsigned long long oess_launch_count(void);
+int oess_profile_begin(void);
+int oess_profile_end(char* buf, size_t buf_bytes);
+
+/* Workspace size for oess_voxel_trilinear / oess_voxel_tbilinear_* (pure host arithmetic). */
+int oess_voxel_ws_bytes(int kind, int mode, int64_t n_events_total, int n_frames, int C, int H, int W,
+                        size_t* ws_bytes);
+
+/* Replaces DSEC/dataset/representations.py:15-43 VoxelGrid.convert (trilinear x/y/t splat, float32).
+ * x, y, pol, t: [n_events_total] float32 SoA exactly as the reference passes them (t already divided by
+ * its last value by sequence_ov.py:155-156; convert() re-normalises with t[first], t[last] of the frame).
+ * out: [F, C, H, W] float32, fully written (no pre-zeroing needed).
+ * normalize != 0 additionally applies representations.py:45-53 per frame (nonzero mean / unbiased std). */
+int oess_voxel_trilinear(const float* x, const float* y, const float* pol, const float* t,
+                         const int64_t* frame_offsets, int64_t n_events_total, int n_frames, int C, int H,
+                         int W, int mode, int normalize, float* out, void* ws, size_t ws_bytes,
+                         oess_stream_t stream);
+
+/* Replaces datasets/data_util.py:51-117 generate_voxel_grid (t-bilinear, integer pixels, float64 weights,
+ * np.add.at order).  ev4: [n_events_total, 4] rows (x, y, t, p), int64 (DDD17 memmap path,
+ * ddd17_events_loader.py:171-177) or float64 (DSEC non-voxel branch, sequence_ov.py:268-274).
+ * mutate_p != 0 reproduces the reference's in-place `p[p == 0] = -1` on the caller's (device) array
+ * (data_util.py:78-79).  out: [F, C, H, W] or, if separate_pol, [F, 2C, H, W] = concat(pos, neg). */
+int oess_voxel_tbilinear_i64(int64_t* ev4, const int64_t* frame_offsets, int64_t n_events_total,
+                             int n_frames, int C, int H, int W, int separate_pol, int mode, int mutate_p,
+                             float* out, void* ws, size_t ws_bytes, oess_stream_t stream);
+int oess_voxel_tbilinear_f64(double* ev4, const int64_t* frame_offsets, int64_t n_events_total,
+                             int n_frames, int C, int H, int W, int separate_pol, int mode, int mutate_p,
+                             float* out, void* ws, size_t ws_bytes, oess_stream_t stream);
+
+/* Replaces datasets/data_util.py:17-35 generate_event_histogram -> out [F, 2, H, W] = stack(neg, pos).
+ * Counts are exact integers in float32 (order independent), so there is a single mode.
+ * status (device int32[1], may be NULL): set to 1 if any event indexes outside the H*W image (the
+ * reference raises IndexError / wraps negative indices there; such events are skipped here). */
+int oess_voxel_histogram_i64(int64_t* ev4, const int64_t* frame_offsets, int64_t n_events_total,
+                             int n_frames, int H, int W, int mutate_p, float* out, int32_t* status,
+                             oess_stream_t stream);
+int oess_voxel_histogram_f64(double* ev4, const int64_t* frame_offsets, int64_t n_events_total,
+                             int n_frames, int H, int W, int mutate_p, float* out, int32_t* status,
+                             oess_stream_t stream);
+
+/* Replaces DSEC/dataset/sequence_ov.py:204-210 rectify_events (gather rectify_map[y, x]) fused with the
+ * per-chunk pre-step of sequence_ov.py:154-159 events_to_voxel_grid (t = f32(t - t[0]); t /= t[-1];
+ * pol = f32(p)), per frame.  Raw DSEC records: x, y uint16, t int64 microseconds (t_offset already added,
+ * DSEC/utils/eventslicer.py), p uint8.  rectify_map: [H, W, 2] float32.
+ * status (device int32[1], may be NULL): 1 if any x >= W or y >= H (sequence_ov.py:208-209 asserts). */
+int oess_dsec_rectify_tnorm(const uint16_t* x, const uint16_t* y, const int64_t* t, const uint8_t* p,
+                            const float* rectify_map, const int64_t* frame_offsets, int64_t n_events_total,
+                            int n_frames, int H, int W, float* xo, float* yo, float* po, float* to,
+                            int32_t* status, oess_stream_t stream);
+
+/* Replaces datasets/data_util.py:38-48 normalize_voxel_grid and e2vid/utils/inference_utils.py:77-85
+ * (EventPreprocessor): x = (x != 0) * (x - mean) / std over the nonzero entries of each group.
+ * x: [n_groups, group_numel] float32, in place.  stats: device float64 [n_groups, 3] = {sum, sumsq, nnz}.
+ *   phase 0: compute stats and apply          (single-GPU / local-batch semantics)
+ *   phase 1: compute stats only               (caller may all-reduce stats across ranks)
+ *   phase 2: apply using the stats given
+ * unbiased != 0 selects representations.py:45-53 semantics instead (torch.std, `std > 0` guard, only
+ * nonzero entries are rewritten). */
+int oess_nonzero_standardize(float* x, int64_t group_numel, int n_groups, double* stats, int phase,
+                             int unbiased, oess_stream_t stream);
+
+/* Replaces training/pretrain_trainer.py:445-465 (superpixel mean-pool via sparse one-hot matmul).
+ * feat [B, Cf, H, W] f32 NCHW, seg [B, H, W] int64 superpixel ids; id' = id + b*S; ids outside [0, M)
+ * are skipped and flagged in status.  pooled [M, Cf] = sum / (count + 1e-6), counts [M] f32.
+ * The backward call scatters d_pooled back: d_feat[b, c, pix] = d_pooled[id', c] / (count[id'] + 1e-6). */
+int oess_segpool_ws_bytes(int B, int Cf, int H, int W, int64_t M, size_t* ws_bytes);
+int oess_segpool_fwd(const float* feat, const int64_t* seg, int B, int Cf, int H, int W, int S, int64_t M,
+                     float* pooled, float* counts, int32_t* status, void* ws, size_t ws_bytes,
+                     oess_stream_t stream);
+int oess_segpool_bwd(const float* d_pooled, const int64_t* seg, const float* counts, int B, int Cf, int H,
+                     int W, int S, int64_t M, float* d_feat, oess_stream_t stream);
+
+/* Replaces utils/loss_functions.py:138-153 NCELoss: loss = mean_i CE((k q^T)/T, i).
+ * k, q [M, D] f32.  loss: device f32[1].  dk/dq (may be NULL) receive d loss / d k, d q.
+ * ws: M floats (row log-sum-exp) + M floats (column scratch); see oess_infonce_ws_bytes. */
+int oess_infonce_ws_bytes(int64_t M, int D, size_t* ws_bytes);
+int oess_infonce(const float* k, const float* q, int64_t M, int D, float temperature, float* loss,
+                 float* dk, float* dq, void* ws, size_t ws_bytes, oess_stream_t stream);
+
+/* Replaces utils/loss_functions.py:6-24 TaskLoss (= :96-135 DiceLoss + CrossEntropyLoss(ignore_index)).
+ * logits [B, K, H, W] f32, target [B, H, W] int64.
+ * partials: device float64 [2K+2] = {inter[K], denom[K], ce_sum, n_valid}; exposed so that ranks can
+ * all-reduce them for exact global-batch semantics.
+ *   oess_dice_ce_partials: one pass over logits -> partials (accumulates into zeroed partials)
+ *   oess_dice_ce_finish  : partials -> losses[3] = {dice, ce, w_dice*dice + w_ce*ce} (device f32)
+ *   oess_dice_ce_bwd     : d(w_dice*dice + w_ce*ce)/d logits * grad_scale[0] -> d_logits            */
+int oess_dice_ce_partials(const float* logits, const int64_t* target, int B, int K, int H, int W,
+                          int64_t ignore_index, double* partials, oess_stream_t stream);
+int oess_dice_ce_finish(const double* partials, int K, float w_dice, float w_ce, float* losses,
+                        oess_stream_t stream);
+int oess_dice_ce_bwd(const float* logits, const int64_t* target, int B, int K, int H, int W,
+                     int64_t ignore_index, const double* partials, float w_dice, float w_ce,
+                     const float* grad_scale, float* d_logits, oess_stream_t stream);
+
+/* Replaces evaluation/metrics.py:4-23 semseg_compute_confusion: conf[gt, pred] += 1 over gt != ignore.
+ * conf: device int64 [K, K], ACCUMULATES (zero it for a fresh matrix).  status: 1 if pred/gt out of range. */
+int oess_confusion(const int64_t* pred, const int64_t* gt, int64_t n, int K, int64_t ignore_label,
+                   int64_t* conf, int32_t* status, oess_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENESS_B200_H */

@@ -1,0 +1,360 @@
+// voxel_tbilinear.cu -- DDD17-style voxel grid (integer pixels, bilinear in t only) + 2-channel histogram.
+// Replaces datasets/data_util.py:51-117 (generate_voxel_grid) and :17-35 (generate_event_histogram).
+//
+// Compile with --fmad=false.  Reference arithmetic: weights are float64, the
+// grids are float32 and np.add.at performs, per event in ascending order, acc = f32(f64(acc) + w).
+// Four passes: pos-left, pos-right, neg-left, neg-right into two grids; result pos - neg or concat.
+//
+// ORDERED mode (bit-exact): stable radix sort of {pixel key, event index} per frame (radix.cuh), CSR
+// offsets per pixel, then one thread per pixel replays its events: left pass then right pass, pos and
+// neg accumulators in registers, float64 add + round-to-f32 per step exactly like np.add.at.
+// ATOMIC mode: one thread per event, 2 red.global.add.f32 (weights rounded to f32 first).
+#include "common.cuh"
+#include "radix.cuh"
+
+namespace oess {
+namespace tb {
+
+struct Geom {
+    int C, H, W;
+    uint32_t invalid_key;  // H*W
+};
+
+template <class T> struct is_int { static constexpr bool value = false; };
+template <> struct is_int<int64_t> { static constexpr bool value = true; };
+
+struct Decoded {
+    long long x, y, ti;
+    double d, ap;
+    bool pos, valid;
+};
+
+template <class T>
+struct FrameTime {
+    T first;
+    double dT;
+};
+
+template <class T>
+__device__ __forceinline__ FrameTime<T> frame_time(const T* __restrict__ ev4, int64_t fbeg, int64_t nf) {
+    FrameTime<T> ft;
+    ft.first = ev4[fbeg * 4 + 2];                          // data_util.py:68
+    const T draw = ev4[(fbeg + nf - 1) * 4 + 2] - ft.first;  // :67,69
+    ft.dT = (draw == (T)0) ? 1.0 : (double)draw;           // :71-72
+    return ft;
+}
+
+template <class T>
+__device__ __forceinline__ Decoded decode(const T* __restrict__ row, const FrameTime<T>& ft, const Geom& g,
+                                          T* p_out) {
+    Decoded r;
+    const T rx = row[0], ry = row[1], rt = row[2];
+    T p = row[3];
+    if (p == (T)0) { p = (T)-1; if (p_out) *p_out = p; }   // :78-79 (in place on the caller's array)
+    const T num = (T)(g.C - 1) * (rt - ft.first);           // :76, array dtype arithmetic
+    const double ts = __ddiv_rn((double)num, ft.dT);        //      then float64 true division
+    r.x = is_int<T>::value ? (long long)rx : cvtt_f64_i64((double)rx);  // :74-75
+    r.y = is_int<T>::value ? (long long)ry : cvtt_f64_i64((double)ry);
+    r.ti = cvtt_f64_i64(ts);                                // :81
+    r.d = __dsub_rn(ts, (double)r.ti);                      // :82
+    r.ap = fabs((double)p);                                 // :83-84
+    r.pos = (p == (T)1);                                    // :85
+    r.valid = (r.x < g.W) && (r.x >= 0) && (r.y < g.H) && (r.y >= 0) && (ts >= 0.0) && (ts < (double)g.C);  // :88
+    return r;
+}
+
+// The sort key of a row needs the frame's first/last timestamps (validity depends on ts), so k_keygen
+// first turns rows into {key, index-in-frame} pairs; the radix passes then move 8-byte pairs only.
+struct SrcPairs {
+    typedef uint2 Item;
+    const uint2* items;
+    __device__ __forceinline__ Item load(int, int64_t fbeg, uint32_t li) const { return items[fbeg + li]; }
+    __device__ __forceinline__ uint32_t key(const Item& it) const { return it.x; }
+};
+
+template <class T>
+__global__ void __launch_bounds__(256)
+k_keygen(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start,
+         int F, Geom g, int mutate_p, uint2* __restrict__ pairs, uint32_t* __restrict__ pix, int64_t pix_stride) {
+    const int gch = blockIdx.x;
+    const int f = find_frame(chunk_start, F, gch);
+    if (f < 0) return;
+    const int c = gch - chunk_start[f];
+    const int64_t fbeg = frame_offsets[f];
+    const int64_t nf = frame_offsets[f + 1] - fbeg;
+    const FrameTime<T> ft = frame_time(ev4, fbeg, nf);
+#pragma unroll 2
+    for (int s = 0; s < radix::kItemsPerThread; ++s) {
+        const int64_t li = (int64_t)c * radix::kChunk + s * radix::kThreads + threadIdx.x;
+        if (li >= nf) break;
+        T* row = ev4 + (fbeg + li) * 4;
+        const Decoded d = decode(row, ft, g, mutate_p ? row + 3 : (T*)nullptr);
+        const uint32_t key = d.valid ? (uint32_t)(d.y * g.W + d.x) : g.invalid_key;
+        pairs[fbeg + li] = make_uint2(key, (uint32_t)li);
+        atomicAdd(&pix[(int64_t)f * pix_stride + key], 1u);
+    }
+}
+
+__device__ __forceinline__ float add_at(float acc, double w) {  // np.add.at(f32 grid, idx, f64 vals)
+    return __double2float_rn(__dadd_rn((double)acc, w));
+}
+
+// CT > 0: one thread per pixel with 2*CT accumulators.  CT == 0: one thread per (bin, pixel).
+template <class T, int CT>
+__global__ void __launch_bounds__(256)
+k_gather(const T* __restrict__ ev4, const uint2* __restrict__ pairs, const int64_t* __restrict__ frame_offsets,
+         const uint32_t* __restrict__ pixoff, int64_t pix_stride, int F, Geom g, int separate_pol,
+         float* __restrict__ out) {
+    const int64_t HW = (int64_t)g.H * g.W;
+    const int64_t per_frame = CT > 0 ? HW : HW * g.C;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per_frame * F) return;
+    const int f = (int)(gid / per_frame);
+    int64_t r = gid - (int64_t)f * per_frame;
+    int my_t = 0;
+    if (CT == 0) { my_t = (int)(r / HW); r -= (int64_t)my_t * HW; }
+    const uint32_t key = (uint32_t)r;
+
+    constexpr int NA = CT > 0 ? CT : 1;
+    float ap[NA], an[NA];
+#pragma unroll
+    for (int c = 0; c < NA; ++c) { ap[c] = 0.0f; an[c] = 0.0f; }
+
+    const int64_t fbeg = frame_offsets[f];
+    const int64_t nf = frame_offsets[f + 1] - fbeg;
+    if (nf > 0) {
+        const uint32_t* off = pixoff + (int64_t)f * pix_stride;
+        const uint32_t s = off[key], e = off[key + 1];
+        if (s != e) {
+            const FrameTime<T> ft = frame_time(ev4, fbeg, nf);
+#pragma unroll
+            for (int right = 0; right < 2; ++right) {       // left pass (:91-92,:102-103) then right (:96-97,:107-108)
+                for (uint32_t j = s; j < e; ++j) {
+                    const uint32_t li = pairs[fbeg + j].y;
+                    const Decoded d = decode(ev4 + (fbeg + li) * 4, ft, g, (T*)nullptr);
+                    const long long tbin = d.ti + right;
+                    if (!(tbin < g.C)) continue;           // :87 / :94
+                    if (CT == 0 && tbin != my_t) continue;
+                    const double w = right ? __dmul_rn(d.ap, d.d) : __dmul_rn(d.ap, __dsub_rn(1.0, d.d));
+                    if (CT > 0) {
+#pragma unroll
+                        for (int c = 0; c < CT; ++c) {
+                            if (c == (int)tbin) {
+                                if (d.pos) ap[c] = add_at(ap[c], w); else an[c] = add_at(an[c], w);
+                            }
+                        }
+                    } else {
+                        if (d.pos) ap[0] = add_at(ap[0], w); else an[0] = add_at(an[0], w);
+                    }
+                }
+            }
+        }
+    }
+    const int planes = separate_pol ? 2 * g.C : g.C;
+    float* o = out + (int64_t)f * planes * HW + r;
+#pragma unroll
+    for (int c = 0; c < NA; ++c) {
+        const int bin = CT > 0 ? c : my_t;
+        if (separate_pol) {
+            __stcs(o + (int64_t)bin * HW, ap[c]);                       // :113-114 concat([pos, neg])
+            __stcs(o + (int64_t)(g.C + bin) * HW, an[c]);
+        } else {
+            __stcs(o + (int64_t)bin * HW, __fsub_rn(ap[c], an[c]));     // :116
+        }
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+k_atomic(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start,
+         int F, Geom g, int separate_pol, int mutate_p, float* __restrict__ out) {
+    const int gch = blockIdx.x;
+    const int f = find_frame(chunk_start, F, gch);
+    if (f < 0) return;
+    const int c = gch - chunk_start[f];
+    const int64_t fbeg = frame_offsets[f];
+    const int64_t nf = frame_offsets[f + 1] - fbeg;
+    const FrameTime<T> ft = frame_time(ev4, fbeg, nf);
+    const int64_t HW = (int64_t)g.H * g.W;
+    const int planes = separate_pol ? 2 * g.C : g.C;
+    float* o = out + (int64_t)f * planes * HW;
+#pragma unroll 2
+    for (int s = 0; s < radix::kItemsPerThread; ++s) {
+        const int64_t li = (int64_t)c * radix::kChunk + s * radix::kThreads + threadIdx.x;
+        if (li >= nf) break;
+        T* row = ev4 + (fbeg + li) * 4;
+        const Decoded d = decode(row, ft, g, mutate_p ? row + 3 : (T*)nullptr);
+        if (!d.valid) continue;
+        const int64_t pixel = d.y * g.W + d.x;
+        const float sign = (separate_pol || d.pos) ? 1.0f : -1.0f;
+        const int64_t plane0 = (separate_pol && !d.pos) ? g.C : 0;
+        if (d.ti < g.C)
+            atomicAdd(o + (plane0 + d.ti) * HW + pixel, sign * (float)(d.ap * (1.0 - d.d)));
+        if (d.ti + 1 < g.C)
+            atomicAdd(o + (plane0 + d.ti + 1) * HW + pixel, sign * (float)(d.ap * d.d));
+    }
+}
+
+// data_util.py:17-35: out[f, 0] = neg counts, out[f, 1] = pos counts; flat index x + W*y.
+// One thread per event over the flat event range; the frame is found by binary search in frame_offsets.
+template <class T>
+__global__ void __launch_bounds__(256)
+k_histogram(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, int64_t n, int F, int H, int W,
+            int mutate_p, float* __restrict__ out, int32_t* __restrict__ status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int lo = 0, hi = F;  // frame_offsets[lo] <= i < frame_offsets[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (frame_offsets[mid] <= i) lo = mid; else hi = mid;
+    }
+    const int64_t HW = (int64_t)H * W;
+    float* o = out + (int64_t)lo * 2 * HW;
+    T* row = ev4 + i * 4;
+    T p = row[3];
+    if (p == (T)0) { p = (T)-1; if (mutate_p) row[3] = p; }   // :26
+    if (p != (T)1 && p != (T)-1) return;                       // :30-31 boolean masks
+    const long long x = is_int<T>::value ? (long long)row[0] : cvtt_f64_i64((double)row[0]);  // :23-24
+    const long long y = is_int<T>::value ? (long long)row[1] : cvtt_f64_i64((double)row[1]);
+    const long long idx = x + (long long)W * y;
+    if (idx < 0 || idx >= HW) { if (status) *status = 1; return; }
+    atomicAdd(o + (p == (T)1 ? HW : 0) + idx, 1.0f);            // :33 stack([neg, pos])
+}
+
+struct Ws {
+    int* chunk_start;
+    uint32_t *hist, *tot, *pix;
+    uint2 *a, *b;
+    int64_t pix_stride;
+    size_t bytes;
+};
+
+static Ws carve(void* ws, int mode, int64_t n, int F, int H, int W) {
+    Ws r{};
+    WsCarver c(ws);
+    r.chunk_start = c.take<int>((size_t)F + 1);
+    if (mode == OESS_MODE_ORDERED) {
+        const int64_t nkeys = (int64_t)H * W + 1;
+        r.pix_stride = (int64_t)align_up((size_t)nkeys + 1, 4);
+        r.hist = c.take<uint32_t>((size_t)radix::max_chunks(n, F) * radix::kBins);
+        r.tot = c.take<uint32_t>((size_t)F * radix::kBins);
+        r.pix = c.take<uint32_t>((size_t)F * r.pix_stride);
+        r.a = c.take<uint2>((size_t)n);
+        r.b = c.take<uint2>((size_t)n);
+    }
+    r.bytes = c.total();
+    return r;
+}
+
+template <class T>
+static int run(T* ev4, const int64_t* frame_offsets, int64_t n, int F, int C, int H, int W, int separate_pol,
+               int mode, int mutate_p, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (n < 0 || F < 0 || C <= 0 || H <= 0 || W <= 0) return OESS_E_ARG;   // data_util.py:59-62 asserts
+    if (mode != OESS_MODE_ORDERED && mode != OESS_MODE_ATOMIC) return OESS_E_ARG;
+    if ((int64_t)H * W + 2 >= (1ll << 31) || n >= (1ll << 31)) return OESS_E_RANGE;
+    if (F == 0) return OESS_OK;
+    if (!frame_offsets || !out || (n > 0 && !ev4)) return OESS_E_ARG;
+    const Ws w = carve(ws, mode, n, F, H, W);
+    if (!ws || ws_bytes < w.bytes) return OESS_E_WORKSPACE;
+    const Geom g{C, H, W, (uint32_t)(H * W)};
+    const int64_t HW = (int64_t)H * W;
+    const int planes = separate_pol ? 2 * C : C;
+
+    OESS_KERNEL("k_chunk_map", st, k_chunk_map<<<1, 1024, 0, st>>>(frame_offsets, F, radix::kChunk, w.chunk_start));
+    const int64_t nch = radix::max_chunks(n, F);
+
+    if (mode == OESS_MODE_ATOMIC) {
+        OESS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)F * planes * HW, st));
+        if (n > 0) {
+            OESS_KERNEL("tb_atomic", st, k_atomic<T><<<(unsigned)nch, radix::kThreads, 0, st>>>(ev4, frame_offsets, w.chunk_start, F, g,
+                                                                  separate_pol, mutate_p, out));
+        }
+        return OESS_OK;
+    }
+    OESS_CUDA(cudaMemsetAsync(w.pix, 0, sizeof(uint32_t) * (size_t)F * w.pix_stride, st));
+    uint2* cur = w.a;
+    if (n > 0) {
+        OESS_KERNEL("tb_keygen", st, k_keygen<T><<<(unsigned)nch, radix::kThreads, 0, st>>>(ev4, frame_offsets, w.chunk_start, F, g, mutate_p,
+                                                              w.a, w.pix, w.pix_stride));
+        const int bits = radix::key_bits(g.invalid_key + 1);
+        const int passes = (bits + radix::kBits - 1) / radix::kBits;
+        const int pbits = (bits + passes - 1) / passes;
+        const uint32_t mask = (1u << pbits) - 1;
+        for (int p = 0; p < passes; ++p) {
+            uint2* dst = (cur == w.a) ? w.b : w.a;
+            SrcPairs src{cur};
+            int rc = radix::run_pass(src, frame_offsets, w.chunk_start, F, nch, p * pbits, mask, w.hist, w.tot,
+                                     (uint32_t*)nullptr, 0, dst, st);
+            if (rc) return rc;
+            cur = dst;
+        }
+    }
+    OESS_KERNEL("k_seg_exscan_u32", st, k_seg_exscan_u32<<<(unsigned)F, 1024, 0, st>>>(w.pix, w.pix_stride, (int64_t)g.invalid_key + 2));
+    if (C == 5) {
+        const int64_t total = (int64_t)F * HW;
+        OESS_KERNEL("tb_gather", st, k_gather<T, 5><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            ev4, cur, frame_offsets, w.pix, w.pix_stride, F, g, separate_pol, out));
+    } else {
+        const int64_t total = (int64_t)F * HW * C;
+        OESS_KERNEL("tb_gather", st, k_gather<T, 0><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+            ev4, cur, frame_offsets, w.pix, w.pix_stride, F, g, separate_pol, out));
+    }
+    return OESS_OK;
+}
+
+template <class T>
+static int run_hist(T* ev4, const int64_t* frame_offsets, int64_t n, int F, int H, int W, int mutate_p,
+                    float* out, int32_t* status, cudaStream_t st) {
+    if (n < 0 || F < 0 || H <= 0 || W <= 0) return OESS_E_ARG;
+    if (F == 0) return OESS_OK;
+    if (!frame_offsets || !out || (n > 0 && !ev4)) return OESS_E_ARG;
+    OESS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)F * 2 * H * W, st));
+    if (status) OESS_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    if (n == 0) return OESS_OK;
+    OESS_KERNEL("k_histogram", st, k_histogram<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ev4, frame_offsets, n, F, H, W, mutate_p, out,
+                                                               status));
+    return OESS_OK;
+}
+
+}  // namespace tb
+}  // namespace oess
+
+using namespace oess;
+
+int oess_voxel_tbilinear_ws_bytes_impl(int mode, int64_t n, int F, int C, int H, int W, size_t* out) {
+    if (!out || n < 0 || F < 0 || C <= 0 || H <= 0 || W <= 0) return OESS_E_ARG;
+    if (mode != OESS_MODE_ORDERED && mode != OESS_MODE_ATOMIC) return OESS_E_ARG;
+    if ((int64_t)H * W + 2 >= (1ll << 31)) return OESS_E_RANGE;
+    *out = tb::carve(nullptr, mode, n, F, H, W).bytes;
+    return OESS_OK;
+}
+
+OESS_API int oess_voxel_tbilinear_i64(int64_t* ev4, const int64_t* frame_offsets, int64_t n, int F, int C, int H,
+                                      int W, int separate_pol, int mode, int mutate_p, float* out, void* ws,
+                                      size_t ws_bytes, oess_stream_t stream) {
+    return tb::run<int64_t>(ev4, frame_offsets, n, F, C, H, W, separate_pol, mode, mutate_p, out, ws, ws_bytes,
+                            (cudaStream_t)stream);
+}
+OESS_API int oess_voxel_tbilinear_f64(double* ev4, const int64_t* frame_offsets, int64_t n, int F, int C, int H,
+                                      int W, int separate_pol, int mode, int mutate_p, float* out, void* ws,
+                                      size_t ws_bytes, oess_stream_t stream) {
+    return tb::run<double>(ev4, frame_offsets, n, F, C, H, W, separate_pol, mode, mutate_p, out, ws, ws_bytes,
+                           (cudaStream_t)stream);
+}
+
+OESS_API int oess_voxel_histogram_i64(int64_t* ev4, const int64_t* frame_offsets, int64_t n, int F, int H, int W,
+                                      int mutate_p, float* out, int32_t* status, oess_stream_t stream) {
+    return tb::run_hist<int64_t>(ev4, frame_offsets, n, F, H, W, mutate_p, out, status, (cudaStream_t)stream);
+}
+OESS_API int oess_voxel_histogram_f64(double* ev4, const int64_t* frame_offsets, int64_t n, int F, int H, int W,
+                                      int mutate_p, float* out, int32_t* status, oess_stream_t stream) {
+    return tb::run_hist<double>(ev4, frame_offsets, n, F, H, W, mutate_p, out, status, (cudaStream_t)stream);
+}
+
+int oess_voxel_trilinear_ws_bytes_impl(int mode, int64_t n, int F, int C, int H, int W, size_t* out);
+
+OESS_API int oess_voxel_ws_bytes(int kind, int mode, int64_t n, int F, int C, int H, int W, size_t* ws_bytes) {
+    if (kind == OESS_KIND_TRILINEAR) return oess_voxel_trilinear_ws_bytes_impl(mode, n, F, C, H, W, ws_bytes);
+    if (kind == OESS_KIND_TBILINEAR) return oess_voxel_tbilinear_ws_bytes_impl(mode, n, F, C, H, W, ws_bytes);
+    return OESS_E_ARG;
+}

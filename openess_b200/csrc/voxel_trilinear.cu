@@ -1,0 +1,266 @@
+// voxel_trilinear.cu -- DSEC-style voxel grid: trilinear (x, y, t) splat of float-pixel events.
+// Replaces DSEC/dataset/representations.py:15-55 (VoxelGrid.convert).
+//
+// Compile with --fmad=false: every float op below must round exactly like the reference's separate
+// torch ops (no FMA contraction).  The rounding-critical expressions additionally use the explicit
+// _rn intrinsics so the intent survives a flag change.
+//
+// ORDERED mode (bit-exact): per voxel the reference adds, in this order (representations.py:33-43,
+// serial put_): for xl in (x0, x0+1): for yl in (y0, y0+1): for tl in (t0, t0+1): events ascending.
+//   1. stable radix sort of each frame's events by source cell (x0, y0)  (radix.cuh) -> float4 records
+//   2. per-frame CSR offsets per source cell (histogram in pass 0 + exclusive scan)
+//   3. one thread per output pixel (xl, yl): walks the 4 source cells (x0, y0) = (xl-dx, yl-dy) in
+//      (dx, dy) order, twice (dt = 0, 1), adding into C register accumulators -> same add order,
+//      same f32 roundings as the reference; writes its C outputs coalesced.  No atomics, no memset.
+// ATOMIC mode: one thread per event, 8 red.global.add.f32 into the zeroed grid.
+#include "common.cuh"
+#include "normalize.cuh"
+#include "radix.cuh"
+
+namespace oess {
+namespace tri {
+
+struct Geom {
+    int C, H, W;
+    uint32_t invalid_key;  // (H+1)*(W+1): events that cannot touch the grid, sorted to the end
+};
+
+__device__ __forceinline__ uint32_t cell_key(float x, float y, const Geom& g) {
+    const int x0 = cvtt_f32_i32(x), y0 = cvtt_f32_i32(y);  // representations.py:27-28
+    // source cell (x0, y0) can reach the grid iff x0 in [-1, W-1] and y0 in [-1, H-1]
+    if (x0 < -1 || x0 > g.W - 1 || y0 < -1 || y0 > g.H - 1) return g.invalid_key;
+    return (uint32_t)(y0 + 1) * (uint32_t)(g.W + 1) + (uint32_t)(x0 + 1);
+}
+
+// record = (x, y, t_raw, pol)
+struct SrcSoA {
+    typedef float4 Item;
+    const float *x, *y, *pol, *t;
+    Geom g;
+    __device__ __forceinline__ Item load(int, int64_t fbeg, uint32_t li) const {
+        const int64_t i = fbeg + li;
+        return make_float4(ld_stream(x + i), ld_stream(y + i), ld_stream(t + i), ld_stream(pol + i));
+    }
+    __device__ __forceinline__ uint32_t key(const Item& it) const { return cell_key(it.x, it.y, g); }
+};
+struct SrcAoS {
+    typedef float4 Item;
+    const float4* items;
+    Geom g;
+    __device__ __forceinline__ Item load(int, int64_t fbeg, uint32_t li) const { return items[fbeg + li]; }
+    __device__ __forceinline__ uint32_t key(const Item& it) const { return cell_key(it.x, it.y, g); }
+};
+
+// representations.py:24-25,29,31,37: per-event normalised time, bin, and the corner weight.
+__device__ __forceinline__ float t_norm(float t, float tfirst, float den, float cm1) {
+    return __fdiv_rn(__fmul_rn(cm1, __fsub_rn(t, tfirst)), den);
+}
+__device__ __forceinline__ float corner_weight(float x, float y, float pol, float tn, int xl, int yl, int tl) {
+    const float val = __fsub_rn(__fmul_rn(2.0f, pol), 1.0f);
+    const float ax = __fsub_rn(1.0f, fabsf(__fsub_rn(__int2float_rn(xl), x)));
+    const float ay = __fsub_rn(1.0f, fabsf(__fsub_rn(__int2float_rn(yl), y)));
+    const float at = __fsub_rn(1.0f, fabsf(__fsub_rn(__int2float_rn(tl), tn)));
+    return __fmul_rn(__fmul_rn(__fmul_rn(val, ax), ay), at);
+}
+
+// CT > 0: one thread per output pixel, CT accumulators.  CT == 0: one thread per output voxel.
+template <int CT>
+__global__ void __launch_bounds__(256)
+k_gather(const float4* __restrict__ items, const float* __restrict__ t_orig,
+         const int64_t* __restrict__ frame_offsets, const uint32_t* __restrict__ pixoff, int64_t pix_stride,
+         int F, Geom g, float* __restrict__ out) {
+    const int64_t HW = (int64_t)g.H * g.W;
+    const int64_t per_frame = CT > 0 ? HW : HW * g.C;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= per_frame * F) return;
+    const int f = (int)(gid / per_frame);
+    int64_t r = gid - (int64_t)f * per_frame;
+    int my_t = 0;
+    if (CT == 0) { my_t = (int)(r / HW); r -= (int64_t)my_t * HW; }
+    const int yl = (int)(r / g.W), xl = (int)(r - (int64_t)yl * g.W);
+
+    float acc[CT > 0 ? CT : 1];
+#pragma unroll
+    for (int c = 0; c < (CT > 0 ? CT : 1); ++c) acc[c] = 0.0f;
+
+    const int64_t fbeg = frame_offsets[f];
+    const int64_t nf = frame_offsets[f + 1] - fbeg;
+    if (nf > 0) {
+        const float tfirst = t_orig[fbeg];
+        const float den = __fsub_rn(t_orig[fbeg + nf - 1], tfirst);
+        const float cm1 = (float)(g.C - 1);
+        const uint32_t* off = pixoff + (int64_t)f * pix_stride;
+        const float4* fit = items + fbeg;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy) {
+                const uint32_t key = (uint32_t)(yl - dy + 1) * (uint32_t)(g.W + 1) + (uint32_t)(xl - dx + 1);
+                const uint32_t s = off[key], e = off[key + 1];
+                if (s == e) continue;
+#pragma unroll
+                for (int dt = 0; dt < 2; ++dt) {
+                    for (uint32_t j = s; j < e; ++j) {
+                        const float4 it = fit[j];
+                        const float tn = t_norm(it.z, tfirst, den, cm1);
+                        const int tl = (int)((unsigned)cvtt_f32_i32(tn) + (unsigned)dt);
+                        if (tl < 0 || tl >= g.C) continue;  // representations.py:36 (x/y already in range)
+                        if (CT == 0 && tl != my_t) continue;
+                        const float w = corner_weight(it.x, it.y, it.w, tn, xl, yl, tl);
+                        if (CT > 0) {
+#pragma unroll
+                            for (int c = 0; c < CT; ++c) acc[c] = (c == tl) ? __fadd_rn(acc[c], w) : acc[c];
+                        } else {
+                            acc[0] = __fadd_rn(acc[0], w);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (CT > 0) {
+        float* o = out + (int64_t)f * g.C * HW + (int64_t)yl * g.W + xl;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) __stcs(o + (int64_t)c * HW, acc[c]);
+    } else {
+        __stcs(out + ((int64_t)f * g.C + my_t) * HW + (int64_t)yl * g.W + xl, acc[0]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_atomic(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ pol,
+         const float* __restrict__ t, const int64_t* __restrict__ frame_offsets,
+         const int* __restrict__ chunk_start, int F, Geom g, float* __restrict__ out) {
+    const int gch = blockIdx.x;
+    const int f = find_frame(chunk_start, F, gch);
+    if (f < 0) return;
+    const int c = gch - chunk_start[f];
+    const int64_t fbeg = frame_offsets[f];
+    const int64_t nf = frame_offsets[f + 1] - fbeg;
+    const float tfirst = t[fbeg];
+    const float den = __fsub_rn(t[fbeg + nf - 1], tfirst);
+    const float cm1 = (float)(g.C - 1);
+    const int64_t HW = (int64_t)g.H * g.W;
+    float* o = out + (int64_t)f * g.C * HW;
+#pragma unroll 4
+    for (int s = 0; s < radix::kItemsPerThread; ++s) {
+        const int64_t li = (int64_t)c * radix::kChunk + s * radix::kThreads + threadIdx.x;
+        if (li >= nf) break;
+        const int64_t i = fbeg + li;
+        const float xi = ld_stream(x + i), yi = ld_stream(y + i), pi = ld_stream(pol + i);
+        const float tn = t_norm(ld_stream(t + i), tfirst, den, cm1);
+        const int x0 = cvtt_f32_i32(xi), y0 = cvtt_f32_i32(yi), t0 = cvtt_f32_i32(tn);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int xl = (int)((unsigned)x0 + (unsigned)(k >> 2));
+            const int yl = (int)((unsigned)y0 + (unsigned)((k >> 1) & 1));
+            const int tl = (int)((unsigned)t0 + (unsigned)(k & 1));
+            if (xl < 0 || xl >= g.W || yl < 0 || yl >= g.H || tl < 0 || tl >= g.C) continue;
+            atomicAdd(o + (int64_t)tl * HW + (int64_t)yl * g.W + xl, corner_weight(xi, yi, pi, tn, xl, yl, tl));
+        }
+    }
+}
+
+struct Ws {
+    int* chunk_start;
+    uint32_t *hist, *tot, *pix;
+    float4 *a, *b;
+    double* stats;
+    int64_t pix_stride;
+    size_t bytes;
+};
+
+static Ws carve(void* ws, int mode, int64_t n, int F, int H, int W) {
+    Ws r{};
+    WsCarver c(ws);
+    r.chunk_start = c.take<int>((size_t)F + 1);
+    r.stats = c.take<double>((size_t)F * 3);
+    if (mode == OESS_MODE_ORDERED) {
+        const int64_t nkeys = (int64_t)(H + 1) * (W + 1) + 1;  // + invalid key
+        r.pix_stride = (int64_t)align_up((size_t)nkeys + 1, 4);
+        r.hist = c.take<uint32_t>((size_t)radix::max_chunks(n, F) * radix::kBins);
+        r.tot = c.take<uint32_t>((size_t)F * radix::kBins);
+        r.pix = c.take<uint32_t>((size_t)F * r.pix_stride);
+        r.a = c.take<float4>((size_t)n);
+        r.b = c.take<float4>((size_t)n);
+    }
+    r.bytes = c.total();
+    return r;
+}
+
+}  // namespace tri
+}  // namespace oess
+
+using namespace oess;
+
+int oess_voxel_trilinear_ws_bytes_impl(int mode, int64_t n, int F, int C, int H, int W, size_t* out) {
+    if (!out || n < 0 || F < 0 || C <= 0 || H <= 0 || W <= 0) return OESS_E_ARG;
+    if (mode != OESS_MODE_ORDERED && mode != OESS_MODE_ATOMIC) return OESS_E_ARG;
+    if ((int64_t)(H + 1) * (W + 1) + 2 >= (1ll << 31)) return OESS_E_RANGE;
+    *out = tri::carve(nullptr, mode, n, F, H, W).bytes;
+    return OESS_OK;
+}
+
+OESS_API int oess_voxel_trilinear(const float* x, const float* y, const float* pol, const float* t,
+                                  const int64_t* frame_offsets, int64_t n, int F, int C, int H, int W,
+                                  int mode, int normalize, float* out, void* ws, size_t ws_bytes,
+                                  oess_stream_t stream) {
+    size_t need = 0;
+    int rc = oess_voxel_trilinear_ws_bytes_impl(mode, n, F, C, H, W, &need);
+    if (rc) return rc;
+    if (F == 0) return OESS_OK;
+    if (!frame_offsets || !out || (n > 0 && (!x || !y || !pol || !t))) return OESS_E_ARG;
+    if (!ws || ws_bytes < need) return OESS_E_WORKSPACE;
+    if (n >= (1ll << 31)) return OESS_E_RANGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const tri::Ws w = tri::carve(ws, mode, n, F, H, W);
+    const tri::Geom g{C, H, W, (uint32_t)((H + 1) * (W + 1))};
+    const int64_t HW = (int64_t)H * W;
+
+    OESS_KERNEL("k_chunk_map", st, k_chunk_map<<<1, 1024, 0, st>>>(frame_offsets, F, radix::kChunk, w.chunk_start));
+    const int64_t nch = radix::max_chunks(n, F);
+
+    if (mode == OESS_MODE_ATOMIC) {
+        OESS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)F * C * HW, st));
+        if (n > 0) {
+            OESS_KERNEL("tri_atomic", st, tri::k_atomic<<<(unsigned)nch, radix::kThreads, 0, st>>>(x, y, pol, t, frame_offsets, w.chunk_start,
+                                                                    F, g, out));
+        }
+    } else {
+        OESS_CUDA(cudaMemsetAsync(w.pix, 0, sizeof(uint32_t) * (size_t)F * w.pix_stride, st));
+        const int bits = radix::key_bits(g.invalid_key + 1);
+        const int passes = (bits + radix::kBits - 1) / radix::kBits;
+        const int pbits = (bits + passes - 1) / passes;
+        const uint32_t mask = (1u << pbits) - 1;
+        float4* cur = nullptr;
+        for (int p = 0; p < passes && n > 0; ++p) {
+            float4* dst = (p & 1) ? w.b : w.a;
+            if (p == 0) {
+                tri::SrcSoA src{x, y, pol, t, g};
+                rc = radix::run_pass(src, frame_offsets, w.chunk_start, F, nch, 0, mask, w.hist, w.tot, w.pix,
+                                     w.pix_stride, dst, st);
+            } else {
+                tri::SrcAoS src{cur, g};
+                rc = radix::run_pass(src, frame_offsets, w.chunk_start, F, nch, p * pbits, mask, w.hist, w.tot,
+                                     (uint32_t*)nullptr, 0, dst, st);
+            }
+            if (rc) return rc;
+            cur = dst;
+        }
+        OESS_KERNEL("k_seg_exscan_u32", st, k_seg_exscan_u32<<<(unsigned)F, 1024, 0, st>>>(w.pix, w.pix_stride, (int64_t)g.invalid_key + 2));
+        if (C == 5) {
+            const int64_t total = (int64_t)F * HW;
+            OESS_KERNEL("tri_gather", st, tri::k_gather<5><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                cur, t, frame_offsets, w.pix, w.pix_stride, F, g, out));
+        } else {
+            const int64_t total = (int64_t)F * HW * C;
+            OESS_KERNEL("tri_gather", st, tri::k_gather<0><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+                cur, t, frame_offsets, w.pix, w.pix_stride, F, g, out));
+        }
+    }
+    if (normalize) {
+        rc = launch_nonzero_standardize(out, (int64_t)C * HW, F, w.stats, 0, 1, st);
+        if (rc) return rc;
+    }
+    return OESS_OK;
+}

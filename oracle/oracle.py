@@ -86,11 +86,13 @@ def histogram(events, shape):
     return out
 
 
-def voxel_trilinear(x, y, pol, t, C, H, W, normalize=False):
-    """representations.py:15-55 (serial put_ order)."""
+def voxel_trilinear(x, y, pol, t, C, H, W, normalize=False, out=None):
+    """representations.py:15-55 (serial put_ order).  `out` may be a reusable [C,H,W] float32 buffer."""
     x, y, pol, t = (np.ascontiguousarray(a, np.float32) for a in (x, y, pol, t))
     assert x.shape == y.shape == pol.shape == t.shape and x.ndim == 1
-    out = np.empty((C, H, W), np.float32)
+    if out is None:
+        out = np.empty((C, H, W), np.float32)
+    assert out.shape == (C, H, W) and out.dtype == np.float32 and out.flags.c_contiguous
     rc = lib().oracle_voxel_trilinear(_p(x, _f32p), _p(y, _f32p), _p(pol, _f32p), _p(t, _f32p),
                                       ctypes.c_int64(x.shape[0]), C, H, W, int(bool(normalize)), _p(out, _f32p))
     _check(rc, "voxel_trilinear")
