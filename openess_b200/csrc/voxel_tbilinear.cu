@@ -5,9 +5,11 @@
 // grids are float32 and np.add.at performs, per event in ascending order, acc = f32(f64(acc) + w).
 // Four passes: pos-left, pos-right, neg-left, neg-right into two grids; result pos - neg or concat.
 //
-// ORDERED mode (bit-exact): stable radix sort of {pixel key, event index} per frame (radix.cuh), CSR
-// offsets per pixel, then one thread per pixel replays its events: left pass then right pass, pos and
-// neg accumulators in registers, float64 add + round-to-f32 per step exactly like np.add.at.
+// ORDERED mode (bit-exact): stable radix sort of {pixel key, event index} per frame (radix.cuh); then
+// THREADS MAP TO SORTED EVENTS (dense lanes: pixels are mostly empty): the first event of every pixel run
+// replays the run -- left pass then right pass, pos and neg accumulators in registers, float64 add +
+// round-to-f32 per step exactly like np.add.at -- and writes that pixel's bins into the zeroed grid.
+// Different pixels never interact (integer pixels), so there are no atomics and no conflicts.
 // ATOMIC mode: one thread per event, 2 red.global.add.f32 (weights rounded to f32 first).
 #include "common.cuh"
 #include "radix.cuh"
@@ -75,7 +77,7 @@ struct SrcPairs {
 template <class T>
 __global__ void __launch_bounds__(256)
 k_keygen(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start,
-         int F, Geom g, int mutate_p, uint2* __restrict__ pairs, uint32_t* __restrict__ pix, int64_t pix_stride) {
+         int F, Geom g, int mutate_p, uint2* __restrict__ pairs) {
     const int gch = blockIdx.x;
     const int f = find_frame(chunk_start, F, gch);
     if (f < 0) return;
@@ -91,7 +93,6 @@ k_keygen(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, const i
         const Decoded d = decode(row, ft, g, mutate_p ? row + 3 : (T*)nullptr);
         const uint32_t key = d.valid ? (uint32_t)(d.y * g.W + d.x) : g.invalid_key;
         pairs[fbeg + li] = make_uint2(key, (uint32_t)li);
-        atomicAdd(&pix[(int64_t)f * pix_stride + key], 1u);
     }
 }
 
@@ -99,67 +100,68 @@ __device__ __forceinline__ float add_at(float acc, double w) {  // np.add.at(f32
     return __double2float_rn(__dadd_rn((double)acc, w));
 }
 
-// CT > 0: one thread per pixel with 2*CT accumulators.  CT == 0: one thread per (bin, pixel).
+// One thread per sorted {key, index} pair; the head of each pixel run replays the run.
+// CT > 0: all CT bins at once (2*CT register accumulators).  CT == 0: any C, one bin at a time.
 template <class T, int CT>
 __global__ void __launch_bounds__(256)
-k_gather(const T* __restrict__ ev4, const uint2* __restrict__ pairs, const int64_t* __restrict__ frame_offsets,
-         const uint32_t* __restrict__ pixoff, int64_t pix_stride, int F, Geom g, int separate_pol,
-         float* __restrict__ out) {
-    const int64_t HW = (int64_t)g.H * g.W;
-    const int64_t per_frame = CT > 0 ? HW : HW * g.C;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= per_frame * F) return;
-    const int f = (int)(gid / per_frame);
-    int64_t r = gid - (int64_t)f * per_frame;
-    int my_t = 0;
-    if (CT == 0) { my_t = (int)(r / HW); r -= (int64_t)my_t * HW; }
-    const uint32_t key = (uint32_t)r;
-
-    constexpr int NA = CT > 0 ? CT : 1;
-    float ap[NA], an[NA];
-#pragma unroll
-    for (int c = 0; c < NA; ++c) { ap[c] = 0.0f; an[c] = 0.0f; }
-
+k_runs(const T* __restrict__ ev4, const uint2* __restrict__ pairs, const int64_t* __restrict__ frame_offsets,
+       const int* __restrict__ chunk_start, int F, Geom g, int separate_pol, float* __restrict__ out) {
+    const int gch = blockIdx.x;
+    const int f = find_frame(chunk_start, F, gch);
+    if (f < 0) return;
+    const int c = gch - chunk_start[f];
     const int64_t fbeg = frame_offsets[f];
     const int64_t nf = frame_offsets[f + 1] - fbeg;
-    if (nf > 0) {
-        const uint32_t* off = pixoff + (int64_t)f * pix_stride;
-        const uint32_t s = off[key], e = off[key + 1];
-        if (s != e) {
-            const FrameTime<T> ft = frame_time(ev4, fbeg, nf);
+    const FrameTime<T> ft = frame_time(ev4, fbeg, nf);
+    const int64_t HW = (int64_t)g.H * g.W;
+    const int planes = separate_pol ? 2 * g.C : g.C;
+    const uint2* pr = pairs + fbeg;
+#pragma unroll 1
+    for (int s = 0; s < radix::kItemsPerThread; ++s) {
+        const int64_t i = (int64_t)c * radix::kChunk + s * radix::kThreads + threadIdx.x;
+        if (i >= nf) break;
+        const uint2 me = pr[i];
+        if (me.x >= g.invalid_key) continue;                      // :88 invalid events sort last
+        if (i > 0 && pr[i - 1].x == me.x) continue;               // not the head of its pixel run
+        float* o = out + (int64_t)f * planes * HW + me.x;
+        constexpr int NA = CT > 0 ? CT : 1;
+        const int nbin_loops = CT > 0 ? 1 : g.C;
+        for (int bin = 0; bin < nbin_loops; ++bin) {
+            float ap[NA], an[NA];
 #pragma unroll
-            for (int right = 0; right < 2; ++right) {       // left pass (:91-92,:102-103) then right (:96-97,:107-108)
-                for (uint32_t j = s; j < e; ++j) {
-                    const uint32_t li = pairs[fbeg + j].y;
-                    const Decoded d = decode(ev4 + (fbeg + li) * 4, ft, g, (T*)nullptr);
+            for (int k = 0; k < NA; ++k) { ap[k] = 0.0f; an[k] = 0.0f; }
+#pragma unroll 1
+            for (int right = 0; right < 2; ++right) {             // left pass (:91-92,:102-103) then right (:96-97,:107-108)
+                for (int64_t j = i; j < nf; ++j) {
+                    const uint2 pj = (j == i) ? me : pr[j];
+                    if (pj.x != me.x) break;
+                    const Decoded d = decode(ev4 + (fbeg + pj.y) * 4, ft, g, (T*)nullptr);
                     const long long tbin = d.ti + right;
-                    if (!(tbin < g.C)) continue;           // :87 / :94
-                    if (CT == 0 && tbin != my_t) continue;
+                    if (!(tbin < g.C)) continue;                  // :87 / :94
+                    if (CT == 0 && tbin != bin) continue;
                     const double w = right ? __dmul_rn(d.ap, d.d) : __dmul_rn(d.ap, __dsub_rn(1.0, d.d));
                     if (CT > 0) {
 #pragma unroll
-                        for (int c = 0; c < CT; ++c) {
-                            if (c == (int)tbin) {
-                                if (d.pos) ap[c] = add_at(ap[c], w); else an[c] = add_at(an[c], w);
-                            }
+                        for (int k = 0; k < CT; ++k) {
+                            const bool hit = (k == (int)tbin);
+                            ap[k] = (hit && d.pos) ? add_at(ap[k], w) : ap[k];
+                            an[k] = (hit && !d.pos) ? add_at(an[k], w) : an[k];
                         }
                     } else {
                         if (d.pos) ap[0] = add_at(ap[0], w); else an[0] = add_at(an[0], w);
                     }
                 }
             }
-        }
-    }
-    const int planes = separate_pol ? 2 * g.C : g.C;
-    float* o = out + (int64_t)f * planes * HW + r;
 #pragma unroll
-    for (int c = 0; c < NA; ++c) {
-        const int bin = CT > 0 ? c : my_t;
-        if (separate_pol) {
-            __stcs(o + (int64_t)bin * HW, ap[c]);                       // :113-114 concat([pos, neg])
-            __stcs(o + (int64_t)(g.C + bin) * HW, an[c]);
-        } else {
-            __stcs(o + (int64_t)bin * HW, __fsub_rn(ap[c], an[c]));     // :116
+            for (int k = 0; k < NA; ++k) {
+                const int b = CT > 0 ? k : bin;
+                if (separate_pol) {
+                    o[(int64_t)b * HW] = ap[k];                             // :113-114 concat([pos, neg])
+                    o[(int64_t)(g.C + b) * HW] = an[k];
+                } else {
+                    o[(int64_t)b * HW] = __fsub_rn(ap[k], an[k]);           // :116
+                }
+            }
         }
     }
 }
@@ -223,9 +225,8 @@ k_histogram(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, int6
 
 struct Ws {
     int* chunk_start;
-    uint32_t *hist, *tot, *pix;
+    uint32_t *hist, *tot;
     uint2 *a, *b;
-    int64_t pix_stride;
     size_t bytes;
 };
 
@@ -234,11 +235,8 @@ static Ws carve(void* ws, int mode, int64_t n, int F, int H, int W) {
     WsCarver c(ws);
     r.chunk_start = c.take<int>((size_t)F + 1);
     if (mode == OESS_MODE_ORDERED) {
-        const int64_t nkeys = (int64_t)H * W + 1;
-        r.pix_stride = (int64_t)align_up((size_t)nkeys + 1, 4);
         r.hist = c.take<uint32_t>((size_t)radix::max_chunks(n, F) * radix::kBins);
         r.tot = c.take<uint32_t>((size_t)F * radix::kBins);
-        r.pix = c.take<uint32_t>((size_t)F * r.pix_stride);
         r.a = c.take<uint2>((size_t)n);
         r.b = c.take<uint2>((size_t)n);
     }
@@ -271,33 +269,29 @@ static int run(T* ev4, const int64_t* frame_offsets, int64_t n, int F, int C, in
         }
         return OESS_OK;
     }
-    OESS_CUDA(cudaMemsetAsync(w.pix, 0, sizeof(uint32_t) * (size_t)F * w.pix_stride, st));
+    OESS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)F * planes * HW, st));
+    if (n == 0) return OESS_OK;
     uint2* cur = w.a;
-    if (n > 0) {
-        OESS_KERNEL("tb_keygen", st, k_keygen<T><<<(unsigned)nch, radix::kThreads, 0, st>>>(ev4, frame_offsets, w.chunk_start, F, g, mutate_p,
-                                                              w.a, w.pix, w.pix_stride));
-        const int bits = radix::key_bits(g.invalid_key + 1);
-        const int passes = (bits + radix::kBits - 1) / radix::kBits;
-        const int pbits = (bits + passes - 1) / passes;
-        const uint32_t mask = (1u << pbits) - 1;
-        for (int p = 0; p < passes; ++p) {
-            uint2* dst = (cur == w.a) ? w.b : w.a;
-            SrcPairs src{cur};
-            int rc = radix::run_pass(src, frame_offsets, w.chunk_start, F, nch, p * pbits, mask, w.hist, w.tot,
-                                     (uint32_t*)nullptr, 0, dst, st);
-            if (rc) return rc;
-            cur = dst;
-        }
+    OESS_KERNEL("tb_keygen", st, k_keygen<T><<<(unsigned)nch, radix::kThreads, 0, st>>>(
+        ev4, frame_offsets, w.chunk_start, F, g, mutate_p, w.a));
+    const int bits = radix::key_bits(g.invalid_key + 1);
+    const int passes = (bits + radix::kBits - 1) / radix::kBits;
+    const int pbits = (bits + passes - 1) / passes;
+    const uint32_t mask = (1u << pbits) - 1;
+    for (int p = 0; p < passes; ++p) {
+        uint2* dst = (cur == w.a) ? w.b : w.a;
+        SrcPairs src{cur};
+        int rc = radix::run_pass(src, frame_offsets, w.chunk_start, F, nch, p * pbits, mask, w.hist, w.tot,
+                                 (uint32_t*)nullptr, 0, dst, st);
+        if (rc) return rc;
+        cur = dst;
     }
-    OESS_KERNEL("k_seg_exscan_u32", st, k_seg_exscan_u32<<<(unsigned)F, 1024, 0, st>>>(w.pix, w.pix_stride, (int64_t)g.invalid_key + 2));
     if (C == 5) {
-        const int64_t total = (int64_t)F * HW;
-        OESS_KERNEL("tb_gather", st, k_gather<T, 5><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-            ev4, cur, frame_offsets, w.pix, w.pix_stride, F, g, separate_pol, out));
+        OESS_KERNEL("tb_runs", st, k_runs<T, 5><<<(unsigned)nch, radix::kThreads, 0, st>>>(
+            ev4, cur, frame_offsets, w.chunk_start, F, g, separate_pol, out));
     } else {
-        const int64_t total = (int64_t)F * HW * C;
-        OESS_KERNEL("tb_gather", st, k_gather<T, 0><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-            ev4, cur, frame_offsets, w.pix, w.pix_stride, F, g, separate_pol, out));
+        OESS_KERNEL("tb_runs", st, k_runs<T, 0><<<(unsigned)nch, radix::kThreads, 0, st>>>(
+            ev4, cur, frame_offsets, w.chunk_start, F, g, separate_pol, out));
     }
     return OESS_OK;
 }

@@ -131,6 +131,7 @@ def _dsec_events(rng, n, W, H, clustered=False):
 @pytest.mark.parametrize("n,H,W,C,clustered", [
     (1000, 33, 47, 5, False), (10000, 120, 160, 5, True), (100000, 480, 640, 5, False),
     (100000, 480, 640, 5, True), (5000, 40, 50, 7, False), (300, 9, 1025, 2, False),
+    (3000, 1030, 12, 5, False), (3000, 1030, 12, 3, True), (2000, 30, 3000, 5, False),
 ])
 def test_trilinear_vs_oracle(dev, oracle, n, H, W, C, clustered):
     from openess_b200 import voxel
