@@ -43,7 +43,7 @@ def synth_frames(rng, F, n=N_EVENTS, clustered_every=2):
     second frame edge-clustered (80 % of the events on line segments)."""
     xs, ys, ps, ts = [], [], [], []
     for f in range(F):
-        if clustered_every and f % clustered_every == 1:
+        if clustered_every and f % clustered_every == clustered_every - 1:
             k = int(0.8 * n)
             seg = rng.integers(0, 16, k)
             a = rng.random(k)
@@ -193,7 +193,7 @@ def run_ours(args):
     mode = args.mode
     rng = np.random.default_rng(1205 + rank)
     # two input sets (each 16 B x F x N = 256 MB at F=160 > 126 MB L2), alternated between steps
-    host_sets = [[torch.from_numpy(a).pin_memory() for a in synth_frames(rng, F)] for _ in range(2)]
+    host_sets = [[torch.from_numpy(a).pin_memory() for a in synth_frames(rng, F, clustered_every=args.clustered_every)] for _ in range(2)]
     dev_sets = [[a.to(dev) for a in hs] for hs in host_sets]
     fo = (torch.arange(F + 1, dtype=torch.int64) * N_EVENTS).to(dev)
     out = torch.empty((F, C, H, W), dtype=torch.float32, device=dev)
@@ -340,6 +340,7 @@ def main():
     ap.add_argument("--frames", type=int, default=160, help="event-frames per step per GPU")
     ap.add_argument("--e2e-sub", type=int, default=40, help="frames per pipelined H2D/compute sub-batch")
     ap.add_argument("--host-output", type=int, default=1, help="also measure e2e with full D2H of the grids")
+    ap.add_argument("--clustered-every", type=int, default=2, help="every k-th frame is edge-clustered (0: none, 1: all)")
     ap.add_argument("--cpu-frames", type=int, default=2000)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

@@ -1,0 +1,44 @@
+"""Mirror of the hot-path part of the reference's e2vid/utils/inference_utils.py: EventPreprocessor
+(:53-87) with the nonzero mean/std normalisation as two fused CUDA passes and no host synchronisation
+(the reference branches on `num_nonzeros > 0` on the host and wraps the block in a CudaTimer sync)."""
+import numpy as np
+import torch
+
+from ... import voxel as _voxel
+
+
+class EventPreprocessor:
+    """inference_utils.py:53-87: hot-pixel zeroing, optional flip, nonzero mean/std normalisation over the
+    WHOLE batch tensor (batch-coupled)."""
+
+    def __init__(self, options):
+        self.no_normalize = options.no_normalize
+        self.hot_pixel_locations = []
+        if getattr(options, "hot_pixels_file", None):
+            try:
+                self.hot_pixel_locations = np.loadtxt(options.hot_pixels_file, delimiter=',').astype(np.int64)
+                print('Will remove {} hot pixels'.format(self.hot_pixel_locations.shape[0]))
+            except IOError:
+                print('WARNING: could not load hot pixels file: {}'.format(options.hot_pixels_file))
+        self.flip = options.flip
+        if self.flip:
+            print('Will flip event tensors.')
+        # exact global-batch statistics under data parallelism: callable all-reducing the float64 [1, 3]
+        # stats tensor in place (openess_b200.parallel.allreduce_sum_); None = local batch
+        self.reduce_stats = None
+
+    def __call__(self, events):
+        for x, y in self.hot_pixel_locations:
+            events[:, :, y, x] = 0
+        if self.flip:
+            events = torch.flip(events, dims=[2, 3])
+        if not self.no_normalize:
+            x = events.to(torch.float32).contiguous().clone()   # the reference returns a new tensor
+            if self.reduce_stats is None:
+                _voxel.nonzero_standardize(x, n_groups=1, unbiased=False, phase=0)
+            else:
+                _, stats = _voxel.nonzero_standardize(x, n_groups=1, unbiased=False, phase=1)
+                self.reduce_stats(stats)
+                _voxel.nonzero_standardize(x, n_groups=1, unbiased=False, phase=2, stats=stats)
+            events = x
+        return events

@@ -1,0 +1,186 @@
+"""GPU parity tests of the loss-side kernels (segment pool, InfoNCE, Dice+CE, confusion, normalise) through the
+reference-mirroring modules.  Golden vectors come from the reference's own torch code; fresh inputs are checked
+against the float64 oracle.  Tolerances: float32 kernels vs float64 oracle / torch float32: rtol 2e-5 on
+losses, 2e-4 on gradients (the reference's float32 reductions carry the same order of error); confusion
+matrices and mIoU are integer-exact."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def test_pool_nce_golden_forward_backward(dev):
+    from openess_b200.training.superpixel import pooled_pair
+    from openess_b200.utils.loss_functions import NCELoss
+    z = load_golden("losses")
+    fv = torch.from_numpy(z["pool__feat_voxel"]).to(dev).requires_grad_(True)
+    ff = torch.from_numpy(z["pool__feat_frame"]).to(dev).requires_grad_(True)
+    sp = torch.from_numpy(z["pool__superpixels"]).to(dev)
+    k, q = pooled_pair(fv, ff, sp, int(z["pool__S"]))
+    assert tuple(k.shape) == z["pool__k"].shape          # M = max id' + 1, incl. the aliasing ids >= S
+    np.testing.assert_allclose(k.detach().cpu().numpy(), z["pool__k"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(q.detach().cpu().numpy(), z["pool__q"], rtol=2e-5, atol=2e-6)
+    loss = NCELoss(0.07)(k, q)
+    assert float(loss) == pytest.approx(float(z["pool__nce"]), rel=2e-5)
+    loss.backward()
+    np.testing.assert_allclose(fv.grad.cpu().numpy(), z["pool__d_feat_voxel"], rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(ff.grad.cpu().numpy(), z["pool__d_feat_frame"], rtol=2e-4, atol=2e-7)
+
+
+def test_task_loss_golden_forward_backward(dev):
+    from openess_b200.utils.loss_functions import DiceLoss, TaskLoss
+    z = load_golden("losses")
+    logits = torch.from_numpy(z["task__logits"]).to(dev).requires_grad_(True)
+    target = torch.from_numpy(z["task__target"]).to(dev)
+    K = logits.shape[1]
+    tl = TaskLoss(losses=["dice", "cross_entropy"], num_classes=K, ignore_index=255)
+    loss = tl(logits, target)
+    assert float(loss) == pytest.approx(float(z["task__total"]), rel=2e-5)
+    (loss * 1.5).backward()
+    np.testing.assert_allclose(logits.grad.cpu().numpy(), 1.5 * z["task__dlogits"], rtol=2e-4, atol=2e-8)
+    dice = DiceLoss(num_classes=K, ignore_index=255)(logits.detach(), target)
+    assert float(dice) == pytest.approx(float(z["task__dice"]), rel=2e-5)
+    ce_only = TaskLoss(losses=["cross_entropy"], num_classes=K, ignore_index=255)(logits.detach(), target)
+    assert float(ce_only) == pytest.approx(float(z["task__total"]) - float(z["task__dice"]), rel=5e-5)
+
+
+def test_metrics_golden_integer_exact(dev):
+    from openess_b200.evaluation import metrics
+    z = load_golden("losses")
+    pred, gt = torch.from_numpy(z["met__pred"]), torch.from_numpy(z["met__gt"])
+    conf = metrics.semseg_compute_confusion(pred.to(dev), gt.to(dev), 11, 255)
+    assert conf.device == dev and conf.dtype == torch.int64
+    assert np.array_equal(conf.cpu().numpy(), z["met__conf"])
+    ms = metrics.MetricsSemseg(11, 255, [str(i) for i in range(11)])
+    ms.update_batch(pred[:2], gt[:2])                       # CPU tensors in, like valBatchStep
+    ms.update_batch(pred[2:].unsqueeze(1), gt[2:].unsqueeze(1))   # [B,1,H,W] accepted (metrics.py:8-13)
+    s = ms.get_metrics_summary()
+    assert float(s["miou"]) == pytest.approx(float(z["met__miou"]), rel=1e-12)
+    assert float(s["acc"]) == pytest.approx(float(z["met__acc"]), rel=1e-12)
+    assert np.array_equal(s["cm"].numpy(), z["met__conf"])
+    with pytest.raises(AssertionError):                     # bincount beyond K*K -> the reference's assert
+        metrics.semseg_compute_confusion(pred.to(dev) + 200, gt.to(dev), 11, 255)
+
+
+@pytest.mark.parametrize("B,Cf,H,W,S", [(2, 32, 24, 36, 12), (3, 256, 40, 64, 25), (1, 7, 15, 17, 5), (4, 64, 110, 160, 100)])
+def test_segpool_vs_oracle(dev, oracle, B, Cf, H, W, S):
+    from openess_b200 import losses
+    rng = np.random.default_rng(B * 100 + Cf)
+    feat = rng.normal(0, 1, (B, Cf, H, W)).astype(np.float32)
+    # blocky superpixels (runs along rows, like SAM / SLIC maps) + a few ids >= S (aliasing quirk)
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    seg = ((yy // max(H // 5, 1)) * 5 + xx // max(W // 5, 1)) % S
+    seg = np.stack([np.roll(seg, b, 1) for b in range(B)]).astype(np.int64)
+    seg[0, 0, :3] = S + 1
+    M = int((seg + np.arange(B)[:, None, None] * S).max()) + 1
+    ref_p, ref_c = oracle.segpool(feat, seg, S, M)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    p, c = losses.segpool_forward(torch.from_numpy(feat).to(dev), torch.from_numpy(seg).to(dev), S, M, status=st)
+    assert int(st.item()) == 0
+    np.testing.assert_array_equal(c.cpu().numpy(), ref_c)
+    np.testing.assert_allclose(p.cpu().numpy(), ref_p, rtol=2e-5, atol=2e-6)
+    # backward: d_feat[b, c, pix] = d_pooled[id', c] / (count + 1e-6)
+    dp = rng.normal(0, 1, (M, Cf)).astype(np.float32)
+    d = losses.segpool_backward(torch.from_numpy(dp).to(dev), torch.from_numpy(seg).to(dev), c, S, (B, Cf, H, W))
+    ids = seg + np.arange(B)[:, None, None] * S
+    want = (dp / (ref_c[:, None] + np.float32(1e-6)))[ids]          # [B,H,W,Cf]
+    np.testing.assert_allclose(d.cpu().numpy(), want.transpose(0, 3, 1, 2), rtol=1e-6, atol=1e-7)
+    # out-of-range ids are skipped and flagged
+    bad = seg.copy()
+    bad[0, 1, 1] = M + 5
+    losses.segpool_forward(torch.from_numpy(feat).to(dev), torch.from_numpy(bad).to(dev), S, M, status=st)
+    assert int(st.item()) == 1
+
+
+@pytest.mark.parametrize("M,D", [(50, 32), (200, 256), (801, 256), (130, 64), (3200, 256)])
+def test_infonce_vs_oracle(dev, oracle, M, D):
+    from openess_b200 import losses
+    rng = np.random.default_rng(M)
+    k = rng.normal(0, 1, (M, D)).astype(np.float32)
+    q = (0.7 * k + 0.5 * rng.normal(0, 1, (M, D))).astype(np.float32)
+    k /= np.linalg.norm(k, axis=1, keepdims=True)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    k[3] = 0                                                         # empty superpixel rows stay (Appendix B.9)
+    big = M > 1000
+    if big:
+        kt, qt = torch.from_numpy(k).double(), torch.from_numpy(q).double()
+        kt.requires_grad_(True); qt.requires_grad_(True)
+        ref = torch.nn.functional.cross_entropy(kt @ qt.T / 0.07, torch.arange(M))
+        ref.backward()
+        ref_loss, rdk, rdq = float(ref), kt.grad.numpy(), qt.grad.numpy()
+    else:
+        ref_loss, rdk, rdq = oracle.infonce(k, q, 0.07, grad=True)
+    kd = torch.from_numpy(k).to(dev).requires_grad_(True)
+    qd = torch.from_numpy(q).to(dev).requires_grad_(True)
+    loss = losses.infonce(kd, qd, 0.07)
+    assert float(loss) == pytest.approx(ref_loss, rel=2e-5)
+    loss.backward()
+    np.testing.assert_allclose(kd.grad.cpu().numpy(), rdk, rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(qd.grad.cpu().numpy(), rdq, rtol=2e-4, atol=2e-7)
+
+
+@pytest.mark.parametrize("B,K,H,W", [(2, 11, 33, 47), (1, 6, 200, 352), (3, 19, 20, 20), (2, 40, 16, 16)])
+def test_dice_ce_vs_oracle(dev, oracle, B, K, H, W):
+    from openess_b200 import losses
+    rng = np.random.default_rng(K)
+    logits = rng.normal(0, 3, (B, K, H, W)).astype(np.float32)
+    target = rng.integers(0, K, (B, H, W)).astype(np.int64)
+    target[rng.random(target.shape) < 0.03] = 255
+    ref = oracle.dice_ce(logits, target, 255, grad=True)
+    ld = torch.from_numpy(logits).to(dev).requires_grad_(True)
+    loss = losses.dice_ce(ld, torch.from_numpy(target).to(dev), 255)
+    assert float(loss) == pytest.approx(ref["total"], rel=2e-5)
+    loss.backward()
+    np.testing.assert_allclose(ld.grad.cpu().numpy(), ref["dlogits"], rtol=3e-4, atol=2e-9)
+    # global-batch semantics: partial sums of two half-batches add up to the full-batch partials
+    if B >= 2:
+        full = losses.dice_ce_partials(ld.detach(), torch.from_numpy(target).to(dev), 255)
+        a = losses.dice_ce_partials(ld.detach()[:1].contiguous(), torch.from_numpy(target[:1]).to(dev), 255)
+        b = losses.dice_ce_partials(ld.detach()[1:].contiguous(), torch.from_numpy(target[1:]).to(dev), 255)
+        torch.testing.assert_close(a + b, full, rtol=1e-9, atol=1e-9)
+
+
+def test_confusion_vs_oracle_fullsize(dev, oracle):
+    from openess_b200 import losses
+    rng = np.random.default_rng(5)
+    pred = rng.integers(0, 11, (8, 440, 640)).astype(np.int64)
+    gt = rng.integers(0, 11, (8, 440, 640)).astype(np.int64)
+    gt[rng.random(gt.shape) < 0.1] = 255
+    ref = oracle.confusion(pred, gt, 11, 255)
+    conf = losses.confusion(torch.from_numpy(pred).to(dev), torch.from_numpy(gt).to(dev), 11, 255)
+    assert np.array_equal(conf.cpu().numpy(), ref)
+    conf2 = losses.confusion(torch.from_numpy(pred).to(dev), torch.from_numpy(gt).to(dev), 11, 255, out=conf)
+    assert np.array_equal(conf2.cpu().numpy(), 2 * ref)            # accumulates
+    assert int(conf2.sum()) == 2 * int((gt != 255).sum())          # checksum: every valid pixel counted once
+    big = losses.confusion(torch.from_numpy(pred % 7).to(dev) * 10, torch.from_numpy(np.where(gt == 255, 255, gt * 9)).to(dev),
+                           100, 255)                                # K*K > smem bins -> global-atomic path
+    assert int(big.sum()) == int((gt != 255).sum())
+
+
+def test_event_preprocessor_matches_oracle(dev, oracle):
+    from types import SimpleNamespace
+    from openess_b200.e2vid.utils.inference_utils import EventPreprocessor
+    rng = np.random.default_rng(9)
+    x = rng.normal(0, 1.2, (2, 5, 56, 72)).astype(np.float32)
+    x[rng.random(x.shape) < 0.75] = 0
+    ref, stats = oracle.nonzero_standardize(x)
+    pre = EventPreprocessor(SimpleNamespace(no_normalize=False, hot_pixels_file=None, flip=False))
+    xin = torch.from_numpy(x).to(dev)
+    out = pre(xin)
+    assert out.data_ptr() != xin.data_ptr() and torch.equal(xin.cpu(), torch.from_numpy(x))   # input untouched
+    assert np.array_equal(out.cpu().numpy() == 0, ref == 0)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-5, atol=2e-6)
+    # two-phase path with an (identity) cross-rank reduction hook gives the same result
+    pre.reduce_stats = lambda s: s
+    np.testing.assert_allclose(pre(xin).cpu().numpy(), out.cpu().numpy(), rtol=0, atol=0)
+    z = torch.zeros(1, 5, 8, 8, device=dev)
+    assert not pre(z).any()                                          # num_nonzeros == 0 -> unchanged
