@@ -347,7 +347,7 @@ enum { NCE_LSE = 0, NCE_DK = 1, NCE_DQ = 2 };
 
 template <int MODE, int DC>   // D = 16 * DC
 __global__ void __launch_bounds__(256)
-k_infonce(const float* __restrict__ A, const float* __restrict__ Bm, int64_t M, float inv_T, float* __restrict__ lse,
+k_infonce(const float* __restrict__ A, const float* __restrict__ Bm, int64_t M, int Dr, float inv_T, float* __restrict__ lse,
           float* __restrict__ diag, float* __restrict__ dA) {
     constexpr int D = 16 * DC;
     constexpr int LD = D + 1;                 // padded rows: conflict-free column access
@@ -361,7 +361,7 @@ k_infonce(const float* __restrict__ A, const float* __restrict__ Bm, int64_t M, 
     const int64_t a0 = (int64_t)blockIdx.x * kNT;
     for (int i = tid; i < kNT * D; i += 256) {
         const int r = i / D, d = i - r * D;
-        As[r * LD + d] = (a0 + r < M) ? A[(a0 + r) * D + d] : 0.f;
+        As[r * LD + d] = (a0 + r < M && d < Dr) ? A[(a0 + r) * Dr + d] : 0.f;   // Dr = real width, zero padded to D
     }
     if (tid < kNT) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; s_d[tid] = 0.f; }
     float acc[4][DC];
@@ -375,7 +375,7 @@ k_infonce(const float* __restrict__ A, const float* __restrict__ Bm, int64_t M, 
         __syncthreads();
         for (int i = tid; i < kNT * D; i += 256) {
             const int r = i / D, d = i - r * D;
-            Bs[r * LD + d] = (b0 + r < M) ? Bm[(b0 + r) * D + d] : 0.f;
+            Bs[r * LD + d] = (b0 + r < M && d < Dr) ? Bm[(b0 + r) * Dr + d] : 0.f;
         }
         __syncthreads();
         // S tile: rows ty*4+r, cols tx+16*c
@@ -460,7 +460,8 @@ k_infonce(const float* __restrict__ A, const float* __restrict__ Bm, int64_t M, 
             const int64_t ga = a0 + ty * 4 + r;
             if (ga >= M) continue;
 #pragma unroll
-            for (int c = 0; c < DC; ++c) dA[ga * D + tx + 16 * c] = acc[r][c];
+            for (int c = 0; c < DC; ++c)
+                if (tx + 16 * c < Dr) dA[ga * Dr + tx + 16 * c] = acc[r][c];
         }
     }
 }
@@ -482,21 +483,21 @@ k_infonce_loss(const float* __restrict__ lse, const float* __restrict__ diag, in
 }
 
 template <int DC>
-static int run_infonce(const float* k, const float* q, int64_t M, float T, float* loss, float* dk, float* dq,
+static int run_infonce(const float* k, const float* q, int64_t M, int Dr, float T, float* loss, float* dk, float* dq,
                        float* lse, float* diag, cudaStream_t st) {
     constexpr int D = 16 * DC;
     const size_t smem = sizeof(float) * (2 * kNT * (D + 1) + kNT * 65);
     const unsigned grid = (unsigned)((M + kNT - 1) / kNT);
     OESS_CUDA(cudaFuncSetAttribute(k_infonce<NCE_LSE, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    OESS_KERNEL("k_infonce", st, k_infonce<NCE_LSE, DC><<<grid, 256, smem, st>>>(k, q, M, 1.0f / T, lse, diag, nullptr));
+    OESS_KERNEL("k_infonce", st, k_infonce<NCE_LSE, DC><<<grid, 256, smem, st>>>(k, q, M, Dr, 1.0f / T, lse, diag, nullptr));
     OESS_KERNEL("k_infonce_loss", st, k_infonce_loss<<<1, 1024, 0, st>>>(lse, diag, M, loss));
     if (dk) {
         OESS_CUDA(cudaFuncSetAttribute(k_infonce<NCE_DK, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OESS_KERNEL("k_infonce", st, k_infonce<NCE_DK, DC><<<grid, 256, smem, st>>>(k, q, M, 1.0f / T, lse, diag, dk));
+        OESS_KERNEL("k_infonce", st, k_infonce<NCE_DK, DC><<<grid, 256, smem, st>>>(k, q, M, Dr, 1.0f / T, lse, diag, dk));
     }
     if (dq) {
         OESS_CUDA(cudaFuncSetAttribute(k_infonce<NCE_DQ, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OESS_KERNEL("k_infonce", st, k_infonce<NCE_DQ, DC><<<grid, 256, smem, st>>>(q, k, M, 1.0f / T, lse, diag, dq));
+        OESS_KERNEL("k_infonce", st, k_infonce<NCE_DQ, DC><<<grid, 256, smem, st>>>(q, k, M, Dr, 1.0f / T, lse, diag, dq));
     }
     return OESS_OK;
 }
@@ -626,11 +627,11 @@ OESS_API int oess_infonce(const float* k, const float* q, int64_t M, int D, floa
     float* lse = (float*)ws;
     float* diag = (float*)((char*)ws + need / 2);
     cudaStream_t st = (cudaStream_t)stream;
-    switch (D) {
-        case 32: return run_infonce<2>(k, q, M, temperature, loss, dk, dq, lse, diag, st);
-        case 64: return run_infonce<4>(k, q, M, temperature, loss, dk, dq, lse, diag, st);
-        case 128: return run_infonce<8>(k, q, M, temperature, loss, dk, dq, lse, diag, st);
-        case 256: return run_infonce<16>(k, q, M, temperature, loss, dk, dq, lse, diag, st);
-        default: return OESS_E_ARG;   // supported feature widths: 32, 64, 128, 256 (OpenESS uses 256)
-    }
+    // feature width D is zero-padded to 16 * DC columns (OpenESS uses D = 256)
+    if (D <= 16) return run_infonce<1>(k, q, M, D, temperature, loss, dk, dq, lse, diag, st);
+    if (D <= 32) return run_infonce<2>(k, q, M, D, temperature, loss, dk, dq, lse, diag, st);
+    if (D <= 64) return run_infonce<4>(k, q, M, D, temperature, loss, dk, dq, lse, diag, st);
+    if (D <= 128) return run_infonce<8>(k, q, M, D, temperature, loss, dk, dq, lse, diag, st);
+    if (D <= 256) return run_infonce<16>(k, q, M, D, temperature, loss, dk, dq, lse, diag, st);
+    return OESS_E_ARG;   // wider features are not used by any OpenESS configuration
 }
