@@ -8,13 +8,16 @@ of N = 100 000 events = one call of VoxelGrid.convert (DSEC/dataset/representati
 One step = one batch of F = 160 event-frames (8 DSEC samples x 20 frames, config `batch_size_b: 8`,
 `nr_events_data: 20`) through ONE batched C-ABI call (oess_voxel_trilinear).
 
- value : frames/s, inputs resident in HBM, CUDA-event timed over exactly K steps, max over ranks.
- e2e   : same metric from PINNED HOST event arrays: per step H2D of the four float32 event arrays,
-         voxelisation, and a D2H read of one grid row per frame (the grids stay on the device because
-         the consumer, the event encoder, runs there).  `e2e_host_output` additionally copies every
-         grid back to pinned host memory (what VoxelGrid.convert returns for CPU inputs; PCIe-bound).
+ value : frames/s of VoxelGrid.convert, its four float32 input arrays resident in HBM, CUDA-event timed over
+         exactly K steps, max over ranks.
+ e2e   : same metric from PINNED HOST buffers holding the raw DSEC records (u16 x, u16 y, u32 t, u8 p = 9 B/event,
+         the on-disk layout): per step H2D of the records, rectification + per-frame time normalisation
+         (oess_dsec_rectify_tnorm_u32 = sequence_ov.py:204-210,154-159), voxelisation, and a D2H read of one grid
+         row per frame (the grids stay on the device because their consumer, the event encoder, runs there).
+         `e2e_host_output` additionally copies every grid back to pinned host memory (what VoxelGrid.convert
+         returns for CPU inputs; PCIe-bound by the 6.1 MB/frame output).
  roofline : dominant kernel, algorithmic bytes (16 N + 4 C H W per frame) / its CUDA-event duration.
- cpu_baseline : the C oracle port of the reference algorithm on the host cores (bounded sample).
+ cpu_baseline : the C oracle port of the same work (rectify + normalise + trilinear splat) on the host cores.
  --impl reference : the CPU arm alone (the reference is pure Python and cannot travel to the GPU box; the
          oracle port restates it in C and is a *stronger* baseline than the reference's numpy/torch code).
 Multi-GPU: frames are sharded over ranks (independent units, no data-path collective) -> weak scaling.
@@ -38,10 +41,16 @@ METRIC = "event-frames/sec at DSEC 640x480 50 ms window"
 UNIT = "frames/s"
 
 
-def synth_frames(rng, F, n=N_EVENTS, clustered_every=2):
-    """raw pixels + identity rectify map with +-0.75 px jitter, t over 50 ms, and every
-    second frame edge-clustered (80 % of the events on line segments)."""
-    xs, ys, ps, ts = [], [], [], []
+def synth_rectify_map(rng):
+    """identity + U(-0.75, 0.75) px jitter: ~0.2 % of corners leave the sensor, some x' < 0."""
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    return (np.stack([xx, yy], -1) + rng.uniform(-0.75, 0.75, (H, W, 2))).astype(np.float32)
+
+
+def synth_raw_frames(rng, F, n=N_EVENTS, clustered_every=2):
+    """Raw DSEC records for F frames of n events over 50 ms; every `clustered_every`-th frame has 80 % of its events
+    on 16 line segments (edge-like, stresses same-voxel accumulation)."""
+    xs, ys, ts, ps = [], [], [], []
     for f in range(F):
         if clustered_every and f % clustered_every == clustered_every - 1:
             k = int(0.8 * n)
@@ -53,35 +62,36 @@ def synth_frames(rng, F, n=N_EVENTS, clustered_every=2):
             perm = rng.permutation(n)
             x, y = x[perm], y[perm]
         else:
-            x = rng.integers(0, W, n) + rng.uniform(-0.75, 0.75, n)
-            y = rng.integers(0, H, n) + rng.uniform(-0.75, 0.75, n)
-        t = np.sort(rng.integers(0, WINDOW_US, n)).astype(np.float64)
-        t = (t - t[0]).astype(np.float32)
-        t = t / t[-1]                                     # sequence_ov.py:155-156
-        xs.append(x.astype(np.float32)); ys.append(y.astype(np.float32))
-        ps.append(rng.integers(0, 2, n).astype(np.float32)); ts.append(t)
-    return [np.concatenate(a) for a in (xs, ys, ps, ts)]
+            x, y = rng.uniform(0, W, n), rng.uniform(0, H, n)
+        xs.append(np.clip(x, 0, W - 1).astype(np.uint16))
+        ys.append(np.clip(y, 0, H - 1).astype(np.uint16))
+        ts.append((np.sort(rng.integers(0, WINDOW_US, n)) + 1_000_000 + f * WINDOW_US).astype(np.uint32))
+        ps.append(rng.integers(0, 2, n).astype(np.uint8))
+    return [np.concatenate(a) for a in (xs, ys, ts, ps)]
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
 def cpu_port_throughput(frames_total, budget_s, threads=None, seed=1205):
-    """Oracle C port of VoxelGrid.convert on `threads` host threads (ctypes releases the GIL)."""
+    """Oracle C port (rectify + t-normalise + VoxelGrid.convert) on `threads` host threads, one frame per call
+    (ctypes releases the GIL)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as orc
     orc.build()
     threads = threads or os.cpu_count() or 1
     rng = np.random.default_rng(seed)
-    base = synth_frames(rng, min(frames_total, 8))
+    rmap = synth_rectify_map(rng)
     nb = min(frames_total, 8)
-    frames = [tuple(a[i * N_EVENTS:(i + 1) * N_EVENTS] for a in base) for i in range(nb)]
-
+    x, y, t, p = synth_raw_frames(rng, nb)
+    t = t.astype(np.int64)
+    frames = [tuple(a[i * N_EVENTS:(i + 1) * N_EVENTS] for a in (x, y, t, p)) for i in range(nb)]
     tls = threading.local()
 
     def work(i):
-        x, y, p, t = frames[i % nb]
+        fx, fy, ft, fp = frames[i % nb]
         if not hasattr(tls, "out"):
             tls.out = np.empty((C, H, W), np.float32)     # one reusable grid per worker thread
-        return float(orc.voxel_trilinear(x, y, p, t, C, H, W, out=tls.out)[0, 0, 0])
+        xo, yo, po, to = orc.dsec_rectify_tnorm(fx, fy, ft, fp, rmap)
+        return float(orc.voxel_trilinear(xo, yo, po, to, C, H, W, out=tls.out)[0, 0, 0])
 
     work(0)  # warm-up (page-in, library load)
     done = 0
@@ -102,22 +112,24 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    per_step = max(threads * 2, 8)
+    per_step = max(threads * 4, 16)
     for _ in range(args.warmup):
-        cpu_port_throughput(min(per_step, threads), 5.0, threads)
+        cpu_port_throughput(threads, 5.0, threads)
+    frames, busy = 0, 0.0
     t0 = time.perf_counter()
-    frames = 0
     for _ in range(args.steps):
-        _, done, _, _ = cpu_port_throughput(per_step, 20.0, threads)
+        _, done, dt, _ = cpu_port_throughput(per_step, 20.0, threads)
         frames += done
-    dt = time.perf_counter() - t0
-    val = frames / dt
+        busy += dt
+    wall = time.perf_counter() - t0
+    val = frames / busy                      # input synthesis between steps is not part of the path
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * busy / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DSEC 640x480, {N_EVENTS} events per 50 ms frame, VoxelGrid.convert trilinear splat, "
-                               f"C={C}; reference arm = C oracle port on host threads, {per_step} frames per step"},
+        "config": {"workload": f"DSEC 640x480, {N_EVENTS} events per 50 ms frame: rectify + t-normalise + VoxelGrid.convert "
+                               f"trilinear splat, C={C}; reference arm = C oracle port on {threads} host threads, "
+                               f"{per_step} frames per step", "wall_s": wall},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{frames} frames of {N_EVENTS} events over {args.steps} steps"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -129,7 +141,7 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(threading.Thread):
-    def __init__(self, index, period=0.1):
+    def __init__(self, index, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -192,10 +204,14 @@ def run_ours(args):
     F, K, Wm = args.frames, args.steps, args.warmup
     mode = args.mode
     rng = np.random.default_rng(1205 + rank)
-    # two input sets (each 16 B x F x N = 256 MB at F=160 > 126 MB L2), alternated between steps
-    host_sets = [[torch.from_numpy(a).pin_memory() for a in synth_frames(rng, F, clustered_every=args.clustered_every)] for _ in range(2)]
-    dev_sets = [[a.to(dev) for a in hs] for hs in host_sets]
+    rmap = torch.from_numpy(synth_rectify_map(rng)).to(dev)
     fo = (torch.arange(F + 1, dtype=torch.int64) * N_EVENTS).to(dev)
+    # two input sets, alternated between steps.  Raw records live in pinned host memory (e2e); the four float32
+    # arrays VoxelGrid.convert takes are derived from them once and stay in HBM (16 B x F x N = 256 MB per set
+    # at F=160 > 126 MB L2).
+    host_sets = [[torch.from_numpy(a).pin_memory() for a in synth_raw_frames(rng, F, clustered_every=args.clustered_every)]
+                 for _ in range(2)]
+    dev_sets = [list(voxel.dsec_rectify_tnorm(*(a.to(dev) for a in hs), rmap, fo)) for hs in host_sets]
     out = torch.empty((F, C, H, W), dtype=torch.float32, device=dev)
 
     def barrier():
@@ -240,10 +256,14 @@ def run_ours(args):
     ms_o, _, _ = timed(lambda i: step(i, other), K)
     value_other = world * F * K / (ms_o * 1e-3)
 
-    # ---- end to end from pinned host buffers: H2D per step + voxelise + D2H of one grid row per frame
+    # ---- end to end from pinned host buffers: H2D of the raw records + rectify/normalise + voxelise + D2H of one
+    #      grid row per frame, pipelined over sub-batches on two streams
     sub = args.e2e_sub
+    assert F % sub == 0
     streams = [torch.cuda.Stream(dev) for _ in range(2)]
-    stage = [[torch.empty(sub * N_EVENTS, dtype=torch.float32, device=dev) for _ in range(4)] for _ in range(2)]
+    dts = (torch.uint16, torch.uint16, torch.uint32, torch.uint8)
+    raw_stage = [[torch.empty(sub * N_EVENTS, dtype=d, device=dev) for d in dts] for _ in range(2)]
+    f32_stage = [tuple(torch.empty(sub * N_EVENTS, dtype=torch.float32, device=dev) for _ in range(4)) for _ in range(2)]
     fo_sub = (torch.arange(sub + 1, dtype=torch.int64) * N_EVENTS).to(dev)
     rows_host = torch.empty((F, C, W), dtype=torch.float32).pin_memory()
     full_host = torch.empty((F, C, H, W), dtype=torch.float32).pin_memory() if args.host_output else None
@@ -251,11 +271,12 @@ def run_ours(args):
     def e2e_step(i, full=False):
         hs = host_sets[i & 1]
         for s, f0 in enumerate(range(0, F, sub)):
-            st = streams[s & 1]
-            with torch.cuda.stream(st):
+            b = s & 1
+            with torch.cuda.stream(streams[b]):
                 for k in range(4):
-                    stage[s & 1][k].copy_(hs[k][f0 * N_EVENTS:(f0 + sub) * N_EVENTS], non_blocking=True)
-                voxel.voxel_trilinear(*stage[s & 1], C, H, W, frame_offsets=fo_sub, mode=mode, out=out[f0:f0 + sub])
+                    raw_stage[b][k].copy_(hs[k][f0 * N_EVENTS:(f0 + sub) * N_EVENTS], non_blocking=True)
+                voxel.dsec_events_to_voxel_grid(*raw_stage[b], rmap, C, frame_offsets=fo_sub, mode=mode,
+                                                out=out[f0:f0 + sub], scratch=f32_stage[b])
                 if full:
                     full_host[f0:f0 + sub].copy_(out[f0:f0 + sub], non_blocking=True)
                 else:
@@ -263,16 +284,17 @@ def run_ours(args):
         for st in streams:
             torch.cuda.current_stream().wait_stream(st)
 
-    assert F % sub == 0
-    ms_e, _, _ = timed(e2e_step, K)
+    ms_e, launches_e, _ = timed(e2e_step, K)
     e2e_value = world * F * K / (ms_e * 1e-3)
-    h2d = 16 * F * N_EVENTS
+    h2d = 9 * F * N_EVENTS
     e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * F * C * W,
-           "ms_per_step": ms_e / K}
+           "ms_per_step": ms_e / K, "input": "raw DSEC records (u16 x, u16 y, u32 t, u8 p) in pinned host memory",
+           "h2d_gbs": h2d / (ms_e / K * 1e-3) / 1e9}
     e2e_host = None
     if args.host_output:
-        ms_h, _, _ = timed(lambda i: e2e_step(i, True), max(2, K // 4))
-        e2e_host = {"value": world * F * max(2, K // 4) / (ms_h * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+        kh = max(2, K // 4)
+        ms_h, _, _ = timed(lambda i: e2e_step(i, True), kh)
+        e2e_host = {"value": world * F * kh / (ms_h * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4 * F * C * H * W}
 
     if rank != 0:
@@ -299,29 +321,31 @@ def run_ours(args):
         traffic = json.load(open(tpath)).get(dom_name)
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel_ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes_frame * F // launches_per_step,
+                "kernel_ms_per_launch": per_launch_ms,
+                "algorithmic_bytes_per_launch": alg_bytes_frame * F // launches_per_step,
                 "path_achieved": path_gbs, "path_frac": path_gbs / peak,
                 "kernel_share_of_step": {k: round(v[1] / (ms if ms else 1), 4) for k, v in kernels.items()}}
 
     # ---- CPU baseline (oracle port, all host threads, bounded sample)
     cpu_val, cpu_frames, cpu_dt, cpu_threads = cpu_port_throughput(args.cpu_frames, args.cpu_budget)
-    cpu1_val, cpu1_frames, _, _ = cpu_port_throughput(8, 10.0, threads=1)
+    cpu1_val, _, _, _ = cpu_port_throughput(8, 10.0, threads=1)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"DSEC 640x480, {N_EVENTS} events per 50 ms frame, VoxelGrid.convert trilinear splat C={C}, "
-                               f"F={F} frames per step per GPU (8 samples x 20 frames), every 2nd frame edge-clustered",
+                               f"F={F} frames per step per GPU (8 samples x 20 frames); every "
+                               f"{args.clustered_every} frame(s) edge-clustered",
                    "mode": mode, "bit_exact_vs_reference": mode == "ordered",
                    "l2": f"inputs {16 * F * N_EVENTS / 1e6:.0f} MB + outputs {4 * F * C * H * W / 1e6:.0f} MB per step > 126 MB L2; "
                          "two input sets alternated",
                    "parallelism": f"frames sharded over {world} GPU(s), no collective"},
         "value_other_mode": {"mode": other, "value": value_other, "unit": UNIT},
         "e2e": e2e, "e2e_host_output": e2e_host,
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "gpu_launches": launches, "gpu_launches_e2e": launches_e, "clocks": clocks, "roofline": roofline,
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
-                         "sample": f"{cpu_frames} frames of {N_EVENTS} events in {cpu_dt:.1f} s (C oracle port of "
-                                   "VoxelGrid.convert, one frame per thread)",
+                         "sample": f"{cpu_frames} frames of {N_EVENTS} events in {cpu_dt:.1f} s (C oracle port: rectify + "
+                                   "t-normalise + VoxelGrid.convert, one frame per thread)",
                          "single_thread_value": cpu1_val},
     }
     print(json.dumps(line))

@@ -107,6 +107,13 @@ int oess_dsec_rectify_tnorm(const uint16_t* x, const uint16_t* y, const int64_t*
                             const float* rectify_map, const int64_t* frame_offsets, int64_t n_events_total,
                             int n_frames, int H, int W, float* xo, float* yo, float* po, float* to,
                             int32_t* status, oess_stream_t stream);
+/* Same, for timestamps in the on-disk DSEC layout (uint32 microseconds relative to the file's t_offset,
+ * DSEC/utils/eventslicer.py): only differences inside a frame are used, so the result is identical as long as
+ * a frame does not wrap 2^32 us.  9 B/event of input instead of 13. */
+int oess_dsec_rectify_tnorm_u32(const uint16_t* x, const uint16_t* y, const uint32_t* t, const uint8_t* p,
+                                const float* rectify_map, const int64_t* frame_offsets, int64_t n_events_total,
+                                int n_frames, int H, int W, float* xo, float* yo, float* po, float* to,
+                                int32_t* status, oess_stream_t stream);
 
 /* Replaces datasets/data_util.py:38-48 normalize_voxel_grid and e2vid/utils/inference_utils.py:77-85
  * (EventPreprocessor): x = (x != 0) * (x - mean) / std over the nonzero entries of each group.

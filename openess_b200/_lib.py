@@ -36,6 +36,7 @@ SIGNATURES = {
     "oess_voxel_histogram_i64": [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp],
     "oess_voxel_histogram_f64": [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp],
     "oess_dsec_rectify_tnorm": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
+    "oess_dsec_rectify_tnorm_u32": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "oess_nonzero_standardize": [_vp, _i64, _int, _vp, _int, _int, _vp],
     "oess_segpool_ws_bytes": [_int, _int, _int, _int, _i64, ctypes.POINTER(_sz)],
     "oess_segpool_fwd": [_vp, _vp, _int, _int, _int, _int, _int, _i64, _vp, _vp, _vp, _vp, _sz, _vp],

@@ -106,25 +106,40 @@ def voxel_histogram(ev4, H, W, frame_offsets=None, mutate_p=True, out=None, stat
     return out
 
 
-def dsec_rectify_tnorm(x, y, t, p, rectify_map, frame_offsets=None, status=None):
-    """sequence_ov.py:204-210 + :154-159 for F frames: raw (u16 x, u16 y, i64 t, u8 p) -> f32 x', y', pol, t."""
+def dsec_rectify_tnorm(x, y, t, p, rectify_map, frame_offsets=None, status=None, out=None):
+    """sequence_ov.py:204-210 + :154-159 for F frames: raw (u16 x, u16 y, i64|u32 t, u8 p) -> f32 x', y', pol, t.
+
+    t may be int64 microseconds (t_offset added, what EventSlicer returns) or the on-disk uint32 timestamps."""
     require_cuda(x, y, t, p, rectify_map)
     dev = x.device
     n = x.numel()
-    if x.dtype != torch.uint16 or y.dtype != torch.uint16 or t.dtype != torch.int64 or p.dtype != torch.uint8:
-        raise TypeError("raw DSEC records are x, y uint16; t int64 (microseconds); p uint8")
+    if x.dtype != torch.uint16 or y.dtype != torch.uint16 or p.dtype != torch.uint8 or \
+            t.dtype not in (torch.int64, torch.uint32):
+        raise TypeError("raw DSEC records are x, y uint16; t int64 or uint32 (microseconds); p uint8")
     if rectify_map.dtype != torch.float32 or rectify_map.ndim != 3 or rectify_map.shape[2] != 2:
         raise ValueError("rectify_map must be float32 [H, W, 2]")
     H, W = rectify_map.shape[:2]
     fo = _offsets(frame_offsets, n, dev)
     F = fo.numel() - 1
-    xo, yo, po, to = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(4))
+    if out is None:
+        out = tuple(torch.empty(n, dtype=torch.float32, device=dev) for _ in range(4))
+    xo, yo, po, to = out
+    fn = lib().oess_dsec_rectify_tnorm if t.dtype == torch.int64 else lib().oess_dsec_rectify_tnorm_u32
     with torch.cuda.device(dev):
-        check(lib().oess_dsec_rectify_tnorm(ptr(x.contiguous()), ptr(y.contiguous()), ptr(t.contiguous()),
-                                            ptr(p.contiguous()), ptr(rectify_map.contiguous()), ptr(fo), n, F, H, W,
-                                            ptr(xo), ptr(yo), ptr(po), ptr(to), ptr(status), stream_ptr(dev)),
-              "oess_dsec_rectify_tnorm")
+        check(fn(ptr(x.contiguous()), ptr(y.contiguous()), ptr(t.contiguous()), ptr(p.contiguous()),
+                 ptr(rectify_map.contiguous()), ptr(fo), n, F, H, W, ptr(xo), ptr(yo), ptr(po), ptr(to), ptr(status),
+                 stream_ptr(dev)), "oess_dsec_rectify_tnorm")
     return xo, yo, po, to
+
+
+def dsec_events_to_voxel_grid(x, y, t, p, rectify_map, C, frame_offsets=None, mode=None, normalize=False, out=None,
+                              scratch=None, status=None):
+    """Raw DSEC records of F frames -> [F, C, H, W] voxel grids on the device: rectify_events +
+    events_to_voxel_grid + VoxelGrid.convert (sequence_ov.py:204-223, representations.py:15-55) in two ABI calls.
+    This is the GPU-side sample assembly of SURVEY.md 7.1 step 3 (F = B * nr_events_data frames per call)."""
+    H, W = rectify_map.shape[:2]
+    xo, yo, po, to = dsec_rectify_tnorm(x, y, t, p, rectify_map, frame_offsets, status=status, out=scratch)
+    return voxel_trilinear(xo, yo, po, to, C, H, W, frame_offsets=frame_offsets, mode=mode, normalize=normalize, out=out)
 
 
 def nonzero_standardize(x, n_groups=1, unbiased=False, phase=0, stats=None):

@@ -283,3 +283,39 @@ def test_fullsize_properties(dev, oracle):
                     w = (2 * pol - 1) * (1 - np.abs(xl - x)) * (1 - np.abs(yl - y)) * (1 - np.abs(tl - tn))
                     tot += w[m].sum()
         assert abs(sums[f] - tot) < 2e-2, (f, sums[f], tot)
+
+
+def test_raw_dsec_records_to_voxel_grid(dev, oracle):
+    """GPU-side sample assembly: raw (u16 x, u16 y, u32|i64 t, u8 p) records of F frames -> rectify -> t-normalise
+    -> trilinear voxel grid == the oracle's per-frame pipeline, bit for bit."""
+    from openess_b200 import voxel
+    rng = np.random.default_rng(77)
+    H, W, C = 96, 128, 5
+    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
+    rmap = (np.stack([xx, yy], -1) + rng.uniform(-0.75, 0.75, (H, W, 2))).astype(np.float32)
+    sizes = [4000, 1, 2500, 0, 9000]
+    xs = [rng.integers(0, W, n).astype(np.uint16) for n in sizes]
+    ys = [rng.integers(0, H, n).astype(np.uint16) for n in sizes]
+    ts = [(np.sort(rng.integers(0, 50000, n)) + 3_000_000_000 + 60000 * i).astype(np.uint32) for i, n in enumerate(sizes)]
+    ps = [rng.integers(0, 2, n).astype(np.uint8) for n in sizes]
+    fo = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64))
+    cat = lambda parts: torch.from_numpy(np.concatenate(parts)).to(dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    for tdt in (np.uint32, np.int64):
+        tcat = torch.from_numpy(np.concatenate(ts).astype(tdt) + (0 if tdt == np.uint32 else 10**12)).to(dev)
+        out = voxel.dsec_events_to_voxel_grid(cat(xs), cat(ys), tcat, cat(ps), torch.from_numpy(rmap).to(dev), C,
+                                              frame_offsets=fo, status=st).cpu().numpy()
+        assert int(st.item()) == 0
+        for f, n in enumerate(sizes):
+            if n == 0:
+                assert not out[f].any()
+                continue
+            with np.errstate(all="ignore"):
+                xo, yo, po, to = oracle.dsec_rectify_tnorm(xs[f], ys[f], ts[f].astype(np.int64), ps[f], rmap)
+                ref = oracle.voxel_trilinear(xo, yo, po, to, C, H, W)
+            assert bits_equal(out[f], ref), (f, tdt)
+    bad = cat(xs).clone()
+    bad[3] = W                                                     # sequence_ov.py:208 assert x.max() < width
+    voxel.dsec_rectify_tnorm(bad, cat(ys), torch.from_numpy(np.concatenate(ts)).to(dev), cat(ps),
+                             torch.from_numpy(rmap).to(dev), fo, status=st)
+    assert int(st.item()) == 1
