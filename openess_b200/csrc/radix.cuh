@@ -28,6 +28,7 @@ static inline int64_t max_chunks(int64_t n_total, int F) { return (n_total + kCh
 //   typedef ... Item;
 //   __device__ Item     load(int f, int64_t fbeg, uint32_t li) const;   // li = index inside the frame
 //   __device__ uint32_t key(const Item&) const;                          // full sort key
+//   __device__ uint32_t key_at(int f, int64_t fbeg, uint32_t li) const;  // == key(load(f, fbeg, li))
 //
 // hist: [total_chunks, kBins] chunk-major.  pix (optional): per-frame full-key counts for the CSR
 // offsets used by the gather kernels (pix[f * pix_stride + key] += 1).
@@ -50,8 +51,7 @@ k_hist(Src src, const int64_t* __restrict__ frame_offsets, const int* __restrict
     for (int s = 0; s < kItemsPerThread; ++s) {
         const uint32_t li = cbeg + s * kThreads + threadIdx.x;
         if (li < nf) {
-            const typename Src::Item it = src.load(f, fbeg, li);
-            const uint32_t key = src.key(it);
+            const uint32_t key = src.key_at(f, fbeg, li);   // may read less than a full record
             atomicAdd(&s_hist[(key >> shift) & mask], 1u);
             if (pix) atomicAdd(&pix[(int64_t)f * pix_stride + key], 1u);
         }
@@ -69,7 +69,7 @@ __global__ void k_prefix_chunks(uint32_t* __restrict__ hist, const int* __restri
 __global__ void k_bin_scan(uint32_t* __restrict__ tot);
 
 template <class Src>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 k_scatter(Src src, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start, int F,
           int shift, uint32_t mask, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ binbase,
           typename Src::Item* __restrict__ dst) {

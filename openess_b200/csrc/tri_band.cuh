@@ -44,18 +44,25 @@ k_rowsort(const float4* __restrict__ src, float4* __restrict__ dst, const int64_
     __syncwarp();
     for (uint32_t i = s + lane; i < e; i += 32) atomicAdd(&cnt[cell_px(in[i].x, W)], 1u);
     __syncwarp();
-    uint32_t carry = s;                                // exclusive scan of the W + 2 bins
-    for (int b0 = 0; b0 < nb; b0 += 32) {
-        const int b = b0 + lane;
-        const uint32_t v = (b < nb) ? cnt[b] : 0;
-        uint32_t incl = v;
+    // exclusive scan of the W + 2 bins: each lane owns an odd-length (bank-conflict-free) segment of bins,
+    // sums it serially, one warp scan of the 32 partials, then rewrites its segment
+    {
+        const int seg = ((nb + 31) / 32) | 1;
+        const int b_lo = min(lane * seg, nb), b_hi = min(b_lo + seg, nb);
+        uint32_t sum = 0;
+        for (int b = b_lo; b < b_hi; ++b) sum += cnt[b];
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += u;
         }
-        if (b < nb) cnt[b] = carry + incl - v;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t run = s + incl - sum;
+        for (int b = b_lo; b < b_hi; ++b) {
+            const uint32_t v = cnt[b];
+            cnt[b] = run;
+            run += v;
+        }
     }
     __syncwarp();
     const unsigned lt = lanemask_lt();
@@ -140,7 +147,8 @@ __device__ __forceinline__ uint32_t corner(const BandCtx& c, const float4& r, bo
     const int tl = __float2int_rz(r.z) + dt;           // :29,35
     const int yrel = yl - c.ty0;
     *wgt = weight_t(weight_xy(r.x, r.y, r.w, xl, yl), r.z, tl);                                   // :37
-    const bool ok = on && xl >= 0 && xl < c.W && yrel >= 0 && yrel < c.rows && tl >= 0 && tl < c.C;   // :36
+    const bool ok = on && (unsigned)xl < (unsigned)c.W && (unsigned)yrel < (unsigned)c.rows &&
+                    (unsigned)tl < (unsigned)c.C;                                                 // :36
     return ok ? (uint32_t)((tl * c.TH + yrel) * c.W + xl) : (0x80000000u | (uint32_t)c.lane);
 }
 
@@ -195,7 +203,7 @@ __device__ __forceinline__ void sweep_two_pass(const BandCtx& c, const float4* _
 __global__ void __launch_bounds__(kBandThreads, 4)
 k_band_splat(const float4* __restrict__ items, const int64_t* __restrict__ frame_offsets,
              const uint32_t* __restrict__ rowoff, const uint32_t* __restrict__ rowflag, Geom g, int TH,
-             float* __restrict__ out) {
+             int stage_cap, int npass, float* __restrict__ out) {
     extern __shared__ __align__(16) float s_acc[];     // [C][TH][W]
     __shared__ int s_robust;
     const int f = blockIdx.y;
@@ -218,19 +226,24 @@ k_band_splat(const float4* __restrict__ items, const int64_t* __restrict__ frame
     const uint32_t* ro = rowoff + (int64_t)f * radix::kBins;
     const uint32_t e_lo = ro[ty0], e_hi = ro[py_hi + 1];
     if (threadIdx.x <= py_hi - ty0 && rowflag[(int64_t)f * radix::kBins + ty0 + threadIdx.x]) s_robust = 1;
-    const float4* it = items + frame_offsets[f];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // per-warp chunk, ends moved to run boundaries
+    // (Staging the band's records in shared memory was measured: no gain -- the passes are issue-bound, not
+    // load-latency bound -- and it costs a resident CTA, so the records are read from L2 in every pass.)
     const uint32_t n = e_hi - e_lo;
+    const float4* __restrict__ it = items + frame_offsets[f];
+    const uint32_t b_lo = e_lo, b_hi = e_hi;
+    (void)stage_cap;
+
+    // per-warp chunk, ends moved to run boundaries
     const uint32_t L = ((n + kBandThreads - 1) / kBandThreads) * 32;
-    const uint32_t a_lo = run_start_at_or_after(it, min(e_lo + warp * L, e_hi), e_lo, e_hi, lane);
-    const uint32_t a_hi = run_start_at_or_after(it, min(e_lo + (warp + 1) * L, e_hi), e_lo, e_hi, lane);
+    const uint32_t a_lo = run_start_at_or_after(it, min(b_lo + warp * L, b_hi), b_lo, b_hi, lane);
+    const uint32_t a_hi = run_start_at_or_after(it, min(b_lo + (warp + 1) * L, b_hi), b_lo, b_hi, lane);
     __syncthreads();
     const bool robust = s_robust != 0;
 
     BandCtx c{s_acc, 0, 0, ty0, rows, C, TH, W, lane};
-    for (int pass = 0; pass < 4; ++pass) {             // :33-34 xlim outer, ylim inner
+    for (int pass = 0; pass < npass; ++pass) {         // :33-34 xlim outer, ylim inner (npass = 4; fewer = profiling only)
         c.dx = pass >> 1;
         c.dy = pass & 1;
         if (robust) {

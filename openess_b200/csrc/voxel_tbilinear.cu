@@ -72,6 +72,7 @@ struct SrcPairs {
     const uint2* items;
     __device__ __forceinline__ Item load(int, int64_t fbeg, uint32_t li) const { return items[fbeg + li]; }
     __device__ __forceinline__ uint32_t key(const Item& it) const { return it.x; }
+    __device__ __forceinline__ uint32_t key_at(int, int64_t fbeg, uint32_t li) const { return items[fbeg + li].x; }
 };
 
 template <class T>

@@ -45,6 +45,15 @@ struct SrcSoA {
         if (row_key) return t_reachable(it.z) ? cell_py(it.y, g.H) : (uint32_t)(g.H + 1);
         return cell_key(it.x, it.y, g);
     }
+    // histogram pass: the row key needs only y and t (8 of the 16 bytes of an event)
+    __device__ __forceinline__ uint32_t key_at(int f, int64_t fbeg, uint32_t li) const {
+        if (!row_key) return key(load(f, fbeg, li));
+        const int64_t i = fbeg + li;
+        const float tfirst = __ldg(t + fbeg);
+        const float den = __fsub_rn(__ldg(t + frame_offsets[f + 1] - 1), tfirst);
+        const float tn = t_norm(ld_stream(t + i), tfirst, den, (float)(g.C - 1));
+        return t_reachable(tn) ? cell_py(ld_stream(y + i), g.H) : (uint32_t)(g.H + 1);
+    }
 };
 struct SrcAoS {
     typedef float4 Item;
@@ -52,6 +61,7 @@ struct SrcAoS {
     Geom g;
     __device__ __forceinline__ Item load(int, int64_t fbeg, uint32_t li) const { return items[fbeg + li]; }
     __device__ __forceinline__ uint32_t key(const Item& it) const { return cell_key(it.x, it.y, g); }
+    __device__ __forceinline__ uint32_t key_at(int f, int64_t fbeg, uint32_t li) const { return key(load(f, fbeg, li)); }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -152,7 +162,7 @@ k_atomic(const float* __restrict__ x, const float* __restrict__ y, const float* 
 // ---------------------------------------------------------------------------------------------
 struct Plan {
     bool banded;
-    int TH;
+    int TH, stage_cap, npass;
     size_t band_smem, row_smem;
 };
 
@@ -167,7 +177,12 @@ static Plan make_plan(int C, int H, int W) {
     }
     while (TH > 1 && sizeof(float) * (size_t)C * TH * W > 56 * 1024) TH >>= 1;
     p.TH = TH;
-    p.band_smem = sizeof(float) * (size_t)C * TH * W;
+    const size_t acc_bytes = align_up(sizeof(float) * (size_t)C * TH * W, 16);
+    const long cap = 0;   // shared-memory record staging: measured no gain (see tri_band.cuh), disabled
+    p.stage_cap = (int)cap;
+    p.npass = 4;
+    if (const char* e = std::getenv("OESS_BAND_NPASS")) p.npass = std::atoi(e);   // < 4: profiling only (wrong results)
+    p.band_smem = acc_bytes + 16 * (size_t)cap;
     p.banded = (H + 2 <= radix::kBins) && p.band_smem <= 200 * 1024 && p.row_smem <= 200 * 1024;
     return p;
 }
@@ -256,7 +271,7 @@ OESS_API int oess_voxel_trilinear(const float* x, const float* y, const float* p
             OESS_CUDA(cudaFuncSetAttribute(tri::k_band_splat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.band_smem));
             OESS_KERNEL("tri_band_splat", st, tri::k_band_splat<<<dim3((unsigned)((H + plan.TH - 1) / plan.TH), (unsigned)F),
                                                                  tri::kBandThreads, plan.band_smem, st>>>(
-                w.b, frame_offsets, w.tot, w.rowflag, g, plan.TH, out));
+                w.b, frame_offsets, w.tot, w.rowflag, g, plan.TH, plan.stage_cap, plan.npass, out));
         } else {
             const tri::Geom g{C, H, W, (uint32_t)((H + 1) * (W + 1))};
             OESS_CUDA(cudaMemsetAsync(w.pix, 0, sizeof(uint32_t) * (size_t)F * w.pix_stride, st));
