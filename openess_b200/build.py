@@ -25,6 +25,7 @@ SOURCES = {
     "dsec_prestep.cu": ["--fmad=false"],
     "normalize.cu": ["--fmad=false"],
     "losses.cu": [],
+    "infonce.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--threads", "0"]

@@ -88,36 +88,30 @@ k_dice_ce_partials(const float* __restrict__ logits, const int64_t* __restrict__
         ce += -__logf(ptg);                                   // lse - logit_t = -log softmax_t
         ++nvalid;
     }
-    // block reduction (float64)
-    __shared__ double s_red[8];
+    // block reduction (float64): every warp shuffles all 2K+2 values down, one barrier, 2K+2 threads finish
+    __shared__ double s_red[8][2 * KMAX + 2];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int q = 0; q < 2 * K + 2; ++q) {
-        double val;
-        if (q < K) {
-            float t = 0.f;
 #pragma unroll
-            for (int c = 0; c < KMAX; ++c) t = (c == q) ? inter[c] : t;
-            val = t;
-        } else if (q < 2 * K) {
-            float t = 0.f;
-#pragma unroll
-            for (int c = 0; c < KMAX; ++c) t = (c == q - K) ? den[c] : t;
-            val = t;
-        } else if (q == 2 * K) {
-            val = ce;
-        } else {
-            val = (double)nvalid;
-        }
+    for (int q = 0; q < 2 * KMAX + 2; ++q) {
+        double val = (q < KMAX) ? (double)inter[q < KMAX ? q : 0]
+                   : (q < 2 * KMAX) ? (double)den[q < 2 * KMAX ? (q - KMAX >= 0 ? q - KMAX : 0) : 0]
+                   : (q == 2 * KMAX) ? (double)ce : (double)nvalid;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-        if (lane == 0) s_red[w] = val;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double a = 0.0;
-            for (int k = 0; k < 8; ++k) a += s_red[k];
-            if (a != 0.0) atomicAdd(&partials[q], a);
-        }
-        __syncthreads();
+        if (lane == 0) s_red[w][q] = val;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * KMAX + 2) {
+        const int q = threadIdx.x;
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += s_red[k][q];
+        // slot layout of `partials`: inter[K], denom[K], ce_sum, n_valid
+        int dst = -1;
+        if (q < KMAX) { if (q < K) dst = q; }
+        else if (q < 2 * KMAX) { if (q - KMAX < K) dst = K + (q - KMAX); }
+        else dst = 2 * K + (q - 2 * KMAX);
+        if (dst >= 0 && a != 0.0) atomicAdd(&partials[dst], a);
     }
 }
 
@@ -333,175 +327,6 @@ k_segpool_bwd(const float* __restrict__ d_pooled, const int64_t* __restrict__ se
     }
 }
 
-// =============================================================================================
-// a16 InfoNCE.  s_ij = (k_i . q_j) / T;  loss = mean_i (logsumexp_j s_ij - s_ii).
-// fp32 SIMT tiles (the reference computes in fp32; M <= a few thousand, D = 256: a few GFLOP).
-// One tiled kernel, three modes:
-//   LSE : A = k (64 rows resident in smem), loop B = q tiles -> online row log-sum-exp + diagonal
-//   DK  : A = k, loop B = q:  dk_a += sum_b G_ab q_b,  G_ab = (exp(s_ab - lse_a) - [a==b]) / (M T)
-//   DQ  : A = q, loop B = k:  dq_a += sum_b G_ba k_b,  G_ba = (exp(s_ba - lse_b) - [a==b]) / (M T)
-// =============================================================================================
-constexpr int kNT = 64;  // tile of rows / cols
-
-enum { NCE_LSE = 0, NCE_DK = 1, NCE_DQ = 2 };
-
-template <int MODE, int DC>   // D = 16 * DC
-__global__ void __launch_bounds__(256)
-k_infonce(const float* __restrict__ A, const float* __restrict__ Bm, int64_t M, int Dr, float inv_T, float* __restrict__ lse,
-          float* __restrict__ diag, float* __restrict__ dA) {
-    constexpr int D = 16 * DC;
-    constexpr int LD = D + 1;                 // padded rows: conflict-free column access
-    extern __shared__ float smem[];
-    float* As = smem;                         // [64][LD]
-    float* Bs = As + kNT * LD;                // [64][LD]
-    float* Gs = Bs + kNT * LD;                // [64][65]
-    __shared__ float s_m[kNT], s_l[kNT], s_d[kNT];
-
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int64_t a0 = (int64_t)blockIdx.x * kNT;
-    for (int i = tid; i < kNT * D; i += 256) {
-        const int r = i / D, d = i - r * D;
-        As[r * LD + d] = (a0 + r < M && d < Dr) ? A[(a0 + r) * Dr + d] : 0.f;   // Dr = real width, zero padded to D
-    }
-    if (tid < kNT) { s_m[tid] = -INFINITY; s_l[tid] = 0.f; s_d[tid] = 0.f; }
-    float acc[4][DC];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < DC; ++c) acc[r][c] = 0.f;
-    const float inv_MT = inv_T / (float)M;
-
-    for (int64_t b0 = 0; b0 < M; b0 += kNT) {
-        __syncthreads();
-        for (int i = tid; i < kNT * D; i += 256) {
-            const int r = i / D, d = i - r * D;
-            Bs[r * LD + d] = (b0 + r < M && d < Dr) ? Bm[(b0 + r) * Dr + d] : 0.f;
-        }
-        __syncthreads();
-        // S tile: rows ty*4+r, cols tx+16*c
-        float s[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) s[r][c] = 0.f;
-#pragma unroll 4
-        for (int d = 0; d < D; ++d) {
-            float av[4], bv[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) av[r] = As[(ty * 4 + r) * LD + d];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) bv[c] = Bs[(tx + 16 * c) * LD + d];
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) s[r][c] = fmaf(av[r], bv[c], s[r][c]);
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const int ra = ty * 4 + r, cb = tx + 16 * c;
-                const int64_t ga = a0 + ra, gb = b0 + cb;
-                float v = s[r][c] * inv_T;
-                if (MODE == NCE_LSE) {
-                    if (gb >= M) v = -INFINITY;
-                } else {
-                    // row index of the logits matrix is the k index: a for DK, b for DQ
-                    const float l = (MODE == NCE_DK) ? ((ga < M) ? lse[ga] : 0.f) : ((gb < M) ? lse[gb] : 0.f);
-                    v = (ga < M && gb < M) ? (__expf(v - l) - (ga == gb ? 1.0f : 0.0f)) * inv_MT : 0.f;
-                }
-                Gs[ra * 65 + cb] = v;
-            }
-        __syncthreads();
-        if (MODE == NCE_LSE) {
-            // 4 threads per row, 16 columns each
-            const int row = tid >> 2, part = tid & 3;
-            float mx = -INFINITY;
-            for (int c = part * 16; c < part * 16 + 16; ++c) mx = fmaxf(mx, Gs[row * 65 + c]);
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            const float m_old = s_m[row];
-            const float m_new = fmaxf(m_old, mx);
-            float sum = 0.f;
-            for (int c = part * 16; c < part * 16 + 16; ++c) sum += __expf(Gs[row * 65 + c] - m_new);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-            if (part == 0) {
-                s_l[row] = s_l[row] * __expf(m_old - m_new) + sum;
-                s_m[row] = m_new;
-                const int64_t ga = a0 + row;
-                if (ga >= b0 && ga < b0 + kNT) s_d[row] = Gs[row * 65 + (int)(ga - b0)];
-            }
-        } else {
-            // acc[r][c] += sum_b G[ra][b] * B[b][tx + 16 c]
-#pragma unroll 2
-            for (int bb = 0; bb < kNT; ++bb) {
-                float gv[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) gv[r] = Gs[(ty * 4 + r) * 65 + bb];
-#pragma unroll
-                for (int c = 0; c < DC; ++c) {
-                    const float bval = Bs[bb * LD + tx + 16 * c];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) acc[r][c] = fmaf(gv[r], bval, acc[r][c]);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    if (MODE == NCE_LSE) {
-        if (tid < kNT && a0 + tid < M) {
-            lse[a0 + tid] = s_m[tid] + __logf(s_l[tid]);
-            diag[a0 + tid] = s_d[tid];
-        }
-    } else {
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int64_t ga = a0 + ty * 4 + r;
-            if (ga >= M) continue;
-#pragma unroll
-            for (int c = 0; c < DC; ++c)
-                if (tx + 16 * c < Dr) dA[ga * Dr + tx + 16 * c] = acc[r][c];
-        }
-    }
-}
-
-__global__ void __launch_bounds__(1024)
-k_infonce_loss(const float* __restrict__ lse, const float* __restrict__ diag, int64_t M, float* __restrict__ loss) {
-    __shared__ double s_red[32];
-    double a = 0.0;
-    for (int64_t i = threadIdx.x; i < M; i += 1024) a += (double)lse[i] - (double)diag[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int k = 0; k < 32; ++k) t += s_red[k];
-        loss[0] = (float)(t / (double)M);                    // CrossEntropyLoss mean reduction
-    }
-}
-
-template <int DC>
-static int run_infonce(const float* k, const float* q, int64_t M, int Dr, float T, float* loss, float* dk, float* dq,
-                       float* lse, float* diag, cudaStream_t st) {
-    constexpr int D = 16 * DC;
-    const size_t smem = sizeof(float) * (2 * kNT * (D + 1) + kNT * 65);
-    const unsigned grid = (unsigned)((M + kNT - 1) / kNT);
-    OESS_CUDA(cudaFuncSetAttribute(k_infonce<NCE_LSE, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    OESS_KERNEL("k_infonce", st, k_infonce<NCE_LSE, DC><<<grid, 256, smem, st>>>(k, q, M, Dr, 1.0f / T, lse, diag, nullptr));
-    OESS_KERNEL("k_infonce_loss", st, k_infonce_loss<<<1, 1024, 0, st>>>(lse, diag, M, loss));
-    if (dk) {
-        OESS_CUDA(cudaFuncSetAttribute(k_infonce<NCE_DK, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OESS_KERNEL("k_infonce", st, k_infonce<NCE_DK, DC><<<grid, 256, smem, st>>>(k, q, M, Dr, 1.0f / T, lse, diag, dk));
-    }
-    if (dq) {
-        OESS_CUDA(cudaFuncSetAttribute(k_infonce<NCE_DQ, DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        OESS_KERNEL("k_infonce", st, k_infonce<NCE_DQ, DC><<<grid, 256, smem, st>>>(q, k, M, Dr, 1.0f / T, lse, diag, dq));
-    }
-    return OESS_OK;
-}
-
 }  // namespace oess
 
 using namespace oess;
@@ -609,29 +434,4 @@ OESS_API int oess_segpool_bwd(const float* d_pooled, const int64_t* seg, const f
     OESS_KERNEL("k_segpool_bwd", st, if (vec4) k_segpool_bwd<4><<<grid, kPoolWarps * 32, 0, st>>>(d_pooled, seg, counts, B, Cf, HW, S, M, cb, d_feat);
     else k_segpool_bwd<1><<<grid, kPoolWarps * 32, 0, st>>>(d_pooled, seg, counts, B, Cf, HW, S, M, cb, d_feat));
     return OESS_OK;
-}
-
-OESS_API int oess_infonce_ws_bytes(int64_t M, int D, size_t* ws_bytes) {
-    if (!ws_bytes || M <= 0 || D <= 0) return OESS_E_ARG;
-    *ws_bytes = align_up(sizeof(float) * (size_t)M, 256) * 2;
-    return OESS_OK;
-}
-
-OESS_API int oess_infonce(const float* k, const float* q, int64_t M, int D, float temperature, float* loss,
-                          float* dk, float* dq, void* ws, size_t ws_bytes, oess_stream_t stream) {
-    size_t need = 0;
-    int rc = oess_infonce_ws_bytes(M, D, &need);
-    if (rc) return rc;
-    if (!k || !q || !loss) return OESS_E_ARG;
-    if (!ws || ws_bytes < need) return OESS_E_WORKSPACE;
-    float* lse = (float*)ws;
-    float* diag = (float*)((char*)ws + need / 2);
-    cudaStream_t st = (cudaStream_t)stream;
-    // feature width D is zero-padded to 16 * DC columns (OpenESS uses D = 256)
-    if (D <= 16) return run_infonce<1>(k, q, M, D, temperature, loss, dk, dq, lse, diag, st);
-    if (D <= 32) return run_infonce<2>(k, q, M, D, temperature, loss, dk, dq, lse, diag, st);
-    if (D <= 64) return run_infonce<4>(k, q, M, D, temperature, loss, dk, dq, lse, diag, st);
-    if (D <= 128) return run_infonce<8>(k, q, M, D, temperature, loss, dk, dq, lse, diag, st);
-    if (D <= 256) return run_infonce<16>(k, q, M, D, temperature, loss, dk, dq, lse, diag, st);
-    return OESS_E_ARG;   // wider features are not used by any OpenESS configuration
 }
