@@ -164,6 +164,26 @@ int oess_dice_ce_bwd(const float* logits, const int64_t* target, int B, int K, i
 int oess_confusion(const int64_t* pred, const int64_t* gt, int64_t n, int K, int64_t ignore_label,
                    int64_t* conf, int32_t* status, oess_stream_t stream);
 
+/* Replaces the pointwise tail of e2vid/model/submodules.py:197-214 (ConvLSTM.forward after the Gates conv):
+ * gates [B, 4C, H, W] = (in, remember, out, cell) chunks, prev_cell [B, C, H, W] or NULL (zero state):
+ *   cell = sigmoid(remember) * prev_cell + sigmoid(in) * tanh(cell_gate);  hidden = sigmoid(out) * tanh(cell).
+ * One fused pass (28 B / element) instead of ~10 elementwise kernels per encoder level and recurrent step. */
+int oess_convlstm_gates(const float* gates, const float* prev_cell, float* hidden, float* cell, int B, int C,
+                        int64_t HW, oess_stream_t stream);
+
+/* Replaces training/openess_trainer.py:456 (:398, :497) torch.nn.L1Loss()(a, b) = mean |a - b|.
+ * loss: device f32[1]; acc: device f64[1] scratch.  bwd: da = sign(a - b) * grad_scale[0] / n, db = -da. */
+int oess_l1_mean(const float* a, const float* b, int64_t n, float* loss, double* acc, oess_stream_t stream);
+int oess_l1_mean_bwd(const float* a, const float* b, int64_t n, const float* grad_scale, float* da, float* db,
+                     oess_stream_t stream);
+
+/* Replaces training/openess_trainer.py:460 (:402, :501) mean(1 - cosine_similarity(a, b, dim=1)) for
+ * a, b [B, K, H, W] (eps = 1e-8, torch semantics).  loss: device f32[1]; acc: device f64[1] scratch. */
+int oess_cos_consistency(const float* a, const float* b, int B, int K, int64_t HW, float* loss, double* acc,
+                         oess_stream_t stream);
+int oess_cos_consistency_bwd(const float* a, const float* b, int B, int K, int64_t HW, const float* grad_scale,
+                             float* da, float* db, oess_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,7 @@ SOURCES = {
     "normalize.cu": ["--fmad=false"],
     "losses.cu": [],
     "infonce.cu": [],
+    "pointwise.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--threads", "0"]

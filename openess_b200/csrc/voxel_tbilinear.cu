@@ -125,6 +125,22 @@ k_runs(const T* __restrict__ ev4, const uint2* __restrict__ pairs, const int64_t
         if (me.x >= g.invalid_key) continue;                      // :88 invalid events sort last
         if (i > 0 && pr[i - 1].x == me.x) continue;               // not the head of its pixel run
         float* o = out + (int64_t)f * planes * HW + me.x;
+        if (i + 1 >= nf || pr[i + 1].x != me.x) {
+            // single-event pixel (the common case): one decode; acc = f32(f64(0) + w) = f32(w) per touched bin,
+            // the other bins stay at the memset zero; pos - neg = +-f32(w) exactly (data_util.py:91-116)
+            const Decoded d = decode(ev4 + (fbeg + me.y) * 4, ft, g, (T*)nullptr);
+            const int64_t plane0 = (separate_pol && !d.pos) ? g.C : 0;
+            const bool negate = !separate_pol && !d.pos;
+            if (d.ti < g.C) {
+                const float v = add_at(0.0f, __dmul_rn(d.ap, __dsub_rn(1.0, d.d)));
+                o[(plane0 + d.ti) * HW] = negate ? __fsub_rn(0.0f, v) : v;
+            }
+            if (d.ti + 1 < g.C) {
+                const float v = add_at(0.0f, __dmul_rn(d.ap, d.d));
+                o[(plane0 + d.ti + 1) * HW] = negate ? __fsub_rn(0.0f, v) : v;
+            }
+            continue;
+        }
         constexpr int NA = CT > 0 ? CT : 1;
         const int nbin_loops = CT > 0 ? 1 : g.C;
         for (int bin = 0; bin < nbin_loops; ++bin) {

@@ -1,0 +1,247 @@
+"""E2VID recurrent event encoder, latent-only and sync-free.
+
+Mirror of the reference's e2vid/model/{model.py:69-100 (E2VIDRecurrent), unet.py:108-170 (UNetRecurrent),
+submodules.py (ConvLayer, RecurrentConvLayer, ConvLSTM, ResidualBlock, TransposedConvLayer)} with the SAME module
+tree and parameter names, so a reference checkpoint (`E2VID_lightweight.pth.tar` -> `state_dict`) loads with
+`load_state_dict(strict=True)`.
+
+What changes on the B200:
+  * every OpenESS trainer consumes only `latent` (unet.py:163, pretrain_trainer.py:441): with `latent_only=True`
+    (default) the three up-sampling decoders, `pred` and the sigmoid are skipped (they stay in the module tree for
+    checkpoint compatibility) -- the image is returned as None;
+  * the ConvLSTM pointwise tail (3 sigmoids, 2 tanh, cell/hidden update: ~10 ATen kernels per level and step) is one
+    fused kernel, `oess_convlstm_gates`;
+  * eval-mode BatchNorm of the frozen encoder is folded into the preceding conv once (`fold_bn()`);
+  * the dense contractions (5x5 / 3x3 convolutions) still run on cuDNN through torch this round: they are the
+    next kernels to be hand-written (tcgen05 implicit GEMM).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import losses as _ops
+
+
+class ConvLayer(nn.Module):
+    """submodules.py:7-31."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, activation='relu', norm=None):
+        super().__init__()
+        bias = False if norm == 'BN' else True
+        self.conv2d = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, bias=bias)
+        self.activation = getattr(torch, activation, 'relu') if activation is not None else None
+        self.norm = norm
+        if norm == 'BN':
+            self.norm_layer = nn.BatchNorm2d(out_channels)
+        elif norm == 'IN':
+            self.norm_layer = nn.InstanceNorm2d(out_channels, track_running_stats=True)
+        self._folded = None
+
+    def fold_bn(self):
+        """Eval-mode BN folded into the conv: w' = w * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps)."""
+        if self.norm == 'BN' and not self.training:
+            bn = self.norm_layer
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            self._folded = ((self.conv2d.weight * scale[:, None, None, None]).detach(),
+                            (bn.bias - bn.running_mean * scale).detach())
+
+    def forward(self, x):
+        if self._folded is not None and not self.training:
+            out = F.conv2d(x, self._folded[0], self._folded[1], self.conv2d.stride, self.conv2d.padding)
+        else:
+            out = self.conv2d(x)
+            if self.norm in ['BN', 'IN']:
+                out = self.norm_layer(out)
+        if self.activation is not None:
+            out = self.activation(out)
+        return out
+
+
+class TransposedConvLayer(nn.Module):
+    """submodules.py:34-63."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, activation='relu', norm=None):
+        super().__init__()
+        bias = False if norm == 'BN' else True
+        self.transposed_conv2d = nn.ConvTranspose2d(in_channels, out_channels, kernel_size, stride=2, padding=padding,
+                                                    output_padding=1, bias=bias)
+        self.activation = getattr(torch, activation, 'relu') if activation is not None else None
+        self.norm = norm
+        if norm == 'BN':
+            self.norm_layer = nn.BatchNorm2d(out_channels)
+        elif norm == 'IN':
+            self.norm_layer = nn.InstanceNorm2d(out_channels, track_running_stats=True)
+
+    def forward(self, x):
+        out = self.transposed_conv2d(x)
+        if self.norm in ['BN', 'IN']:
+            out = self.norm_layer(out)
+        if self.activation is not None:
+            out = self.activation(out)
+        return out
+
+
+class ConvLSTM(nn.Module):
+    """submodules.py:175-214; the pointwise tail is the fused CUDA kernel when running without grad on the GPU."""
+
+    def __init__(self, input_size, hidden_size, kernel_size):
+        super().__init__()
+        self.input_size = input_size
+        self.hidden_size = hidden_size
+        self.Gates = nn.Conv2d(input_size + hidden_size, 4 * hidden_size, kernel_size, padding=kernel_size // 2)
+
+    def forward(self, input_, prev_state=None):
+        if prev_state is None:
+            # zero state: the hidden half of the stacked input contributes nothing -> convolve the input half only
+            w = self.Gates.weight[:, :self.input_size]
+            gates = F.conv2d(input_, w, self.Gates.bias, padding=self.Gates.padding)
+            prev_cell = None
+        else:
+            prev_hidden, prev_cell = prev_state
+            gates = self.Gates(torch.cat((input_, prev_hidden), 1))
+        if gates.is_cuda and not torch.is_grad_enabled():
+            return _ops.convlstm_gates(gates, prev_cell)
+        in_gate, remember_gate, out_gate, cell_gate = gates.chunk(4, 1)      # differentiable path (unfrozen E2VID)
+        prev_c = 0 if prev_cell is None else prev_cell
+        cell = torch.sigmoid(remember_gate) * prev_c + torch.sigmoid(in_gate) * torch.tanh(cell_gate)
+        hidden = torch.sigmoid(out_gate) * torch.tanh(cell)
+        return hidden, cell
+
+
+class RecurrentConvLayer(nn.Module):
+    """submodules.py:96-115 (convlstm only: the only recurrent block type OpenESS uses)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=0, recurrent_block_type='convlstm',
+                 activation='relu', norm=None):
+        super().__init__()
+        assert recurrent_block_type == 'convlstm', "OpenESS runs E2VID with ConvLSTM blocks"
+        self.recurrent_block_type = recurrent_block_type
+        self.conv = ConvLayer(in_channels, out_channels, kernel_size, stride, padding, activation, norm)
+        self.recurrent_block = ConvLSTM(input_size=out_channels, hidden_size=out_channels, kernel_size=3)
+
+    def forward(self, x, prev_state):
+        x = self.conv(x)
+        state = self.recurrent_block(x, prev_state)
+        return state[0], state
+
+
+class ResidualBlock(nn.Module):
+    """submodules.py:140-172."""
+
+    def __init__(self, in_channels, out_channels, stride=1, downsample=None, norm=None):
+        super().__init__()
+        bias = False if norm == 'BN' else True
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=stride, padding=1, bias=bias)
+        self.norm = norm
+        if norm == 'BN':
+            self.bn1 = nn.BatchNorm2d(out_channels)
+            self.bn2 = nn.BatchNorm2d(out_channels)
+        elif norm == 'IN':
+            self.bn1 = nn.InstanceNorm2d(out_channels)
+            self.bn2 = nn.InstanceNorm2d(out_channels)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, stride=1, padding=1, bias=bias)
+        self.downsample = downsample
+
+    def forward(self, x):
+        residual = x
+        out = self.conv1(x)
+        if self.norm in ['BN', 'IN']:
+            out = self.bn1(out)
+        out = self.relu(out)
+        out = self.conv2(out)
+        if self.norm in ['BN', 'IN']:
+            out = self.bn2(out)
+        if self.downsample:
+            residual = self.downsample(x)
+        out = out + residual
+        return self.relu(out)
+
+
+class UNetRecurrent(nn.Module):
+    """unet.py:16-63 (BaseUNet) + :108-170 (UNetRecurrent), skip_type 'sum' or 'concat', TransposedConv decoders."""
+
+    def __init__(self, num_input_channels, num_output_channels=1, skip_type='sum', recurrent_block_type='convlstm',
+                 activation='sigmoid', num_encoders=4, base_num_channels=32, num_residual_blocks=2, norm=None,
+                 use_upsample_conv=True):
+        super().__init__()
+        if use_upsample_conv:
+            raise NotImplementedError("UpsampleConvLayer decoders are dead code on the OpenESS latent path; the "
+                                      "lightweight checkpoint uses TransposedConvLayer")
+        self.skip_type = skip_type
+        self.num_encoders = num_encoders
+        self.norm = norm
+        self.activation = getattr(torch, activation, 'sigmoid')
+        c = base_num_channels
+        self.max_num_channels = c * pow(2, num_encoders)
+        self.head = ConvLayer(num_input_channels, c, kernel_size=5, stride=1, padding=2)
+        self.encoders = nn.ModuleList()
+        for i in range(num_encoders):
+            self.encoders.append(RecurrentConvLayer(c * pow(2, i), c * pow(2, i + 1), kernel_size=5, stride=2, padding=2,
+                                                    recurrent_block_type=recurrent_block_type, norm=norm))
+        self.resblocks = nn.ModuleList([ResidualBlock(self.max_num_channels, self.max_num_channels, norm=norm)
+                                        for _ in range(num_residual_blocks)])
+        self.decoders = nn.ModuleList()
+        for input_size in reversed([c * pow(2, i + 1) for i in range(num_encoders)]):
+            self.decoders.append(TransposedConvLayer(input_size if skip_type == 'sum' else 2 * input_size,
+                                                     input_size // 2, kernel_size=5, padding=2, norm=norm))
+        self.pred = ConvLayer(c if skip_type == 'sum' else 2 * c, num_output_channels, 1, activation=None, norm=norm)
+
+    def _skip(self, a, b):
+        return a + b if self.skip_type == 'sum' else torch.cat([a, b], dim=1)
+
+    def forward(self, x, prev_states, latent_only=True):
+        x = self.head(x)
+        head = x
+        if prev_states is None:
+            prev_states = [None] * self.num_encoders
+        blocks, states = [], []
+        for i, encoder in enumerate(self.encoders):
+            x, state = encoder(x, prev_states[i])
+            blocks.append(x)
+            states.append(state)
+        latent = {1: head}
+        for i in range(self.num_encoders):
+            latent[2 ** (i + 1)] = blocks[i]
+        if self.num_encoders > 3:                       # unet.py:163 keeps exactly {1, 2, 4, 8}
+            latent = {k: latent[k] for k in (1, 2, 4, 8)}
+        if latent_only:
+            return None, states, latent                 # resblocks + decoders + pred feed only the image
+        for resblock in self.resblocks:
+            x = resblock(x)
+        for i, decoder in enumerate(self.decoders):
+            x = decoder(self._skip(x, blocks[self.num_encoders - i - 1]))
+        img = self.activation(self.pred(self._skip(x, head)))
+        return img, states, latent
+
+
+class E2VIDRecurrent(nn.Module):
+    """model.py:69-100 with the config keys of model.py:13-46 (same defaults)."""
+
+    def __init__(self, config, latent_only=True):
+        super().__init__()
+        assert 'num_bins' in config
+        self.num_bins = int(config['num_bins'])
+        self.skip_type = str(config.get('skip_type', 'sum'))
+        self.num_encoders = int(config.get('num_encoders', 4))
+        self.base_num_channels = int(config.get('base_num_channels', 32))
+        self.num_residual_blocks = int(config.get('num_residual_blocks', 2))
+        self.norm = str(config['norm']) if 'norm' in config else None
+        self.use_upsample_conv = bool(config.get('use_upsample_conv', True))
+        self.recurrent_block_type = str(config.get('recurrent_block_type', 'convlstm'))
+        self.latent_only = latent_only
+        self.unetrecurrent = UNetRecurrent(num_input_channels=self.num_bins, num_output_channels=1,
+                                           skip_type=self.skip_type, recurrent_block_type=self.recurrent_block_type,
+                                           activation='sigmoid', num_encoders=self.num_encoders,
+                                           base_num_channels=self.base_num_channels,
+                                           num_residual_blocks=self.num_residual_blocks, norm=self.norm,
+                                           use_upsample_conv=self.use_upsample_conv)
+
+    def fold_bn(self):
+        for m in self.modules():
+            if isinstance(m, ConvLayer):
+                m.fold_bn()
+        return self
+
+    def forward(self, event_tensor, prev_states):
+        return self.unetrecurrent.forward(event_tensor, prev_states, latent_only=self.latent_only)

@@ -178,3 +178,89 @@ def confusion(pred, gt, num_classes, ignore_label, out=None, status=None):
         check(lib().oess_confusion(ptr(pred), ptr(gt), pred.numel(), int(num_classes), int(ignore_label), ptr(out),
                                    ptr(status), stream_ptr(pred.device)), "oess_confusion")
     return out
+
+
+# ------------------------------------------------------------------------------------------ consistency losses
+class _L1Mean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _f32c(a), _f32c(b)
+        require_cuda(a, b)
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        acc = torch.empty(1, dtype=torch.float64, device=a.device)
+        with torch.cuda.device(a.device):
+            check(lib().oess_l1_mean(ptr(a), ptr(b), a.numel(), ptr(loss), ptr(acc), stream_ptr(a.device)), "oess_l1_mean")
+        ctx.save_for_backward(a, b)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        gs = g.reshape(1).to(torch.float32).contiguous()
+        with torch.cuda.device(a.device):
+            check(lib().oess_l1_mean_bwd(ptr(a), ptr(b), a.numel(), ptr(gs), ptr(da), ptr(db), stream_ptr(a.device)),
+                  "oess_l1_mean_bwd")
+        return da, db
+
+
+def l1_mean(a, b):
+    """torch.nn.L1Loss()(a, b) (openess_trainer.py:456): mean |a - b|, fused forward and backward."""
+    if a.shape != b.shape:
+        raise ValueError("shapes differ")
+    return _L1Mean.apply(a, b)
+
+
+class _CosConsistency(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = _f32c(a), _f32c(b)
+        require_cuda(a, b)
+        B, K = a.shape[:2]
+        HW = a.numel() // (B * K)
+        loss = torch.empty(1, dtype=torch.float32, device=a.device)
+        acc = torch.empty(1, dtype=torch.float64, device=a.device)
+        with torch.cuda.device(a.device):
+            check(lib().oess_cos_consistency(ptr(a), ptr(b), B, K, HW, ptr(loss), ptr(acc), stream_ptr(a.device)),
+                  "oess_cos_consistency")
+        ctx.save_for_backward(a, b)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        B, K = a.shape[:2]
+        HW = a.numel() // (B * K)
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        gs = g.reshape(1).to(torch.float32).contiguous()
+        with torch.cuda.device(a.device):
+            check(lib().oess_cos_consistency_bwd(ptr(a), ptr(b), B, K, HW, ptr(gs), ptr(da), ptr(db),
+                                                 stream_ptr(a.device)), "oess_cos_consistency_bwd")
+        return da, db
+
+
+def cosine_consistency(a, b):
+    """mean(1 - cosine_similarity(a, b, dim=1)) for [B, K, H, W] maps (openess_trainer.py:460)."""
+    if a.shape != b.shape or a.ndim < 2:
+        raise ValueError("a and b must have the same [B, K, ...] shape")
+    return _CosConsistency.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------ ConvLSTM gates
+def convlstm_gates(gates, prev_cell=None):
+    """Fused pointwise tail of ConvLSTM.forward (e2vid/model/submodules.py:203-212) -> (hidden, cell). No grad:
+    the E2VID encoder is frozen and run under no_grad in every OpenESS trainer."""
+    require_cuda(gates)
+    gates = _f32c(gates)
+    B, C4 = gates.shape[:2]
+    C = C4 // 4
+    HW = gates.numel() // (B * C4)
+    hidden = torch.empty((B, C) + tuple(gates.shape[2:]), dtype=torch.float32, device=gates.device)
+    cell = torch.empty_like(hidden)
+    pc = None if prev_cell is None else _f32c(prev_cell)
+    with torch.cuda.device(gates.device):
+        check(lib().oess_convlstm_gates(ptr(gates), ptr(pc), ptr(hidden), ptr(cell), B, C, HW, stream_ptr(gates.device)),
+              "oess_convlstm_gates")
+    return hidden, cell

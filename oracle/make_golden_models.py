@@ -1,0 +1,70 @@
+"""Golden vectors for the model-side rows (a9/a10 E2VID recurrent encoder, a18 consistency losses), produced by
+the REFERENCE's own modules on CPU in the build container (needs /root/reference):
+
+    python oracle/make_golden_models.py        # -> tests/golden/e2vid_tiny.npz, tests/golden/consistency.npz
+
+e2vid/model/model.py:E2VIDRecurrent is imported unmodified (sys.modules is pre-seeded for the `e2vid` namespace
+package; `e2vid.base` needs nothing that is missing here).  A tiny config keeps the weights small enough to commit."""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("OPENESS_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+CFG = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
+       'base_num_channels': 4, 'num_residual_blocks': 2, 'norm': 'BN', 'use_upsample_conv': False}
+
+
+def main():
+    torch.set_num_threads(1)
+    sys.path.insert(0, REF)
+    from e2vid.model.model import E2VIDRecurrent          # the reference class, unmodified
+    torch.manual_seed(1205)
+    m = E2VIDRecurrent(CFG).eval()
+    with torch.no_grad():                                  # non-trivial BN statistics / affine
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.3)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.normal_(0, 0.2)
+    rng = np.random.default_rng(1205)
+    steps = [rng.normal(0, 1, (2, 5, 24, 32)).astype(np.float32) for _ in range(3)]
+    for s in steps:
+        s[rng.random(s.shape) < 0.6] = 0
+    out = {"cfg_keys": np.array(list(CFG.keys())), "cfg_vals": np.array([str(v) for v in CFG.values()])}
+    for k, v in m.state_dict().items():
+        out["sd__" + k] = v.numpy()
+    states = None
+    with torch.no_grad():
+        for i, s in enumerate(steps):
+            img, states, latent = m(torch.from_numpy(s), states)
+            out[f"in{i}"] = s
+            out[f"img{i}"] = img.numpy()
+            for kk, vv in latent.items():
+                out[f"latent{i}__{kk}"] = vv.numpy()
+            for li, (h, c) in enumerate(states):
+                out[f"state{i}__{li}__h"], out[f"state{i}__{li}__c"] = h.numpy(), c.numpy()
+    np.savez_compressed(os.path.join(OUT, "e2vid_tiny.npz"), **out)
+
+    # a18: torch.nn.L1Loss and mean(1 - cosine_similarity(dim=1)) with gradients (openess_trainer.py:456-462)
+    a = torch.from_numpy(rng.normal(0, 1, (2, 16, 14, 18)).astype(np.float32)).requires_grad_(True)
+    b = torch.from_numpy(rng.normal(0, 1, (2, 16, 14, 18)).astype(np.float32)).requires_grad_(True)
+    l1 = torch.nn.L1Loss()(a, b)
+    l1.backward()
+    la = torch.from_numpy(rng.normal(0, 2, (2, 11, 14, 18)).astype(np.float32)).requires_grad_(True)
+    lb = torch.from_numpy(rng.normal(0, 2, (2, 11, 14, 18)).astype(np.float32)).requires_grad_(True)
+    cs = torch.mean(1 - torch.nn.functional.cosine_similarity(la, lb, dim=1))
+    cs.backward()
+    np.savez_compressed(os.path.join(OUT, "consistency.npz"), a=a.detach().numpy(), b=b.detach().numpy(),
+                        l1=np.array(l1.item()), da=a.grad.numpy(), db=b.grad.numpy(), la=la.detach().numpy(),
+                        lb=lb.detach().numpy(), cos=np.array(cs.item()), dla=la.grad.numpy(), dlb=lb.grad.numpy())
+    for f in ("e2vid_tiny.npz", "consistency.npz"):
+        print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

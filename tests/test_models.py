@@ -1,0 +1,117 @@
+"""E2VID recurrent encoder mirror (a9/a10) and consistency losses (a18) against goldens produced by the
+reference's own modules (oracle/make_golden_models.py).  Tolerances: float32 convolutions in a different
+summation order (cuDNN vs the reference's CPU kernels, folded BN): 2e-4 abs on O(1) activations."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+
+def _build(z, latent_only):
+    from openess_b200.e2vid.model.model import E2VIDRecurrent
+    cfg = {}
+    for k, v in zip(z["cfg_keys"], z["cfg_vals"]):
+        cfg[str(k)] = (v == "True") if str(v) in ("True", "False") else (int(v) if str(v).isdigit() else str(v))
+    m = E2VIDRecurrent(cfg, latent_only=latent_only)
+    sd = {k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd__")}
+    m.load_state_dict(sd, strict=True)          # same module tree + parameter names as the reference checkpoint
+    return m.eval()
+
+
+def test_e2vid_mirror_state_dict_and_cpu_forward():
+    z = load_golden("e2vid_tiny")
+    m = _build(z, latent_only=False)
+    states = None
+    with torch.no_grad():
+        for i in range(3):
+            img, states, latent = m(torch.from_numpy(z[f"in{i}"]), states)
+            np.testing.assert_allclose(img.numpy(), z[f"img{i}"], atol=2e-5)
+            assert sorted(latent) == [1, 2, 4, 8]
+            for k in latent:
+                np.testing.assert_allclose(latent[k].numpy(), z[f"latent{i}__{k}"], atol=2e-5)
+    assert sum(p.numel() for p in m.parameters()) == sum(z[k].size for k in z.files if k.startswith("sd__") and
+                                                         "running" not in k and "num_batches" not in k)
+
+
+@pytest.mark.gpu
+def test_e2vid_latent_only_gpu_fused_gates_and_folded_bn():
+    z = load_golden("e2vid_tiny")
+    dev = torch.device("cuda:0")
+    m = _build(z, latent_only=True).to(dev).fold_bn()
+    states = None
+    with torch.no_grad():
+        for i in range(3):
+            img, states, latent = m(torch.from_numpy(z[f"in{i}"]).to(dev), states)
+            assert img is None                                 # decoders / pred / sigmoid skipped
+            for k in latent:
+                np.testing.assert_allclose(latent[k].cpu().numpy(), z[f"latent{i}__{k}"], atol=2e-4)
+            for li, (h, c) in enumerate(states):
+                np.testing.assert_allclose(h.cpu().numpy(), z[f"state{i}__{li}__h"], atol=2e-4)
+                np.testing.assert_allclose(c.cpu().numpy(), z[f"state{i}__{li}__c"], atol=2e-4)
+
+
+@pytest.mark.gpu
+def test_convlstm_gates_kernel_vs_torch():
+    from openess_b200 import losses
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    for shape in [(2, 8, 12, 16), (1, 3, 5, 7)]:               # vectorised and scalar paths
+        B, C, H, W = shape
+        gates = (torch.randn((B, 4 * C, H, W), generator=g) * 3).to(dev)
+        pc = torch.randn(shape, generator=g).to(dev)
+        for prev in (pc, None):
+            h, c = losses.convlstm_gates(gates, prev)
+            i_, r_, o_, c_ = gates.double().chunk(4, 1)
+            cell = torch.sigmoid(r_) * (0 if prev is None else prev.double()) + torch.sigmoid(i_) * torch.tanh(c_)
+            hid = torch.sigmoid(o_) * torch.tanh(cell)
+            torch.testing.assert_close(c.double(), cell, atol=3e-6, rtol=3e-6)
+            torch.testing.assert_close(h.double(), hid, atol=3e-6, rtol=3e-6)
+
+
+@pytest.mark.gpu
+def test_image_reconstructor_mirror_runs_recurrence(oracle):
+    from types import SimpleNamespace
+    from openess_b200.e2vid.image_reconstructor import ImageReconstructor
+    z = load_golden("e2vid_tiny")
+    dev = torch.device("cuda:0")
+    m = _build(z, latent_only=True).to(dev).fold_bn()
+    opts = SimpleNamespace(no_normalize=False, hot_pixels_file=None, flip=False, no_recurrent=False)
+    rec = ImageReconstructor(m, 24, 32, 5, dev, opts)
+    assert rec.crop.is_noop
+    rec.last_states_for_each_channel = {'grayscale': None}      # what the trainers do before every sample
+    ref_states = None
+    for i in range(3):
+        x = z[f"in{i}"]
+        _, states, latent = rec.update_reconstruction(torch.from_numpy(x))
+        with torch.no_grad():                                   # same pipeline composed from checked pieces
+            xn, _ = oracle.nonzero_standardize(x)
+            _, ref_states, ref_latent = m(torch.from_numpy(xn).to(dev), ref_states)
+        for k in latent:
+            torch.testing.assert_close(latent[k], ref_latent[k], atol=2e-4, rtol=1e-4)
+    assert rec.last_states_for_each_channel['grayscale'] is states
+    rec2 = ImageReconstructor(m, 25, 33, 5, dev, opts)          # padding to a multiple of 8 (ReflectionPad2d)
+    assert not rec2.crop.is_noop and rec2.crop.width_crop_size == 40 and rec2.crop.height_crop_size == 32
+    _, _, lat = rec2.update_reconstruction(torch.zeros(1, 5, 25, 33))
+    assert tuple(lat[1].shape[2:]) == (32, 40) and tuple(lat[8].shape[2:]) == (4, 5)
+
+
+@pytest.mark.gpu
+def test_consistency_losses_golden():
+    from openess_b200.training.consistency import L1Loss, prediction_consistency
+    z = load_golden("consistency")
+    dev = torch.device("cuda:0")
+    a = torch.from_numpy(z["a"]).to(dev).requires_grad_(True)
+    b = torch.from_numpy(z["b"]).to(dev).requires_grad_(True)
+    l1 = L1Loss()(a, b)
+    assert float(l1.detach()) == pytest.approx(float(z["l1"]), rel=2e-6)
+    (2 * l1).backward()
+    np.testing.assert_allclose(a.grad.cpu().numpy(), 2 * z["da"], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(b.grad.cpu().numpy(), 2 * z["db"], rtol=1e-6, atol=1e-10)
+    la = torch.from_numpy(z["la"]).to(dev).requires_grad_(True)
+    lb = torch.from_numpy(z["lb"]).to(dev).requires_grad_(True)
+    cs = prediction_consistency(la, lb)
+    assert float(cs.detach()) == pytest.approx(float(z["cos"]), rel=5e-6)
+    cs.backward()
+    np.testing.assert_allclose(la.grad.cpu().numpy(), z["dla"], rtol=2e-4, atol=2e-9)
+    np.testing.assert_allclose(lb.grad.cpu().numpy(), z["dlb"], rtol=2e-4, atol=2e-9)
