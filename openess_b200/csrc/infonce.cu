@@ -98,6 +98,7 @@ k_infonce(const float* __restrict__ A, const float* __restrict__ Bm, int64_t M, 
             for (int c = part4 * 16; c < part4 * 16 + 16; ++c) sum += __expf(Gs[row * 65 + c] - m_new);
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            __syncwarp();                      // all 4 lanes of the row have read s_m[row] before lane 0 rewrites it
             if (part4 == 0) {
                 s_l[row] = s_l[row] * __expf(m_old - m_new) + sum;
                 s_m[row] = m_new;
