@@ -184,6 +184,18 @@ int oess_cos_consistency(const float* a, const float* b, int B, int K, int64_t H
 int oess_cos_consistency_bwd(const float* a, const float* b, int B, int K, int64_t HW, const float* grad_scale,
                              float* da, float* db, oess_stream_t stream);
 
+/* Per-pixel linear map on NCHW tensors with Cin, Cout <= 64: y[b,k,p] = bias[k] + sum_c W[k,c] x[b,c,p].
+ * Building block of the fused SemSegE2VID head: models/style_networks.py:163-165 chains conv1x1(32->256),
+ * conv1x1(256->512) and conv(text_embeddings) with no non-linearity, so logits = (T W512 W256) x32 + T (W512 b256
+ * + b512) -- computed directly, the 256/512-channel full-resolution maps (2.3 + 4.6 GB at batch 8) never exist.
+ * W: [Cout, Cin] row-major; bias may be NULL.  Backward w.r.t. x = the same call with W^T and no bias.
+ * wgrad: dW[k,c] = sum_{b,p} dy[b,k,p] x[b,c,p], db[k] = sum dy (db may be NULL); deterministic reduction. */
+int oess_pixel_linear(const float* x, const float* W, const float* bias, int B, int Cin, int Cout, int64_t HW,
+                      float* y, oess_stream_t stream);
+int oess_pixel_linear_wgrad_ws_bytes(int Cin, int Cout, size_t* ws_bytes);
+int oess_pixel_linear_wgrad(const float* dy, const float* x, int B, int Cin, int Cout, int64_t HW, float* dW,
+                            float* db, void* ws, size_t ws_bytes, oess_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,6 +52,9 @@ SIGNATURES = {
     "oess_l1_mean_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp],
     "oess_cos_consistency": [_vp, _vp, _int, _int, _i64, _vp, _vp, _vp],
     "oess_cos_consistency_bwd": [_vp, _vp, _int, _int, _i64, _vp, _vp, _vp, _vp],
+    "oess_pixel_linear": [_vp, _vp, _vp, _int, _int, _int, _i64, _vp, _vp],
+    "oess_pixel_linear_wgrad_ws_bytes": [_int, _int, ctypes.POINTER(_sz)],
+    "oess_pixel_linear_wgrad": [_vp, _vp, _int, _int, _int, _i64, _vp, _vp, _vp, _sz, _vp],
 }
 
 _lib = None

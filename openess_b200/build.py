@@ -27,6 +27,7 @@ SOURCES = {
     "losses.cu": [],
     "infonce.cu": [],
     "pointwise.cu": [],
+    "pixel_linear.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--threads", "0"]

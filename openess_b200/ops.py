@@ -1,0 +1,63 @@
+"""Small dense ops over the C ABI with autograd: the per-pixel linear map used by the fused segmentation head."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, require_cuda, stream_ptr
+
+
+def _f32c(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
+def _pixel_linear_raw(x, W, bias):
+    B, Cin = x.shape[:2]
+    Cout = W.shape[0]
+    HW = x.numel() // (B * Cin)
+    y = torch.empty((B, Cout) + tuple(x.shape[2:]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().oess_pixel_linear(ptr(x), ptr(W), ptr(bias), B, Cin, Cout, HW, ptr(y), stream_ptr(x.device)),
+              "oess_pixel_linear")
+    return y
+
+
+class _PixelLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W, bias):
+        require_cuda(x, W)
+        x, W = _f32c(x), _f32c(W)
+        b = None if bias is None else _f32c(bias)
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = bias is not None
+        return _pixel_linear_raw(x, W, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = _f32c(dy)
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _pixel_linear_raw(dy, W.t().contiguous(), None)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            B, Cin = x.shape[:2]
+            Cout = W.shape[0]
+            HW = x.numel() // (B * Cin)
+            nb = ctypes.c_size_t(0)
+            check(lib().oess_pixel_linear_wgrad_ws_bytes(Cin, Cout, ctypes.byref(nb)), "oess_pixel_linear_wgrad_ws_bytes")
+            dW = torch.empty_like(W)
+            db = torch.empty(Cout, dtype=torch.float32, device=x.device) if ctx.has_bias else None
+            with torch.cuda.device(x.device):
+                ws = _lib.workspace(nb.value, x.device)
+                check(lib().oess_pixel_linear_wgrad(ptr(dy), ptr(x), B, Cin, Cout, HW, ptr(dW), ptr(db), ptr(ws),
+                                                    ws.numel(), stream_ptr(x.device)), "oess_pixel_linear_wgrad")
+        return dx, dW, db
+
+
+def pixel_linear(x, W, bias=None):
+    """y[b, k, ...] = bias[k] + sum_c W[k, c] x[b, c, ...]  for x [B, Cin, *spatial], Cin and Cout <= 64."""
+    if W.ndim != 2 or W.shape[1] != x.shape[1]:
+        raise ValueError("W must be [Cout, Cin]")
+    if W.shape[0] > 64 or W.shape[1] > 64:
+        raise ValueError("pixel_linear supports at most 64 input and 64 output channels")
+    return _PixelLinear.apply(x, W, bias)

@@ -64,7 +64,59 @@ def main():
                         lb=lb.detach().numpy(), cos=np.array(cs.item()), dla=la.grad.numpy(), dlb=lb.grad.numpy())
     for f in ("e2vid_tiny.npz", "consistency.npz"):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+    golden_semseg()
+
+
+
+
+def golden_semseg():
+    """models/style_networks.py:SemSegE2VID (reference class, tiny width) forward + gradients + superpixel pooling."""
+    sys.modules.setdefault("models", types.ModuleType("models")).__path__ = [os.path.join(REF, "models")]
+    from models.style_networks import SemSegE2VID          # the reference class, unmodified
+    torch.manual_seed(7)
+    K, S, B, H, W = 6, 10, 2, 16, 24
+    m = SemSegE2VID(input_c=32, output_c=K, skip_connect=True, skip_type='concat', text_embeddings_path=None)
+    with torch.no_grad():
+        m.text_embeddings.normal_(0, 0.3)
+        for p in m.parameters():
+            if p.ndim == 4:
+                p.mul_(8.0)                                 # gaussian_weights_init std 0.02 is too small to exercise anything
+    rng = np.random.default_rng(7)
+    lat = {8: torch.from_numpy(rng.normal(0, 1, (B, 32, H // 8, W // 8)).astype(np.float32)).requires_grad_(True),
+           4: torch.from_numpy(rng.normal(0, 1, (B, 16, H // 4, W // 4)).astype(np.float32)).requires_grad_(True),
+           2: torch.from_numpy(rng.normal(0, 1, (B, 8, H // 2, W // 2)).astype(np.float32)).requires_grad_(True),
+           1: torch.from_numpy(rng.normal(0, 1, (B, 4, H, W)).astype(np.float32))}
+    sp = torch.from_numpy(rng.integers(0, S, (B, H, W)).astype(np.int64))
+    out, x256 = m(lat)
+    superpixels = torch.arange(0, B * S, S)[:, None, None] + sp      # pretrain_trainer.py:446-459
+    sI = superpixels.flatten()
+    with torch.no_grad():
+        oh = torch.sparse_coo_tensor(torch.stack((sI, torch.arange(sI.shape[0])), 0), torch.ones(sI.shape[0]))
+    k = oh @ x256.permute(0, 2, 3, 1).flatten(0, 2)
+    k = k / (torch.sparse.sum(oh, 1).to_dense()[:, None] + 1e-6)
+    loss = out[1].square().mean() + 3.0 * k.square().mean()
+    loss.backward()
+    d = {"K": np.array(K), "S": np.array(S), "sp": sp.numpy(), "logits": out[1].detach().numpy(),
+         "out2": out[2].detach().numpy(), "out4": out[4].detach().numpy(), "x256": x256.detach().numpy(),
+         "k": k.detach().numpy(), "loss": np.array(loss.item())}
+    for kk, v in lat.items():
+        d[f"lat{kk}"] = v.detach().numpy()
+        if v.grad is not None:
+            d[f"dlat{kk}"] = v.grad.numpy()
+    for n, p in m.state_dict().items():
+        d["sd__" + n] = p.numpy()
+    for n, p in m.named_parameters():
+        if p.grad is not None and n.startswith(("decoder_ch", "text_emb", "decoder_scale_4")):
+            d["grad__" + n] = p.grad.numpy()
+    d["nograd"] = np.array([n for n, p in m.named_parameters() if p.grad is None])
+    np.savez_compressed(os.path.join(OUT, "semseg_tiny.npz"), **d)
+    print("semseg_tiny.npz", os.path.getsize(os.path.join(OUT, "semseg_tiny.npz")) // 1024, "KiB")
 
 
 if __name__ == "__main__":
-    main()
+    if "--semseg" in sys.argv:
+        sys.path.insert(0, REF)
+        torch.set_num_threads(1)
+        golden_semseg()
+    else:
+        main()

@@ -1,0 +1,97 @@
+"""SemSegE2VID mirror with the collapsed (fused) head (a11) against a golden produced by the reference class
+(oracle/make_golden_models.py --semseg), and the pixel_linear kernels against torch convolutions.
+The collapsed head is mathematically exact but rounds differently (32-term instead of 256/512-term dot products):
+tolerance 1e-4 relative to the logits' scale."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+
+
+def _build(z, dev="cpu"):
+    from openess_b200.models.style_networks import SemSegE2VID
+    m = SemSegE2VID(input_c=32, output_c=int(z["K"]), skip_connect=True, skip_type='concat', text_embeddings_path=None)
+    m.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd__")}, strict=True)
+    return m.to(dev)
+
+
+def _latents(z, dev, grad=False):
+    lat = {k: torch.from_numpy(z[f"lat{k}"]).to(dev) for k in (8, 4, 2, 1)}
+    if grad:
+        for k in (8, 4, 2):
+            lat[k].requires_grad_(True)
+    return lat
+
+
+def test_semseg_mirror_state_dict_and_cpu_forward():
+    z = load_golden("semseg_tiny")
+    m = _build(z)
+    out, x256 = m(_latents(z, "cpu"))
+    scale = np.abs(z["logits"]).max()
+    np.testing.assert_allclose(out[1].detach().numpy(), z["logits"], atol=1e-4 * scale)
+    np.testing.assert_allclose(out[2].detach().numpy(), z["out2"], atol=1e-5)
+    np.testing.assert_allclose(out[4].detach().numpy(), z["out4"], atol=1e-5)
+    np.testing.assert_allclose(x256.detach().numpy(), z["x256"], atol=1e-5)
+    assert sorted(out) == [1, 2, 4, 8]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,Cin,Cout,H,W", [(2, 32, 11, 20, 28), (1, 4, 6, 16, 24), (3, 64, 64, 9, 13), (2, 11, 32, 7, 5)])
+def test_pixel_linear_vs_torch(B, Cin, Cout, H, W):
+    from openess_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(Cin * 100 + Cout)
+    x = torch.randn((B, Cin, H, W), generator=g).to(dev).requires_grad_(True)
+    Wt = torch.randn((Cout, Cin), generator=g).to(dev).requires_grad_(True)
+    b = torch.randn(Cout, generator=g).to(dev).requires_grad_(True)
+    gy = torch.randn((B, Cout, H, W), generator=g).to(dev)
+    y = ops.pixel_linear(x, Wt, b)
+    y.backward(gy)
+    got = [t.grad.clone() for t in (x, Wt, b)]
+    for t in (x, Wt, b):
+        t.grad = None
+    yr = torch.nn.functional.conv2d(x.double(), Wt.double()[:, :, None, None], b.double())
+    yr.backward(gy.double())
+    torch.testing.assert_close(y.double(), yr, atol=1e-5, rtol=1e-5)
+    for a, t in zip(got, (x, Wt, b)):
+        torch.testing.assert_close(a.double(), t.grad.double(), atol=2e-4, rtol=1e-5)
+    y2 = ops.pixel_linear(x.detach(), Wt.detach())                 # no bias
+    torch.testing.assert_close(y2.double(), torch.nn.functional.conv2d(x.detach().double(), Wt.detach().double()[:, :, None, None]),
+                               atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_semseg_fused_head_forward_backward_golden():
+    z = load_golden("semseg_tiny")
+    dev = torch.device("cuda:0")
+    m = _build(z, dev)
+    lat = _latents(z, dev, grad=True)
+    sp = torch.from_numpy(z["sp"]).to(dev)
+    out, k = m.forward_pooled(lat, sp, int(z["S"]))
+    scale = float(np.abs(z["logits"]).max())
+    np.testing.assert_allclose(out[1].detach().cpu().numpy(), z["logits"], atol=2e-4 * scale)
+    np.testing.assert_allclose(k.detach().cpu().numpy(), z["k"], atol=2e-4 * float(np.abs(z["k"]).max()))
+    loss = out[1].square().mean() + 3.0 * k.square().mean()
+    assert float(loss.detach()) == pytest.approx(float(z["loss"]), rel=2e-4)
+    loss.backward()
+    for kk in (8, 4, 2):
+        ref = z[f"dlat{kk}"]
+        np.testing.assert_allclose(lat[kk].grad.cpu().numpy(), ref, atol=3e-4 * float(np.abs(ref).max()))
+    named = dict(m.named_parameters())
+    checked = 0
+    for key in z.files:
+        if key.startswith("grad__"):
+            ref = z[key]
+            got = named[key[6:]].grad
+            assert got is not None, key
+            np.testing.assert_allclose(got.cpu().numpy(), ref, atol=3e-4 * float(np.abs(ref).max()) + 1e-9)
+            checked += 1
+    assert checked >= 7
+    # parameters that get no gradient in the reference forward get none here either (decoder_scale_5)
+    for n in z["nograd"]:
+        assert named[str(n)].grad is None
+    # reference-signature forward on the GPU (materialises x_ch256 but not the 512-channel map)
+    out2, x256 = m({k_: v.detach() for k_, v in lat.items()})
+    np.testing.assert_allclose(x256.detach().cpu().numpy(), z["x256"], atol=2e-4)
+    np.testing.assert_allclose(out2[1].detach().cpu().numpy(), out[1].detach().cpu().numpy(), atol=1e-5 * scale)
