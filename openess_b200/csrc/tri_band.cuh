@@ -24,7 +24,8 @@ constexpr float kCanonicalBadX = -8.0f;
 
 __global__ void __launch_bounds__(kRowWarps * 32)
 k_rowsort(const float4* __restrict__ src, float4* __restrict__ dst, const int64_t* __restrict__ frame_offsets,
-          const uint32_t* __restrict__ rowoff, uint32_t* __restrict__ rowflag, int H, int W) {
+          const uint32_t* __restrict__ rowoff, uint32_t* __restrict__ rowflag, int H, int W,
+          uint32_t* __restrict__ coloff, int NS, int WC) {
     extern __shared__ uint32_t s_cnt_all[];           // [kRowWarps][W + 2]
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kRowWarps + w;        // py in [0, H]
@@ -32,8 +33,12 @@ k_rowsort(const float4* __restrict__ src, float4* __restrict__ dst, const int64_
     if (row > H) return;
     const uint32_t* ro = rowoff + (int64_t)f * radix::kBins;
     const uint32_t s = ro[row], e = ro[row + 1];
+    // strip formulation (tri_strip.cuh): coloff[f][row][2 k + j] = first record with column >= min(k WC, W) + j
+    const int KT = 2 * (NS + 1);
+    uint32_t* T = coloff ? coloff + ((int64_t)f * (H + 1) + row) * KT : nullptr;
     if (s == e) {
         if (lane == 0) rowflag[(int64_t)f * radix::kBins + row] = 0;
+        if (T) for (int k = lane; k < KT; k += 32) T[k] = s;
         return;
     }
     const int nb = W + 2;
@@ -64,6 +69,8 @@ k_rowsort(const float4* __restrict__ src, float4* __restrict__ dst, const int64_
             run += v;
         }
     }
+    __syncwarp();
+    if (T) for (int k = lane; k < KT; k += 32) T[k] = cnt[min((k >> 1) * WC, W) + (k & 1)];
     __syncwarp();
     const unsigned lt = lanemask_lt();
     for (uint32_t i0 = s; i0 < e; i0 += 32) {

@@ -23,6 +23,7 @@
 #include "radix.cuh"
 #include "tri_band.cuh"
 #include "tri_common.cuh"
+#include "tri_strip.cuh"
 
 namespace oess {
 namespace tri {
@@ -160,10 +161,13 @@ k_atomic(const float* __restrict__ x, const float* __restrict__ y, const float* 
 }
 
 // ---------------------------------------------------------------------------------------------
+constexpr int kStripWC = 64;   // output columns per warp strip (~21 events per source row at 100 k events / frame)
+
 struct Plan {
     bool banded;
-    int TH, stage_cap, npass;
-    size_t band_smem, row_smem;
+    bool strip;      // step 3 = k_strip_splat (default) instead of k_band_splat (OESS_TRI_SPLAT=band)
+    int TH, stage_cap, npass, NS, strip_minb, strip_warps;
+    size_t band_smem, row_smem, strip_smem;
 };
 
 static Plan make_plan(int C, int H, int W) {
@@ -184,12 +188,45 @@ static Plan make_plan(int C, int H, int W) {
     if (const char* e = std::getenv("OESS_BAND_NPASS")) p.npass = std::atoi(e);   // < 4: profiling only (wrong results)
     p.band_smem = acc_bytes + 16 * (size_t)cap;
     p.banded = (H + 2 <= radix::kBins) && p.band_smem <= 200 * 1024 && p.row_smem <= 200 * 1024;
+    p.NS = (W + kStripWC - 1) / kStripWC;
+    // warps (= strips) per CTA: small CTAs free their SM slot as soon as their slowest strip is done (measured:
+    // 2 warps 0.372 / 1.098 ms, 5 warps 0.388 / 1.109 ms, 1 warp 0.454 / 1.129 ms on uniform / clustered frames)
+    p.strip_warps = (p.NS % 2 == 0) ? 2 : 1;
+    if (const char* e = std::getenv("OESS_STRIP_WARPS")) {
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 8) p.strip_warps = v;
+    }
+    p.strip_smem = sizeof(float) * (size_t)p.strip_warps * C * kStripWC;
+    p.strip = p.strip_smem <= 200 * 1024;
+    if (const char* e = std::getenv("OESS_TRI_SPLAT")) p.strip = p.strip && e[0] != 'b';
+    p.strip_minb = 6;
+    if (const char* e = std::getenv("OESS_STRIP_MINB")) p.strip_minb = std::atoi(e);   // tuning knob (4, 6, 8 CTAs / SM)
     return p;
+}
+
+template <int CT>
+static int launch_strip_ct(const Plan& plan, const float4* items, const int64_t* frame_offsets, const uint32_t* coloff,
+                           const uint32_t* rowflag, const Geom& g, int F, float* out, cudaStream_t st) {
+    auto kern = k_strip_splat<kStripWC, CT, 8>;
+    if (plan.strip_minb == 7) kern = k_strip_splat<kStripWC, CT, 7>;
+    if (plan.strip_minb == 6) kern = k_strip_splat<kStripWC, CT, 6>;
+    if (plan.strip_minb == 5) kern = k_strip_splat<kStripWC, CT, 5>;
+    if (plan.strip_minb == 4) kern = k_strip_splat<kStripWC, CT, 4>;
+    OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.strip_smem));
+    const dim3 grid((unsigned)((plan.NS + plan.strip_warps - 1) / plan.strip_warps), (unsigned)g.H, (unsigned)F);
+    OESS_KERNEL("tri_strip_splat", st, kern<<<grid, plan.strip_warps * 32, plan.strip_smem, st>>>(
+        items, frame_offsets, coloff, rowflag, g, plan.NS, out));
+    return 0;
+}
+static int launch_strip(const Plan& plan, const float4* items, const int64_t* frame_offsets, const uint32_t* coloff,
+                        const uint32_t* rowflag, const Geom& g, int F, float* out, cudaStream_t st) {
+    if (g.C == 5) return launch_strip_ct<5>(plan, items, frame_offsets, coloff, rowflag, g, F, out, st);
+    return launch_strip_ct<0>(plan, items, frame_offsets, coloff, rowflag, g, F, out, st);
 }
 
 struct Ws {
     int* chunk_start;
-    uint32_t *hist, *tot, *pix, *rowflag;
+    uint32_t *hist, *tot, *pix, *rowflag, *coloff;
     float4 *a, *b;
     double* stats;
     int64_t pix_stride;
@@ -205,7 +242,9 @@ static Ws carve(void* ws, int mode, int64_t n, int F, int C, int H, int W) {
         r.hist = c.take<uint32_t>((size_t)radix::max_chunks(n, F) * radix::kBins);
         r.tot = c.take<uint32_t>((size_t)F * radix::kBins);
         r.rowflag = c.take<uint32_t>((size_t)F * radix::kBins);
-        if (!make_plan(C, H, W).banded) {
+        const Plan plan = make_plan(C, H, W);
+        if (plan.banded && plan.strip) r.coloff = c.take<uint32_t>((size_t)F * (H + 1) * 2 * (plan.NS + 1));
+        if (!plan.banded) {
             const int64_t nkeys = (int64_t)(H + 1) * (W + 1) + 1;  // + invalid key
             r.pix_stride = (int64_t)align_up((size_t)nkeys + 1, 4);
             r.pix = c.take<uint32_t>((size_t)F * r.pix_stride);
@@ -267,11 +306,16 @@ OESS_API int oess_voxel_trilinear(const float* x, const float* y, const float* p
             OESS_CUDA(cudaFuncSetAttribute(tri::k_rowsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.row_smem));
             OESS_KERNEL("tri_rowsort", st, tri::k_rowsort<<<dim3((unsigned)((H + 1 + tri::kRowWarps - 1) / tri::kRowWarps), (unsigned)F),
                                                            tri::kRowWarps * 32, plan.row_smem, st>>>(
-                w.a, w.b, frame_offsets, w.tot, w.rowflag, H, W));
-            OESS_CUDA(cudaFuncSetAttribute(tri::k_band_splat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.band_smem));
-            OESS_KERNEL("tri_band_splat", st, tri::k_band_splat<<<dim3((unsigned)((H + plan.TH - 1) / plan.TH), (unsigned)F),
-                                                                 tri::kBandThreads, plan.band_smem, st>>>(
-                w.b, frame_offsets, w.tot, w.rowflag, g, plan.TH, plan.stage_cap, plan.npass, out));
+                w.a, w.b, frame_offsets, w.tot, w.rowflag, H, W, plan.strip ? w.coloff : nullptr, plan.NS, tri::kStripWC));
+            if (plan.strip) {
+                rc = tri::launch_strip(plan, w.b, frame_offsets, w.coloff, w.rowflag, g, F, out, st);
+                if (rc) return rc;
+            } else {
+                OESS_CUDA(cudaFuncSetAttribute(tri::k_band_splat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.band_smem));
+                OESS_KERNEL("tri_band_splat", st, tri::k_band_splat<<<dim3((unsigned)((H + plan.TH - 1) / plan.TH), (unsigned)F),
+                                                                     tri::kBandThreads, plan.band_smem, st>>>(
+                    w.b, frame_offsets, w.tot, w.rowflag, g, plan.TH, plan.stage_cap, plan.npass, out));
+            }
         } else {
             const tri::Geom g{C, H, W, (uint32_t)((H + 1) * (W + 1))};
             OESS_CUDA(cudaMemsetAsync(w.pix, 0, sizeof(uint32_t) * (size_t)F * w.pix_stride, st));

@@ -12,6 +12,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The goldens are the reference's fp32 CPU outputs: keep the cuDNN / cuBLAS layers that still run under the
+    # mirrors in true fp32 (torch's default lets cuDNN convolutions use TF32, ~1e-3 relative error).
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def load_golden(name):

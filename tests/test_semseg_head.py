@@ -85,7 +85,13 @@ def test_semseg_fused_head_forward_backward_golden():
             ref = z[key]
             got = named[key[6:]].grad
             assert got is not None, key
-            np.testing.assert_allclose(got.cpu().numpy(), ref, atol=3e-4 * float(np.abs(ref).max()) + 1e-9)
+            atol = 3e-4 * float(np.abs(ref).max()) + 1e-9
+            wkey = key[:-4] + "weight"
+            if key.endswith(".model.0.bias") and wkey in z.files:
+                # a bias in front of an affine-free InstanceNorm has an exactly-zero gradient; the reference's
+                # value is float round-off noise (5e-4 next to weight grads of 1e3), so only its scale is compared
+                atol += 3e-6 * float(np.abs(z[wkey]).max())
+            np.testing.assert_allclose(got.cpu().numpy(), ref, atol=atol)
             checked += 1
     assert checked >= 7
     # parameters that get no gradient in the reference forward get none here either (decoder_scale_5)
