@@ -196,6 +196,16 @@ int oess_pixel_linear_wgrad_ws_bytes(int Cin, int Cout, size_t* ws_bytes);
 int oess_pixel_linear_wgrad(const float* dy, const float* x, int B, int Cin, int Cout, int64_t HW, float* dW,
                             float* db, void* ws, size_t ws_bytes, oess_stream_t stream);
 
+/* Tensor-core GEMM (tcgen05.mma.kind::tf32, TMA-staged operands, accumulator in TMEM):
+ *   C[M, N] = A[M, K] * B[N, K]^T + bias[N]     (A, B, C row-major float32; bias may be NULL)
+ * = nn.Linear / a 1x1 convolution over channels-last pixels.  Replaces the cuBLAS / cuDNN call behind
+ * models/image_model.py:121-124 (decoder conv 2048 -> 256), models/style_networks.py:163-165 (head convs) and the
+ * ViT linears of models/maskclip_model.py:448-541.  Inputs are read as TF32 (what torch's default cuDNN path does
+ * on the reference's GPU), accumulation is fp32; tolerance 2e-3 * sum_k |a||b|.
+ * Requirements: K % 4 == 0 and 16-byte aligned pointers (TMA). */
+int oess_gemm_tf32(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int K,
+                   oess_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

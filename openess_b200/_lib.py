@@ -55,6 +55,7 @@ SIGNATURES = {
     "oess_pixel_linear": [_vp, _vp, _vp, _int, _int, _int, _i64, _vp, _vp],
     "oess_pixel_linear_wgrad_ws_bytes": [_int, _int, ctypes.POINTER(_sz)],
     "oess_pixel_linear_wgrad": [_vp, _vp, _int, _int, _int, _i64, _vp, _vp, _vp, _sz, _vp],
+    "oess_gemm_tf32": [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp],
 }
 
 _lib = None

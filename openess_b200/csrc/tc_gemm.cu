@@ -1,0 +1,186 @@
+// tc_gemm.cu -- TF32 tensor-core GEMM for the dense contractions of the path that are plain matrix products:
+//     C[M, N] = A[M, K] * B[N, K]^T (+ bias[N])          A, B, C row-major float32
+// i.e. nn.Linear / a 1x1 convolution over channels-last pixels (models/image_model.py:121-124 decoder conv
+// 2048 -> 256, models/maskclip_model.py ViT linears, models/style_networks.py:163-165 head convs).
+//
+// sm_100a structure: one CTA per 128 x BN output tile; warp 0 = TMA producer (cp.async.bulk.tensor into a
+// 4-stage 128B-swizzled shared-memory ring), warp 1 = MMA issuer (one thread, tcgen05.mma.kind::tf32, accumulator
+// in TMEM), warps 2..5 = epilogue (tcgen05.ld -> + bias -> global).  Operands are fp32 in memory; the tensor core
+// reads them as TF32 (10-bit mantissa), accumulation is fp32 -- the same arithmetic class torch's default cuDNN /
+// cuBLAS-TF32 convolution path uses on the reference's GPU run.  Stated tolerance: 2e-3 relative to |A||B|.
+#include "tc_common.cuh"
+
+namespace oess {
+namespace tc {
+
+static EncodeTiledFn g_encode = nullptr;
+
+EncodeTiledFn encode_tiled_fn() {
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_encode = (EncodeTiledFn)fn;
+    }
+    return g_encode;
+}
+
+int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i + 1 < rank) gstr[i] = strides_bytes[i];
+    }
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+constexpr int kBM = 128;
+constexpr int kStages = 4;
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+struct GemmSmem {
+    static constexpr int kABytes = kBM * kBlockK * 4;      // 16 KB
+    static constexpr int kBBytes = BN * kBlockK * 4;
+    static constexpr int kBytes = 1024 + kStages * (kABytes + kBBytes) + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const float* __restrict__ bias, float* __restrict__ C, int64_t M, int N, int K) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = GemmSmem<BN>;
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned tiles
+    uint8_t* sA = base;
+    uint8_t* sB = base + kStages * S::kABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + kStages * S::kBBytes);
+    uint64_t* empty = full + kStages;
+    uint64_t* acc_full = empty + kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * kBM;
+    const int n0 = blockIdx.y * BN;
+    const int kblocks = (K + kBlockK - 1) / kBlockK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                  // ===== TMA producer =====
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
+                mbar_expect_tx(&full[s], S::kABytes + S::kBBytes);
+                tma_load_2d(sA + s * S::kABytes, &tmA, &full[s], kb * kBlockK, (int)m0);
+                tma_load_2d(sB + s * S::kBBytes, &tmB, &full[s], kb * kBlockK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                  // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kStages;
+                mbar_wait(&full[s], (kb / kStages) & 1);
+                tc_fence_after();
+                const uint64_t da = umma_desc_k128(smem_u32(sA + s * S::kABytes));
+                const uint64_t db = umma_desc_k128(smem_u32(sB + s * S::kBBytes));
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)   // +32 bytes (>> 4 = 2) per K = 8 step inside the swizzle line
+                    umma_tf32(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&empty[s]);                   // frees the smem stage once these MMAs have read it
+            }
+            umma_commit(acc_full);                        // accumulator complete
+        }
+    } else {                                              // ===== epilogue: warps 2..5 =====
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int64_t row = m0 + q * 32 + lane;
+        float* crow = C + row * (int64_t)N;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            const int col = n0 + c0;
+            if (row < M && col < N) {
+                if (col + 32 <= N && (N & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        if (bias) {
+                            const float4 b = *reinterpret_cast<const float4*>(bias + col + j);
+                            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        }
+                        *reinterpret_cast<float4*>(crow + col + j) = o;
+                    }
+                } else {
+                    for (int j = 0; j < 32 && col + j < N; ++j) crow[col + j] = v[j] + (bias ? bias[col + j] : 0.0f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, BN);
+}
+
+template <int BN>
+static int launch_gemm(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int K, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)K * 4};
+    const uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)K * 4};
+    const uint32_t bA[2] = {kBlockK, kBM}, bB[2] = {kBlockK, (uint32_t)BN};
+    int rc = make_tmap_f32(&tmA, A, 2, dA, sA, bA);
+    if (rc) return rc;
+    rc = make_tmap_f32(&tmB, B, 2, dB, sB, bB);
+    if (rc) return rc;
+    auto kern = k_gemm_tf32<BN>;
+    OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kBytes));
+    const dim3 grid((unsigned)((M + kBM - 1) / kBM), (unsigned)((N + BN - 1) / BN));
+    OESS_KERNEL("tc_gemm_tf32", st, kern<<<grid, kGemmThreads, GemmSmem<BN>::kBytes, st>>>(tmA, tmB, bias, C, M, N, K));
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace oess
+
+using namespace oess;
+
+OESS_API int oess_gemm_tf32(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int K,
+                            oess_stream_t stream) {
+    if (M < 0 || N <= 0 || K <= 0) return OESS_E_ARG;
+    if (M == 0) return OESS_OK;
+    if (!A || !B || !C) return OESS_E_ARG;
+    // TMA: 16-byte aligned bases and row strides
+    if ((K & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15) || ((uintptr_t)bias & 15)) return OESS_E_ARG;
+    if (M >= (1ll << 31)) return OESS_E_RANGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N > 128) return tc::launch_gemm<256>(A, B, bias, C, M, N, K, st);
+    if (N > 64) return tc::launch_gemm<128>(A, B, bias, C, M, N, K, st);
+    return tc::launch_gemm<64>(A, B, bias, C, M, N, K, st);
+}

@@ -61,3 +61,24 @@ def pixel_linear(x, W, bias=None):
     if W.shape[0] > 64 or W.shape[1] > 64:
         raise ValueError("pixel_linear supports at most 64 input and 64 output channels")
     return _PixelLinear.apply(x, W, bias)
+
+
+def gemm_tf32(a, b, bias=None, out=None):
+    """out[M, N] = a[M, K] @ b[N, K].T + bias  on the tensor cores (tcgen05.mma.kind::tf32, fp32 accumulate).
+
+    a, b: contiguous float32 CUDA tensors (b in nn.Linear weight layout); K % 4 == 0."""
+    _lib.require_cuda(a, b, bias)
+    a, b = _f32c(a), _f32c(b)
+    if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("gemm_tf32: a must be [M, K] and b [N, K]")
+    M, K = a.shape
+    N = b.shape[0]
+    if bias is not None:
+        bias = _f32c(bias)
+        if bias.numel() != N:
+            raise ValueError("gemm_tf32: bias must have N elements")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().oess_gemm_tf32(ptr(a), ptr(b), ptr(bias), ptr(out), M, N, K, stream_ptr(a.device)), "oess_gemm_tf32")
+    return out
