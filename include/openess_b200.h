@@ -206,6 +206,18 @@ int oess_pixel_linear_wgrad(const float* dy, const float* x, int B, int Cin, int
 int oess_gemm_tf32(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int K,
                    oess_stream_t stream);
 
+/* One ConvLSTM step of the E2VID recurrent encoder as one tensor-core kernel (tcgen05 implicit GEMM, TMA 4-D boxes
+ * supply the 9 shifted taps with hardware zero padding, LSTM pointwise math fused into the TMEM epilogue).
+ * Replaces e2vid/model/submodules.py:175-214 ConvLSTM.forward = cat(x, h_prev) -> Conv2d(2C, 4C, 3, padding=1) ->
+ * chunk(in, remember, out, cell) -> c = sigmoid(remember) * c_prev + sigmoid(in) * tanh(cell); h = sigmoid(out) * tanh(c).
+ * x, h_prev, c_prev, h_out, c_out: [B, H, W, C] CHANNELS-LAST float32; h_prev / c_prev may be NULL (zero state, :190-199).
+ * w_packed: [4C, 2 * 9 * C], row chunk * 256 + gate * 64 + c (hidden channel chunk * 64 + c), column
+ * (source: 0 = x, 1 = h; tap = ky * 3 + kx; channel) -- openess_b200/ops.py:convlstm_pack builds it from Gates.weight;
+ * bias_packed: [4C] in the same row order.  C % 64 == 0.  TF32 operands, fp32 accumulate (tolerance 2e-3 * sum |x||w|). */
+int oess_convlstm_step_nhwc(const float* x, const float* h_prev, const float* c_prev, const float* w_packed,
+                            const float* bias_packed, float* h_out, float* c_out, int B, int H, int W, int C,
+                            oess_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,182 @@
+// tc_convlstm.cu -- one ConvLSTM step of the E2VID recurrent encoder as ONE tensor-core kernel:
+//     gates = Conv3x3(cat(x, h_prev)) + bias;  c = sigmoid(f) * c_prev + sigmoid(i) * tanh(g);  h = sigmoid(o) * tanh(c)
+// Replaces e2vid/model/submodules.py:175-214 (ConvLSTM.forward: torch.cat + cuDNN conv + ~10 pointwise kernels; the
+// [B, 4C, H, W] gate tensor is never materialised here).  The three encoder levels run it 20 times per sample: it is
+// 65 % of the encoder's FLOPs.
+//
+// Implicit GEMM on tcgen05, channels-last activations:
+//   M = 128 pixels = an 8 x 16 spatial patch, N = 256 = 4 gates x 64 hidden channels, K = 9 taps x 2C input channels.
+//   A tile of K block (source, tap, 32-channel chunk) = the patch shifted by the tap, fetched by ONE 4-D TMA box
+//   {32 ch, 16 w, 8 h, 1 b} -- out-of-image coordinates are zero-filled by TMA, which IS the conv's zero padding.
+//   B tile = 256 rows of the gate weights repacked once on the host to [4C (chunk, gate, c), (source, tap, ch)].
+//   warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma.kind::tf32, fp32 accumulator in 256 TMEM columns),
+//   warps 2..5 = epilogue: tcgen05.ld the four gates of 16 channels of one pixel, LSTM pointwise math, write h and c.
+// fp32 operands are read as TF32 (torch's default cuDNN conv arithmetic on the reference's GPU run), fp32 accumulate.
+#include "tc_common.cuh"
+
+namespace oess {
+namespace tc {
+
+constexpr int kTW = 16, kTH = 8;            // spatial patch of one M tile (16 x 8 = 128 pixels)
+constexpr int kCN = 256;                    // N tile: 4 gates x 64 hidden channels
+constexpr int kCStages = 4;
+constexpr int kCABytes = 128 * kBlockK * 4; // 16 KB
+constexpr int kCBBytes = kCN * kBlockK * 4; // 32 KB
+constexpr int kCSmem = 1024 + kCStages * (kCABytes + kCBBytes) + 256;
+
+__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+__global__ void __launch_bounds__(192, 1)
+k_convlstm_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
+              const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias, const float* __restrict__ c_prev,
+              float* __restrict__ h_out, float* __restrict__ c_out, int H, int W, int C, int has_h, int tiles_w) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;
+    uint8_t* sB = base + kCStages * kCABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + kCStages * kCBBytes);
+    uint64_t* empty = full + kCStages;
+    uint64_t* acc_full = empty + kCStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
+    const int h0 = th * kTH, w0 = tw * kTW;
+    const int nchunk = blockIdx.y, b = blockIdx.z;
+    const int chunks = C / kBlockK;
+    const int kblocks = (has_h ? 2 : 1) * 9 * chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmH);
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < kCStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, kCN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                  // ===== TMA producer =====
+            int src = 0, tap = 0, chunk = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kCStages;
+                mbar_wait(&empty[s], ((kb / kCStages) & 1) ^ 1);
+                mbar_expect_tx(&full[s], kCABytes + kCBBytes);
+                const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                tma_load_4d(sA + s * kCABytes, src ? &tmH : &tmX, &full[s], chunk * kBlockK, w0 + dx, h0 + dy, b);
+                tma_load_2d(sB + s * kCBBytes, &tmW, &full[s], kb * kBlockK, nchunk * kCN);
+                if (++chunk == chunks) { chunk = 0; if (++tap == 9) { tap = 0; ++src; } }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                  // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_tf32(128, kCN);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kCStages;
+                mbar_wait(&full[s], (kb / kCStages) & 1);
+                tc_fence_after();
+                const uint64_t da = umma_desc_k128(smem_u32(sA + s * kCABytes));
+                const uint64_t db = umma_desc_k128(smem_u32(sB + s * kCBBytes));
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                    umma_tf32(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&empty[s]);
+            }
+            umma_commit(acc_full);
+        }
+    } else {                                              // ===== epilogue: warps 2..5 =====
+        const int q = warp & 3;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int r = q * 32 + lane;                      // accumulator row = pixel of the patch (h-major, w-minor)
+        const int y = h0 + r / kTW, x = w0 + r % kTW;
+        const bool valid = y < H && x < W;
+        const int64_t pix = (((int64_t)b * H + y) * W + x) * C + nchunk * 64;
+        const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
+        const float* bn = bias + nchunk * kCN;
+#pragma unroll 1
+        for (int sub = 0; sub < 4; ++sub) {               // 16 hidden channels at a time
+            float gi[16], gf[16], go[16], gg[16];
+            tmem_ld16_nowait(trow + 0 * 64 + sub * 16, gi);   // submodules.py:203 chunk order: in, remember, out, cell
+            tmem_ld16_nowait(trow + 1 * 64 + sub * 16, gf);
+            tmem_ld16_nowait(trow + 2 * 64 + sub * 16, go);
+            tmem_ld16_nowait(trow + 3 * 64 + sub * 16, gg);
+            tmem_ld_wait();
+            if (valid) {
+                const int64_t e = pix + sub * 16;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c_prev) pc = *reinterpret_cast<const float4*>(c_prev + e + j);
+                    const float4 bi = __ldg(reinterpret_cast<const float4*>(bn + 0 * 64 + sub * 16 + j));
+                    const float4 bf = __ldg(reinterpret_cast<const float4*>(bn + 1 * 64 + sub * 16 + j));
+                    const float4 bo = __ldg(reinterpret_cast<const float4*>(bn + 2 * 64 + sub * 16 + j));
+                    const float4 bg = __ldg(reinterpret_cast<const float4*>(bn + 3 * 64 + sub * 16 + j));
+                    float4 c, h;
+                    c.x = sigm(gf[j] + bf.x) * pc.x + sigm(gi[j] + bi.x) * tanhf(gg[j] + bg.x);
+                    c.y = sigm(gf[j + 1] + bf.y) * pc.y + sigm(gi[j + 1] + bi.y) * tanhf(gg[j + 1] + bg.y);
+                    c.z = sigm(gf[j + 2] + bf.z) * pc.z + sigm(gi[j + 2] + bi.z) * tanhf(gg[j + 2] + bg.z);
+                    c.w = sigm(gf[j + 3] + bf.w) * pc.w + sigm(gi[j + 3] + bi.w) * tanhf(gg[j + 3] + bg.w);
+                    h.x = sigm(go[j] + bo.x) * tanhf(c.x);
+                    h.y = sigm(go[j + 1] + bo.y) * tanhf(c.y);
+                    h.z = sigm(go[j + 2] + bo.z) * tanhf(c.z);
+                    h.w = sigm(go[j + 3] + bo.w) * tanhf(c.w);
+                    *reinterpret_cast<float4*>(c_out + e + j) = c;
+                    *reinterpret_cast<float4*>(h_out + e + j) = h;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, kCN);
+}
+
+}  // namespace tc
+}  // namespace oess
+
+using namespace oess;
+
+// x, h_prev, c_prev, h_out, c_out: [B, H, W, C] channels-last float32 (h_prev / c_prev NULL = zero state).
+// w_packed: [4C, 2 * 9 * C] with row n' = chunk * 256 + gate * 64 + c  (hidden channel chunk * 64 + c) and column
+// (source, tap = ky * 3 + kx, channel); bias_packed: [4C] in the same row order.  C % 64 == 0.
+OESS_API int oess_convlstm_step_nhwc(const float* x, const float* h_prev, const float* c_prev, const float* w_packed,
+                                     const float* bias_packed, float* h_out, float* c_out, int B, int H, int W, int C,
+                                     oess_stream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 64) != 0) return OESS_E_ARG;
+    if (!x || !w_packed || !bias_packed || !h_out || !c_out) return OESS_E_ARG;
+    if (((uintptr_t)x | (uintptr_t)h_prev | (uintptr_t)c_prev | (uintptr_t)w_packed | (uintptr_t)bias_packed |
+         (uintptr_t)h_out | (uintptr_t)c_out) & 15)
+        return OESS_E_ARG;
+    if (B > 65535 || C / 64 > 65535) return OESS_E_RANGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    // w_packed always holds both sources' columns ([4C, 2 * 9 * C]); with a zero hidden state the kernel reads only the
+    // first 9 * C columns of every row (source 0), so the tensor map keeps the full row stride.
+    const uint64_t Kfull = (uint64_t)2 * 9 * C;
+    CUtensorMap tmX, tmH, tmW;
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+    const uint32_t box[4] = {tc::kBlockK, tc::kTW, tc::kTH, 1};
+    int rc = tc::make_tmap_f32(&tmX, x, 4, dims, strides, box);
+    if (rc) return rc;
+    rc = tc::make_tmap_f32(&tmH, h_prev ? h_prev : x, 4, dims, strides, box);
+    if (rc) return rc;
+    const uint64_t dW[2] = {Kfull, (uint64_t)4 * C}, sW[1] = {Kfull * 4};
+    const uint32_t bW[2] = {tc::kBlockK, tc::kCN};
+    rc = tc::make_tmap_f32(&tmW, w_packed, 2, dW, sW, bW);
+    if (rc) return rc;
+    OESS_CUDA(cudaFuncSetAttribute(tc::k_convlstm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kCSmem));
+    const int tiles_w = (W + tc::kTW - 1) / tc::kTW, tiles_h = (H + tc::kTH - 1) / tc::kTH;
+    const dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(C / 64), (unsigned)B);
+    OESS_KERNEL("tc_convlstm_step", st, tc::k_convlstm_tc<<<grid, 192, tc::kCSmem, st>>>(
+        tmX, tmH, tmW, bias_packed, c_prev, h_out, c_out, H, W, C, h_prev ? 1 : 0, tiles_w));
+    return 0;
+}

@@ -12,14 +12,22 @@ What changes on the B200:
   * the ConvLSTM pointwise tail (3 sigmoids, 2 tanh, cell/hidden update: ~10 ATen kernels per level and step) is one
     fused kernel, `oess_convlstm_gates`;
   * eval-mode BatchNorm of the frozen encoder is folded into the preceding conv once (`fold_bn()`);
-  * the dense contractions (5x5 / 3x3 convolutions) still run on cuDNN through torch this round: they are the
-    next kernels to be hand-written (tcgen05 implicit GEMM).
+  * the ConvLSTM step (cat + 3x3 Gates conv + pointwise tail = 65 % of the encoder's FLOPs) is ONE tensor-core
+    kernel, `oess_convlstm_step_nhwc` (tcgen05 implicit GEMM, TF32 operands / fp32 accumulate, channels-last), for the
+    hidden sizes of the real E2VID config (multiples of 64); `USE_TENSOR_CORES = False` (or OESS_E2VID_TC=0) keeps the
+    strict-fp32 cuDNN + fused-gates path;
+  * the strided 5x5 encoder convolutions still run on cuDNN through torch (next kernels to hand-write).
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
 from ... import losses as _ops
+from ... import ops as _tc
+
+USE_TENSOR_CORES = os.environ.get("OESS_E2VID_TC", "1") != "0"
 
 
 class ConvLayer(nn.Module):
@@ -89,8 +97,21 @@ class ConvLSTM(nn.Module):
         self.input_size = input_size
         self.hidden_size = hidden_size
         self.Gates = nn.Conv2d(input_size + hidden_size, 4 * hidden_size, kernel_size, padding=kernel_size // 2)
+        self._packed = None
+
+    def _tc_weights(self):
+        """Gates.weight / bias repacked for the tensor-core kernel; rebuilt when the parameters change or move."""
+        w, b = self.Gates.weight, self.Gates.bias
+        key = (w.data_ptr(), w._version, b.data_ptr(), b._version, w.device)
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key,) + _tc.convlstm_pack(w, b, self.hidden_size)
+        return self._packed[1], self._packed[2]
 
     def forward(self, input_, prev_state=None):
+        if (USE_TENSOR_CORES and input_.is_cuda and not torch.is_grad_enabled() and self.hidden_size % 64 == 0
+                and self.input_size == self.hidden_size and tuple(self.Gates.kernel_size) == (3, 3)):
+            wp, bp = self._tc_weights()
+            return _tc.convlstm_step(input_, prev_state, wp, bp)
         if prev_state is None:
             # zero state: the hidden half of the stacked input contributes nothing -> convolve the input half only
             w = self.Gates.weight[:, :self.input_size]

@@ -82,3 +82,35 @@ def gemm_tf32(a, b, bias=None, out=None):
     with torch.cuda.device(a.device):
         check(lib().oess_gemm_tf32(ptr(a), ptr(b), ptr(bias), ptr(out), M, N, K, stream_ptr(a.device)), "oess_gemm_tf32")
     return out
+
+
+def convlstm_pack(weight, bias, hidden):
+    """Repack ConvLSTM.Gates (e2vid/model/submodules.py:186: Conv2d(2C, 4C, 3, padding=1), input = cat(x, h)) for
+    oess_convlstm_step_nhwc: rows (chunk, gate, c) so one 256-column tile holds all four gates of 64 hidden channels,
+    columns (source, tap, channel) in the kernel's K order."""
+    C = int(hidden)
+    if weight.shape != (4 * C, 2 * C, 3, 3) or C % 64:
+        raise ValueError("convlstm_pack: expects Gates.weight [4C, 2C, 3, 3] with input_size == hidden_size, C % 64 == 0")
+    w = weight.detach().float().reshape(4, C // 64, 64, 2, C, 9)           # gate, chunk, c, source, ch, tap
+    w = w.permute(1, 0, 2, 3, 5, 4).contiguous().reshape(4 * C, 2 * 9 * C)  # chunk, gate, c | source, tap, ch
+    b = bias.detach().float().reshape(4, C // 64, 64).permute(1, 0, 2).contiguous().reshape(4 * C)
+    return w, b
+
+
+def convlstm_step(x, prev_state, w_packed, b_packed):
+    """(hidden, cell) of one ConvLSTM step on the tensor cores.  x: [B, C, H, W]; prev_state None or (h, c).
+    Tensors are handled channels-last (the kernel's layout); the returned tensors are [B, C, H, W] channels-last."""
+    _lib.require_cuda(x, w_packed, b_packed)
+    B, C, H, W = x.shape
+    cl = torch.channels_last
+    xc = x.float().contiguous(memory_format=cl)
+    hp = cp = None
+    if prev_state is not None:
+        hp = prev_state[0].float().contiguous(memory_format=cl)
+        cp = prev_state[1].float().contiguous(memory_format=cl)
+    h = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device, memory_format=cl)
+    c = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device, memory_format=cl)
+    with torch.cuda.device(x.device):
+        check(lib().oess_convlstm_step_nhwc(ptr(xc), ptr(hp), ptr(cp), ptr(w_packed), ptr(b_packed), ptr(h), ptr(c),
+                                            B, H, W, C, stream_ptr(x.device)), "oess_convlstm_step_nhwc")
+    return h, c

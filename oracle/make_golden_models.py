@@ -113,8 +113,43 @@ def golden_semseg():
     print("semseg_tiny.npz", os.path.getsize(os.path.join(OUT, "semseg_tiny.npz")) // 1024, "KiB")
 
 
+CFG_TC = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
+          'base_num_channels': 32, 'num_residual_blocks': 2, 'norm': 'BN', 'use_upsample_conv': False}
+
+
+def golden_e2vid_full_width():
+    """The real E2VID-lightweight width (ConvLSTM hidden sizes 64 / 128 / 256: the sizes the tcgen05 ConvLSTM kernel
+    serves) at a small spatial size.  10.7 M weights are not committed: tests/seeded_weights.py regenerates them."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+    from seeded_weights import seeded_state_dict
+    from e2vid.model.model import E2VIDRecurrent          # the reference class, unmodified
+    m = E2VIDRecurrent(CFG_TC).eval()
+    m.load_state_dict(seeded_state_dict(m, 1205), strict=True)
+    rng = np.random.default_rng(99)
+    steps = [rng.normal(0, 1, (1, 5, 24, 40)).astype(np.float32) for _ in range(3)]
+    for s_ in steps:
+        s_[rng.random(s_.shape) < 0.6] = 0
+    out = {"cfg_keys": np.array(list(CFG_TC.keys())), "cfg_vals": np.array([str(v) for v in CFG_TC.values()]),
+           "seed": np.array(1205)}
+    states = None
+    with torch.no_grad():
+        for i, s_ in enumerate(steps):
+            _, states, latent = m(torch.from_numpy(s_), states)
+            out[f"in{i}"] = s_
+    for kk, vv in latent.items():                          # outputs of the LAST step (they depend on all three)
+        out[f"latent__{kk}"] = vv.numpy()
+    for li, (h, c) in enumerate(states):
+        out[f"state__{li}__c"] = c.numpy()
+    np.savez_compressed(os.path.join(OUT, "e2vid_full_width.npz"), **out)
+    print("e2vid_full_width.npz", os.path.getsize(os.path.join(OUT, "e2vid_full_width.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    if "--semseg" in sys.argv:
+    if "--e2vid-full" in sys.argv:
+        sys.path.insert(0, REF)
+        torch.set_num_threads(1)
+        golden_e2vid_full_width()
+    elif "--semseg" in sys.argv:
         sys.path.insert(0, REF)
         torch.set_num_threads(1)
         golden_semseg()

@@ -52,6 +52,48 @@ def test_e2vid_latent_only_gpu_fused_gates_and_folded_bn():
 
 
 @pytest.mark.gpu
+def test_e2vid_full_width_tensor_core_convlstm_vs_reference_golden():
+    """Real E2VID-lightweight width (ConvLSTM hidden 64 / 128 / 256): every ConvLSTM step runs on the tcgen05 kernel.
+    Golden = the REFERENCE E2VIDRecurrent on CPU fp32 (oracle/make_golden_models.py --e2vid-full), weights regenerated
+    from the committed seed.  Tolerances: strict-fp32 path (cuDNN + fused gates) 3e-4; tensor-core path (TF32 operands,
+    what torch's default cuDNN conv does on the reference's GPU run) 1e-2 abs on O(1) activations after three recurrent
+    steps through three levels."""
+    from seeded_weights import seeded_state_dict
+    from openess_b200 import _lib
+    from openess_b200.e2vid.model import model as mm
+    z = load_golden("e2vid_full_width")
+    dev = torch.device("cuda:0")
+    cfg = {}
+    for k, v in zip(z["cfg_keys"], z["cfg_vals"]):
+        cfg[str(k)] = (v == "True") if str(v) in ("True", "False") else (int(v) if str(v).isdigit() else str(v))
+    m = mm.E2VIDRecurrent(cfg, latent_only=True)
+    m.load_state_dict(seeded_state_dict(m, int(z["seed"])), strict=True)
+    m = m.eval().to(dev).fold_bn()
+    errs = {}
+    for use_tc in (False, True):
+        mm.USE_TENSOR_CORES = use_tc
+        try:
+            states = None
+            with _lib.profile() as prof:
+                with torch.no_grad():
+                    for i in range(3):
+                        _, states, latent = m(torch.from_numpy(z[f"in{i}"]).to(dev), states)
+            tol = 1e-2 if use_tc else 3e-4
+            worst = 0.0
+            for k in latent:
+                worst = max(worst, float(np.abs(latent[k].cpu().numpy() - z[f"latent__{k}"]).max()))
+                np.testing.assert_allclose(latent[k].cpu().numpy(), z[f"latent__{k}"], atol=tol)
+            for li, (h, c) in enumerate(states):
+                np.testing.assert_allclose(c.cpu().numpy(), z[f"state__{li}__c"], atol=tol)
+            errs[use_tc] = worst
+            launched = prof.kernels.get("tc_convlstm_step", (0, 0.0))[0]
+            assert launched == (9 if use_tc else 0)       # 3 levels x 3 steps on the tensor cores, none otherwise
+        finally:
+            mm.USE_TENSOR_CORES = True
+    print("max |latent error| fp32 path %.2e, tensor-core path %.2e" % (errs[False], errs[True]))
+
+
+@pytest.mark.gpu
 def test_convlstm_gates_kernel_vs_torch():
     from openess_b200 import losses
     dev = torch.device("cuda:0")

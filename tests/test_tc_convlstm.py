@@ -1,0 +1,82 @@
+"""tcgen05 ConvLSTM step (oess_convlstm_step_nhwc) against the reference formulation of
+e2vid/model/submodules.py:175-214 evaluated in float64.  Tolerance: TF32 operands (2^-11 relative truncation each),
+fp32 accumulate -> gate pre-activations within 2e-3 * sum |x||w|; sigmoid / tanh are 1-Lipschitz or better, so h and c
+are compared with atol 2e-3 * (1 + max|c_prev|) * max pre-activation bound."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(x, state, weight, bias):
+    """float64 on the CPU (float64 convolutions on the GPU take minutes)."""
+    dev = x.device
+    x, weight, bias = x.cpu(), weight.cpu(), bias.cpu()
+    if state is not None:
+        state = (state[0].cpu(), state[1].cpu())
+    h, c = _ref_cpu(x, state, weight, bias)
+    return h.to(dev), c.to(dev)
+
+
+def _ref_cpu(x, state, weight, bias):
+    xd = x.double()
+    C = x.shape[1]
+    if state is None:
+        gates = F.conv2d(xd, weight.double()[:, :C], bias.double(), padding=1)
+        pc = 0.0
+    else:
+        gates = F.conv2d(torch.cat((xd, state[0].double()), 1), weight.double(), bias.double(), padding=1)
+        pc = state[1].double()
+    i, f, o, g = gates.chunk(4, 1)
+    c = torch.sigmoid(f) * pc + torch.sigmoid(i) * torch.tanh(g)
+    h = torch.sigmoid(o) * torch.tanh(c)
+    return h, c
+
+
+@pytest.mark.parametrize("B,C,H,W,with_state", [
+    (1, 64, 8, 16, False),       # exactly one tile, zero state (first recurrent step)
+    (1, 64, 8, 16, True),
+    (2, 64, 20, 40, True),       # ragged tiles in H and W, batch
+    (1, 128, 13, 22, True),      # two hidden-channel chunks, DDD17 /8-like odd sizes
+    (1, 256, 7, 10, True),       # four chunks (E2VID /8 level)
+])
+def test_convlstm_step_matches_reference(B, C, H, W, with_state):
+    from openess_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = torch.randn(B, C, H, W, device="cuda", generator=g)
+    weight = torch.randn(4 * C, 2 * C, 3, 3, device="cuda", generator=g) / (18 * C) ** 0.5
+    bias = torch.randn(4 * C, device="cuda", generator=g) * 0.1
+    state = None
+    if with_state:
+        state = (torch.tanh(torch.randn(B, C, H, W, device="cuda", generator=g)),
+                 torch.randn(B, C, H, W, device="cuda", generator=g))
+    wp, bp = ops.convlstm_pack(weight, bias, C)
+    h, c = ops.convlstm_step(x, state, wp, bp)
+    hr, cr = _ref(x, state, weight, bias)
+    assert h.shape == (B, C, H, W) and c.shape == (B, C, H, W)
+    # pre-activation error bound: 2e-3 * sum |in||w| ~ 2e-3 * sqrt-ish magnitudes; measured in practice < 3e-3 abs here
+    assert float((c.double() - cr).abs().max()) < 5e-3
+    assert float((h.double() - hr).abs().max()) < 5e-3
+    # and it is not trivially passing: compare against a deliberately wrong reference (state dropped)
+    if with_state:
+        hw, _ = _ref(x, None, weight, bias)
+        assert float((h.double() - hw).abs().max()) > 5e-2
+
+
+def test_convlstm_step_exact_on_tf32_representable_inputs():
+    """Integer-valued inputs / weights are exact in TF32 and their sums exact in fp32: the gate pre-activations are then
+    exact, so h and c must agree with the fp32 torch formulation to a few ulp of the transcendental functions."""
+    from openess_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, C, H, W = 1, 64, 9, 17
+    x = torch.randint(-2, 3, (B, C, H, W), device="cuda", generator=g).float()
+    hp = torch.randint(-1, 2, (B, C, H, W), device="cuda", generator=g).float()
+    cp = torch.randint(-2, 3, (B, C, H, W), device="cuda", generator=g).float()
+    weight = torch.randint(-1, 2, (4 * C, 2 * C, 3, 3), device="cuda", generator=g).float() / 64.0
+    bias = torch.randint(-2, 3, (4 * C,), device="cuda", generator=g).float() / 4.0
+    wp, bp = ops.convlstm_pack(weight, bias, C)
+    h, c = ops.convlstm_step(x, (hp, cp), wp, bp)
+    hr, cr = _ref(x, (hp, cp), weight, bias)
+    assert float((c.double() - cr).abs().max()) < 2e-6 * float(cr.abs().max() + 1)
+    assert float((h.double() - hr).abs().max()) < 2e-6
