@@ -318,7 +318,8 @@ def run_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")   # per-launch dram bytes from the committed ncu capture
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(dom_name)
+        tj = json.load(open(tpath))      # keyed by __global__ name; the launch recorder names kernels "tri_<x>" for "k_<x>"
+        traffic = tj.get(dom_name, tj.get("k_" + str(dom_name).split("_", 1)[-1]))
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "kernel_ms_per_launch": per_launch_ms,

@@ -19,6 +19,9 @@ KEYS = [
     "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
     "sm__throughput.avg.pct_of_peak_sustained_elapsed",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_tc.sum.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
