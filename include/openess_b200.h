@@ -218,6 +218,19 @@ int oess_convlstm_step_nhwc(const float* x, const float* h_prev, const float* c_
                             const float* bias_packed, float* h_out, float* c_out, int B, int H, int W, int C,
                             oess_stream_t stream);
 
+/* 2-D convolution over channels-last activations as a tcgen05 implicit GEMM (TF32 operands, fp32 accumulate), with
+ * bias, optional residual add and optional ReLU fused into the TMEM epilogue.  Serves the frozen / inference
+ * convolutions of the path: E2VID's strided 5x5 encoder convs with folded eval-mode BatchNorm + ReLU
+ * (e2vid/model/submodules.py:7-31, e2vid/model/unet.py:128-135), 1x1 / 3x3 / dilated convs of models/_resnet.py:73-114
+ * and models/deeplabv3.py:319-348.
+ * x: [B, H, W, Cin] channels-last, Cin % 4 == 0; w_packed: [Cout, KH * KW * Cin_p] with Cin_p = Cin rounded up to 32
+ * (zero padded), column (tap = ky * KW + kx, channel) -- openess_b200/ops.py:conv2d_pack; bias: [Cout] or NULL;
+ * residual: [B, Ho, Wo, Cout] or NULL; y: [B, Ho, Wo, Cout], Ho = (H + 2 pad - dil (KH - 1) - 1) / stride + 1.
+ * Zero padding is the TMA unit's out-of-bounds fill; stride is a strided TMA box traversal. */
+int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
+                          int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                          int relu, oess_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,7 @@ SIGNATURES = {
     "oess_pixel_linear_wgrad": [_vp, _vp, _int, _int, _int, _i64, _vp, _vp, _vp, _sz, _vp],
     "oess_gemm_tf32": [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp],
     "oess_convlstm_step_nhwc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp],
+    "oess_conv2d_nhwc_tf32": [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _vp],
 }
 
 _lib = None

@@ -1,0 +1,213 @@
+// tc_conv.cu -- 2-D convolution over channels-last activations as a tcgen05 implicit GEMM (TF32 operands, fp32 accumulate):
+//     y[b, oy, ox, :] = act( bias + sum_{ky,kx,c} w[:, ky, kx, c] * x[b, oy*s - p + ky*d, ox*s - p + kx*d, c]  (+ residual) )
+// Serves the frozen / inference convolutions of the path: the strided 5x5 encoder convolutions of E2VID with folded
+// eval-mode BatchNorm + ReLU (e2vid/model/submodules.py:7-31, unet.py:128-135), and any 1x1 / 3x3 (dilated) convolution
+// with Cin % 4 == 0 (models/_resnet.py bottlenecks, models/deeplabv3.py ASPP).
+//
+// Same skeleton as tc_convlstm.cu: M = 128 output pixels = an 8 x 16 patch, N = 64 / 128 / 256 output channels,
+// K = taps x Cin (Cin padded to 32 per tap in the packed weights; the activation box is zero-filled beyond Cin by TMA).
+// The A tile of one (tap, 32-channel chunk) is ONE 4-D TMA box {32 ch, 16 s, 8 s, 1} with element strides {1, s, s, 1}
+// (stride-s convolution = strided box traversal) at coordinates shifted by the tap (dilation d): the TMA unit's
+// out-of-bounds zero fill is the convolution's zero padding.
+#include "tc_common.cuh"
+
+namespace oess {
+namespace tc {
+
+constexpr int kVW = 16, kVH = 8;
+constexpr int kVStages = 4;
+constexpr int kVABytes = 128 * kBlockK * 4;
+
+template <int BN>
+struct ConvSmem {
+    static constexpr int kBBytes = BN * kBlockK * 4;
+    static constexpr int kBytes = 1024 + kVStages * (kVABytes + kBBytes) + 256;
+};
+
+struct ConvArgs {
+    int Ho, Wo, Cout, KW, taps, chunks, stride, pad, dil, relu, tiles_w;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
+          const float* __restrict__ residual, float* __restrict__ y, const ConvArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = ConvSmem<BN>;
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;
+    uint8_t* sB = base + kVStages * kVABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + kVStages * S::kBBytes);
+    uint64_t* empty = full + kVStages;
+    uint64_t* acc_full = empty + kVStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int th = blockIdx.x / a.tiles_w, tw = blockIdx.x - th * a.tiles_w;
+    const int h0 = th * kVH, w0 = tw * kVW;
+    const int n0 = blockIdx.y * BN, b = blockIdx.z;
+    const int kblocks = a.taps * a.chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < kVStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                  // ===== TMA producer =====
+            int tap = 0, chunk = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kVStages;
+                mbar_wait(&empty[s], ((kb / kVStages) & 1) ^ 1);
+                mbar_expect_tx(&full[s], kVABytes + S::kBBytes);
+                const int ky = tap / a.KW, kx = tap - ky * a.KW;
+                tma_load_4d(sA + s * kVABytes, &tmX, &full[s], chunk * kBlockK, w0 * a.stride - a.pad + kx * a.dil,
+                            h0 * a.stride - a.pad + ky * a.dil, b);
+                tma_load_2d(sB + s * S::kBBytes, &tmW, &full[s], kb * kBlockK, n0);
+                if (++chunk == a.chunks) { chunk = 0; ++tap; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                  // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % kVStages;
+                mbar_wait(&full[s], (kb / kVStages) & 1);
+                tc_fence_after();
+                const uint64_t da = umma_desc_k128(smem_u32(sA + s * kVABytes));
+                const uint64_t db = umma_desc_k128(smem_u32(sB + s * S::kBBytes));
+#pragma unroll
+                for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                    umma_tf32(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                umma_commit(&empty[s]);
+            }
+            umma_commit(acc_full);
+        }
+    } else {                                              // ===== epilogue: warps 2..5 =====
+        const int q = warp & 3;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int r = q * 32 + lane;
+        const int oy = h0 + r / kVW, ox = w0 + r % kVW;
+        const bool valid = oy < a.Ho && ox < a.Wo;
+        const int64_t pix = (((int64_t)b * a.Ho + oy) * a.Wo + ox) * a.Cout;
+        const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
+        const bool vec = (a.Cout & 3) == 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            float v[16];
+            tmem_ld16_nowait(trow + c0, v);
+            tmem_ld_wait();
+            const int col = n0 + c0;
+            if (!valid || col >= a.Cout) continue;
+            if (vec && col + 16 <= a.Cout) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col + j));
+                        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    }
+                    if (residual) {
+                        const float4 rr = *reinterpret_cast<const float4*>(residual + pix + col + j);
+                        o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+                    }
+                    if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    *reinterpret_cast<float4*>(y + pix + col + j) = o;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (col + j < a.Cout) {
+                        float o = v[j] + (bias ? bias[col + j] : 0.f) + (residual ? residual[pix + col + j] : 0.f);
+                        y[pix + col + j] = a.relu ? fmaxf(o, 0.f) : o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, BN);
+}
+
+template <int BN>
+static int launch_conv(const CUtensorMap& tmX, const float* w_packed, int Cout, int Ktot, const float* bias,
+                       const float* residual, float* y, const ConvArgs& a, int B, cudaStream_t st) {
+    CUtensorMap tmW;
+    const uint64_t dW[2] = {(uint64_t)Ktot, (uint64_t)Cout}, sW[1] = {(uint64_t)Ktot * 4};
+    const uint32_t bW[2] = {kBlockK, (uint32_t)BN};
+    int rc = make_tmap_f32(&tmW, w_packed, 2, dW, sW, bW);
+    if (rc) return rc;
+    auto kern = k_conv_tc<BN>;
+    OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN>::kBytes));
+    const int tiles_h = (a.Ho + kVH - 1) / kVH;
+    const dim3 grid((unsigned)(a.tiles_w * tiles_h), (unsigned)((Cout + BN - 1) / BN), (unsigned)B);
+    OESS_KERNEL("tc_conv2d", st, kern<<<grid, 192, ConvSmem<BN>::kBytes, st>>>(tmX, tmW, bias, residual, y, a));
+    return 0;
+}
+
+// strided variant of make_tmap_f32 (element strides per dimension)
+static int make_tmap_f32_strided(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                 const uint32_t* box, const uint32_t* estr) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return (int)cudaErrorNotSupported;
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = estr[i];
+        if (i + 1 < rank) gstr[i] = strides_bytes[i];
+    }
+    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
+}
+
+}  // namespace tc
+}  // namespace oess
+
+using namespace oess;
+
+// x: [B, H, W, Cin] channels-last; w_packed: [Cout, KH * KW * Cin_p] (Cin_p = Cin rounded up to 32, zero padded; column
+// (tap = ky * KW + kx, channel)); bias [Cout] or NULL; residual [B, Ho, Wo, Cout] or NULL; y: [B, Ho, Wo, Cout].
+OESS_API int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
+                                   int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                   int relu, oess_stream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || dil <= 0 || pad < 0)
+        return OESS_E_ARG;
+    if (!x || !w_packed || !y) return OESS_E_ARG;
+    if ((Cin & 3) || stride > 8 || KH * KW > 64) return OESS_E_ARG;      // TMA: 16-byte pixel stride; box <= 256 per dim
+    if (((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)y) & 15) return OESS_E_ARG;
+    if (B > 65535) return OESS_E_RANGE;
+    const int Ho = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+    const int Wo = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+    if (Ho <= 0 || Wo <= 0) return OESS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = (Cin + tc::kBlockK - 1) / tc::kBlockK;
+    const int Ktot = KH * KW * chunks * tc::kBlockK;
+    CUtensorMap tmX;
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+    const uint32_t box[4] = {tc::kBlockK, (uint32_t)(tc::kVW * stride), (uint32_t)(tc::kVH * stride), 1};
+    const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int rc = tc::make_tmap_f32_strided(&tmX, x, 4, dims, strides, box, estr);
+    if (rc) return rc;
+    tc::ConvArgs a{Ho, Wo, Cout, KW, KH * KW, chunks, stride, pad, dil, relu ? 1 : 0, (Wo + tc::kVW - 1) / tc::kVW};
+    if (Cout > 128) return tc::launch_conv<256>(tmX, w_packed, Cout, Ktot, bias, residual, y, a, B, st);
+    if (Cout > 64) return tc::launch_conv<128>(tmX, w_packed, Cout, Ktot, bias, residual, y, a, B, st);
+    return tc::launch_conv<64>(tmX, w_packed, Cout, Ktot, bias, residual, y, a, B, st);
+}

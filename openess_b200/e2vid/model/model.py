@@ -16,7 +16,9 @@ What changes on the B200:
     kernel, `oess_convlstm_step_nhwc` (tcgen05 implicit GEMM, TF32 operands / fp32 accumulate, channels-last), for the
     hidden sizes of the real E2VID config (multiples of 64); `USE_TENSOR_CORES = False` (or OESS_E2VID_TC=0) keeps the
     strict-fp32 cuDNN + fused-gates path;
-  * the strided 5x5 encoder convolutions still run on cuDNN through torch (next kernels to hand-write).
+  * the strided 5x5 encoder convolutions (folded BN + ReLU fused in the epilogue) run on the same tensor-core
+    skeleton, `oess_conv2d_nhwc_tf32` (strided 4-D TMA boxes); only the 5-channel head conv (Cin = 5: too thin for a
+    128-byte TMA row, 1.5 % of the FLOPs) stays on cuDNN.
 """
 import os
 
@@ -44,6 +46,22 @@ class ConvLayer(nn.Module):
         elif norm == 'IN':
             self.norm_layer = nn.InstanceNorm2d(out_channels, track_running_stats=True)
         self._folded = None
+        self._packed = None
+
+    def _tc_ok(self, x):
+        c = self.conv2d
+        return (USE_TENSOR_CORES and x.is_cuda and not torch.is_grad_enabled() and not self.training
+                and c.in_channels % 4 == 0 and c.in_channels >= 16 and c.groups == 1 and c.padding_mode == 'zeros'
+                and c.kernel_size[0] == c.kernel_size[1] and c.stride[0] == c.stride[1] and c.padding[0] == c.padding[1]
+                and c.dilation[0] == c.dilation[1] and (self.norm is None or self._folded is not None)
+                and self.activation in (None, torch.relu))
+
+    def _tc_weights(self):
+        w, b = self._folded if self._folded is not None else (self.conv2d.weight, self.conv2d.bias)
+        key = (w.data_ptr(), w._version, w.device)
+        if self._packed is None or self._packed[0] != key:
+            self._packed = (key, _tc.conv2d_pack(w), None if b is None else b.detach().float().contiguous())
+        return self._packed[1], self._packed[2]
 
     def fold_bn(self):
         """Eval-mode BN folded into the conv: w' = w * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps)."""
@@ -54,6 +72,11 @@ class ConvLayer(nn.Module):
                             (bn.bias - bn.running_mean * scale).detach())
 
     def forward(self, x):
+        if self._tc_ok(x):
+            wp, b = self._tc_weights()
+            c = self.conv2d
+            return _tc.conv2d_tc(x, wp, b, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0],
+                                 relu=self.activation is not None)
         if self._folded is not None and not self.training:
             out = F.conv2d(x, self._folded[0], self._folded[1], self.conv2d.stride, self.conv2d.padding)
         else:

@@ -114,3 +114,34 @@ def convlstm_step(x, prev_state, w_packed, b_packed):
         check(lib().oess_convlstm_step_nhwc(ptr(xc), ptr(hp), ptr(cp), ptr(w_packed), ptr(b_packed), ptr(h), ptr(c),
                                             B, H, W, C, stream_ptr(x.device)), "oess_convlstm_step_nhwc")
     return h, c
+
+
+def conv2d_pack(weight):
+    """[Cout, Cin, KH, KW] -> [Cout, KH * KW * Cin_p] (Cin_p = Cin rounded up to 32, zero padded), column (tap, channel):
+    the K order of oess_conv2d_nhwc_tf32."""
+    Cout, Cin, KH, KW = weight.shape
+    cin_p = (Cin + 31) // 32 * 32
+    w = torch.zeros(Cout, KH * KW, cin_p, dtype=torch.float32, device=weight.device)
+    w[:, :, :Cin] = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin)
+    return w.reshape(Cout, KH * KW * cin_p).contiguous()
+
+
+def conv2d_tc(x, w_packed, bias, kernel_size, stride=1, padding=0, dilation=1, relu=False, residual=None):
+    """Convolution on the tensor cores (tcgen05 implicit GEMM, TF32 operands, fp32 accumulate).
+    x: [B, Cin, H, W] (any memory format; handled channels-last), Cin % 4 == 0; returns [B, Cout, Ho, Wo] channels-last."""
+    _lib.require_cuda(x, w_packed, bias, residual)
+    B, Cin, H, W = x.shape
+    KH, KW = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+    Cout = w_packed.shape[0]
+    cl = torch.channels_last
+    xc = x.float().contiguous(memory_format=cl)
+    Ho = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
+    Wo = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+    y = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=cl)
+    rc = None if residual is None else residual.float().contiguous(memory_format=cl)
+    bc = None if bias is None else _f32c(bias)
+    with torch.cuda.device(x.device):
+        check(lib().oess_conv2d_nhwc_tf32(ptr(xc), ptr(w_packed), ptr(bc), ptr(rc), ptr(y), B, H, W, Cin, Cout, KH, KW,
+                                          stride, padding, dilation, 1 if relu else 0, stream_ptr(x.device)),
+              "oess_conv2d_nhwc_tf32")
+    return y

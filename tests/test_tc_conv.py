@@ -1,0 +1,49 @@
+"""tcgen05 implicit-GEMM convolution (oess_conv2d_nhwc_tf32) against torch's conv2d evaluated in float64 on the CPU.
+Tolerance: TF32 operands, fp32 accumulate -> |err| <= 2e-3 * conv(|x|, |w|) (stated in include/openess_b200.h)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,s,p,d,relu,res", [
+    (1, 32, 64, 16, 32, 5, 2, 2, 1, True, False),     # E2VID encoder 1 (unet.py:128-135): 5x5 stride 2 + ReLU
+    (2, 64, 128, 22, 40, 5, 2, 2, 1, True, False),    # encoder 2, ragged tiles
+    (1, 128, 256, 11, 20, 5, 2, 2, 1, True, False),   # encoder 3, odd input size
+    (1, 64, 64, 9, 17, 3, 1, 1, 1, False, True),      # 3x3 + residual (ResidualBlock, submodules.py:140-172)
+    (1, 64, 64, 12, 20, 3, 1, 2, 2, True, False),     # dilated 3x3 (ResNet layer with replace_stride_with_dilation)
+    (1, 256, 64, 10, 16, 1, 1, 0, 1, True, False),    # 1x1 bottleneck reduce
+    (1, 20, 24, 8, 16, 3, 1, 1, 1, False, False),     # Cin not a multiple of 32 (zero-filled chunk), Cout % 16 != 0
+    (1, 8, 10, 8, 16, 3, 2, 1, 1, True, False),       # scalar store path (Cout % 4 != 0)
+])
+def test_conv2d_tc(B, Cin, Cout, H, W, k, s, p, d, relu, res):
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(Cin * 7 + k)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p, dilation=d)
+    bound = 2e-3 * F.conv2d(x.abs().double(), w.abs().double(), None, stride=s, padding=p, dilation=d) + 1e-6
+    r = None
+    if res:
+        r = torch.randn(ref.shape, generator=g)
+        ref = ref + r.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    y = ops.conv2d_tc(x.cuda(), ops.conv2d_pack(w.cuda()), b.cuda(), k, s, p, d, relu, None if r is None else r.cuda())
+    assert tuple(y.shape) == tuple(ref.shape)
+    err = (y.cpu().double() - ref).abs()
+    assert bool((err <= bound).all()), f"max err {float(err.max())}, bound min {float(bound.min())}"
+    assert float(err.max()) < 0.05 * float(ref.abs().max())
+
+
+def test_conv2d_tc_exact_on_tf32_representable_inputs():
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randint(-3, 4, (2, 32, 13, 19), generator=g).float()
+    w = torch.randint(-2, 3, (48, 32, 5, 5), generator=g).float() / 8.0
+    b = torch.randint(-4, 5, (48,), generator=g).float() / 2.0
+    ref = F.conv2d(x, w, b, stride=2, padding=2).clamp_min(0)
+    y = ops.conv2d_tc(x.cuda(), ops.conv2d_pack(w.cuda()), b.cuda(), 5, 2, 2, 1, True)
+    assert torch.equal(y.cpu(), ref)

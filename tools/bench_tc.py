@@ -72,6 +72,32 @@ def convlstm():
                           "torch_cudnn_tf32_nchw_plus_fused_gates_ms": t_lib2}))
 
 
+def e2vid_step():
+    """One recurrent step of the latent-only E2VID encoder on a DSEC batch (B = 8, 5 x 440 x 640), real width."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from seeded_weights import seeded_state_dict
+    from openess_b200.e2vid.model import model as mm
+    cfg = {'num_bins': 5, 'skip_type': 'sum', 'recurrent_block_type': 'convlstm', 'num_encoders': 3,
+           'base_num_channels': 32, 'num_residual_blocks': 2, 'norm': 'BN', 'use_upsample_conv': False}
+    m = mm.E2VIDRecurrent(cfg, latent_only=True)
+    m.load_state_dict(seeded_state_dict(m, 1205), strict=True)
+    m = m.eval().cuda().fold_bn()
+    x = torch.randn(8, 5, 440, 640, device="cuda")
+    res = {}
+    for use_tc in (True, False):
+        mm.USE_TENSOR_CORES = use_tc
+        with torch.no_grad():
+            _, st, _ = m(x, None)
+
+            def step():
+                m(x, st)
+            res[use_tc] = timeit(step, iters=10)
+    mm.USE_TENSOR_CORES = True
+    print(json.dumps({"op": "e2vid_latent_only_step", "B": 8, "H": 440, "W": 640, "ms_tensor_core_path": res[True],
+                      "ms_cudnn_tf32_path": res[False], "frames_per_s_tensor_core_path": 8 / res[True] * 1e3}))
+
+
 if __name__ == "__main__":
     main()
     convlstm()
+    e2vid_step()
