@@ -231,6 +231,17 @@ int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bi
                           int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                           int relu, oess_stream_t stream);
 
+/* BatchNorm2d (torch.nn.BatchNorm2d semantics) over channels-last rows x [R = B*H*W, C], IN PLACE, with optional residual
+ * add and ReLU: the normalisation between the teacher's tensor-core convolutions.  The OpenESS trainers call `.train()`
+ * on the frozen ResNet-50 teacher every step (training/pretrain_trainer.py:370-371; models/image_model.py:116-117), so
+ * training != 0 (batch statistics + running-statistics update with `momentum`, unbiased running variance) is the
+ * reference's real operating point; training == 0 uses the running statistics.  No host synchronisation.
+ * ws: oess_bn_ws_bytes(C) bytes of device scratch.  C % 4 == 0 and (C / 4 divides 256 or is a multiple of 256). */
+int oess_bn_ws_bytes(int C, size_t* ws_bytes);
+int oess_batchnorm_nhwc(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, float eps, float momentum, int training, const float* residual, int relu,
+                        void* ws, size_t ws_bytes, oess_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

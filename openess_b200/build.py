@@ -31,6 +31,7 @@ SOURCES = {
     "tc_gemm.cu": [],
     "tc_convlstm.cu": [],
     "tc_conv.cu": [],
+    "bn_nhwc.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--threads", "0"]

@@ -1,0 +1,140 @@
+// bn_nhwc.cu -- BatchNorm2d over channels-last activations, the way the OpenESS trainers really run the "frozen"
+// ResNet-50 teacher: `.train()` is called on it every step (training/pretrain_trainer.py:370-371), so its BatchNorm
+// layers normalise with BATCH statistics and update their running statistics although the weights are frozen
+// (models/image_model.py:116-117 only clears requires_grad).  torch.nn.BatchNorm2d semantics (torch/nn/modules/
+// batchnorm.py): y = (x - mean) / sqrt(var_biased + eps) * gamma + beta; running = (1 - m) running + m stat, with the
+// UNBIASED variance for running_var.
+//   k_bn_stats   : per-channel sum / sum of squares of x [R, C] (R = B H W rows), fp32 per-thread partials, fp64 combine
+//   k_bn_finalize: scale / shift per channel (+ running-statistics update) on the device: no host synchronisation
+//   k_bn_apply   : y = act(x * scale[c] + shift[c] (+ residual)), in place, 128-bit accesses
+// All three are HBM-bound: 4 B / element read (stats), 8-12 B / element (apply).
+#include "common.cuh"
+
+namespace oess {
+
+// grid.x = row blocks; block = 256 threads = (C4 = C / 4 channel quads) x (256 / C4 row lanes); C4 <= 256, C4 | 256
+// for C4 > 256 (C = 2048: C4 = 512) the quad index also runs over blockIdx.y.
+__global__ void __launch_bounds__(256)
+k_bn_stats(const float* __restrict__ x, int64_t R, int C, int rows_per_block, double* __restrict__ sums) {
+    const int C4 = C >> 2;
+    const int qpb = min(C4, 256);                      // channel quads handled by this block
+    const int lanes = 256 / qpb;                       // row lanes
+    const int q = blockIdx.y * qpb + (threadIdx.x % qpb);
+    const int rl = threadIdx.x / qpb;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t r1 = min(r0 + rows_per_block, R);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = r0 + rl; r < r1; r += lanes) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C) + q);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        ss.x += v.x * v.x; ss.y += v.y * v.y; ss.z += v.z * v.z; ss.w += v.w * v.w;
+    }
+    __shared__ float4 sh_s[256], sh_ss[256];
+    sh_s[threadIdx.x] = s;
+    sh_ss[threadIdx.x] = ss;
+    __syncthreads();
+    if (rl == 0) {
+        double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+        for (int l = 0; l < lanes; ++l) {
+            const float4 u = sh_s[l * qpb + threadIdx.x], w = sh_ss[l * qpb + threadIdx.x];
+            a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+            b[0] += w.x; b[1] += w.y; b[2] += w.z; b[3] += w.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&sums[q * 4 + j], a[j]);
+            atomicAdd(&sums[C + q * 4 + j], b[j]);
+        }
+    }
+}
+
+__global__ void k_bn_finalize(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              float* __restrict__ running_mean, float* __restrict__ running_var, int C, double count,
+                              float eps, float momentum, int training, float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double mean, var;
+    if (training) {
+        mean = sums[c] / count;
+        var = sums[C + c] / count - mean * mean;       // biased
+        if (var < 0) var = 0;
+        if (running_mean) {
+            const double unbiased = count > 1 ? var * count / (count - 1) : var;
+            running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+            running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+        }
+    } else {
+        mean = running_mean[c];
+        var = running_var[c];
+    }
+    const double inv = 1.0 / sqrt(var + (double)eps);
+    const double g = gamma ? (double)gamma[c] : 1.0;
+    scale[c] = (float)(g * inv);
+    shift[c] = (float)((beta ? (double)beta[c] : 0.0) - mean * g * inv);
+}
+
+__global__ void __launch_bounds__(256)
+k_bn_apply(float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+           const float* __restrict__ residual, int64_t total4, int C4, int relu) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+        const int q = (int)(i % C4);
+        float4 v = reinterpret_cast<float4*>(x)[i];
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + q);
+        const float4 sf = __ldg(reinterpret_cast<const float4*>(shift) + q);
+        v.x = v.x * sc.x + sf.x; v.y = v.y * sc.y + sf.y; v.z = v.z * sc.z + sf.z; v.w = v.w * sc.w + sf.w;
+        if (residual) {
+            const float4 r = __ldcs(reinterpret_cast<const float4*>(residual) + i);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        reinterpret_cast<float4*>(x)[i] = v;
+    }
+}
+
+}  // namespace oess
+
+using namespace oess;
+
+// x: [R, C] channels-last rows (R = B * H * W), normalised IN PLACE.  ws: 2 C doubles + 2 C floats of device scratch
+// (oess_bn_ws_bytes).  training != 0: batch statistics (+ running-statistics update when running_mean != NULL);
+// training == 0: running statistics.  residual (same shape) is added after the affine map, before the ReLU.
+OESS_API int oess_bn_ws_bytes(int C, size_t* ws_bytes) {
+    if (!ws_bytes || C <= 0) return OESS_E_ARG;
+    *ws_bytes = align_up(sizeof(double) * 2 * (size_t)C, 256) + align_up(sizeof(float) * 2 * (size_t)C, 256);
+    return OESS_OK;
+}
+
+OESS_API int oess_batchnorm_nhwc(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
+                                 float* running_var, float eps, float momentum, int training, const float* residual,
+                                 int relu, void* ws, size_t ws_bytes, oess_stream_t stream) {
+    size_t need = 0;
+    if (oess_bn_ws_bytes(C, &need)) return OESS_E_ARG;
+    if (!x || R < 0 || (C & 3)) return OESS_E_ARG;
+    if (!training && (!running_mean || !running_var)) return OESS_E_ARG;
+    if (!ws || ws_bytes < need) return OESS_E_WORKSPACE;
+    if (((uintptr_t)x | (uintptr_t)residual | (uintptr_t)ws) & 15) return OESS_E_ARG;
+    if (R == 0) return OESS_OK;
+    const int C4 = C >> 2;
+    if (C4 > 256 ? (C4 % 256) != 0 : (256 % C4) != 0) return OESS_E_ARG;     // C in {4, 8, .., 1024, 2048, ...}
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sums = (double*)ws;
+    float* scale = (float*)((char*)ws + align_up(sizeof(double) * 2 * (size_t)C, 256));
+    float* shift = scale + C;
+    if (training) {
+        OESS_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st));
+        const int qpb = C4 < 256 ? C4 : 256;
+        const int lanes = 256 / qpb;
+        // ~4 waves of CTAs; every row lane walks >= 8 rows
+        int64_t rpb = (R + (int64_t)kNumSMs * 16 - 1) / ((int64_t)kNumSMs * 16);
+        if (rpb < (int64_t)lanes * 8) rpb = (int64_t)lanes * 8;
+        const dim3 grid((unsigned)((R + rpb - 1) / rpb), (unsigned)((C4 + qpb - 1) / qpb));
+        OESS_KERNEL("bn_stats", st, k_bn_stats<<<grid, 256, 0, st>>>(x, R, C, (int)rpb, sums));
+    }
+    OESS_KERNEL("bn_finalize", st, k_bn_finalize<<<(C + 127) / 128, 128, 0, st>>>(
+        sums, gamma, beta, running_mean, running_var, C, (double)R, eps, momentum, training ? 1 : 0, scale, shift));
+    const int64_t total4 = R * C4;
+    const unsigned blocks = (unsigned)((total4 + 255) / 256 < (int64_t)kNumSMs * 16 ? (total4 + 255) / 256 : (int64_t)kNumSMs * 16);
+    OESS_KERNEL("bn_apply", st, k_bn_apply<<<blocks, 256, 0, st>>>(x, scale, shift, residual, total4, C4, relu ? 1 : 0));
+    return OESS_OK;
+}

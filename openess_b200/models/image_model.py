@@ -1,0 +1,131 @@
+"""Dilated ResNet-50 teacher: mirror of models/image_model.py:90-143 (DilationFeatureExtractor) and
+models/modules/resnet_encoder.py:8-38 (ResNetEncoder = torchvision ResNet-50 without fc / avgpool,
+replace_stride_with_dilation=[True, True, True] -> output stride 4) with the SAME module tree and state_dict keys
+(`encoder.*`, `decoder.0.*`), so the reference's teacher weights (dino / moco / swav / imagenet .pt files, adapted by
+image_model.py:26-74) load with `load_state_dict(strict=True)`.
+
+What changes on the B200 (`forward` on a CUDA tensor that does not require grad -- the encoder is frozen, every trainer
+feeds it the raw frame):
+  * all 52 bottleneck convolutions (1x1, dilated 3x3, downsample 1x1: 99 % of the 845 GFLOP / sample) run as tcgen05
+    implicit GEMMs over channels-last activations (`oess_conv2d_nhwc_tf32`, TF32 operands / fp32 accumulate);
+  * BatchNorm runs the way the trainers really run it -- `.train()` is called on the frozen teacher every step
+    (pretrain_trainer.py:370-371), so BATCH statistics are used and the running statistics are updated -- as the fused
+    channels-last kernels of `oess_batchnorm_nhwc` (stats -> finalize on device -> affine + residual + ReLU in place);
+    in eval mode BN is folded into the conv and bias / residual / ReLU go into the conv epilogue (no BN pass at all);
+  * the 3-channel 7x7 stem conv + maxpool (1 % of the FLOPs; Cin = 3 is too thin for a 128-byte TMA row) and the
+    trainable decoder (1x1 conv 2048 -> 256 with autograd, x4 bilinear upsample, L2 normalise) stay torch ops.
+Preprocessing is `None` in every trainer (pretrain_trainer.py:185-187): raw [0, 1] RGB goes in, as in the reference.
+"""
+import os
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torchvision.models.resnet import Bottleneck, ResNet
+
+from .. import ops as _tc
+
+USE_TENSOR_CORES = os.environ.get("OESS_TEACHER_TC", "1") != "0"
+
+
+class ResNetEncoder(ResNet):
+    """models/modules/resnet_encoder.py:8-38."""
+
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        del self.fc
+        del self.avgpool
+        self._packed = {}
+
+    def load_state_dict(self, state_dict, **kwargs):
+        state_dict.pop("fc.bias", None)
+        state_dict.pop("fc.weight", None)
+        return super().load_state_dict(state_dict, **kwargs)
+
+    # ---- reference formulation (CPU / autograd / USE_TENSOR_CORES = False) ----
+    def forward_torch(self, x):
+        x = self.relu(self.bn1(self.conv1(x)))
+        x = self.layer1(self.maxpool(x))
+        return self.layer4(self.layer3(self.layer2(x)))
+
+    # ---- tensor-core formulation ----
+    def _w(self, conv, bn):
+        """Packed weights of `conv`; in eval mode with BN folded in (w * g / sqrt(var + eps), beta - mean * g / sqrt(..))."""
+        fold = not bn.training
+        key = (id(conv), fold)
+        ver = (conv.weight.data_ptr(), conv.weight._version, conv.weight.device,
+               (bn.running_var._version, bn.weight._version, bn.bias._version) if fold else None)
+        hit = self._packed.get(key)
+        if hit is None or hit[0] != ver:
+            w, b = conv.weight.detach(), None
+            if fold:
+                scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+                w = w * scale[:, None, None, None]
+                b = (bn.bias.detach() - bn.running_mean * scale).float().contiguous()
+            hit = (ver, _tc.conv2d_pack(w), b)
+            self._packed[key] = hit
+        return hit[1], hit[2]
+
+    def _conv_bn(self, x, conv, bn, relu, residual=None):
+        wp, b = self._w(conv, bn)
+        k, s, p, d = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
+        if not bn.training:                                   # folded: everything in the conv epilogue
+            return _tc.conv2d_tc(x, wp, b, k, s, p, d, relu=relu, residual=residual)
+        y = _tc.conv2d_tc(x, wp, None, k, s, p, d)
+        return _tc.batchnorm_nhwc_(y, bn, residual=residual, relu=relu)
+
+    def _bottleneck(self, blk, x):
+        out = self._conv_bn(x, blk.conv1, blk.bn1, True)
+        out = self._conv_bn(out, blk.conv2, blk.bn2, True)
+        identity = x
+        if blk.downsample is not None:
+            identity = self._conv_bn(x, blk.downsample[0], blk.downsample[1], False)
+        return self._conv_bn(out, blk.conv3, blk.bn3, True, residual=identity)     # relu(bn3(conv3) + identity)
+
+    def forward_tc(self, x):
+        x = self.relu(self.bn1(self.conv1(x)))               # stem: torch (Cin = 3)
+        x = self.maxpool(x).contiguous(memory_format=torch.channels_last)
+        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
+            for blk in layer:
+                x = self._bottleneck(blk, x)
+        return x
+
+    def forward(self, x):
+        tc_ok = (USE_TENSOR_CORES and x.is_cuda and not x.requires_grad and x.dtype == torch.float32
+                 and not any(p.requires_grad for p in self.layer1[0].parameters()))
+        if tc_ok:
+            with torch.no_grad():
+                return self.forward_tc(x)
+        return self.forward_torch(x)
+
+
+class DilationFeatureExtractor(nn.Module):
+    """models/image_model.py:90-143.  `image_weights`: None or a state_dict for the encoder (the reference downloads
+    dino / moco / swav weights with `requests`, image_model.py:38-44 -- out of scope offline; pass the adapted dict)."""
+
+    def __init__(self, image_weights=None, preprocessing=None):
+        super().__init__()
+        self.encoder = ResNetEncoder(block=Bottleneck, layers=[3, 4, 6, 3],
+                                     replace_stride_with_dilation=[True, True, True])
+        if isinstance(image_weights, dict):
+            self.encoder.load_state_dict(dict(image_weights))
+        elif image_weights is not None:
+            raise NotImplementedError("named teacher weights are downloaded by the reference at run time; load the "
+                                      "adapted state_dict and pass it as `image_weights`")
+        for param in self.encoder.parameters():
+            param.requires_grad = False
+        self.decoder = nn.Sequential(nn.Conv2d(2048, 256, 1),
+                                     nn.Upsample(scale_factor=4, mode="bilinear", align_corners=True))
+        self.preprocessing = preprocessing
+        self.normalize_feature = True
+        self.channel_avgpooling = nn.AvgPool2d((32, 1), stride=(32, 1))
+        self.upsample4 = nn.Upsample(scale_factor=4, mode="bilinear", align_corners=True)
+
+    def forward(self, x):
+        if self.preprocessing:
+            x = self.preprocessing(x)
+        x = self.encoder(x)                                   # [B, 2048, H/4, W/4]
+        x = self.decoder(x)                                   # [B, 256, H, W]
+        if self.normalize_feature:
+            x = F.normalize(x, p=2, dim=1)
+        return x

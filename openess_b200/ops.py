@@ -145,3 +145,28 @@ def conv2d_tc(x, w_packed, bias, kernel_size, stride=1, padding=0, dilation=1, r
                                           stride, padding, dilation, 1 if relu else 0, stream_ptr(x.device)),
               "oess_conv2d_nhwc_tf32")
     return y
+
+
+def batchnorm_nhwc_(x, bn, residual=None, relu=False):
+    """In-place torch.nn.BatchNorm2d (module `bn`: batch statistics + running-stat update when bn.training, running
+    statistics otherwise) on a channels-last [B, C, H, W] tensor, with optional residual add and ReLU fused."""
+    _lib.require_cuda(x)
+    B, C, H, W = x.shape
+    if not x.is_contiguous(memory_format=torch.channels_last) or x.dtype != torch.float32:
+        raise ValueError("batchnorm_nhwc_: x must be a float32 channels-last tensor")
+    res = None if residual is None else residual.float().contiguous(memory_format=torch.channels_last)
+    training = bn.training or bn.running_mean is None
+    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    nb = ctypes.c_size_t(0)
+    check(lib().oess_bn_ws_bytes(C, ctypes.byref(nb)), "oess_bn_ws_bytes")
+    track = training and bn.track_running_stats and bn.running_mean is not None
+    with torch.cuda.device(x.device):
+        ws = _lib.workspace(nb.value, x.device)
+        check(lib().oess_batchnorm_nhwc(ptr(x), B * H * W, C, ptr(bn.weight), ptr(bn.bias),
+                                        ptr(bn.running_mean) if (track or not training) else None,
+                                        ptr(bn.running_var) if (track or not training) else None,
+                                        float(bn.eps), mom, 1 if training else 0, ptr(res), 1 if relu else 0,
+                                        ptr(ws), ws.numel(), stream_ptr(x.device)), "oess_batchnorm_nhwc")
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+    return x

@@ -144,8 +144,38 @@ def golden_e2vid_full_width():
     print("e2vid_full_width.npz", os.path.getsize(os.path.join(OUT, "e2vid_full_width.npz")) // 1024, "KiB")
 
 
+def golden_teacher():
+    """models/image_model.py:DilationFeatureExtractor (reference class, unmodified, image_weights=None) in TRAIN mode --
+    how the trainers run it (pretrain_trainer.py:370-371).  24 M weights regenerated from tests/seeded_weights.py."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+    from seeded_weights import seeded_state_dict
+    sys.modules.setdefault("models", types.ModuleType("models")).__path__ = [os.path.join(REF, "models")]
+    from models.image_model import DilationFeatureExtractor
+    m = DilationFeatureExtractor(image_weights=None)
+    m.load_state_dict(seeded_state_dict(m, 77), strict=True)
+    m.train()
+    rng = np.random.default_rng(5)
+    x = rng.random((2, 3, 64, 96)).astype(np.float32)
+    with torch.no_grad():
+        feats = m.encoder(torch.from_numpy(x))
+    m.load_state_dict(seeded_state_dict(m, 77), strict=True)      # undo the running-stat update of the probe call
+    y = m(torch.from_numpy(x))
+    sd = m.state_dict()
+    out = {"seed": np.array(77), "x": x, "feats_sub": feats[:, ::16].numpy(), "y_sub": y.detach()[:, ::8, ::4, ::4].numpy(),
+           "feats_absmax": np.array(float(feats.abs().max())),
+           "rm_l4": sd["encoder.layer4.2.bn3.running_mean"].numpy(), "rv_l1": sd["encoder.layer1.0.bn1.running_var"].numpy(),
+           "rv_ds": sd["encoder.layer2.0.downsample.1.running_var"].numpy(),
+           "nbt": sd["encoder.layer3.5.bn2.num_batches_tracked"].numpy()}
+    np.savez_compressed(os.path.join(OUT, "teacher_r50.npz"), **out)
+    print("teacher_r50.npz", os.path.getsize(os.path.join(OUT, "teacher_r50.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    if "--e2vid-full" in sys.argv:
+    if "--teacher" in sys.argv:
+        sys.path.insert(0, REF)
+        torch.set_num_threads(4)
+        golden_teacher()
+    elif "--e2vid-full" in sys.argv:
         sys.path.insert(0, REF)
         torch.set_num_threads(1)
         golden_e2vid_full_width()

@@ -11,13 +11,13 @@ def seeded_state_dict(module, seed):
     for name, t in module.state_dict().items():
         shape = tuple(t.shape)
         if name.endswith("num_batches_tracked"):
-            sd[name] = t.clone()
+            sd[name] = torch.zeros_like(t)
             continue
         if name.endswith("running_var"):
             v = rng.uniform(0.5, 1.5, shape)
         elif name.endswith("running_mean"):
             v = rng.normal(0, 0.1, shape)
-        elif t.ndim == 1 and ("norm" in name or "bn" in name) and name.endswith("weight"):
+        elif t.ndim == 1 and name.endswith("weight"):          # norm-layer gains (conv / linear weights are >= 2-D)
             v = rng.uniform(0.8, 1.2, shape)
         elif t.ndim == 1:
             v = rng.normal(0, 0.1, shape)

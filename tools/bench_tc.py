@@ -97,7 +97,37 @@ def e2vid_step():
                       "ms_cudnn_tf32_path": res[False], "frames_per_s_tensor_core_path": 8 / res[True] * 1e3}))
 
 
+def teacher():
+    """Forward of the dilated ResNet-50 teacher encoder on a DSEC batch (frames 3 x 440 x 640), train-mode BN (the
+    trainers' operating point) and eval-mode (folded BN)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from seeded_weights import seeded_state_dict
+    from openess_b200.models import image_model as im
+    m = im.DilationFeatureExtractor()
+    m.load_state_dict(seeded_state_dict(m, 77), strict=True)
+    m = m.cuda()
+    for B in (2, 8):
+        x = torch.rand(B, 3, 440, 640, device="cuda")
+        for mode in ("train", "eval"):
+            m.train(mode == "train")
+            res = {}
+            for use_tc in (True, False):
+                im.USE_TENSOR_CORES = use_tc
+                with torch.no_grad():
+                    res[use_tc] = timeit(lambda: m.encoder(x), iters=5, warm=2)
+            im.USE_TENSOR_CORES = True
+            fl = 845.1e9 * B
+            print(json.dumps({"op": "teacher_r50_dilated_encoder_fwd", "B": B, "bn": mode, "ms_tensor_core_path": res[True],
+                              "tflops": fl / res[True] / 1e9, "ms_torch_cudnn_tf32_nchw": res[False],
+                              "torch_tflops": fl / res[False] / 1e9}))
+        del x
+        torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
+    if "--teacher" in sys.argv:
+        teacher()
+        sys.exit(0)
     main()
     convlstm()
     e2vid_step()
