@@ -72,20 +72,22 @@ k_dice_ce_partials(const float* __restrict__ logits, const int64_t* __restrict__
             v[c] = (c < K) ? __ldcs(lp + (int64_t)c * HW) : -INFINITY;
             mx = fmaxf(mx, v[c]);
         }
-        float z = 0.f;
+        float z = 0.f, vt = 0.f;                              // vt = logit_t - max
 #pragma unroll
-        for (int c = 0; c < KMAX; ++c) { v[c] = (c < K) ? __expf(v[c] - mx) : 0.f; z += v[c]; }
+        for (int c = 0; c < KMAX; ++c) {
+            vt = (c == (int)tg) ? v[c] - mx : vt;
+            v[c] = (c < K) ? __expf(v[c] - mx) : 0.f;
+            z += v[c];
+        }
         const float inv = 1.0f / z;
-        float ptg = 0.f;
 #pragma unroll
         for (int c = 0; c < KMAX; ++c) {
             const float p = v[c] * inv;
             const bool is_t = (c == (int)tg);
             den[c] += p * p + (is_t ? 1.0f : 0.0f);
             inter[c] += is_t ? p : 0.0f;
-            ptg = is_t ? p : ptg;
         }
-        ce += -__logf(ptg);                                   // lse - logit_t = -log softmax_t
+        ce += logf(z) - vt;                                   // log-sum-exp form: finite even when softmax_t underflows
         ++nvalid;
     }
     // block reduction (float64): every warp shuffles all 2K+2 values down, one barrier, 2K+2 threads finish

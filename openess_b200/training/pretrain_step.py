@@ -1,0 +1,120 @@
+"""The OpenESS stage-1 pretraining step (config_option 'frame2voxel': frame-to-event InfoNCE on superpixels +
+text-to-event Dice/CE against FC-CLIP pseudo-labels), SURVEY.md 8a row a19.
+
+Mirror of training/pretrain_trainer.py: `createOptimizerDict` :211-243 (two AdamW), `train_step` :324-361,
+`task_train_step` :364-372 + :427-472 (frame2voxel branch), `trainTaskStepPretrain` :550-562 -- same attribute names
+(`models_dict`, `optimizers_dict`, `reconstructor`, `task_loss`, `nce_loss`), same batch tuple
+`(event, label, frame, pl, superpixels, ...)`, same returned `(losses, outputs, final_loss)`.
+
+What changes on the B200:
+  * batch[0] may be the reference's dense event tensor [B, 20*5, H, W] OR a `RawEvents` slab (the raw DSEC records of
+    the sample windows): the slab is rectified, time-normalised and voxelised on the device in one batched call
+    (F = B * 20 frames), replacing the 123 MB / sample host->device copy by 18 MB / sample;
+  * E2VID (20 recurrent steps) and the frozen teacher run on the tcgen05 kernels, sync-free;
+  * `SemSegE2VID.forward_pooled` + `superpixel_pool` replace the sparse one-hot matmuls on permuted 2.3 GB copies
+    (:446-465) -- k and q are produced by fused segment reductions, the 256 / 512-channel event-branch maps never exist;
+  * `NCELoss` / `TaskLoss` are the fused kernels; under data parallelism `allreduce_gradients` averages the gradients
+    of the two trainable modules over NCCL after backward (the reference is single-GPU, README.md:303).
+"""
+from collections import namedtuple
+
+import torch
+
+from .. import parallel as _parallel
+from .. import voxel as _voxel
+from ..losses import superpixel_pool
+
+# raw DSEC records of B samples x nr_events_data windows: x, y uint16; t uint32 or int64 (us); p uint8; frame_offsets
+# int64 [B * nr_events_data + 1]; rectify_map float32 [Hs, Ws, 2] (sequence_ov.py:204-210); sensor (Hs, Ws); crop rows
+RawEvents = namedtuple("RawEvents", "x y t p frame_offsets rectify_map sensor_hw crop_h")
+
+
+class OpenESSPretrainStep:
+    def __init__(self, reconstructor, back_end, model_frame, task_loss, nce_loss, *, nr_events_data_b=20,
+                 input_channels_b=5, superpixel_size=100, weight_task_loss=1.0, if_spatial_contrastive=True,
+                 if_dense_clip_supervision=True, lr_voxel=5e-4, lr_frame=5e-4, device=None, data_parallel=False):
+        self.reconstructor = reconstructor
+        self.models_dict = {"front_sensor_b": reconstructor.model, "back_end": back_end, "model_frame": model_frame}
+        self.task_loss, self.nce_loss = task_loss, nce_loss
+        self.nr_events_data_b, self.input_channels_b = nr_events_data_b, input_channels_b
+        self.superpixel_size, self.weight_task_loss = superpixel_size, weight_task_loss
+        self.if_spatial_contrastive, self.if_dense_clip_supervision = if_spatial_contrastive, if_dense_clip_supervision
+        self.device = device if device is not None else next(back_end.parameters()).device
+        self.data_parallel = data_parallel
+        for p in reconstructor.model.parameters():             # pretrain_trainer.py:154-157: frozen E2VID
+            p.requires_grad = False
+        # :231-243
+        params_voxel = [p for p in back_end.parameters() if p.requires_grad]
+        params_frame = [p for p in model_frame.parameters() if p.requires_grad]
+        fused = self.device.type == "cuda"
+        self.optimizers_dict = {"optimizer_voxel": torch.optim.AdamW(params_voxel, lr=lr_voxel, fused=fused),
+                                "optimizer_frame": torch.optim.AdamW(params_frame, lr=lr_frame, fused=fused)}
+        self._trainable = params_voxel + params_frame
+
+    # ---- sample assembly on the device (replaces Sequence.__getitem__'s voxel branch, sequence_ov.py:282-307) ----
+    def event_tensor(self, ev):
+        if not isinstance(ev, RawEvents):
+            return ev.to(self.device)                          # reference format: dense [B, 20*5, H, W]
+        C = self.input_channels_b
+        Hs, Ws = ev.sensor_hw
+        dev = self.device
+        x, y, t, p = (a.to(dev, non_blocking=True) for a in (ev.x, ev.y, ev.t, ev.p))
+        fo = ev.frame_offsets.to(dev, non_blocking=True)
+        grids = _voxel.dsec_events_to_voxel_grid(x, y, t, p, ev.rectify_map.to(dev), C, frame_offsets=fo,
+                                                 mode="ordered")                        # [F, C, Hs, Ws]
+        F = fo.numel() - 1
+        B = F // self.nr_events_data_b
+        dense = grids.view(B, self.nr_events_data_b * C, Hs, Ws)
+        return dense[:, :, :ev.crop_h, :]                      # sequence_ov.py:307 bottom crop, a view
+
+    # ---- pretrain_trainer.py:550-562 ----
+    def trainTaskStepPretrain(self, content_features, pl, superpixels, losses):
+        content_features = {k: v.detach() for k, v in content_features.items()}
+        back_end = self.models_dict["back_end"]
+        if self.if_spatial_contrastive and hasattr(back_end, "forward_pooled"):
+            pred, k = back_end.forward_pooled(content_features, superpixels, self.superpixel_size)
+        else:
+            pred, k = back_end(content_features)[0], None
+        loss = self.task_loss(pred[1], pl) * self.weight_task_loss
+        losses["dense_clip_loss"] = loss.detach()
+        return loss, pred, k
+
+    # ---- pretrain_trainer.py:364-372, 427-472 ----
+    def task_train_step(self, batch):
+        losses, outputs, t_loss = {}, {}, 0.0
+        for name, m in self.models_dict.items():
+            m.train()                                          # :370-371 (the "frozen" teacher's BN uses batch statistics)
+            if name == "front_sensor_b":
+                m.eval()                                       # :372-374
+        event = self.event_tensor(batch[0])
+        frame = batch[2].to(self.device)
+        pl = batch[3].to(self.device)
+        superpixels = batch[4].to(self.device) if self.if_spatial_contrastive else None
+        feat_frame = self.models_dict["model_frame"](frame)
+        self.reconstructor.last_states_for_each_channel = {"grayscale": None}
+        C = self.input_channels_b
+        for i in range(self.nr_events_data_b):
+            _, _, latent_real = self.reconstructor.update_reconstruction(event[:, i * C:(i + 1) * C])
+        loss_dense, pred, k = self.trainTaskStepPretrain(latent_real, pl, superpixels, losses)
+        if self.if_spatial_contrastive:
+            M = k.shape[0]
+            q = superpixel_pool(feat_frame, superpixels, self.superpixel_size, M)       # :461-463
+            loss_nce = self.nce_loss(k, q)                                              # :467
+            losses["contrastive_nce_loss"] = loss_nce.detach()
+            t_loss = t_loss + loss_nce
+        if self.if_dense_clip_supervision:
+            t_loss = t_loss + loss_dense
+        outputs["pred"] = pred
+        return t_loss, losses, outputs
+
+    # ---- pretrain_trainer.py:324-361 ----
+    def train_step(self, input_batch):
+        for opt in self.optimizers_dict.values():
+            opt.zero_grad(set_to_none=True)
+        final_loss, losses, outputs = self.task_train_step(input_batch)
+        final_loss.backward()
+        if self.data_parallel:
+            _parallel.allreduce_gradients(self._trainable)
+        for opt in self.optimizers_dict.values():
+            opt.step()
+        return losses, outputs, final_loss

@@ -1,0 +1,169 @@
+"""OpenESS stage-1 pretraining step (row a19): the fused step of openess_b200/training/pretrain_step.py against the
+LITERAL formulation of training/pretrain_trainer.py:427-472 + :550-562 + utils/loss_functions.py (restated here with
+plain torch ops: sparse one-hot pooling on permuted copies, materialised x_ch256, softmax / one-hot Dice, CE) evaluated on
+the same modules.  Every module is separately pinned to a reference golden; this pins the composition and the gradients."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import load_golden
+from seeded_weights import seeded_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(dev):
+    from types import SimpleNamespace
+    from openess_b200.e2vid.image_reconstructor import ImageReconstructor
+    from openess_b200.e2vid.model.model import E2VIDRecurrent
+    from openess_b200.models.image_model import DilationFeatureExtractor
+    from openess_b200.models.style_networks import SemSegE2VID
+    z = load_golden("e2vid_tiny")
+    cfg = {}
+    for k, v in zip(z["cfg_keys"], z["cfg_vals"]):
+        cfg[str(k)] = (v == "True") if str(v) in ("True", "False") else (int(v) if str(v).isdigit() else str(v))
+    e2vid = E2VIDRecurrent(cfg, latent_only=True)
+    e2vid.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd__")}, strict=True)
+    e2vid = e2vid.eval().to(dev).fold_bn()
+    zs = load_golden("semseg_tiny")
+    back = SemSegE2VID(input_c=32, output_c=int(zs["K"]), skip_connect=True, skip_type='concat', text_embeddings_path=None)
+    back.load_state_dict({k[4:]: torch.from_numpy(zs[k]) for k in zs.files if k.startswith("sd__")}, strict=True)
+    teacher = DilationFeatureExtractor()
+    teacher.load_state_dict(seeded_state_dict(teacher, 77), strict=True)
+    opts = SimpleNamespace(no_normalize=False, hot_pixels_file=None, flip=False, no_recurrent=False)
+    return e2vid, back.to(dev), teacher.to(dev), opts, int(zs["K"])
+
+
+def _literal_step(e2vid, back, teacher, event, frame, pl, sp, S, steps):
+    """pretrain_trainer.py:427-472 with the reference's own torch formulation of every block."""
+    feat_frame = teacher(frame)                                                     # :434
+    states = None
+    for i in range(steps):                                                          # :437-441
+        ev = event[:, 5 * i:5 * i + 5]
+        nz = ev != 0                                                                # inference_utils.py:77-85
+        n = nz.sum()
+        mean = ev.sum() / n
+        std = torch.sqrt((ev ** 2).sum() / n - mean ** 2)
+        ev = nz.float() * (ev - mean) / std
+        with torch.no_grad():
+            _, states, latent = e2vid(ev, states)
+    pred, feat_voxel = back({k: v.detach() for k, v in latent.items()})            # :551-553
+    logits = pred[1]
+    ce = F.cross_entropy(logits, pl, ignore_index=255)                              # loss_functions.py:17-24
+    mask = (pl != 255)
+    onehot = F.one_hot((pl * mask).long(), logits.shape[1]).permute(0, 3, 1, 2).float() * mask[:, None]
+    prob = logits.softmax(1) * mask[:, None]
+    dice = 0
+    for c in range(logits.shape[1]):                                                # loss_functions.py:80-90, 114-135
+        num = 2 * (prob[:, c] * onehot[:, c]).sum() + 1
+        den = (prob[:, c] ** 2 + onehot[:, c] ** 2).sum() + 1
+        dice = dice + (1 - num / den)
+    loss_dense = dice / logits.shape[1] + ce
+    B = feat_voxel.shape[0]
+    spx = torch.arange(0, B * S, S, device=sp.device)[:, None, None] + sp          # :446-449
+    sI = spx.flatten()
+    idx = torch.arange(sI.shape[0], device=sp.device)
+    with torch.no_grad():
+        one_hot = torch.sparse_coo_tensor(torch.stack((sI, idx), 0), torch.ones(sI.shape[0], device=sp.device))
+    cnt = torch.sparse.sum(one_hot, 1).to_dense()[:, None] + 1e-6
+    k = (one_hot @ feat_voxel.permute(0, 2, 3, 1).flatten(0, 2)) / cnt             # :456-459
+    q = (one_hot @ feat_frame.permute(0, 2, 3, 1).flatten(0, 2)) / cnt             # :461-463
+    nce = F.cross_entropy((k @ q.t()) / 0.07, torch.arange(k.shape[0], device=k.device))    # loss_functions.py:147-153
+    return nce + loss_dense, nce, loss_dense
+
+
+def test_pretrain_step_matches_literal_reference_formulation():
+    from openess_b200.e2vid.image_reconstructor import ImageReconstructor
+    from openess_b200.models import image_model as im
+    from openess_b200.training.pretrain_step import OpenESSPretrainStep
+    from openess_b200.utils.loss_functions import NCELoss, TaskLoss
+    dev = torch.device("cuda:0")
+    e2vid, back, teacher, opts, K = _models(dev)
+    Bn, H, W, S, steps = 2, 32, 48, 10, 3
+    g = torch.Generator().manual_seed(11)
+    event = torch.randn(Bn, 5 * steps, H, W, generator=g)
+    event[torch.rand(event.shape, generator=g) < 0.6] = 0
+    frame = torch.rand(Bn, 3, H, W, generator=g)
+    pl = torch.randint(0, K, (Bn, H, W), generator=g)
+    pl[torch.rand(pl.shape, generator=g) < 0.03] = 255
+    sp = torch.randint(0, S, (Bn, H, W), generator=g)
+    event, frame, pl, sp = (t.to(dev) for t in (event, frame, pl, sp))
+    sd_back = {k: v.clone() for k, v in back.state_dict().items()}
+    sd_teacher = {k: v.clone() for k, v in teacher.state_dict().items()}
+
+    im.USE_TENSOR_CORES = False                       # identical fp32 modules on both sides: pins the composition
+    try:
+        teacher.train(); back.train()
+        ref_total, ref_nce, ref_dense = _literal_step(e2vid, back, teacher, event, frame, pl, sp, S, steps)
+        ref_total.backward()
+        ref_grads = {n: p.grad.clone() for n, p in list(back.named_parameters()) + list(teacher.named_parameters())
+                     if p.grad is not None}
+        for p in list(back.parameters()) + list(teacher.parameters()):
+            p.grad = None
+        back.load_state_dict(sd_back); teacher.load_state_dict(sd_teacher)        # undo BN running-stat updates
+
+        rec = ImageReconstructor(e2vid, H, W, 5, dev, opts)
+        step = OpenESSPretrainStep(rec, back, teacher, TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255),
+                                   NCELoss(temperature=0.07), nr_events_data_b=steps, superpixel_size=S, lr_voxel=1e-3, lr_frame=1e-3)
+        total, losses, _ = step.task_train_step((event, None, frame, pl, sp))
+        assert float(losses["contrastive_nce_loss"]) == pytest.approx(float(ref_nce), rel=2e-4)
+        assert float(losses["dense_clip_loss"]) == pytest.approx(float(ref_dense), rel=2e-4)
+        assert float(total) == pytest.approx(float(ref_total), rel=2e-4)
+        total.backward()
+        checked = 0
+        for n, p in list(back.named_parameters()) + list(teacher.named_parameters()):
+            if n in ref_grads:
+                assert p.grad is not None, n
+                ref = ref_grads[n]
+                atol = 2e-3 * float(ref.abs().max()) + 1e-7
+                if n.endswith(".model.0.bias") or n.endswith(".model.3.bias"):
+                    continue                          # bias in front of an affine-free InstanceNorm: gradient is round-off noise
+                np.testing.assert_allclose(p.grad.cpu().numpy(), ref.cpu().numpy(), atol=atol, err_msg=n)
+                checked += 1
+            else:
+                assert p.grad is None, n              # decoder_scale_5, frozen encoder
+        assert checked >= 20
+        # full train_step: both AdamW optimisers move exactly the trainable parameters
+        for p in list(back.parameters()) + list(teacher.parameters()):
+            p.grad = None
+        before = {n: p.detach().clone() for n, p in teacher.named_parameters()}
+        w_before = back.decoder_ch256[0].weight.detach().clone()
+        step.train_step((event, None, frame, pl, sp))
+        assert not torch.equal(back.decoder_ch256[0].weight, w_before)
+        for n, p in teacher.named_parameters():
+            assert torch.equal(p, before[n]) == (not n.startswith("decoder")), n
+    finally:
+        im.USE_TENSOR_CORES = True
+
+    # tensor-core teacher (the production configuration): same step, loss in the same noise class
+    back.load_state_dict(sd_back); teacher.load_state_dict(sd_teacher)
+    total_tc, losses_tc, _ = step.task_train_step((event, None, frame, pl, sp))
+    assert float(losses_tc["dense_clip_loss"]) == pytest.approx(float(ref_dense), rel=2e-4)     # event branch: no TF32 here
+    assert float(losses_tc["contrastive_nce_loss"]) == pytest.approx(float(ref_nce), rel=5e-2)
+
+
+def test_pretrain_step_raw_event_slab_equals_dense_event_tensor():
+    """GPU-side sample assembly: raw DSEC records -> the same dense [B, 20*5, H, W] tensor the reference's loader builds."""
+    from openess_b200 import voxel
+    from openess_b200.training.pretrain_step import OpenESSPretrainStep, RawEvents
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    Hs, Ws, crop, C, Bn, steps, n = 40, 64, 32, 5, 2, 3, 500
+    F_ = Bn * steps
+    x = torch.from_numpy(rng.integers(0, Ws, F_ * n).astype(np.uint16))
+    y = torch.from_numpy(rng.integers(0, Hs, F_ * n).astype(np.uint16))
+    t = torch.from_numpy(np.concatenate([np.sort(rng.integers(0, 50000, n)) + 1000 + 50000 * f for f in range(F_)]).astype(np.int64))
+    p = torch.from_numpy(rng.integers(0, 2, F_ * n).astype(np.uint8))
+    yy, xx = np.meshgrid(np.arange(Hs), np.arange(Ws), indexing="ij")
+    rmap = torch.from_numpy((np.stack([xx, yy], -1) + rng.uniform(-0.7, 0.7, (Hs, Ws, 2))).astype(np.float32))
+    fo = torch.arange(0, (F_ + 1) * n, n, dtype=torch.int64)
+    step = OpenESSPretrainStep.__new__(OpenESSPretrainStep)
+    step.device, step.input_channels_b, step.nr_events_data_b = dev, C, steps
+    dense = step.event_tensor(RawEvents(x, y, t, p, fo, rmap, (Hs, Ws), crop))
+    assert tuple(dense.shape) == (Bn, steps * C, crop, Ws)
+    for f in range(F_):                                   # frame by frame through the single-frame mirror of VoxelGrid
+        sl = slice(f * n, (f + 1) * n)
+        g = voxel.dsec_events_to_voxel_grid(x[sl].to(dev), y[sl].to(dev), t[sl].to(dev), p[sl].to(dev), rmap.to(dev), C)
+        b, i = divmod(f, steps)
+        assert torch.equal(dense[b, i * C:(i + 1) * C], g[0, :, :crop])
