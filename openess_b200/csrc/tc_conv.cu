@@ -15,13 +15,14 @@ namespace oess {
 namespace tc {
 
 constexpr int kVW = 16, kVH = 8;
-constexpr int kVStages = 4;
 constexpr int kVABytes = 128 * kBlockK * 4;
 
+// ring depth chosen so that TWO CTAs fit one SM (<= ~100 KB each): one CTA's epilogue overlaps the other's main loop
 template <int BN>
 struct ConvSmem {
     static constexpr int kBBytes = BN * kBlockK * 4;
-    static constexpr int kBytes = 1024 + kVStages * (kVABytes + kBBytes) + 256;
+    static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
+    static constexpr int kBytes = 1024 + kStages * (kVABytes + kBBytes) + 256;
 };
 
 struct ConvArgs {
@@ -29,11 +30,12 @@ struct ConvArgs {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
           const float* __restrict__ residual, float* __restrict__ y, const ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
     using S = ConvSmem<BN>;
+    constexpr int kVStages = S::kStages;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = base;
     uint8_t* sB = base + kVStages * kVABytes;

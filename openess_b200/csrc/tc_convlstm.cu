@@ -19,14 +19,14 @@ namespace tc {
 
 constexpr int kTW = 16, kTH = 8;            // spatial patch of one M tile (16 x 8 = 128 pixels)
 constexpr int kCN = 256;                    // N tile: 4 gates x 64 hidden channels
-constexpr int kCStages = 4;
+constexpr int kCStages = 2;               // 2 x 48 KB per CTA -> two CTAs per SM: one's epilogue overlaps the other's main loop
 constexpr int kCABytes = 128 * kBlockK * 4; // 16 KB
 constexpr int kCBBytes = kCN * kBlockK * 4; // 32 KB
 constexpr int kCSmem = 1024 + kCStages * (kCABytes + kCBBytes) + 256;
 
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(192, 2)
 k_convlstm_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
               const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias, const float* __restrict__ c_prev,
               float* __restrict__ h_out, float* __restrict__ c_out, int H, int W, int C, int has_h, int tiles_w) {
