@@ -28,8 +28,8 @@ k_rowsort(const float4* __restrict__ src, float4* __restrict__ dst, const int64_
           uint32_t* __restrict__ coloff, int NS, int WC) {
     extern __shared__ uint32_t s_cnt_all[];           // [kRowWarps][W + 2]
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * kRowWarps + w;        // py in [0, H]
-    const int f = blockIdx.y;
+    const int row = blockIdx.y * kRowWarps + w;        // py in [0, H]
+    const int f = blockIdx.x;                          // frame-major launch order: heavy and light frames interleave
     if (row > H) return;
     const uint32_t* ro = rowoff + (int64_t)f * radix::kBins;
     const uint32_t s = ro[row], e = ro[row + 1];

@@ -187,17 +187,20 @@ __device__ __forceinline__ void strip_windows(const StripCtx& c, const float4* _
     }
 }
 
-// grid (ceil(NS / warps per CTA), H, F); CT = compile-time C (0: runtime g.C)
+// grid (ceil(NS / warps per CTA), H, F) or frame-major (F, H, ceil(NS / warps)); CT = compile-time C (0: runtime g.C)
 template <int WC, int CT, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 k_strip_splat(const float4* __restrict__ items, const int64_t* __restrict__ frame_offsets,
               const uint32_t* __restrict__ coloff, const uint32_t* __restrict__ rowflag, Geom g, int NS,
-              float* __restrict__ out) {
+              int F_, float* __restrict__ out) {
     extern __shared__ __align__(16) float s_strip[];  // [warps][C][WC]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int s = blockIdx.x * (blockDim.x >> 5) + warp;
+    // frame-major launch order (OESS_STRIP_ORDER=1): consecutive CTAs take the same (row, strip) of consecutive frames,
+    // so heavy (edge-clustered) and light frames interleave in time instead of forming a heavy tail
+    const bool fmajor = gridDim.z != (unsigned)F_;
+    const int s = (fmajor ? blockIdx.z : blockIdx.x) * (blockDim.x >> 5) + warp;
     if (s >= NS) return;                               // warps are independent: no CTA-wide barrier below
-    const int Y = blockIdx.y, f = blockIdx.z;
+    const int Y = blockIdx.y, f = fmajor ? blockIdx.x : blockIdx.z;
     const int C = CT ? CT : g.C;
     const int H = g.H, W = g.W;
     const int xbase = s * WC;

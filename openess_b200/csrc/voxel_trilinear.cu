@@ -213,9 +213,13 @@ static int launch_strip_ct(const Plan& plan, const float4* items, const int64_t*
     if (plan.strip_minb == 5) kern = k_strip_splat<kStripWC, CT, 5>;
     if (plan.strip_minb == 4) kern = k_strip_splat<kStripWC, CT, 4>;
     OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.strip_smem));
-    const dim3 grid((unsigned)((plan.NS + plan.strip_warps - 1) / plan.strip_warps), (unsigned)g.H, (unsigned)F);
+    const unsigned gs = (unsigned)((plan.NS + plan.strip_warps - 1) / plan.strip_warps);
+    static const bool fmajor_env = [] { const char* e = std::getenv("OESS_STRIP_ORDER"); return !(e && e[0] == '0'); }();
+    // frame-major needs gridDim.z != F to be told apart in the kernel and gs <= 65535
+    const bool fmajor = fmajor_env && gs != (unsigned)F;
+    const dim3 grid = fmajor ? dim3((unsigned)F, (unsigned)g.H, gs) : dim3(gs, (unsigned)g.H, (unsigned)F);
     OESS_KERNEL("tri_strip_splat", st, kern<<<grid, plan.strip_warps * 32, plan.strip_smem, st>>>(
-        items, frame_offsets, coloff, rowflag, g, plan.NS, out));
+        items, frame_offsets, coloff, rowflag, g, plan.NS, F, out));
     return 0;
 }
 static int launch_strip(const Plan& plan, const float4* items, const int64_t* frame_offsets, const uint32_t* coloff,
@@ -304,7 +308,7 @@ OESS_API int oess_voxel_trilinear(const float* x, const float* y, const float* p
                                  (uint32_t*)nullptr, 0, w.a, st);
             if (rc) return rc;
             OESS_CUDA(cudaFuncSetAttribute(tri::k_rowsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.row_smem));
-            OESS_KERNEL("tri_rowsort", st, tri::k_rowsort<<<dim3((unsigned)((H + 1 + tri::kRowWarps - 1) / tri::kRowWarps), (unsigned)F),
+            OESS_KERNEL("tri_rowsort", st, tri::k_rowsort<<<dim3((unsigned)F, (unsigned)((H + 1 + tri::kRowWarps - 1) / tri::kRowWarps)),
                                                            tri::kRowWarps * 32, plan.row_smem, st>>>(
                 w.a, w.b, frame_offsets, w.tot, w.rowflag, H, W, plan.strip ? w.coloff : nullptr, plan.NS, tri::kStripWC));
             if (plan.strip) {
