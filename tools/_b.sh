@@ -1,2 +1,5 @@
-python bench.py --steps 10 --warmup 3 --host-output 0 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value']), round(d['ms_per_step'],3), {k: round(v*d['ms_per_step'],3) for k,v in d['roofline']['kernel_share_of_step'].items()})"
-python -m pytest tests/test_voxel_gpu.py -m gpu -x -q 2>&1 | tail -2
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/r01c_bench.json 2>/dev/null; cat gpurun_out/r01c_bench.json | cut -c1-1500
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r01c_bench_reference.json 2>/dev/null
+python tools/bench_tc.py > gpurun_out/r01c_tc_bench.jsonl 2>&1; python tools/bench_tc.py --teacher >> gpurun_out/r01c_tc_bench.jsonl 2>&1
+python tools/bench_train_step.py --batch 4 --steps 5 --warmup 2 > gpurun_out/r01c_train_step.json 2>&1; tail -1 gpurun_out/r01c_train_step.json | cut -c1-400
