@@ -242,6 +242,18 @@ int oess_batchnorm_nhwc(float* x, int64_t R, int C, const float* gamma, const fl
                         float* running_var, float eps, float momentum, int training, const float* residual, int relu,
                         void* ws, size_t ws_bytes, oess_stream_t stream);
 
+/* Frame-branch teacher tail fused with the superpixel pooling that consumes it (never materialises the [B,256,H,W] map):
+ *   pooled_sum[m] = sum_{pixels of superpixel m} normalize_C( bilinear upsample (align_corners=True) of d )[pixel]
+ * Replaces models/image_model.py:121-124,139-141 (nn.Upsample x4 + F.normalize) followed by
+ * training/pretrain_trainer.py:446-463 (one-hot sparse matmul; the division by count + 1e-6 stays with the caller).
+ * d: [B, h, w, 256] channels-last decoder output; seg: int64 [B, H, W] ids (b * S added inside, ids outside [0, M) are
+ * skipped and flagged in *status); pooled_sum [M, 256], counts [M]: zeroed and filled.  The backward entry takes the
+ * gradient w.r.t. pooled_sum and produces d_grad [B, h, w, 256] (zeroed inside). */
+int oess_upnorm_pool_fwd(const float* d, const int64_t* seg, int B, int h, int w, int C, int H, int W, int S, int64_t M,
+                         float* pooled_sum, float* counts, int32_t* status, oess_stream_t stream);
+int oess_upnorm_pool_bwd(const float* d, const int64_t* seg, const float* g_sum, int B, int h, int w, int C, int H, int W,
+                         int S, int64_t M, float* d_grad, oess_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

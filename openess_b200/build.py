@@ -32,6 +32,7 @@ SOURCES = {
     "tc_convlstm.cu": [],
     "tc_conv.cu": [],
     "bn_nhwc.cu": [],
+    "upnorm_pool.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--threads", "0"]

@@ -24,7 +24,18 @@ k_bn_stats(const float* __restrict__ x, int64_t R, int C, int rows_per_block, do
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = min(r0 + rows_per_block, R);
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = r0 + rl; r < r1; r += lanes) {
+    int64_t r = r0 + rl;
+    for (; r + 3 * (int64_t)lanes < r1; r += 4 * (int64_t)lanes) {        // 4 independent 128-bit loads in flight
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(x + (r + (int64_t)u * lanes) * C) + q);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+            ss.x += v[u].x * v[u].x; ss.y += v[u].y * v[u].y; ss.z += v[u].z * v[u].z; ss.w += v[u].w * v[u].w;
+        }
+    }
+    for (; r < r1; r += lanes) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C) + q);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
         ss.x += v.x * v.x; ss.y += v.y * v.y; ss.z += v.z * v.z; ss.w += v.w * v.w;
@@ -125,9 +136,9 @@ OESS_API int oess_batchnorm_nhwc(float* x, int64_t R, int C, const float* gamma,
         OESS_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st));
         const int qpb = C4 < 256 ? C4 : 256;
         const int lanes = 256 / qpb;
-        // ~4 waves of CTAs; every row lane walks >= 8 rows
+        // ~16 CTAs per SM; every row lane walks >= 32 rows (8 rounds of 4 independent loads)
         int64_t rpb = (R + (int64_t)kNumSMs * 16 - 1) / ((int64_t)kNumSMs * 16);
-        if (rpb < (int64_t)lanes * 8) rpb = (int64_t)lanes * 8;
+        if (rpb < (int64_t)lanes * 32) rpb = (int64_t)lanes * 32;
         const dim3 grid((unsigned)((R + rpb - 1) / rpb), (unsigned)((C4 + qpb - 1) / qpb));
         OESS_KERNEL("bn_stats", st, k_bn_stats<<<grid, 256, 0, st>>>(x, R, C, (int)rpb, sums));
     }

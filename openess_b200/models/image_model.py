@@ -129,3 +129,11 @@ class DilationFeatureExtractor(nn.Module):
         if self.normalize_feature:
             x = F.normalize(x, p=2, dim=1)
         return x
+
+    def forward_pooled(self, x, superpixels, superpixel_size, M):
+        """Fused training path: q [M, 256] = superpixel mean-pool of forward(x) (pretrain_trainer.py:434 + :461-463)
+        without materialising the [B, 256, H, W] map: encoder -> decoder 1x1 conv (autograd) -> `oess_upnorm_pool`."""
+        if self.preprocessing:
+            x = self.preprocessing(x)
+        d = self.decoder[0](self.encoder(x))                  # [B, 256, H/4, W/4]
+        return _tc.upnorm_pool(d, superpixels, superpixel_size, M, scale=4)

@@ -170,3 +170,45 @@ def batchnorm_nhwc_(x, bn, residual=None, relu=False):
         if track and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
     return x
+
+
+class _UpNormPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, d, seg, S, M, H, W):
+        B, C, h, w = d.shape
+        dc = d.float().contiguous(memory_format=torch.channels_last)
+        seg = seg.contiguous()
+        pooled = torch.empty(M, C, dtype=torch.float32, device=d.device)
+        counts = torch.empty(M, dtype=torch.float32, device=d.device)
+        with torch.cuda.device(d.device):
+            check(lib().oess_upnorm_pool_fwd(ptr(dc), ptr(seg), B, h, w, C, H, W, S, M, ptr(pooled), ptr(counts), None,
+                                             stream_ptr(d.device)), "oess_upnorm_pool_fwd")
+        ctx.save_for_backward(dc, seg)
+        ctx.meta = (S, M, H, W)
+        ctx.mark_non_differentiable(counts)
+        return pooled, counts
+
+    @staticmethod
+    def backward(ctx, g_pooled, _g_counts):
+        dc, seg = ctx.saved_tensors
+        S, M, H, W = ctx.meta
+        B, C, h, w = dc.shape
+        g = _f32c(g_pooled)
+        d_grad = torch.empty_like(dc)                       # channels-last
+        with torch.cuda.device(dc.device):
+            check(lib().oess_upnorm_pool_bwd(ptr(dc), ptr(seg), ptr(g), B, h, w, C, H, W, S, M, ptr(d_grad),
+                                             stream_ptr(dc.device)), "oess_upnorm_pool_bwd")
+        return d_grad, None, None, None, None, None
+
+
+def upnorm_pool(d, superpixels, superpixel_size, M, scale=4):
+    """q [M, 256] = superpixel mean-pool (sum / (count + 1e-6), pretrain_trainer.py:461-463) of
+    F.normalize(Upsample(scale, bilinear, align_corners=True)(d), dim=1) (image_model.py:121-124,139-141) without ever
+    materialising the full-resolution map.  d: [B, 256, h, w]; superpixels: int64 [B, h * scale, w * scale]."""
+    _lib.require_cuda(d, superpixels)
+    B, C, h, w = d.shape
+    H, W = h * scale, w * scale
+    if tuple(superpixels.shape) != (B, H, W) or superpixels.dtype != torch.int64:
+        raise ValueError("upnorm_pool: superpixels must be int64 [B, h * scale, w * scale]")
+    pooled, counts = _UpNormPool.apply(d, superpixels, int(superpixel_size), int(M), H, W)
+    return pooled / (counts[:, None] + 1e-6)

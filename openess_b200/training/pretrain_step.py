@@ -90,7 +90,9 @@ class OpenESSPretrainStep:
         frame = batch[2].to(self.device)
         pl = batch[3].to(self.device)
         superpixels = batch[4].to(self.device) if self.if_spatial_contrastive else None
-        feat_frame = self.models_dict["model_frame"](frame)
+        model_frame = self.models_dict["model_frame"]
+        fused_q = self.if_spatial_contrastive and frame.is_cuda and hasattr(model_frame, "forward_pooled")
+        feat_frame = None if fused_q else model_frame(frame)                                 # :434
         self.reconstructor.last_states_for_each_channel = {"grayscale": None}
         C = self.input_channels_b
         for i in range(self.nr_events_data_b):
@@ -98,8 +100,11 @@ class OpenESSPretrainStep:
         loss_dense, pred, k = self.trainTaskStepPretrain(latent_real, pl, superpixels, losses)
         if self.if_spatial_contrastive:
             M = k.shape[0]
-            q = superpixel_pool(feat_frame, superpixels, self.superpixel_size, M)       # :461-463
-            loss_nce = self.nce_loss(k, q)                                              # :467
+            if fused_q:                                                                      # :434 + :461-463 in one pass
+                q = model_frame.forward_pooled(frame, superpixels, self.superpixel_size, M)
+            else:
+                q = superpixel_pool(feat_frame, superpixels, self.superpixel_size, M)       # :461-463
+            loss_nce = self.nce_loss(k, q)                                                  # :467
             losses["contrastive_nce_loss"] = loss_nce.detach()
             t_loss = t_loss + loss_nce
         if self.if_dense_clip_supervision:

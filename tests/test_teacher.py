@@ -116,3 +116,30 @@ def test_batchnorm_nhwc_vs_torch(C, training, res, relu):
     torch.testing.assert_close(bn.running_mean, bn_ref.running_mean, atol=1e-6, rtol=1e-5)
     torch.testing.assert_close(bn.running_var, bn_ref.running_var, atol=1e-6, rtol=1e-5)
     assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,h,w,S", [(2, 11, 16, 12), (1, 5, 9, 7)])
+def test_upnorm_pool_fused_vs_torch_formulation(B, h, w, S):
+    """oess_upnorm_pool (fwd + bwd) against Upsample(x4, bilinear, align_corners=True) + F.normalize + the one-hot
+    sparse pooling of pretrain_trainer.py:446-463, in float64."""
+    import torch.nn.functional as F
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(h * 31 + w)
+    C, H, W = 256, 4 * h, 4 * w
+    d = torch.randn(B, C, h, w, generator=g).cuda().requires_grad_(True)
+    sp = torch.randint(0, S, (B, H, W), generator=g).cuda()
+    sp[:, :, : W // 2] = sp[:, :1, :1]                       # long runs of one id (the register-accumulation path)
+    M = B * S
+    q = ops.upnorm_pool(d, sp, S, M)
+    wgt = torch.randn(M, C, generator=g).cuda()
+    (q * wgt).sum().backward()
+    dd = d.detach().double().requires_grad_(True)
+    feat = F.normalize(F.interpolate(dd, scale_factor=4, mode="bilinear", align_corners=True), p=2, dim=1)
+    ids = (torch.arange(0, B * S, S, device=sp.device)[:, None, None] + sp).flatten()
+    onehot = torch.zeros(M, ids.numel(), dtype=torch.float64, device=sp.device)
+    onehot[ids, torch.arange(ids.numel(), device=sp.device)] = 1
+    qr = (onehot @ feat.permute(0, 2, 3, 1).flatten(0, 2)) / (onehot.sum(1, keepdim=True) + 1e-6)
+    (qr * wgt.double()).sum().backward()
+    torch.testing.assert_close(q.double(), qr, atol=2e-5, rtol=2e-5)
+    torch.testing.assert_close(d.grad.double(), dd.grad, atol=2e-4 * float(dd.grad.abs().max()), rtol=1e-3)
