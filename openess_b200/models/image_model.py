@@ -24,6 +24,7 @@ import torch.nn.functional as F
 from torchvision.models.resnet import Bottleneck, ResNet
 
 from .. import ops as _tc
+from . import _tc_resnet as _tcr
 
 USE_TENSOR_CORES = os.environ.get("OESS_TEACHER_TC", "1") != "0"
 
@@ -35,7 +36,7 @@ class ResNetEncoder(ResNet):
         super().__init__(**kwargs)
         del self.fc
         del self.avgpool
-        self._packed = {}
+        self._cache = _tcr.PackedConvCache()
 
     def load_state_dict(self, state_dict, **kwargs):
         state_dict.pop("fc.bias", None)
@@ -48,51 +49,13 @@ class ResNetEncoder(ResNet):
         x = self.layer1(self.maxpool(x))
         return self.layer4(self.layer3(self.layer2(x)))
 
-    # ---- tensor-core formulation ----
-    def _w(self, conv, bn):
-        """Packed weights of `conv`; in eval mode with BN folded in (w * g / sqrt(var + eps), beta - mean * g / sqrt(..))."""
-        fold = not bn.training
-        key = (id(conv), fold)
-        ver = (conv.weight.data_ptr(), conv.weight._version, conv.weight.device,
-               (bn.running_var._version, bn.weight._version, bn.bias._version) if fold else None)
-        hit = self._packed.get(key)
-        if hit is None or hit[0] != ver:
-            w, b = conv.weight.detach(), None
-            if fold:
-                scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
-                w = w * scale[:, None, None, None]
-                b = (bn.bias.detach() - bn.running_mean * scale).float().contiguous()
-            hit = (ver, _tc.conv2d_pack(w), b)
-            self._packed[key] = hit
-        return hit[1], hit[2]
-
-    def _conv_bn(self, x, conv, bn, relu, residual=None):
-        wp, b = self._w(conv, bn)
-        k, s, p, d = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
-        if not bn.training:                                   # folded: everything in the conv epilogue
-            return _tc.conv2d_tc(x, wp, b, k, s, p, d, relu=relu, residual=residual)
-        y = _tc.conv2d_tc(x, wp, None, k, s, p, d)
-        return _tc.batchnorm_nhwc_(y, bn, residual=residual, relu=relu)
-
-    def _bottleneck(self, blk, x):
-        out = self._conv_bn(x, blk.conv1, blk.bn1, True)
-        out = self._conv_bn(out, blk.conv2, blk.bn2, True)
-        identity = x
-        if blk.downsample is not None:
-            identity = self._conv_bn(x, blk.downsample[0], blk.downsample[1], False)
-        return self._conv_bn(out, blk.conv3, blk.bn3, True, residual=identity)     # relu(bn3(conv3) + identity)
-
+    # ---- tensor-core formulation (models/_tc_resnet.py) ----
     def forward_tc(self, x):
-        x = self.relu(self.bn1(self.conv1(x)))               # stem: torch (Cin = 3)
-        x = self.maxpool(x).contiguous(memory_format=torch.channels_last)
-        for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
-            for blk in layer:
-                x = self._bottleneck(blk, x)
-        return x
+        return _tcr.resnet_stages(self._cache, self, x)
 
     def forward(self, x):
         tc_ok = (USE_TENSOR_CORES and x.is_cuda and not x.requires_grad and x.dtype == torch.float32
-                 and not any(p.requires_grad for p in self.layer1[0].parameters()))
+                 and _tcr.frozen(self))
         if tc_ok:
             with torch.no_grad():
                 return self.forward_tc(x)

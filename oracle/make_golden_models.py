@@ -170,8 +170,44 @@ def golden_teacher():
     print("teacher_r50.npz", os.path.getsize(os.path.join(OUT, "teacher_r50.npz")) // 1024, "KiB")
 
 
+def golden_deeplab():
+    """models/deeplabv3.py:deeplabv3_resnet50 (reference class, unmodified) as BASELINE config 4 builds it: K = 11,
+    yaml output_stride 32 (-> effective 16), if_finetuning + frozen_backbone.  Train-mode forward (batch-stat BN, Dropout
+    disabled for determinism by p = 0) + head gradients, and eval-mode forward.  41 M weights from tests/seeded_weights.py."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+    from seeded_weights import seeded_state_dict
+    sys.modules.setdefault("models", types.ModuleType("models")).__path__ = [os.path.join(REF, "models")]
+    from models.deeplabv3 import deeplabv3_resnet50
+    m = deeplabv3_resnet50(num_classes=11, text_embeddings_path=None, output_stride=32, pretrained_backbone='',
+                           if_finetuning=True, frozen_backbone=True)
+    sd0 = seeded_state_dict(m, 4)
+    m.load_state_dict(sd0, strict=True)
+    m.classifier.ASPP.project[3].p = 0.0                   # Dropout(0.1) is random: disabled in the golden AND the test
+    rng = np.random.default_rng(8)
+    x = rng.random((2, 3, 64, 96)).astype(np.float32)
+    out = {"seed": np.array(4), "x": x, "nkeys": np.array(len(sd0)), "nparams": np.array(sum(p.numel() for p in m.parameters()))}
+    m.eval()
+    with torch.no_grad():
+        le, fe = m(torch.from_numpy(x))
+    out["eval_logits_sub"], out["eval_feats_sub"] = le[:, :, ::2, ::2].numpy(), fe[:, ::8, ::4, ::4].numpy()
+    m.train()
+    lt, ft = m(torch.from_numpy(x))
+    (lt.square().mean() + ft.square().mean()).backward()
+    out["train_logits_sub"], out["train_feats_sub"] = lt.detach()[:, :, ::2, ::2].numpy(), ft.detach()[:, ::8, ::4, ::4].numpy()
+    out["grad_text"] = m.classifier.text_embeddings.grad.numpy()
+    out["grad_proj_sub"] = m.classifier.ASPP.project[0].weight.grad[::4, ::16, 0, 0].numpy()
+    out["rm_l4"] = m.state_dict()["backbone.layer4.2.bn3.running_mean"].numpy()
+    out["backbone_has_grad"] = np.array(any(p.grad is not None for p in m.backbone.parameters()))
+    np.savez_compressed(os.path.join(OUT, "deeplab_r50.npz"), **out)
+    print("deeplab_r50.npz", os.path.getsize(os.path.join(OUT, "deeplab_r50.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    if "--teacher" in sys.argv:
+    if "--deeplab" in sys.argv:
+        sys.path.insert(0, REF)
+        torch.set_num_threads(4)
+        golden_deeplab()
+    elif "--teacher" in sys.argv:
         sys.path.insert(0, REF)
         torch.set_num_threads(4)
         golden_teacher()
