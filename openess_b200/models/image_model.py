@@ -62,6 +62,30 @@ class ResNetEncoder(ResNet):
         return self.forward_torch(x)
 
 
+def adapt_weights(architecture):
+    """models/image_model.py:26-74 for weight files already on disk (`weights/<architecture>.pt`): same key rewriting per
+    source (moco / swav / deepcluster / dino / pixpro / obow).  The reference additionally downloads a missing file with
+    `requests` (:38-44): network ingest is out of scope -- a missing file raises FileNotFoundError here."""
+    if architecture == "imagenet" or architecture is None:
+        return None
+    path = f"weights/{architecture}.pt"
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path} not found: place the teacher weights there (the reference downloads them at "
+                                "run time, models/image_model.py:38-44)")
+    weights = torch.load(path, map_location="cpu")
+    if architecture == "obow":
+        return weights["network"]
+    if architecture == "pixpro":
+        return {k.replace("module.encoder.", ""): v for k, v in weights["model"].items() if k.startswith("module.encoder.")}
+    if architecture in ("moco_v1", "moco_v2", "moco_coco"):
+        return {k.replace("module.encoder_q.", ""): v for k, v in weights["state_dict"].items()
+                if k.startswith("module.encoder_q.") and not k.startswith("module.encoder_q.fc")}
+    if architecture in ("swav", "deepcluster_v2"):
+        return {k.replace("module.", ""): v for k, v in weights.items()
+                if k.startswith("module.") and not k.startswith("module.pro")}
+    return weights                                            # dino
+
+
 class DilationFeatureExtractor(nn.Module):
     """models/image_model.py:90-143.  `image_weights`: None or a state_dict for the encoder (the reference downloads
     dino / moco / swav weights with `requests`, image_model.py:38-44 -- out of scope offline; pass the adapted dict)."""
@@ -72,9 +96,14 @@ class DilationFeatureExtractor(nn.Module):
                                      replace_stride_with_dilation=[True, True, True])
         if isinstance(image_weights, dict):
             self.encoder.load_state_dict(dict(image_weights))
-        elif image_weights is not None:
-            raise NotImplementedError("named teacher weights are downloaded by the reference at run time; load the "
-                                      "adapted state_dict and pass it as `image_weights`")
+        elif image_weights == 'imagenet':
+            raise FileNotFoundError("image_weights='imagenet' downloads torchvision's checkpoint in the reference "
+                                    "(image_model.py:107-108): load it yourself and pass the state_dict")
+        else:
+            weights = adapt_weights(image_weights)             # :110-113
+            if weights is not None:
+                self.encoder.load_state_dict(weights)
+                print("Loaded '{}' weights for the teacher network~".format(image_weights))
         for param in self.encoder.parameters():
             param.requires_grad = False
         self.decoder = nn.Sequential(nn.Conv2d(2048, 256, 1),

@@ -70,5 +70,24 @@ def patch_reference(ref_root, voxel_mode=None):
         rebind(iu, ["EventPreprocessor"], b_iu)
     except Exception as e:  # pragma: no cover - depends on the reference's optional imports
         done["e2vid.utils.inference_utils.EventPreprocessor"] = e
+    # model mirrors (state_dict-compatible; tensor-core forward paths).  These reference modules import their
+    # environment's optional packages (mmcv via models/__init__.py, cv2, ...): rebinding is best effort per module.
+    def try_rebind(ref_name, rel, names, src_mod):
+        try:
+            src = __import__(src_mod, fromlist=["_"])
+            mod = _load(ref_root, ref_name, rel)
+            rebind(mod, names, src)
+        except Exception as e:  # pragma: no cover - depends on the reference's optional imports
+            for n in names:
+                done[f"{ref_name}.{n}"] = e
+
+    try_rebind("models.style_networks", "models/style_networks.py", ["SemSegE2VID"], "openess_b200.models.style_networks")
+    try_rebind("models.image_model", "models/image_model.py", ["DilationFeatureExtractor"], "openess_b200.models.image_model")
+    try_rebind("models.deeplabv3", "models/deeplabv3.py", ["deeplabv3_resnet50"], "openess_b200.models.deeplabv3")
+    # e2vid.utils.loading_utils.load_model does `from e2vid.model.model import *` + eval(arch)(config): rebinding the class
+    # in e2vid.model.model makes the reference's own checkpoint loader build the mirror (same state_dict keys).
+    try_rebind("e2vid.model.model", "e2vid/model/model.py", ["E2VIDRecurrent"], "openess_b200.e2vid.model.model")
+    try_rebind("e2vid.image_reconstructor", "e2vid/image_reconstructor.py", ["ImageReconstructor"],
+               "openess_b200.e2vid.image_reconstructor")
     _PATCHED.update(done)
     return done
