@@ -164,6 +164,11 @@ int oess_dice_ce_bwd(const float* logits, const int64_t* target, int B, int K, i
 int oess_confusion(const int64_t* pred, const int64_t* gt, int64_t n, int K, int64_t ignore_label,
                    int64_t* conf, int32_t* status, oess_stream_t stream);
 
+/* Validation loop fused: training/base_trainer_ov.py:463-466 `pred = logits.argmax(dim=1)` +
+ * evaluation/metrics.py:4-23 in one pass over logits [B, K, H, W] (K <= 64); conf ACCUMULATES like oess_confusion. */
+int oess_argmax_confusion(const float* logits, const int64_t* gt, int B, int K, int H, int W, int64_t ignore_label,
+                          int64_t* conf, int32_t* status, oess_stream_t stream);
+
 /* Replaces the pointwise tail of e2vid/model/submodules.py:197-214 (ConvLSTM.forward after the Gates conv):
  * gates [B, 4C, H, W] = (in, remember, out, cell) chunks, prev_cell [B, C, H, W] or NULL (zero state):
  *   cell = sigmoid(remember) * prev_cell + sigmoid(in) * tanh(cell_gate);  hidden = sigmoid(out) * tanh(cell).

@@ -47,6 +47,7 @@ SIGNATURES = {
     "oess_dice_ce_finish": [_vp, _int, _f32, _f32, _vp, _vp],
     "oess_dice_ce_bwd": [_vp, _vp, _int, _int, _int, _int, _i64, _vp, _f32, _f32, _vp, _vp, _vp],
     "oess_confusion": [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp],
+    "oess_argmax_confusion": [_vp, _vp, _int, _int, _int, _int, _i64, _vp, _vp, _vp],
     "oess_convlstm_gates": [_vp, _vp, _vp, _vp, _int, _int, _i64, _vp],
     "oess_l1_mean": [_vp, _vp, _i64, _vp, _vp, _vp],
     "oess_l1_mean_bwd": [_vp, _vp, _i64, _vp, _vp, _vp, _vp],

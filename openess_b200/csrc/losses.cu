@@ -40,6 +40,37 @@ k_confusion(const int64_t* __restrict__ pred, const int64_t* __restrict__ gt, in
     }
 }
 
+// Validation loop fused: argmax over the K logits of a pixel + confusion update in one pass; the int64
+// prediction map of base_trainer_ov.py:463-466 (`pred.argmax(dim=1)`) is never materialised.  torch.argmax semantics:
+// first index of the maximum, NaN counts as the maximum.
+__global__ void __launch_bounds__(256)
+k_argmax_confusion(const float* __restrict__ logits, const int64_t* __restrict__ gt, int B, int K, int64_t HW,
+                   int64_t ignore, unsigned long long* __restrict__ conf, int32_t* __restrict__ status) {
+    __shared__ unsigned int s_bins[kConfSmemBins];
+    const int KK = K * K;
+    for (int i = threadIdx.x; i < KK; i += blockDim.x) s_bins[i] = 0;
+    __syncthreads();
+    const int64_t total = (int64_t)B * HW;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t g = __ldcs(gt + i);
+        if (g == ignore) continue;
+        if (g < 0 || g >= K) { if (status) *status = 1; continue; }
+        const int64_t b = i / HW, px = i - b * HW;
+        const float* lp = logits + (b * K) * HW + px;
+        float best = __ldcs(lp);
+        int arg = 0;
+        for (int c = 1; c < K; ++c) {
+            const float v = __ldcs(lp + (int64_t)c * HW);
+            if ((v > best && best == best) || (v != v && best == best)) { best = v; arg = c; }
+        }
+        atomicAdd(&s_bins[(int)g * K + arg], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < KK; i += blockDim.x)
+        if (s_bins[i]) atomicAdd(&conf[i], (unsigned long long)s_bins[i]);
+}
+
 // =============================================================================================
 // a17 Dice + CE.  One pass over the logits (4*K + 8 B / pixel), per-thread register partials,
 // block reduction in float64, one atomicAdd(double) per class per CTA.
@@ -343,6 +374,19 @@ OESS_API int oess_confusion(const int64_t* pred, const int64_t* gt, int64_t n, i
     int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     OESS_KERNEL("k_confusion", st, k_confusion<<<(unsigned)blocks, 256, 0, st>>>(pred, gt, n, K, ignore_label, (unsigned long long*)conf, status));
+    return OESS_OK;
+}
+
+OESS_API int oess_argmax_confusion(const float* logits, const int64_t* gt, int B, int K, int H, int W, int64_t ignore_label,
+                                   int64_t* conf, int32_t* status, oess_stream_t stream) {
+    if (B <= 0 || K <= 0 || K > 64 || H <= 0 || W <= 0 || !logits || !gt || !conf) return OESS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (status) OESS_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    const int64_t n = (int64_t)B * H * W;
+    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+    OESS_KERNEL("k_argmax_confusion", st, k_argmax_confusion<<<(unsigned)blocks, 256, 0, st>>>(
+        logits, gt, B, K, (int64_t)H * W, ignore_label, (unsigned long long*)conf, status));
     return OESS_OK;
 }
 

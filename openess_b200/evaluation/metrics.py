@@ -58,7 +58,20 @@ class MetricsSemseg:
             else:
                 self.metrics_acc += metrics_batch
 
+    def update_batch_logits(self, logits, y_lbl):
+        """Fused validation step: `update_batch(logits.argmax(dim=1), y_lbl)` of base_trainer_ov.py:463-471
+        in one kernel, accumulated on the DEVICE (no per-batch .cpu() round trip); get_metrics_summary() is unchanged."""
+        with torch.no_grad():
+            if self.metrics_acc is None or not self.metrics_acc.is_cuda:
+                prev = self.metrics_acc
+                self.metrics_acc = torch.zeros((self.num_classes, self.num_classes), dtype=torch.int64, device=logits.device)
+                if prev is not None:
+                    self.metrics_acc += prev.to(logits.device)
+            _losses.argmax_confusion(logits, y_lbl.to(logits.device), self.ignore_label, out=self.metrics_acc)
+
     def get_metrics_summary(self):
+        if self.metrics_acc is not None and self.metrics_acc.is_cuda:
+            self.metrics_acc = self.metrics_acc.cpu()       # the float64 summary is computed on the host, like the reference
         iou_mean, iou_per_class = semseg_accum_confusion_to_iou(self.metrics_acc)
         out = {self.class_names[i]: iou for i, iou in enumerate(iou_per_class)}
         out['miou'] = iou_mean

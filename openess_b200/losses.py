@@ -180,6 +180,23 @@ def confusion(pred, gt, num_classes, ignore_label, out=None, status=None):
     return out
 
 
+def argmax_confusion(logits, gt, ignore_label, out=None, status=None):
+    """base_trainer_ov.py:463-466 + metrics.py:4-23 fused: conf[gt, argmax_c logits] += 1 over gt != ignore, without
+    materialising the prediction map.  logits [B, K, H, W] float32, gt int64 [B, H, W]; accumulates into `out`."""
+    require_cuda(logits, gt)
+    logits = _f32c(logits)
+    gt = gt.to(torch.int64).contiguous()
+    B, K, H, W = logits.shape
+    if gt.numel() != B * H * W:
+        raise ValueError("gt must have B*H*W elements")
+    if out is None:
+        out = torch.zeros((K, K), dtype=torch.int64, device=logits.device)
+    with torch.cuda.device(logits.device):
+        check(lib().oess_argmax_confusion(ptr(logits), ptr(gt), B, K, H, W, int(ignore_label), ptr(out), ptr(status),
+                                          stream_ptr(logits.device)), "oess_argmax_confusion")
+    return out
+
+
 # ------------------------------------------------------------------------------------------ consistency losses
 class _L1Mean(torch.autograd.Function):
     @staticmethod

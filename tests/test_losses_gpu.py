@@ -184,3 +184,29 @@ def test_event_preprocessor_matches_oracle(dev, oracle):
     np.testing.assert_allclose(pre(xin).cpu().numpy(), out.cpu().numpy(), rtol=0, atol=0)
     z = torch.zeros(1, 5, 8, 8, device=dev)
     assert not pre(z).any()                                          # num_nonzeros == 0 -> unchanged
+
+
+@pytest.mark.gpu
+def test_argmax_confusion_fused_vs_oracle_and_metrics(dev, oracle):
+    """Fused validation step: argmax + confusion in one pass == oracle.confusion(argmax(logits), gt),
+    integer exact, including ties (first maximum wins, like torch.argmax / np.argmax) and ignore pixels."""
+    from openess_b200 import losses
+    from openess_b200.evaluation.metrics import MetricsSemseg
+    rng = np.random.default_rng(9)
+    B, K, H, W = 3, 11, 88, 128
+    logits = rng.normal(0, 1, (B, K, H, W)).astype(np.float32)
+    logits[:, 3] = np.where(rng.random((B, H, W)) < 0.2, logits[:, 7], logits[:, 3])      # exact ties between classes 3 and 7
+    gt = rng.integers(0, K, (B, H, W)).astype(np.int64)
+    gt[rng.random(gt.shape) < 0.1] = 255
+    ref = oracle.confusion(np.argmax(logits, 1).astype(np.int64), gt, K, 255)
+    lg, g = torch.from_numpy(logits).to(dev), torch.from_numpy(gt).to(dev)
+    conf = losses.argmax_confusion(lg, g, 255)
+    assert np.array_equal(conf.cpu().numpy(), ref)
+    names = [str(i) for i in range(K)]
+    m1, m2 = MetricsSemseg(K, 255, names), MetricsSemseg(K, 255, names)
+    for _ in range(2):
+        m1.update_batch(lg.argmax(dim=1), g)                   # reference call sequence (base_trainer_ov.py:463-471)
+        m2.update_batch_logits(lg, g)                          # fused, accumulated on the device
+    s1, s2 = m1.get_metrics_summary(), m2.get_metrics_summary()
+    assert np.array_equal(s1['cm'].cpu().numpy(), s2['cm'].cpu().numpy()) and np.array_equal(s2['cm'].cpu().numpy(), 2 * ref)
+    assert float(s1['miou']) == float(s2['miou']) and float(s1['acc']) == float(s2['acc'])
