@@ -236,6 +236,16 @@ int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bi
                           int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                           int relu, oess_stream_t stream);
 
+/* oess_conv2d_nhwc_tf32 that additionally accumulates the BatchNorm batch statistics of its RAW output in the epilogue
+ * (bn_sums[0..Cout) = sum over rows of y, bn_sums[Cout..2 Cout) = sum of y^2; device doubles, zeroed inside), and the
+ * train-mode BatchNorm that consumes them (ws = the same buffer: its first 2 C doubles are bn_sums). */
+int oess_conv2d_nhwc_tf32_stats(const float* x, const float* w_packed, const float* bias, float* y, int B, int H, int W,
+                                int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, double* bn_sums,
+                                oess_stream_t stream);
+int oess_batchnorm_nhwc_sums(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, float eps, float momentum, const float* residual, int relu, void* ws,
+                             size_t ws_bytes, oess_stream_t stream);
+
 /* BatchNorm2d (torch.nn.BatchNorm2d semantics) over channels-last rows x [R = B*H*W, C], IN PLACE, with optional residual
  * add and ReLU: the normalisation between the teacher's tensor-core convolutions.  The OpenESS trainers call `.train()`
  * on the frozen ResNet-50 teacher every step (training/pretrain_trainer.py:370-371; models/image_model.py:116-117), so

@@ -60,6 +60,8 @@ SIGNATURES = {
     "oess_convlstm_step_nhwc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp],
     "oess_upnorm_pool_fwd": [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _i64, _vp, _vp, _vp, _vp],
     "oess_upnorm_pool_bwd": [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _i64, _vp, _vp],
+    "oess_conv2d_nhwc_tf32_stats": [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _vp],
+    "oess_batchnorm_nhwc_sums": [_vp, _i64, _int, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _int, _vp, _sz, _vp],
     "oess_bn_ws_bytes": [_int, ctypes.POINTER(_sz)],
     "oess_batchnorm_nhwc": [_vp, _i64, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _vp, _int, _vp, _sz, _vp],
     "oess_conv2d_nhwc_tf32": [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _vp],

@@ -116,9 +116,9 @@ OESS_API int oess_bn_ws_bytes(int C, size_t* ws_bytes) {
     return OESS_OK;
 }
 
-OESS_API int oess_batchnorm_nhwc(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
-                                 float* running_var, float eps, float momentum, int training, const float* residual,
-                                 int relu, void* ws, size_t ws_bytes, oess_stream_t stream) {
+static int batchnorm_impl(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
+                          float* running_var, float eps, float momentum, int training, const float* residual,
+                          int relu, void* ws, size_t ws_bytes, int have_sums, oess_stream_t stream) {
     size_t need = 0;
     if (oess_bn_ws_bytes(C, &need)) return OESS_E_ARG;
     if (!x || R < 0 || (C & 3)) return OESS_E_ARG;
@@ -132,7 +132,7 @@ OESS_API int oess_batchnorm_nhwc(float* x, int64_t R, int C, const float* gamma,
     double* sums = (double*)ws;
     float* scale = (float*)((char*)ws + align_up(sizeof(double) * 2 * (size_t)C, 256));
     float* shift = scale + C;
-    if (training) {
+    if (training && !have_sums) {
         OESS_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * (size_t)C, st));
         const int qpb = C4 < 256 ? C4 : 256;
         const int lanes = 256 / qpb;
@@ -148,4 +148,20 @@ OESS_API int oess_batchnorm_nhwc(float* x, int64_t R, int C, const float* gamma,
     const unsigned blocks = (unsigned)((total4 + 255) / 256 < (int64_t)kNumSMs * 16 ? (total4 + 255) / 256 : (int64_t)kNumSMs * 16);
     OESS_KERNEL("bn_apply", st, k_bn_apply<<<blocks, 256, 0, st>>>(x, scale, shift, residual, total4, C4, relu ? 1 : 0));
     return OESS_OK;
+}
+
+OESS_API int oess_batchnorm_nhwc(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
+                                 float* running_var, float eps, float momentum, int training, const float* residual,
+                                 int relu, void* ws, size_t ws_bytes, oess_stream_t stream) {
+    return batchnorm_impl(x, R, C, gamma, beta, running_mean, running_var, eps, momentum, training, residual, relu, ws,
+                          ws_bytes, 0, stream);
+}
+
+// Train-mode variant whose per-channel sums were already accumulated into the first 2 C doubles of `ws` by
+// oess_conv2d_nhwc_tf32_stats (the statistics pass fused into the producing convolution's epilogue).
+OESS_API int oess_batchnorm_nhwc_sums(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
+                                      float* running_var, float eps, float momentum, const float* residual, int relu,
+                                      void* ws, size_t ws_bytes, oess_stream_t stream) {
+    return batchnorm_impl(x, R, C, gamma, beta, running_mean, running_var, eps, momentum, 1, residual, relu, ws, ws_bytes,
+                          1, stream);
 }

@@ -22,7 +22,8 @@ template <int BN>
 struct ConvSmem {
     static constexpr int kBBytes = BN * kBlockK * 4;
     static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
-    static constexpr int kBytes = 1024 + kStages * (kVABytes + kBBytes) + 256;
+    static constexpr int kStatBytes = 2 * 4 * BN * 4;      // per epilogue warp: column sums and sums of squares
+    static constexpr int kBytes = 1024 + kStages * (kVABytes + kBBytes) + 256 + kStatBytes;
 };
 
 struct ConvArgs {
@@ -32,7 +33,7 @@ struct ConvArgs {
 template <int BN>
 __global__ void __launch_bounds__(192, 2)
 k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
-          const float* __restrict__ residual, float* __restrict__ y, const ConvArgs a) {
+          const float* __restrict__ residual, float* __restrict__ y, double* __restrict__ bn_sums, const ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
     using S = ConvSmem<BN>;
     constexpr int kVStages = S::kStages;
@@ -43,6 +44,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
     uint64_t* empty = full + kVStages;
     uint64_t* acc_full = empty + kVStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    float* s_stat = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [2][4 warps][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int th = blockIdx.x / a.tiles_w, tw = blockIdx.x - th * a.tiles_w;
@@ -112,6 +114,34 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
             tmem_ld16_nowait(trow + c0, v);
             tmem_ld_wait();
             const int col = n0 + c0;
+            if (bn_sums) {
+                // BatchNorm batch statistics of the raw conv output, fused: per-column sum / sum of squares over the
+                // warp's 32 rows by recursive halving (16 shuffles each), staged per warp in shared memory.
+                float s8[16], q8[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const float t = valid ? v[j] : 0.f; s8[j] = t; q8[j] = t * t; }
+#pragma unroll
+                for (int step = 0; step < 4; ++step) {                 // xor 16, 8, 4, 2: keep half of the columns
+                    const int m = 16 >> step, half = 8 >> step;
+                    const bool up = (lane & m) != 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < half) {
+                            const float send_s = up ? s8[j] : s8[j + half], send_q = up ? q8[j] : q8[j + half];
+                            const float keep_s = up ? s8[j + half] : s8[j], keep_q = up ? q8[j + half] : q8[j];
+                            s8[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, m);
+                            q8[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, m);
+                        }
+                    }
+                }
+                s8[0] += __shfl_xor_sync(0xffffffffu, s8[0], 1);
+                q8[0] += __shfl_xor_sync(0xffffffffu, q8[0], 1);
+                if ((lane & 1) == 0) {
+                    const int cj = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    s_stat[q * BN + c0 + cj] = s8[0];
+                    s_stat[(4 + q) * BN + c0 + cj] = q8[0];
+                }
+            }
             if (!valid || col >= a.Cout) continue;
             if (vec && col + 16 <= a.Cout) {
 #pragma unroll
@@ -138,6 +168,17 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                 }
             }
         }
+        if (bn_sums) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");             // the four epilogue warps only
+            for (int c = (int)threadIdx.x - 64; c < BN; c += 128) {
+                if (n0 + c < a.Cout) {
+                    const float ts = s_stat[c] + s_stat[BN + c] + s_stat[2 * BN + c] + s_stat[3 * BN + c];
+                    const float tq = s_stat[4 * BN + c] + s_stat[5 * BN + c] + s_stat[6 * BN + c] + s_stat[7 * BN + c];
+                    atomicAdd(&bn_sums[n0 + c], (double)ts);
+                    atomicAdd(&bn_sums[a.Cout + n0 + c], (double)tq);
+                }
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -146,7 +187,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
 
 template <int BN>
 static int launch_conv(const CUtensorMap& tmX, const float* w_packed, int Cout, int Ktot, const float* bias,
-                       const float* residual, float* y, const ConvArgs& a, int B, cudaStream_t st) {
+                       const float* residual, float* y, double* bn_sums, const ConvArgs& a, int B, cudaStream_t st) {
     CUtensorMap tmW;
     const uint64_t dW[2] = {(uint64_t)Ktot, (uint64_t)Cout}, sW[1] = {(uint64_t)Ktot * 4};
     const uint32_t bW[2] = {kBlockK, (uint32_t)BN};
@@ -156,7 +197,7 @@ static int launch_conv(const CUtensorMap& tmX, const float* w_packed, int Cout, 
     OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN>::kBytes));
     const int tiles_h = (a.Ho + kVH - 1) / kVH;
     const dim3 grid((unsigned)(a.tiles_w * tiles_h), (unsigned)((Cout + BN - 1) / BN), (unsigned)B);
-    OESS_KERNEL("tc_conv2d", st, kern<<<grid, 192, ConvSmem<BN>::kBytes, st>>>(tmX, tmW, bias, residual, y, a));
+    OESS_KERNEL("tc_conv2d", st, kern<<<grid, 192, ConvSmem<BN>::kBytes, st>>>(tmX, tmW, bias, residual, y, bn_sums, a));
     return 0;
 }
 
@@ -186,9 +227,9 @@ using namespace oess;
 
 // x: [B, H, W, Cin] channels-last; w_packed: [Cout, KH * KW * Cin_p] (Cin_p = Cin rounded up to 32, zero padded; column
 // (tap = ky * KW + kx, channel)); bias [Cout] or NULL; residual [B, Ho, Wo, Cout] or NULL; y: [B, Ho, Wo, Cout].
-OESS_API int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
-                                   int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
-                                   int relu, oess_stream_t stream) {
+static int conv2d_impl(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
+                       int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                       int relu, double* bn_sums, oess_stream_t stream) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || dil <= 0 || pad < 0)
         return OESS_E_ARG;
     if (!x || !w_packed || !y) return OESS_E_ARG;
@@ -209,7 +250,24 @@ OESS_API int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const 
     int rc = tc::make_tmap_f32_strided(&tmX, x, 4, dims, strides, box, estr);
     if (rc) return rc;
     tc::ConvArgs a{Ho, Wo, Cout, KW, KH * KW, chunks, stride, pad, dil, relu ? 1 : 0, (Wo + tc::kVW - 1) / tc::kVW};
-    if (Cout > 128) return tc::launch_conv<256>(tmX, w_packed, Cout, Ktot, bias, residual, y, a, B, st);
-    if (Cout > 64) return tc::launch_conv<128>(tmX, w_packed, Cout, Ktot, bias, residual, y, a, B, st);
-    return tc::launch_conv<64>(tmX, w_packed, Cout, Ktot, bias, residual, y, a, B, st);
+    if (bn_sums) OESS_CUDA(cudaMemsetAsync(bn_sums, 0, sizeof(double) * 2 * (size_t)Cout, st));
+    if (Cout > 128) return tc::launch_conv<256>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
+    if (Cout > 64) return tc::launch_conv<128>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
+    return tc::launch_conv<64>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
+}
+
+OESS_API int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
+                                   int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                   int relu, oess_stream_t stream) {
+    return conv2d_impl(x, w_packed, bias, residual, y, B, H, W, Cin, Cout, KH, KW, stride, pad, dil, relu, nullptr, stream);
+}
+
+// Same, additionally accumulating the BatchNorm batch statistics of y (the RAW conv output: pass residual = NULL,
+// relu = 0) into bn_sums[0..Cout) = sum_rows y, bn_sums[Cout..2 Cout) = sum_rows y^2 (zeroed here): the statistics pass
+// of oess_batchnorm_nhwc fused into the conv epilogue (feed the result to oess_batchnorm_nhwc_sums).
+OESS_API int oess_conv2d_nhwc_tf32_stats(const float* x, const float* w_packed, const float* bias, float* y, int B, int H,
+                                         int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                         double* bn_sums, oess_stream_t stream) {
+    if (!bn_sums) return OESS_E_ARG;
+    return conv2d_impl(x, w_packed, bias, nullptr, y, B, H, W, Cin, Cout, KH, KW, stride, pad, dil, 0, bn_sums, stream);
 }

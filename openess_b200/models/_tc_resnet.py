@@ -10,6 +10,9 @@ import torch
 from .. import ops as _tc
 
 
+FUSE_BN_STATS = True      # batch statistics accumulated in the conv epilogue instead of a separate pass
+
+
 class PackedConvCache:
     """Packed (and, in eval mode, BN-folded) weights per (conv, mode); rebuilt when parameters change or move."""
 
@@ -47,6 +50,8 @@ def conv_bn(cache, x, conv, bn, relu, residual=None):
     k, s, p, d = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
     if bn is None or not bn.training:
         return _tc.conv2d_tc(x, wp, b, k, s, p, d, relu=relu, residual=residual)
+    if FUSE_BN_STATS and bn.weight.numel() % 4 == 0:
+        return _tc.conv_bn_train(x, wp, b, k, s, p, d, bn, residual=residual, relu=relu)
     y = _tc.conv2d_tc(x, wp, b, k, s, p, d)
     return _tc.batchnorm_nhwc_(y, bn, residual=residual, relu=relu)
 

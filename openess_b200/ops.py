@@ -212,3 +212,35 @@ def upnorm_pool(d, superpixels, superpixel_size, M, scale=4):
         raise ValueError("upnorm_pool: superpixels must be int64 [B, h * scale, w * scale]")
     pooled, counts = _UpNormPool.apply(d, superpixels, int(superpixel_size), int(M), H, W)
     return pooled / (counts[:, None] + 1e-6)
+
+
+def conv_bn_train(x, w_packed, bias, kernel_size, stride, padding, dilation, bn, residual=None, relu=False):
+    """act(BatchNorm_train(conv(x)) + residual) with the batch statistics accumulated in the conv's TMEM epilogue
+    (oess_conv2d_nhwc_tf32_stats -> oess_batchnorm_nhwc_sums): one pass over the activation less than conv + BN."""
+    _lib.require_cuda(x, w_packed)
+    B, Cin, H, W = x.shape
+    KH = KW = int(kernel_size)
+    Cout = w_packed.shape[0]
+    cl = torch.channels_last
+    xc = x.float().contiguous(memory_format=cl)
+    Ho = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
+    Wo = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+    y = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=cl)
+    res = None if residual is None else residual.float().contiguous(memory_format=cl)
+    bc = None if bias is None else _f32c(bias)
+    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    track = bn.track_running_stats and bn.running_mean is not None
+    nb = ctypes.c_size_t(0)
+    check(lib().oess_bn_ws_bytes(Cout, ctypes.byref(nb)), "oess_bn_ws_bytes")
+    with torch.cuda.device(x.device):
+        ws = _lib.workspace(nb.value, x.device)
+        st = stream_ptr(x.device)
+        check(lib().oess_conv2d_nhwc_tf32_stats(ptr(xc), ptr(w_packed), ptr(bc), ptr(y), B, H, W, Cin, Cout, KH, KW, stride,
+                                                padding, dilation, ptr(ws), st), "oess_conv2d_nhwc_tf32_stats")
+        check(lib().oess_batchnorm_nhwc_sums(ptr(y), B * Ho * Wo, Cout, ptr(bn.weight), ptr(bn.bias),
+                                             ptr(bn.running_mean) if track else None, ptr(bn.running_var) if track else None,
+                                             float(bn.eps), mom, ptr(res), 1 if relu else 0, ptr(ws), ws.numel(), st),
+              "oess_batchnorm_nhwc_sums")
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+    return y

@@ -47,3 +47,29 @@ def test_conv2d_tc_exact_on_tf32_representable_inputs():
     ref = F.conv2d(x, w, b, stride=2, padding=2).clamp_min(0)
     y = ops.conv2d_tc(x.cuda(), ops.conv2d_pack(w.cuda()), b.cuda(), 5, 2, 2, 1, True)
     assert torch.equal(y.cpu(), ref)
+
+
+@pytest.mark.parametrize("C,Cout,H,W,k,s,p,d", [(64, 256, 22, 37, 1, 1, 0, 1), (64, 64, 19, 30, 3, 1, 2, 2), (128, 32, 17, 20, 3, 2, 1, 1)])
+def test_conv_bn_train_fused_stats_vs_torch(C, Cout, H, W, k, s, p, d):
+    """conv + train-mode BatchNorm with the batch statistics accumulated in the conv's TMEM epilogue, against torch
+    (fp64 conv on the CPU, then torch.nn.BatchNorm2d in train mode)."""
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(C + Cout)
+    x = torch.randn(2, C, H, W, generator=g)
+    w = torch.randn(Cout, C, k, k, generator=g) / (C * k * k) ** 0.5
+    bn_ref = torch.nn.BatchNorm2d(Cout).double()
+    with torch.no_grad():
+        bn_ref.weight.uniform_(0.5, 1.5)
+        bn_ref.bias.normal_(0, 0.3)
+    bn = torch.nn.BatchNorm2d(Cout)
+    bn.load_state_dict({k_: v.float() if v.is_floating_point() else v for k_, v in bn_ref.state_dict().items()})
+    bn = bn.cuda().train()
+    bn_ref.train()
+    r = torch.randn(2, Cout, (H + 2 * p - d * (k - 1) - 1) // s + 1, (W + 2 * p - d * (k - 1) - 1) // s + 1, generator=g)
+    with torch.no_grad():
+        ref = (bn_ref(F.conv2d(x.double(), w.double(), None, stride=s, padding=p, dilation=d)) + r.double()).relu()
+    y = ops.conv_bn_train(x.cuda(), ops.conv2d_pack(w.cuda()), None, k, s, p, d, bn, residual=r.cuda(), relu=True)
+    assert float((y.cpu().double() - ref).abs().max()) < 1e-2                      # TF32 conv, normalised to unit scale
+    torch.testing.assert_close(bn.running_mean.cpu().double(), bn_ref.running_mean, atol=2e-4, rtol=1e-3)
+    torch.testing.assert_close(bn.running_var.cpu().double(), bn_ref.running_var, atol=2e-4, rtol=2e-3)
+    assert int(bn.num_batches_tracked) == 1

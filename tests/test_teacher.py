@@ -41,7 +41,7 @@ def test_teacher_tensor_core_train_mode_vs_reference_golden():
     x = torch.from_numpy(z["x"]).cuda()
     with _lib.profile() as prof:
         feats = m.encoder(x)
-    assert prof.kernels["tc_conv2d"][0] == 52 and prof.kernels["bn_stats"][0] == 52 and prof.kernels["bn_apply"][0] == 52
+    assert prof.kernels["tc_conv2d"][0] == 52 and "bn_stats" not in prof.kernels and prof.kernels["bn_apply"][0] == 52
     err_f = np.abs(feats[:, ::16].cpu().numpy() - z["feats_sub"])
     # the noise class this has to stay in: torch's own default GPU arithmetic for the same network (cuDNN TF32
     # convolutions, what the reference's GPU run does) against the same CPU fp32 golden
