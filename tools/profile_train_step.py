@@ -1,3 +1,5 @@
+"""torch.profiler breakdown (top kernels by device time) of tools/bench_train_step.py -- used to find where the end-to-end
+pretraining step spends its time (profiles/README.md)."""
 import sys, os, json
 sys.argv = ["bench_train_step.py", "--batch", "4", "--steps", "2", "--warmup", "2"]
 import torch
