@@ -80,9 +80,9 @@ __device__ __forceinline__ void fold_commit(float* a, float w, bool ok, const Sl
         float wk = __shfl_down_sync(0xffffffffu, w, 1);
         if (S.cnt > 1) v = __fadd_rn(v, wk);
         if (S.maxcnt > 2) {
-#pragma unroll 2
+#pragma unroll 4
             for (int k = 2; k < S.maxcnt; ++k) {
-                wk = __shfl_down_sync(0xffffffffu, wk, 1);            // = w of lane + k
+                wk = __shfl_down_sync(0xffffffffu, w, k);
                 if (S.cnt > k) v = __fadd_rn(v, wk);
             }
         }
