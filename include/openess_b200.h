@@ -269,6 +269,13 @@ int oess_upnorm_pool_fwd(const float* d, const int64_t* seg, int B, int h, int w
 int oess_upnorm_pool_bwd(const float* d, const int64_t* seg, const float* g_sum, int B, int h, int w, int C, int H, int W,
                          int S, int64_t M, float* d_grad, oess_stream_t stream);
 
+/* x [B, C, HW] planes (NCHW) -> y [B, HW, Cp] channels-last, channels zero-padded to Cp (multiple of 4); stats != NULL
+ * (double[3] = sum, sum of squares, non-zero count of x, from oess_nonzero_standardize phase 1) additionally applies the
+ * EventPreprocessor normalisation of e2vid/utils/inference_utils.py:77-85 on the way.  Input transform in front of the
+ * tensor-core head convolution of E2VID (e2vid/model/unet.py:126-127: 5 event channels). */
+int oess_planes_to_nhwc_padded(const float* x, int B, int C, int64_t HW, const double* stats, int Cp, float* y,
+                               oess_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

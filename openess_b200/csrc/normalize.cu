@@ -85,10 +85,59 @@ k_apply(float* __restrict__ x, int64_t group_numel, const double* __restrict__ s
     }
 }
 
+// x [B, C, HW] planes -> y [B, HW, Cp] channels-last with the channels zero-padded to Cp (a multiple of 4), optionally
+// applying the EventPreprocessor normalisation (biased, inference_utils.py:77-85) from precomputed stats on the way:
+// the input transform in front of the tensor-core head convolution of E2VID (a 5-channel plane tensor is too thin for
+// a 16-byte-aligned TMA row).
+__global__ void __launch_bounds__(kThreads)
+k_to_nhwc_padded(const float* __restrict__ x, int C, int64_t HW, int64_t total, const double* __restrict__ stats, int Cp,
+                 float* __restrict__ y) {
+    bool norm = false;
+    float mean = 0.f, sd = 1.f;
+    if (stats) {
+        const double sum = stats[0], sumsq = stats[1], nnz = stats[2];
+        if (nnz > 0) {
+            const float fn = (float)nnz;
+            mean = __fdiv_rn((float)sum, fn);
+            sd = __fsqrt_rn(__fsub_rn(__fdiv_rn((float)sumsq, fn), __fmul_rn(mean, mean)));
+            norm = true;
+        }
+    }
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
+        const int64_t b = i / HW, px = i - b * HW;
+        const float* xp = x + b * C * HW + px;
+        float* yp = y + i * Cp;
+        for (int c0 = 0; c0 < Cp; c0 += 4) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j;
+                float t = (c < C) ? __ldcs(xp + (int64_t)c * HW) : 0.f;
+                if (norm && c < C) t = __fdiv_rn(__fmul_rn((t != 0.0f) ? 1.0f : 0.0f, __fsub_rn(t, mean)), sd);
+                v[j] = t;
+            }
+            *reinterpret_cast<float4*>(yp + c0) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
 }  // namespace norm
 }  // namespace oess
 
 using namespace oess;
+
+OESS_API int oess_planes_to_nhwc_padded(const float* x, int B, int C, int64_t HW, const double* stats, int Cp, float* y,
+                                        oess_stream_t stream) {
+    if (!x || !y || B <= 0 || C <= 0 || HW <= 0 || Cp < C || (Cp & 3) || ((uintptr_t)y & 15)) return OESS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = (int64_t)B * HW;
+    int64_t blocks = (total + norm::kThreads - 1) / norm::kThreads;
+    if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+    OESS_KERNEL("k_to_nhwc_padded", st, norm::k_to_nhwc_padded<<<(unsigned)blocks, norm::kThreads, 0, st>>>(
+        x, C, HW, total, stats, Cp, y));
+    return OESS_OK;
+}
 
 int launch_nonzero_standardize(float* x, int64_t group_numel, int n_groups, double* stats, int phase,
                                int unbiased, cudaStream_t st) {

@@ -17,8 +17,9 @@ What changes on the B200:
     hidden sizes of the real E2VID config (multiples of 64); `USE_TENSOR_CORES = False` (or OESS_E2VID_TC=0) keeps the
     strict-fp32 cuDNN + fused-gates path;
   * the strided 5x5 encoder convolutions (folded BN + ReLU fused in the epilogue) run on the same tensor-core
-    skeleton, `oess_conv2d_nhwc_tf32` (strided 4-D TMA boxes); only the 5-channel head conv (Cin = 5: too thin for a
-    128-byte TMA row, 1.5 % of the FLOPs) stays on cuDNN.
+    skeleton, `oess_conv2d_nhwc_tf32` (strided 4-D TMA boxes); the 5-channel head conv (Cin = 5: too thin for a
+    128-byte TMA row) goes through a repack to channels-last with zero-padded channels (`oess_planes_to_nhwc_padded`) and
+    the same kernel: the whole latent-only encoder runs on hand-written kernels.
 """
 import os
 
@@ -234,8 +235,28 @@ class UNetRecurrent(nn.Module):
     def _skip(self, a, b):
         return a + b if self.skip_type == 'sum' else torch.cat([a, b], dim=1)
 
+    def _head_tc(self, x):
+        """Head conv (Cin = num_bins = 5: too thin for a 16-byte TMA row) on the tensor cores: the input planes are
+        repacked to channels-last with the channels zero-padded to 8, the weights get matching zero channels."""
+        conv = self.head.conv2d
+        w, b = conv.weight, conv.bias
+        key = (w.data_ptr(), w._version, w.device)
+        if getattr(self, "_head_packed", None) is None or self._head_packed[0] != key:
+            wpad = torch.zeros(w.shape[0], 8, w.shape[2], w.shape[3], dtype=torch.float32, device=w.device)
+            wpad[:, :w.shape[1]] = w.detach()
+            self._head_packed = (key, _tc.conv2d_pack(wpad), None if b is None else b.detach().float().contiguous())
+        x8 = _tc.planes_to_nhwc_padded(x, 8)
+        return _tc.conv2d_tc(x8, self._head_packed[1], self._head_packed[2], conv.kernel_size[0], conv.stride[0],
+                             conv.padding[0], conv.dilation[0], relu=self.head.activation is not None)
+
     def forward(self, x, prev_states, latent_only=True):
-        x = self.head(x)
+        hc = self.head.conv2d
+        if (USE_TENSOR_CORES and x.is_cuda and not torch.is_grad_enabled() and self.head.norm is None
+                and hc.in_channels <= 8 and hc.out_channels % 4 == 0 and hc.out_channels >= 16
+                and self.head.activation in (None, torch.relu)):
+            x = self._head_tc(x)
+        else:
+            x = self.head(x)
         head = x
         if prev_states is None:
             prev_states = [None] * self.num_encoders

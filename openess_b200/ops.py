@@ -244,3 +244,16 @@ def conv_bn_train(x, w_packed, bias, kernel_size, stride, padding, dilation, bn,
         if track and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
     return y
+
+
+def planes_to_nhwc_padded(x, cp, stats=None):
+    """[B, C, H, W] contiguous planes -> [B, cp, H, W] CHANNELS-LAST tensor whose channels C..cp-1 are zero; `stats`
+    (float64 [3] from voxel.nonzero_standardize(phase=1)) applies the EventPreprocessor normalisation on the way."""
+    _lib.require_cuda(x)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    y = torch.empty((B, cp, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        check(lib().oess_planes_to_nhwc_padded(ptr(x), B, C, H * W, ptr(stats), cp, ptr(y), stream_ptr(x.device)),
+              "oess_planes_to_nhwc_padded")
+    return y

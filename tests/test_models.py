@@ -86,8 +86,9 @@ def test_e2vid_full_width_tensor_core_convlstm_vs_reference_golden():
             for li, (h, c) in enumerate(states):
                 np.testing.assert_allclose(c.cpu().numpy(), z[f"state__{li}__c"], atol=tol)
             errs[use_tc] = worst
-            for kern in ("tc_convlstm_step", "tc_conv2d"):    # 3 levels x 3 steps on the tensor cores, none otherwise
-                assert prof.kernels.get(kern, (0, 0.0))[0] == (9 if use_tc else 0), kern
+            # 3 levels x 3 steps of ConvLSTM and encoder convs + 3 head convs on the tensor cores, none otherwise
+            assert prof.kernels.get("tc_convlstm_step", (0, 0.0))[0] == (9 if use_tc else 0)
+            assert prof.kernels.get("tc_conv2d", (0, 0.0))[0] == (12 if use_tc else 0)
         finally:
             mm.USE_TENSOR_CORES = True
     print("max |latent error| fp32 path %.2e, tensor-core path %.2e" % (errs[False], errs[True]))
