@@ -132,6 +132,9 @@ def _dsec_events(rng, n, W, H, clustered=False):
     (1000, 33, 47, 5, False), (10000, 120, 160, 5, True), (100000, 480, 640, 5, False),
     (100000, 480, 640, 5, True), (5000, 40, 50, 7, False), (300, 9, 1025, 2, False),
     (3000, 1030, 12, 5, False), (3000, 1030, 12, 3, True), (2000, 30, 3000, 5, False),
+    # BASELINE config 5 (sweep up to 1e7 events / frame): dense frames -- long same-cell runs, hot voxels with
+    # thousands of sequential adds, strips of thousands of records
+    (1000000, 480, 640, 5, False), (1000000, 480, 640, 5, True), (3000000, 480, 640, 5, True),
 ])
 def test_trilinear_vs_oracle(dev, oracle, n, H, W, C, clustered):
     from openess_b200 import voxel
@@ -144,7 +147,8 @@ def test_trilinear_vs_oracle(dev, oracle, n, H, W, C, clustered):
     out2 = voxel.voxel_trilinear(*d, C, H, W, mode="ordered")[0].cpu().numpy()
     assert bits_equal(out, out2), "ordered mode must be deterministic"
     outa = voxel.voxel_trilinear(*d, C, H, W, mode="atomic")[0].cpu().numpy()
-    np.testing.assert_allclose(outa, ref, rtol=0, atol=ATOMIC_ATOL)
+    # float atomics add in arrival order: the noise scales with the magnitude of hot voxels (thousands of adds)
+    np.testing.assert_allclose(outa, ref, rtol=1e-5, atol=ATOMIC_ATOL)
 
 
 def test_trilinear_batched_ragged_frames(dev, oracle):
