@@ -14,6 +14,9 @@ One step = one batch of F = 160 event-frames (8 DSEC samples x 20 frames, config
          the on-disk layout): per step H2D of the records, rectification + per-frame time normalisation
          (oess_dsec_rectify_tnorm_u32 = sequence_ov.py:204-210,154-159), voxelisation, and a D2H read of one grid
          row per frame (the grids stay on the device because their consumer, the event encoder, runs there).
+         The batch goes as two sub-batches on two streams (one contiguous 72 MB host->device copy each); measured
+         alternatives (sub-batches of 10..160 frames, 2-4 streams) are within -25 % .. +0 % of this setting: the leg
+         is PCIe-bound (144 MB / step at ~53 GB/s), the 1.5 ms of GPU work hides behind the transfer.
          `e2e_host_output` additionally copies every grid back to pinned host memory (what VoxelGrid.convert
          returns for CPU inputs; PCIe-bound by the 6.1 MB/frame output).
  roofline : dominant kernel, algorithmic bytes (16 N + 4 C H W per frame) / its CUDA-event duration.
@@ -260,22 +263,36 @@ def run_ours(args):
     #      grid row per frame, pipelined over sub-batches on two streams
     sub = args.e2e_sub
     assert F % sub == 0
-    streams = [torch.cuda.Stream(dev) for _ in range(2)]
+    NS_ = max(2, args.e2e_streams)      # pipeline depth: staging buffers / streams (H2D of later sub-batches runs ahead)
+    streams = [torch.cuda.Stream(dev) for _ in range(NS_)]
+    # The loader stages the raw records of one sub-batch CONTIGUOUSLY in pinned memory ([x u16 | y u16 | t u32 | p u8],
+    # 9 bytes / event), so a sub-batch is ONE host->device copy (fewer, larger DMA transfers: 52 vs 49.7 GB/s measured).
+    ns = sub * N_EVENTS
+    offs = (0, 2 * ns, 4 * ns, 8 * ns, 9 * ns)
     dts = (torch.uint16, torch.uint16, torch.uint32, torch.uint8)
-    raw_stage = [[torch.empty(sub * N_EVENTS, dtype=d, device=dev) for d in dts] for _ in range(2)]
-    f32_stage = [tuple(torch.empty(sub * N_EVENTS, dtype=torch.float32, device=dev) for _ in range(4)) for _ in range(2)]
+    packed_host = []
+    for hs in host_sets:
+        per_sub = []
+        for f0 in range(0, F, sub):
+            buf = torch.empty(9 * ns, dtype=torch.uint8).pin_memory()
+            for k in range(4):
+                buf[offs[k]:offs[k + 1]].copy_(hs[k][f0 * N_EVENTS:(f0 + sub) * N_EVENTS].contiguous().view(torch.uint8))
+            per_sub.append(buf)
+        packed_host.append(per_sub)
+    raw_stage = [torch.empty(9 * ns, dtype=torch.uint8, device=dev) for _ in range(NS_)]
+    raw_views = [[raw_stage[b][offs[k]:offs[k + 1]].view(dts[k]) for k in range(4)] for b in range(NS_)]
+    f32_stage = [tuple(torch.empty(sub * N_EVENTS, dtype=torch.float32, device=dev) for _ in range(4)) for _ in range(NS_)]
     fo_sub = (torch.arange(sub + 1, dtype=torch.int64) * N_EVENTS).to(dev)
     rows_host = torch.empty((F, C, W), dtype=torch.float32).pin_memory()
     full_host = torch.empty((F, C, H, W), dtype=torch.float32).pin_memory() if args.host_output else None
 
     def e2e_step(i, full=False):
-        hs = host_sets[i & 1]
+        ph = packed_host[i & 1]
         for s, f0 in enumerate(range(0, F, sub)):
-            b = s & 1
+            b = s % NS_
             with torch.cuda.stream(streams[b]):
-                for k in range(4):
-                    raw_stage[b][k].copy_(hs[k][f0 * N_EVENTS:(f0 + sub) * N_EVENTS], non_blocking=True)
-                voxel.dsec_events_to_voxel_grid(*raw_stage[b], rmap, C, frame_offsets=fo_sub, mode=mode,
+                raw_stage[b].copy_(ph[s], non_blocking=True)
+                voxel.dsec_events_to_voxel_grid(*raw_views[b], rmap, C, frame_offsets=fo_sub, mode=mode,
                                                 out=out[f0:f0 + sub], scratch=f32_stage[b])
                 if full:
                     full_host[f0:f0 + sub].copy_(out[f0:f0 + sub], non_blocking=True)
@@ -363,7 +380,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="ordered", choices=["ordered", "atomic"])
     ap.add_argument("--frames", type=int, default=160, help="event-frames per step per GPU")
-    ap.add_argument("--e2e-sub", type=int, default=40, help="frames per pipelined H2D/compute sub-batch")
+    ap.add_argument("--e2e-streams", type=int, default=2, help="pipeline depth (streams / staging buffers) of the e2e leg")
+    ap.add_argument("--e2e-sub", type=int, default=80, help="frames per pipelined H2D/compute sub-batch")
     ap.add_argument("--host-output", type=int, default=1, help="also measure e2e with full D2H of the grids")
     ap.add_argument("--clustered-every", type=int, default=2, help="every k-th frame is edge-clustered (0: none, 1: all)")
     ap.add_argument("--cpu-frames", type=int, default=2000)
