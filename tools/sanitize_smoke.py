@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from openess_b200 import losses, voxel  # noqa: E402
+from openess_b200 import losses, ops, voxel  # noqa: E402
 
 dev = torch.device("cuda:0")
 rng = np.random.default_rng(0)
@@ -46,5 +46,36 @@ tg[0, :3] = 255
 (losses.dice_ce(lg, tg, 255) + losses.cosine_consistency(lg, lg.detach() * 0.5 + 1) + losses.l1_mean(lg, lg.detach() + 1)).backward()
 losses.confusion(lg.argmax(1), tg, 11, 255)
 losses.convlstm_gates(torch.randn(2, 16, 6, 8, device=dev), torch.randn(2, 4, 6, 8, device=dev))
+# strip splat: dense rows (window path with cuts, runs >= 32 -> sweep path), several strips, odd width (scalar write-out)
+for (Hs, Ws, ns) in ((24, 200, 40000), (16, 70, 9000)):
+    xs = torch.from_numpy(rng.uniform(-1.2, Ws + 0.2, ns).astype(np.float32)).to(dev)
+    ys = torch.from_numpy(rng.uniform(-1.2, Hs + 0.2, ns).astype(np.float32)).to(dev)
+    xs[: ns // 4] = xs[: ns // 4].round() % 3 + 65.4       # a hot cell column crossing a strip boundary
+    ps = torch.from_numpy(rng.integers(0, 2, ns).astype(np.float32)).to(dev)
+    ts = torch.from_numpy(np.sort(rng.random(ns)).astype(np.float32)).to(dev)
+    voxel.voxel_trilinear(xs, ys, ps, ts, C, Hs, Ws, mode="ordered")
+    voxel.voxel_trilinear(xs, ys, ps, ts.flip(0).contiguous(), C, Hs, Ws, mode="ordered")     # robust path, long ranges
+losses.argmax_confusion(lg.detach(), tg, 255)
+# tensor-core kernels (tcgen05 / TMA / TMEM), BatchNorm, fused teacher tail
+a = torch.randn(300, 96, device=dev)
+b = torch.randn(200, 96, device=dev)
+ops.gemm_tf32(a, b, torch.randn(200, device=dev))
+Cc = 64
+wgt = torch.randn(4 * Cc, 2 * Cc, 3, 3, device=dev) * 0.03
+wp, bp = ops.convlstm_pack(wgt, torch.randn(4 * Cc, device=dev) * 0.1, Cc)
+xc = torch.randn(2, Cc, 13, 22, device=dev)
+h1, c1 = ops.convlstm_step(xc, None, wp, bp)
+ops.convlstm_step(xc, (h1, c1), wp, bp)
+wc = torch.randn(48, 32, 5, 5, device=dev) * 0.05
+yc = ops.conv2d_tc(torch.randn(2, 32, 17, 23, device=dev), ops.conv2d_pack(wc), torch.randn(48, device=dev), 5, 2, 2, 1, relu=True)
+bn = torch.nn.BatchNorm2d(64).to(dev).train()
+w3 = torch.randn(64, 32, 3, 3, device=dev) * 0.05
+xb = torch.randn(2, 32, 11, 19, device=dev)
+ops.conv_bn_train(xb, ops.conv2d_pack(w3), None, 3, 1, 2, 2, bn, residual=torch.randn(2, 64, 11, 19, device=dev), relu=True)
+ops.batchnorm_nhwc_(ops.conv2d_tc(xb, ops.conv2d_pack(w3), None, 3, 1, 1, 1), bn.eval(), relu=True)
+ops.planes_to_nhwc_padded(torch.randn(2, 5, 9, 14, device=dev), 8)
+d = torch.randn(2, 256, 6, 9, device=dev, requires_grad=True)
+sp = torch.randint(0, 7, (2, 24, 36), device=dev)
+ops.upnorm_pool(d, sp, 7, 14).square().sum().backward()
 torch.cuda.synchronize()
 print("sanitize smoke done")
