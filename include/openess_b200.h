@@ -246,6 +246,16 @@ int oess_batchnorm_nhwc_sums(float* x, int64_t R, int C, const float* gamma, con
                              float* running_var, float eps, float momentum, const float* residual, int relu, void* ws,
                              size_t ws_bytes, oess_stream_t stream);
 
+/* Conv + InstanceNorm2d(affine=False) (+ residual) (+ ReLU) of the SemSegE2VID task decoder (models/style_networks.py:
+ * 252-289 ReLUINSConv2d / INSResBlock) for its forward-only uses (validation, linear probing, test.py): the conv
+ * accumulates PER-SAMPLE statistics in its epilogue (in_sums [B][2 Cout] doubles, zeroed inside), the second call
+ * normalises y [B, HW, C] in place. */
+int oess_conv2d_nhwc_tf32_instats(const float* x, const float* w_packed, const float* bias, float* y, int B, int H, int W,
+                                  int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, double* in_sums,
+                                  oess_stream_t stream);
+int oess_instancenorm_nhwc_sums(float* x, int B, int64_t HW, int C, const double* sums, float eps, const float* residual,
+                                int relu, oess_stream_t stream);
+
 /* BatchNorm2d (torch.nn.BatchNorm2d semantics) over channels-last rows x [R = B*H*W, C], IN PLACE, with optional residual
  * add and ReLU: the normalisation between the teacher's tensor-core convolutions.  The OpenESS trainers call `.train()`
  * on the frozen ResNet-50 teacher every step (training/pretrain_trainer.py:370-371; models/image_model.py:116-117), so

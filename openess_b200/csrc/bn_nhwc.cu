@@ -103,9 +103,52 @@ k_bn_apply(float* __restrict__ x, const float* __restrict__ scale, const float* 
     }
 }
 
+// InstanceNorm2d (affine = False, no running statistics: torch.nn.InstanceNorm2d defaults, models/style_networks.py:257,274,277)
+// from per-sample sums: y = (x - mean_bc) / sqrt(var_bc + eps) (+ residual) (ReLU), in place, channels-last.
+__global__ void __launch_bounds__(256)
+k_in_apply(float* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ residual, int64_t HW, int C,
+           int64_t total4, float eps, int relu) {
+    const int C4 = C >> 2;
+    const int64_t per_sample4 = HW * C4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+        const int64_t b = i / per_sample4;
+        const int q = (int)(i % C4);
+        const double* sb = sums + b * 2 * C;
+        float4 v = reinterpret_cast<float4*>(x)[i];
+        float o[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = q * 4 + j;
+            const double mean = sb[c] / (double)HW;
+            double var = sb[C + c] / (double)HW - mean * mean;
+            if (var < 0) var = 0;
+            o[j] = (float)(((double)o[j] - mean) * rsqrt(var + (double)eps));
+        }
+        if (residual) {
+            const float4 r = __ldcs(reinterpret_cast<const float4*>(residual) + i);
+            o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+        }
+        if (relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
+        reinterpret_cast<float4*>(x)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 }  // namespace oess
 
 using namespace oess;
+
+// x: [B, HW, C] channels-last, in place; sums: [B][2 C] doubles from oess_conv2d_nhwc_tf32_instats.
+OESS_API int oess_instancenorm_nhwc_sums(float* x, int B, int64_t HW, int C, const double* sums, float eps,
+                                         const float* residual, int relu, oess_stream_t stream) {
+    if (!x || !sums || B <= 0 || HW <= 0 || C <= 0 || (C & 3)) return OESS_E_ARG;
+    if (((uintptr_t)x | (uintptr_t)residual) & 15) return OESS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total4 = (int64_t)B * HW * (C >> 2);
+    const unsigned blocks = (unsigned)((total4 + 255) / 256 < (int64_t)kNumSMs * 16 ? (total4 + 255) / 256 : (int64_t)kNumSMs * 16);
+    OESS_KERNEL("in_apply", st, k_in_apply<<<blocks, 256, 0, st>>>(x, sums, residual, HW, C, total4, eps, relu ? 1 : 0));
+    return OESS_OK;
+}
 
 // x: [R, C] channels-last rows (R = B * H * W), normalised IN PLACE.  ws: 2 C doubles + 2 C floats of device scratch
 // (oess_bn_ws_bytes).  training != 0: batch statistics (+ running-statistics update when running_mean != NULL);

@@ -28,6 +28,7 @@ struct ConvSmem {
 
 struct ConvArgs {
     int Ho, Wo, Cout, KW, taps, chunks, stride, pad, dil, relu, tiles_w;
+    int stats_stride;   // doubles between the statistics of consecutive samples (0: one set for the whole batch)
 };
 
 template <int BN>
@@ -119,7 +120,11 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                 // warp's 32 rows by recursive halving (16 shuffles each), staged per warp in shared memory.
                 float s8[16], q8[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { const float t = valid ? v[j] : 0.f; s8[j] = t; q8[j] = t * t; }
+                for (int j = 0; j < 16; ++j) {
+                    const float t = valid ? v[j] + ((bias && col + j < a.Cout) ? __ldg(bias + col + j) : 0.f) : 0.f;   // statistics of y
+                    s8[j] = t;
+                    q8[j] = t * t;
+                }
 #pragma unroll
                 for (int step = 0; step < 4; ++step) {                 // xor 16, 8, 4, 2: keep half of the columns
                     const int m = 16 >> step, half = 8 >> step;
@@ -174,8 +179,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                 if (n0 + c < a.Cout) {
                     const float ts = s_stat[c] + s_stat[BN + c] + s_stat[2 * BN + c] + s_stat[3 * BN + c];
                     const float tq = s_stat[4 * BN + c] + s_stat[5 * BN + c] + s_stat[6 * BN + c] + s_stat[7 * BN + c];
-                    atomicAdd(&bn_sums[n0 + c], (double)ts);
-                    atomicAdd(&bn_sums[a.Cout + n0 + c], (double)tq);
+                    double* sums = bn_sums + (size_t)b * a.stats_stride;
+                    atomicAdd(&sums[n0 + c], (double)ts);
+                    atomicAdd(&sums[a.Cout + n0 + c], (double)tq);
                 }
             }
         }
@@ -229,7 +235,7 @@ using namespace oess;
 // (tap = ky * KW + kx, channel)); bias [Cout] or NULL; residual [B, Ho, Wo, Cout] or NULL; y: [B, Ho, Wo, Cout].
 static int conv2d_impl(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
                        int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
-                       int relu, double* bn_sums, oess_stream_t stream) {
+                       int relu, double* bn_sums, int per_sample, oess_stream_t stream) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || dil <= 0 || pad < 0)
         return OESS_E_ARG;
     if (!x || !w_packed || !y) return OESS_E_ARG;
@@ -249,8 +255,9 @@ static int conv2d_impl(const float* x, const float* w_packed, const float* bias,
     const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     int rc = tc::make_tmap_f32_strided(&tmX, x, 4, dims, strides, box, estr);
     if (rc) return rc;
-    tc::ConvArgs a{Ho, Wo, Cout, KW, KH * KW, chunks, stride, pad, dil, relu ? 1 : 0, (Wo + tc::kVW - 1) / tc::kVW};
-    if (bn_sums) OESS_CUDA(cudaMemsetAsync(bn_sums, 0, sizeof(double) * 2 * (size_t)Cout, st));
+    tc::ConvArgs a{Ho, Wo, Cout, KW, KH * KW, chunks, stride, pad, dil, relu ? 1 : 0, (Wo + tc::kVW - 1) / tc::kVW,
+                   per_sample ? 2 * Cout : 0};
+    if (bn_sums) OESS_CUDA(cudaMemsetAsync(bn_sums, 0, sizeof(double) * 2 * (size_t)Cout * (per_sample ? B : 1), st));
     if (Cout > 128) return tc::launch_conv<256>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
     if (Cout > 64) return tc::launch_conv<128>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
     return tc::launch_conv<64>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
@@ -259,7 +266,7 @@ static int conv2d_impl(const float* x, const float* w_packed, const float* bias,
 OESS_API int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
                                    int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                                    int relu, oess_stream_t stream) {
-    return conv2d_impl(x, w_packed, bias, residual, y, B, H, W, Cin, Cout, KH, KW, stride, pad, dil, relu, nullptr, stream);
+    return conv2d_impl(x, w_packed, bias, residual, y, B, H, W, Cin, Cout, KH, KW, stride, pad, dil, relu, nullptr, 0, stream);
 }
 
 // Same, additionally accumulating the BatchNorm batch statistics of y (the RAW conv output: pass residual = NULL,
@@ -269,5 +276,14 @@ OESS_API int oess_conv2d_nhwc_tf32_stats(const float* x, const float* w_packed, 
                                          int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                                          double* bn_sums, oess_stream_t stream) {
     if (!bn_sums) return OESS_E_ARG;
-    return conv2d_impl(x, w_packed, bias, nullptr, y, B, H, W, Cin, Cout, KH, KW, stride, pad, dil, 0, bn_sums, stream);
+    return conv2d_impl(x, w_packed, bias, nullptr, y, B, H, W, Cin, Cout, KH, KW, stride, pad, dil, 0, bn_sums, 0, stream);
+}
+
+// Same with PER-SAMPLE statistics, in_sums[b][0..Cout) / [b][Cout..2 Cout): the input of InstanceNorm2d
+// (oess_instancenorm_nhwc_sums; models/style_networks.py:252-289 ReLUINSConv2d / INSResBlock).
+OESS_API int oess_conv2d_nhwc_tf32_instats(const float* x, const float* w_packed, const float* bias, float* y, int B, int H,
+                                           int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                           double* in_sums, oess_stream_t stream) {
+    if (!in_sums) return OESS_E_ARG;
+    return conv2d_impl(x, w_packed, bias, nullptr, y, B, H, W, Cin, Cout, KH, KW, stride, pad, dil, 0, in_sums, 1, stream);
 }

@@ -10,13 +10,20 @@ W_eff = T W512 W256 (one HBM-bound `oess_pixel_linear` pass, autograd-exact chai
 (it still returns the 256-channel map x_ch256); `forward_pooled()` is the fully fused training path: it returns the
 superpixel-pooled contrastive features k directly (pool the 32-channel map, then apply decoder_ch256 to the [M, 32]
 means -- exact by linearity), so the 2.3 GB x_ch256 map never exists either.
-The 3x3 convolutions + InstanceNorm of decoder_scale_1..4 still run on cuDNN this round."""
+Forward-only uses (validation / test.py under no_grad, linear probing with the trunk frozen) run the trunk on the tensor
+cores: conv + InstanceNorm (+ residual) (+ ReLU) = `oess_conv2d_nhwc_tf32_instats` (per-sample statistics in the TMEM
+epilogue) + `oess_instancenorm_nhwc_sums`.  Under autograd (pretraining: the trunk trains) the 3x3 convolutions +
+InstanceNorm of decoder_scale_1..4 still run on cuDNN (backward kernels: DESIGN.md 8)."""
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as f
 
 from .. import ops as _ops
 from ..losses import segpool_forward, superpixel_pool  # noqa: F401
+
+USE_TENSOR_CORES = os.environ.get("OESS_SEMSEG_TC", "1") != "0"
 
 
 def skip_concat(x1, x2):
@@ -97,6 +104,7 @@ class SemSegE2VID(nn.Module):
         self.decoder_scale_5 = nn.Sequential(nn.Conv2d(tch, output_c, kernel_size=1, stride=1, padding=0))   # unused (:167)
         self.decoder_ch256 = nn.Sequential(nn.Conv2d(tch, 256, kernel_size=1, stride=1, padding=0))
         self.decoder_ch512 = nn.Sequential(nn.Conv2d(256, 512, kernel_size=1, stride=1, padding=0))
+        self._pack_cache = {}
         self.if_linear_probing = if_linear_probing
         if if_linear_probing:
             for blk in (self.decoder_scale_1, self.decoder_scale_2, self.decoder_scale_3, self.decoder_scale_4,
@@ -112,6 +120,8 @@ class SemSegE2VID(nn.Module):
 
     # ---- trunk: decoder_scale_1..4 (style_networks.py:146-160) -> 32-channel full-resolution map
     def trunk(self, input_dict, out):
+        if self._tc_trunk_ok(input_dict):
+            return self.trunk_tc(input_dict, out)
         sz_in = input_dict[1].shape[3]
         x = self.decoder_scale_1(input_dict[8])
         x = f.interpolate(x, scale_factor=2, mode='nearest')
@@ -124,6 +134,55 @@ class SemSegE2VID(nn.Module):
         self.update_skip_dict(out, x, sz_in)
         x = f.interpolate(x, scale_factor=2, mode='nearest')
         return self.decoder_scale_4(x)
+
+    # ---- trunk on the tensor cores, forward only (validation, test.py, linear probing: no gradient reaches the trunk)
+    def _tc_trunk_ok(self, input_dict):
+        x = input_dict[8]
+        trunk_frozen = not any(p.requires_grad for blk in (self.decoder_scale_1, self.decoder_scale_2, self.decoder_scale_3,
+                                                            self.decoder_scale_4) for p in blk.parameters())
+        return (USE_TENSOR_CORES and x.is_cuda and x.dtype == torch.float32 and self.skip_type == 'concat'
+                and (not torch.is_grad_enabled() or trunk_frozen) and not any(v.requires_grad for v in input_dict.values())
+                and all(v.shape[1] % 4 == 0 for v in input_dict.values()))
+
+    def _packed(self, conv):
+        key = (conv.weight.data_ptr(), conv.weight._version, conv.weight.device)
+        hit = self._pack_cache.get(id(conv))
+        if hit is None or hit[0] != key:
+            hit = (key, _ops.conv2d_pack(conv.weight), None if conv.bias is None else conv.bias.detach().float().contiguous())
+            self._pack_cache[id(conv)] = hit
+        return hit[1], hit[2]
+
+    def _conv_in(self, x, conv, norm, relu, residual=None):
+        wp, b = self._packed(conv)
+        return _ops.conv_in(x, wp, b, conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0], eps=norm.eps,
+                            residual=residual, relu=relu)
+
+    def _seq_tc(self, seq, x):
+        for blk in seq:
+            if isinstance(blk, INSResBlock):                      # conv-IN-ReLU-conv-IN, + x (style_networks.py:266-289)
+                m = blk.model
+                h = self._conv_in(x, m[0], m[1], True)
+                x = self._conv_in(h, m[3], m[4], False, residual=x)
+            else:                                                 # ReLUINSConv2d: conv-IN-ReLU (:252-263)
+                m = blk.model
+                x = self._conv_in(x, m[0], m[1], True)
+        return x
+
+    def trunk_tc(self, input_dict, out):
+        """`trunk` with every conv + InstanceNorm (+ residual) (+ ReLU) on `oess_conv2d_nhwc_tf32_instats` /
+        `oess_instancenorm_nhwc_sums`; nearest x2 upsampling and the skip concatenations stay (channels-last) torch ops."""
+        with torch.no_grad():
+            cl = torch.channels_last
+            sz_in = input_dict[1].shape[3]
+            x = self._seq_tc(self.decoder_scale_1, input_dict[8])
+            x = torch.cat([f.interpolate(x, scale_factor=2, mode='nearest'), input_dict[4]], dim=1).contiguous(memory_format=cl)
+            x = self._seq_tc(self.decoder_scale_2, x)
+            self.update_skip_dict(out, x, sz_in)
+            x = torch.cat([f.interpolate(x, scale_factor=2, mode='nearest'), input_dict[2]], dim=1).contiguous(memory_format=cl)
+            x = self._seq_tc(self.decoder_scale_3, x)
+            self.update_skip_dict(out, x, sz_in)
+            x = f.interpolate(x, scale_factor=2, mode='nearest').contiguous(memory_format=cl)
+            return self._seq_tc(self.decoder_scale_4, x)
 
     # ---- collapsed head weights (tiny, differentiable w.r.t. decoder_ch256 / decoder_ch512 / text_embeddings / linear_probe)
     def collapsed_head(self):

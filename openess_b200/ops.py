@@ -257,3 +257,27 @@ def planes_to_nhwc_padded(x, cp, stats=None):
         check(lib().oess_planes_to_nhwc_padded(ptr(x), B, C, H * W, ptr(stats), cp, ptr(y), stream_ptr(x.device)),
               "oess_planes_to_nhwc_padded")
     return y
+
+
+def conv_in(x, w_packed, bias, kernel_size, stride=1, padding=0, dilation=1, eps=1e-5, residual=None, relu=False):
+    """act(InstanceNorm2d(conv(x) + bias) + residual) on the tensor cores, forward only (no autograd): per-sample
+    statistics are accumulated in the conv's TMEM epilogue, one in-place pass normalises."""
+    _lib.require_cuda(x, w_packed)
+    B, Cin, H, W = x.shape
+    KH = KW = int(kernel_size)
+    Cout = w_packed.shape[0]
+    cl = torch.channels_last
+    xc = x.float().contiguous(memory_format=cl)
+    Ho = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
+    Wo = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+    y = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=cl)
+    res = None if residual is None else residual.float().contiguous(memory_format=cl)
+    bc = None if bias is None else _f32c(bias)
+    with torch.cuda.device(x.device):
+        ws = _lib.workspace(8 * 2 * Cout * B, x.device)
+        st = stream_ptr(x.device)
+        check(lib().oess_conv2d_nhwc_tf32_instats(ptr(xc), ptr(w_packed), ptr(bc), ptr(y), B, H, W, Cin, Cout, KH, KW, stride,
+                                                  padding, dilation, ptr(ws), st), "oess_conv2d_nhwc_tf32_instats")
+        check(lib().oess_instancenorm_nhwc_sums(ptr(y), B, Ho * Wo, Cout, ptr(ws), float(eps), ptr(res), 1 if relu else 0, st),
+              "oess_instancenorm_nhwc_sums")
+    return y

@@ -124,9 +124,29 @@ def teacher():
         torch.cuda.empty_cache()
 
 
+def semseg():
+    """SemSegE2VID forward (validation / linear-probing path) on a DSEC batch of E2VID latents, real width, K = 11."""
+    from openess_b200.models import style_networks as sn
+    m = sn.SemSegE2VID(input_c=256, output_c=11, skip_connect=True, skip_type='concat', text_embeddings_path=None).cuda().eval()
+    B, H, W = 8, 440, 640
+    lat = {8: torch.randn(B, 256, H // 8, W // 8, device="cuda"), 4: torch.randn(B, 128, H // 4, W // 4, device="cuda"),
+           2: torch.randn(B, 64, H // 2, W // 2, device="cuda"), 1: torch.randn(B, 32, H, W, device="cuda")}
+    res = {}
+    for use_tc in (True, False):
+        sn.USE_TENSOR_CORES = use_tc
+        with torch.no_grad():
+            res[use_tc] = timeit(lambda: m.forward_pooled(lat, torch.zeros(B, H, W, dtype=torch.int64, device="cuda"), 100, 800)[0][1],
+                                 iters=5, warm=2)
+    sn.USE_TENSOR_CORES = True
+    fl = 175.0e9 * B
+    print(json.dumps({"op": "semseg_e2vid_fwd_logits", "B": B, "ms_tensor_core_path": res[True], "tflops": fl / res[True] / 1e9,
+                      "ms_torch_cudnn_tf32": res[False], "torch_tflops": fl / res[False] / 1e9}))
+
+
 if __name__ == "__main__":
     if "--teacher" in sys.argv:
         teacher()
+        semseg()
         sys.exit(0)
     main()
     convlstm()
