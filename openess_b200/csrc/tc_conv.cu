@@ -21,7 +21,7 @@ constexpr int kVABytes = 128 * kBlockK * 4;
 template <int BN>
 struct ConvSmem {
     static constexpr int kBBytes = BN * kBlockK * 4;
-    static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : 4);
+    static constexpr int kStages = BN >= 256 ? 2 : (BN >= 128 ? 3 : (BN >= 64 ? 4 : 5));
     static constexpr int kStatBytes = 2 * 4 * BN * 4;      // per epilogue warp: column sums and sums of squares
     static constexpr int kBytes = 1024 + kStages * (kVABytes + kBBytes) + 256 + kStatBytes;
 };
@@ -260,7 +260,8 @@ static int conv2d_impl(const float* x, const float* w_packed, const float* bias,
     if (bn_sums) OESS_CUDA(cudaMemsetAsync(bn_sums, 0, sizeof(double) * 2 * (size_t)Cout * (per_sample ? B : 1), st));
     if (Cout > 128) return tc::launch_conv<256>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
     if (Cout > 64) return tc::launch_conv<128>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
-    return tc::launch_conv<64>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
+    if (Cout > 32) return tc::launch_conv<64>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
+    return tc::launch_conv<32>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
 }
 
 OESS_API int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
