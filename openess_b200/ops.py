@@ -281,3 +281,13 @@ def conv_in(x, w_packed, bias, kernel_size, stride=1, padding=0, dilation=1, eps
         check(lib().oess_instancenorm_nhwc_sums(ptr(y), B, Ho * Wo, Cout, ptr(ws), float(eps), ptr(res), 1 if relu else 0, st),
               "oess_instancenorm_nhwc_sums")
     return y
+
+
+def conv2d_dgrad_pack(weight, padding, dilation=1):
+    """Input-gradient of a stride-1 convolution as a forward convolution: dX = conv(dY, W^T rotated by 180 degrees) with
+    padding dilation * (K - 1) - padding.  Returns (packed weights for conv2d_tc, the padding to use)."""
+    Cout, Cin, KH, KW = weight.shape
+    if KH != KW:
+        raise ValueError("square kernels only")
+    wt = weight.detach().float().flip(2, 3).permute(1, 0, 2, 3).contiguous()      # [Cin, Cout, KH, KW]
+    return conv2d_pack(wt), dilation * (KH - 1) - padding

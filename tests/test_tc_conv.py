@@ -73,3 +73,21 @@ def test_conv_bn_train_fused_stats_vs_torch(C, Cout, H, W, k, s, p, d):
     torch.testing.assert_close(bn.running_mean.cpu().double(), bn_ref.running_mean, atol=2e-4, rtol=1e-3)
     torch.testing.assert_close(bn.running_var.cpu().double(), bn_ref.running_var, atol=2e-4, rtol=2e-3)
     assert int(bn.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("C,Cout,k,p,d", [(32, 64, 3, 1, 1), (64, 32, 3, 2, 2), (128, 64, 1, 0, 1), (32, 32, 5, 2, 1)])
+def test_conv2d_dgrad_is_the_forward_kernel_on_repacked_weights(C, Cout, k, p, d):
+    """dL/dx of a stride-1 conv == conv2d_tc(dL/dy, rot180(W)^T, padding = d (k - 1) - p): the backward-data pass needs no
+    new kernel.  Checked against torch autograd in float64."""
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(C + Cout + k)
+    x = torch.randn(2, C, 14, 19, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(Cout, C, k, k, generator=g, dtype=torch.float64) / (C * k * k) ** 0.5
+    y = F.conv2d(x, w, None, padding=p, dilation=d)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    wp, pad = ops.conv2d_dgrad_pack(w.float().cuda(), p, d)
+    dx = ops.conv2d_tc(dy.float().cuda(), wp, None, k, 1, pad, d)
+    assert tuple(dx.shape) == tuple(x.shape)
+    bound = 2e-3 * F.conv2d(dy.abs(), w.abs().flip(2, 3).permute(1, 0, 2, 3), None, padding=pad, dilation=d) + 1e-6
+    assert bool(((dx.cpu().double() - x.grad).abs() <= bound).all())
