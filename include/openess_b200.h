@@ -286,6 +286,15 @@ int oess_upnorm_pool_bwd(const float* d, const int64_t* seg, const float* g_sum,
 int oess_planes_to_nhwc_padded(const float* x, int B, int C, int64_t HW, const double* stats, int Cp, float* y,
                                oess_stream_t stream);
 
+/* Weight gradient of a stride-1 convolution as a tcgen05 split-K GEMM over pixels (TF32 operands, fp32 accumulate):
+ *   dW[co, ci, ky, kx] = sum_{b,y,x} dy[b, co, y, x] * x[b, ci, y + ky dil - pad, x + kx dil - pad]
+ * x: [B, H, W, Cin], dy: [B, Ho, Wo, Cout] CHANNELS-LAST (both operands MN-major); dW: [Cout, Cin, KH, KW] (torch
+ * layout), overwritten.  Cin % 4 == 0, Cout % 4 == 0, KW <= 5.
+ * With oess_conv2d_nhwc_tf32 (forward, and backward-data on rotated weights) this is what torch autograd's
+ * ConvolutionBackward does through cuDNN for the trainable convs of the path (models/image_model.py:121-124 decoder). */
+int oess_conv2d_wgrad_nhwc_tf32(const float* x, const float* dy, float* dW, int B, int H, int W, int Cin, int Cout, int KH,
+                                int KW, int pad, int dil, oess_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

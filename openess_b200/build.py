@@ -31,6 +31,7 @@ SOURCES = {
     "tc_gemm.cu": [],
     "tc_convlstm.cu": [],
     "tc_conv.cu": [],
+    "tc_wgrad.cu": [],
     "bn_nhwc.cu": [],
     "upnorm_pool.cu": [],
 }

@@ -114,6 +114,18 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major operand of 32-bit elements (tf32): layout type 1 = SWIZZLE_128B_BASE32B (32-byte chunks swizzled inside a
+// 128-byte line, Swizzle<2,5,2>; the TMA side is CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  One 128-byte line = 32 consecutive
+// M (or N) elements of ONE k; the canonical atom is 4 lines (512 B) = 4 k, so one tcgen05.mma.kind::tf32 (K = 8) spans two
+// atoms `stride byte offset` = 512 B apart; `lbo_bytes` = distance between successive 32-element MN groups.
+__device__ __forceinline__ uint64_t umma_desc_mn128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | (32ull << 32) | (1ull << 46) |
+           (1ull << 61);
+}
+// kind::tf32 instruction descriptor with A and B MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // kind::tf32, fp32 accumulate, A and B K-major: c_format F32 (1) at bit 4, a/b format TF32 (2) at bits 7 / 10,
 // N >> 3 at bit 17, M >> 4 at bit 24.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
@@ -142,6 +154,9 @@ EncodeTiledFn encode_tiled_fn();   // resolved once through cudaGetDriverEntryPo
 // fp32 tensor of `rank` dims (dims[0] innermost, strides in bytes for dims 1..), box[0] = 32 floats = 128 B, 128B swizzle
 int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
+// same with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (MN-major tf32 operands)
+int make_tmap_f32_atom32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box);
 
 }  // namespace tc
 }  // namespace oess

@@ -291,3 +291,52 @@ def conv2d_dgrad_pack(weight, padding, dilation=1):
         raise ValueError("square kernels only")
     wt = weight.detach().float().flip(2, 3).permute(1, 0, 2, 3).contiguous()      # [Cin, Cout, KH, KW]
     return conv2d_pack(wt), dilation * (KH - 1) - padding
+
+
+def conv2d_wgrad(x, dy, kernel_size, padding=0, dilation=1):
+    """dL/dW [Cout, Cin, K, K] of a stride-1 convolution on the tensor cores (split-K GEMM over pixels).
+    x: [B, Cin, H, W], dy: [B, Cout, Ho, Wo]; both are used channels-last (copied if they are not)."""
+    _lib.require_cuda(x, dy)
+    xc = x.float().contiguous(memory_format=torch.channels_last)
+    dyc = dy.float().contiguous(memory_format=torch.channels_last)
+    B, Cin, H, W = xc.shape
+    Cout = dyc.shape[1]
+    K = int(kernel_size)
+    dW = torch.empty((Cout, Cin, K, K), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().oess_conv2d_wgrad_nhwc_tf32(ptr(xc), ptr(dyc), ptr(dW), B, H, W, Cin, Cout, K, K, int(padding),
+                                                int(dilation), stream_ptr(x.device)), "oess_conv2d_wgrad_nhwc_tf32")
+    return dW
+
+
+class _ConvTC(torch.autograd.Function):
+    """Stride-1 convolution whose forward, backward-data and backward-weight passes all run on the tcgen05 kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, padding, dilation):
+        K = weight.shape[2]
+        y = conv2d_tc(x, conv2d_pack(weight), bias, K, 1, padding, dilation)
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (K, padding, dilation, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        K, padding, dilation, has_bias = ctx.meta
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            wp, pad = conv2d_dgrad_pack(weight, padding, dilation)
+            dx = conv2d_tc(dy, wp, None, K, 1, pad, dilation)
+        if ctx.needs_input_grad[1]:
+            dW = conv2d_wgrad(x, dy, K, padding, dilation)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(dim=(0, 2, 3))
+        return dx, dW, db, None, None
+
+
+def conv2d_tc_autograd(x, weight, bias=None, padding=0, dilation=1):
+    """Differentiable stride-1 convolution on the tensor cores (TF32 operands, fp32 accumulate)."""
+    if weight.shape[2] != weight.shape[3]:
+        raise ValueError("square kernels only")
+    return _ConvTC.apply(x, weight, bias, int(padding), int(dilation))

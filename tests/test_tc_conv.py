@@ -91,3 +91,35 @@ def test_conv2d_dgrad_is_the_forward_kernel_on_repacked_weights(C, Cout, k, p, d
     assert tuple(dx.shape) == tuple(x.shape)
     bound = 2e-3 * F.conv2d(dy.abs(), w.abs().flip(2, 3).permute(1, 0, 2, 3), None, padding=pad, dilation=d) + 1e-6
     assert bool(((dx.cpu().double() - x.grad).abs() <= bound).all())
+
+
+@pytest.mark.parametrize("B,C,Cout,H,W,k,p,d", [
+    (2, 64, 32, 12, 20, 3, 1, 1),          # SemSegE2VID-like 3x3
+    (1, 2048, 256, 11, 16, 1, 0, 1),       # teacher decoder 1x1 conv 2048 -> 256 (image_model.py:121-124)
+    (2, 32, 48, 9, 36, 3, 2, 2),           # dilated, Cout not a multiple of 128, W not a multiple of 32
+    (1, 16, 16, 8, 8, 5, 2, 1),            # 5x5
+    (3, 256, 512, 7, 12, 3, 1, 1),         # DeepLab classifier 3x3 256 -> 512: several co tiles, split K over images
+])
+def test_conv2d_autograd_tensor_cores_vs_torch(B, C, Cout, H, W, k, p, d):
+    """forward + backward-data + backward-weight of ops.conv2d_tc_autograd against torch autograd in float64.
+    Tolerance: TF32 operands -> 2e-3 * (sum of |terms|), evaluated with the same convolutions on absolute values."""
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(B * C + Cout + k)
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(Cout, C, k, k, generator=g, dtype=torch.float64) / (C * k * k) ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, generator=g, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(x, w, b, padding=p, dilation=d)
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    xg = x.detach().float().cuda().requires_grad_(True)
+    wg = w.detach().float().cuda().requires_grad_(True)
+    bg = b.detach().float().cuda().requires_grad_(True)
+    yg = ops.conv2d_tc_autograd(xg, wg, bg, p, d)
+    yg.backward(dy.float().cuda())
+    xa, wa, dya = x.detach().abs(), w.detach().abs(), dy.abs()
+    bound_w = 2e-3 * torch.autograd.grad(F.conv2d(xa, wa.requires_grad_(True), None, padding=p, dilation=d), wa, dya)[0] + 1e-5
+    bound_x = 2e-3 * torch.autograd.grad(F.conv2d(xa.requires_grad_(True), wa.detach(), None, padding=p, dilation=d), xa, dya)[0] + 1e-5
+    assert bool(((wg.grad.cpu().double() - w.grad).abs() <= bound_w).all()), float((wg.grad.cpu().double() - w.grad).abs().max())
+    assert bool(((xg.grad.cpu().double() - x.grad).abs() <= bound_x).all())
+    torch.testing.assert_close(bg.grad.cpu().double(), b.grad, atol=1e-4, rtol=1e-5)
+    assert float((yg.detach().cpu().double() - y.detach()).abs().max()) < 1e-2
