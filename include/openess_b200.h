@@ -256,6 +256,15 @@ int oess_conv2d_nhwc_tf32_instats(const float* x, const float* w_packed, const f
 int oess_instancenorm_nhwc_sums(float* x, int B, int64_t HW, int C, const double* sums, float eps, const float* residual,
                                 int relu, oess_stream_t stream);
 
+/* Training variants of the conv + InstanceNorm block: the forward keeps x_hat (in place of the conv output) and writes
+ * y = act(x_hat + residual) to y_out; the backward turns dy into the gradient dz of the conv output (and d_res):
+ *   g = dy * [y > 0];  dz = inv_std * (g - mean_hw(g) - x_hat * mean_hw(g x_hat))      (y = NULL: no ReLU in the forward). */
+int oess_instancenorm_nhwc_sums_train(float* x, int B, int64_t HW, int C, const double* sums, float eps,
+                                      const float* residual, int relu, float* y_out, oess_stream_t stream);
+int oess_instancenorm_nhwc_bwd(const float* dy, const float* y, const float* xhat, int B, int64_t HW, int C,
+                               const double* fwd_sums, double* bwd_sums, float eps, float* dz, float* d_res,
+                               oess_stream_t stream);
+
 /* BatchNorm2d (torch.nn.BatchNorm2d semantics) over channels-last rows x [R = B*H*W, C], IN PLACE, with optional residual
  * add and ReLU: the normalisation between the teacher's tensor-core convolutions.  The OpenESS trainers call `.train()`
  * on the frozen ResNet-50 teacher every step (training/pretrain_trainer.py:370-371; models/image_model.py:116-117), so

@@ -107,7 +107,7 @@ k_bn_apply(float* __restrict__ x, const float* __restrict__ scale, const float* 
 // from per-sample sums: y = (x - mean_bc) / sqrt(var_bc + eps) (+ residual) (ReLU), in place, channels-last.
 __global__ void __launch_bounds__(256)
 k_in_apply(float* __restrict__ x, const double* __restrict__ sums, const float* __restrict__ residual, int64_t HW, int C,
-           int64_t total4, float eps, int relu) {
+           int64_t total4, float eps, int relu, float* __restrict__ y_out) {
     const int C4 = C >> 2;
     const int64_t per_sample4 = HW * C4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -125,12 +125,95 @@ k_in_apply(float* __restrict__ x, const double* __restrict__ sums, const float* 
             if (var < 0) var = 0;
             o[j] = (float)(((double)o[j] - mean) * rsqrt(var + (double)eps));
         }
+        if (y_out) reinterpret_cast<float4*>(x)[i] = make_float4(o[0], o[1], o[2], o[3]);   // training: keep x_hat, y separately
         if (residual) {
             const float4 r = __ldcs(reinterpret_cast<const float4*>(residual) + i);
             o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
         }
         if (relu) { o[0] = fmaxf(o[0], 0.f); o[1] = fmaxf(o[1], 0.f); o[2] = fmaxf(o[2], 0.f); o[3] = fmaxf(o[3], 0.f); }
-        reinterpret_cast<float4*>(x)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(y_out ? y_out : x)[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// InstanceNorm backward, pass 1: per (sample, channel) sums of g and g * x_hat, g = dy (* [y > 0] when the forward applied a
+// ReLU).  grid (row blocks, channel-quad blocks, B); same thread layout as k_bn_stats.
+__global__ void __launch_bounds__(256)
+k_in_bwd_stats(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ xhat, int64_t HW, int C,
+               int rows_per_block, double* __restrict__ sums) {
+    const int C4 = C >> 2;
+    const int qpb = min(C4, 256);
+    const int lanes = 256 / qpb;
+    const int q = blockIdx.y * qpb + (threadIdx.x % qpb);
+    const int rl = threadIdx.x / qpb;
+    const int b = blockIdx.z;
+    const int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, HW);
+    const int64_t base = (int64_t)b * HW;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < C4) {
+        for (int64_t r = r0 + rl; r < r1; r += lanes) {
+            const int64_t i = (base + r) * C4 + q;
+            float4 g = __ldg(reinterpret_cast<const float4*>(dy) + i);
+            if (y) {
+                const float4 yy = __ldg(reinterpret_cast<const float4*>(y) + i);
+                g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+            }
+            const float4 xh = __ldg(reinterpret_cast<const float4*>(xhat) + i);
+            s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+            ss.x += g.x * xh.x; ss.y += g.y * xh.y; ss.z += g.z * xh.z; ss.w += g.w * xh.w;
+        }
+    }
+    __shared__ float4 sh_s[256], sh_ss[256];
+    sh_s[threadIdx.x] = s;
+    sh_ss[threadIdx.x] = ss;
+    __syncthreads();
+    if (rl == 0 && q < C4) {
+        double a[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+        for (int l = 0; l < lanes; ++l) {
+            const float4 u = sh_s[l * qpb + threadIdx.x], w = sh_ss[l * qpb + threadIdx.x];
+            a[0] += u.x; a[1] += u.y; a[2] += u.z; a[3] += u.w;
+            c[0] += w.x; c[1] += w.y; c[2] += w.z; c[3] += w.w;
+        }
+        double* sb = sums + (int64_t)b * 2 * C;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(&sb[q * 4 + j], a[j]);
+            atomicAdd(&sb[C + q * 4 + j], c[j]);
+        }
+    }
+}
+
+// pass 2: dz = inv_std * (g - mean(g) - x_hat * mean(g x_hat)); optionally d_res = g (the residual branch's gradient)
+__global__ void __launch_bounds__(256)
+k_in_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ xhat,
+               const double* __restrict__ fwd_sums, const double* __restrict__ bwd_sums, int64_t HW, int C, int64_t total4,
+               float eps, float* __restrict__ dz, float* __restrict__ d_res) {
+    const int C4 = C >> 2;
+    const int64_t per_sample4 = HW * C4;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
+        const int64_t b = i / per_sample4;
+        const int q = (int)(i % C4);
+        const double* fs = fwd_sums + b * 2 * C;
+        const double* bs = bwd_sums + b * 2 * C;
+        float4 g = __ldg(reinterpret_cast<const float4*>(dy) + i);
+        if (y) {
+            const float4 yy = __ldg(reinterpret_cast<const float4*>(y) + i);
+            g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
+        }
+        const float4 xh = __ldg(reinterpret_cast<const float4*>(xhat) + i);
+        const float gg[4] = {g.x, g.y, g.z, g.w}, xx[4] = {xh.x, xh.y, xh.z, xh.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = q * 4 + j;
+            const double mean = fs[c] / (double)HW;
+            double var = fs[C + c] / (double)HW - mean * mean;
+            if (var < 0) var = 0;
+            const double inv = rsqrt(var + (double)eps);
+            o[j] = (float)(inv * ((double)gg[j] - bs[c] / (double)HW - (double)xx[j] * (bs[C + c] / (double)HW)));
+        }
+        reinterpret_cast<float4*>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        if (d_res) reinterpret_cast<float4*>(d_res)[i] = g;
     }
 }
 
@@ -139,6 +222,40 @@ k_in_apply(float* __restrict__ x, const double* __restrict__ sums, const float* 
 using namespace oess;
 
 // x: [B, HW, C] channels-last, in place; sums: [B][2 C] doubles from oess_conv2d_nhwc_tf32_instats.
+// Backward of y = act(InstanceNorm(z) + residual): dy, y (NULL when the forward had no ReLU), x_hat [B, HW, C] channels-last;
+// fwd_sums = the forward's per-sample sums of z; bwd_sums [B][2 C] doubles of scratch (zeroed inside); dz (gradient w.r.t.
+// the conv output z) and optionally d_res (gradient of the residual input) are written.
+OESS_API int oess_instancenorm_nhwc_bwd(const float* dy, const float* y, const float* xhat, int B, int64_t HW, int C,
+                                        const double* fwd_sums, double* bwd_sums, float eps, float* dz, float* d_res,
+                                        oess_stream_t stream) {
+    if (!dy || !xhat || !fwd_sums || !bwd_sums || !dz || B <= 0 || HW <= 0 || C <= 0 || (C & 3) || B > 65535) return OESS_E_ARG;
+    const int C4 = C >> 2;
+    if (C4 > 256 ? (C4 % 256) != 0 : (256 % C4) != 0) return OESS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    OESS_CUDA(cudaMemsetAsync(bwd_sums, 0, sizeof(double) * 2 * (size_t)C * B, st));
+    const int qpb = C4 < 256 ? C4 : 256;
+    const int lanes = 256 / qpb;
+    int64_t rpb = (HW * B + (int64_t)kNumSMs * 16 - 1) / ((int64_t)kNumSMs * 16);
+    if (rpb < (int64_t)lanes * 16) rpb = (int64_t)lanes * 16;
+    const dim3 grid((unsigned)((HW + rpb - 1) / rpb), (unsigned)((C4 + qpb - 1) / qpb), (unsigned)B);
+    OESS_KERNEL("in_bwd_stats", st, k_in_bwd_stats<<<grid, 256, 0, st>>>(dy, y, xhat, HW, C, (int)rpb, bwd_sums));
+    const int64_t total4 = (int64_t)B * HW * C4;
+    const unsigned blocks = (unsigned)((total4 + 255) / 256 < (int64_t)kNumSMs * 16 ? (total4 + 255) / 256 : (int64_t)kNumSMs * 16);
+    OESS_KERNEL("in_bwd_apply", st, k_in_bwd_apply<<<blocks, 256, 0, st>>>(dy, y, xhat, fwd_sums, bwd_sums, HW, C, total4, eps, dz, d_res));
+    return OESS_OK;
+}
+
+// Training forward: x is overwritten with x_hat (kept for the backward pass), y_out receives act(x_hat + residual).
+OESS_API int oess_instancenorm_nhwc_sums_train(float* x, int B, int64_t HW, int C, const double* sums, float eps,
+                                               const float* residual, int relu, float* y_out, oess_stream_t stream) {
+    if (!x || !sums || !y_out || B <= 0 || HW <= 0 || C <= 0 || (C & 3)) return OESS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total4 = (int64_t)B * HW * (C >> 2);
+    const unsigned blocks = (unsigned)((total4 + 255) / 256 < (int64_t)kNumSMs * 16 ? (total4 + 255) / 256 : (int64_t)kNumSMs * 16);
+    OESS_KERNEL("in_apply", st, k_in_apply<<<blocks, 256, 0, st>>>(x, sums, residual, HW, C, total4, eps, relu ? 1 : 0, y_out));
+    return OESS_OK;
+}
+
 OESS_API int oess_instancenorm_nhwc_sums(float* x, int B, int64_t HW, int C, const double* sums, float eps,
                                          const float* residual, int relu, oess_stream_t stream) {
     if (!x || !sums || B <= 0 || HW <= 0 || C <= 0 || (C & 3)) return OESS_E_ARG;
@@ -146,7 +263,7 @@ OESS_API int oess_instancenorm_nhwc_sums(float* x, int B, int64_t HW, int C, con
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total4 = (int64_t)B * HW * (C >> 2);
     const unsigned blocks = (unsigned)((total4 + 255) / 256 < (int64_t)kNumSMs * 16 ? (total4 + 255) / 256 : (int64_t)kNumSMs * 16);
-    OESS_KERNEL("in_apply", st, k_in_apply<<<blocks, 256, 0, st>>>(x, sums, residual, HW, C, total4, eps, relu ? 1 : 0));
+    OESS_KERNEL("in_apply", st, k_in_apply<<<blocks, 256, 0, st>>>(x, sums, residual, HW, C, total4, eps, relu ? 1 : 0, nullptr));
     return OESS_OK;
 }
 

@@ -340,3 +340,61 @@ def conv2d_tc_autograd(x, weight, bias=None, padding=0, dilation=1):
     if weight.shape[2] != weight.shape[3]:
         raise ValueError("square kernels only")
     return _ConvTC.apply(x, weight, bias, int(padding), int(dilation))
+
+
+class _ConvINAct(torch.autograd.Function):
+    """y = act(InstanceNorm2d(conv(x) + bias) + residual), stride 1, every pass on hand-written kernels: tcgen05 conv with
+    per-sample statistics in its epilogue, in-place normalisation, and in the backward pass the InstanceNorm Jacobian
+    (two HBM-bound kernels) followed by the tcgen05 backward-data and backward-weight convolutions."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, padding, dilation, eps, relu):
+        B, Cin, H, W = x.shape
+        Cout, _, K, _ = weight.shape
+        cl = torch.channels_last
+        xc = x.float().contiguous(memory_format=cl)
+        Ho = H + 2 * padding - dilation * (K - 1)
+        Wo = W + 2 * padding - dilation * (K - 1)
+        xhat = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=cl)
+        y = torch.empty_like(xhat)
+        sums = torch.empty(B * 2 * Cout, dtype=torch.float64, device=x.device)
+        res = None if residual is None else residual.float().contiguous(memory_format=cl)
+        bc = None if bias is None else _f32c(bias)
+        wp = conv2d_pack(weight)
+        with torch.cuda.device(x.device):
+            st = stream_ptr(x.device)
+            check(lib().oess_conv2d_nhwc_tf32_instats(ptr(xc), ptr(wp), ptr(bc), ptr(xhat), B, H, W, Cin, Cout, K, K, 1,
+                                                      padding, dilation, ptr(sums), st), "oess_conv2d_nhwc_tf32_instats")
+            check(lib().oess_instancenorm_nhwc_sums_train(ptr(xhat), B, Ho * Wo, Cout, ptr(sums), float(eps), ptr(res),
+                                                          1 if relu else 0, ptr(y), st), "oess_instancenorm_nhwc_sums_train")
+        ctx.save_for_backward(xc, weight, xhat, y if relu else None, sums)
+        ctx.meta = (K, padding, dilation, float(eps), bias is not None, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, weight, xhat, y, sums = ctx.saved_tensors
+        K, padding, dilation, eps, has_bias, has_res = ctx.meta
+        B, Cout, Ho, Wo = xhat.shape
+        cl = torch.channels_last
+        dyc = dy.float().contiguous(memory_format=cl)
+        dz = torch.empty_like(xhat)
+        d_res = torch.empty_like(xhat) if (has_res and ctx.needs_input_grad[3]) else None
+        bsums = torch.empty(B * 2 * Cout, dtype=torch.float64, device=dy.device)
+        with torch.cuda.device(dy.device):
+            check(lib().oess_instancenorm_nhwc_bwd(ptr(dyc), ptr(y), ptr(xhat), B, Ho * Wo, Cout, ptr(sums), ptr(bsums), eps,
+                                                   ptr(dz), ptr(d_res), stream_ptr(dy.device)), "oess_instancenorm_nhwc_bwd")
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            wpd, pad = conv2d_dgrad_pack(weight, padding, dilation)
+            dx = conv2d_tc(dz, wpd, None, K, 1, pad, dilation)
+        if ctx.needs_input_grad[1]:
+            dW = conv2d_wgrad(xc, dz, K, padding, dilation)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = dz.sum(dim=(0, 2, 3))                       # exactly zero in exact arithmetic (a bias in front of InstanceNorm)
+        return dx, dW, db, d_res, None, None, None, None
+
+
+def conv_in_autograd(x, weight, bias=None, residual=None, padding=0, dilation=1, eps=1e-5, relu=False):
+    """Differentiable act(InstanceNorm2d(conv(x) + bias) + residual) on hand-written kernels (see _ConvINAct)."""
+    return _ConvINAct.apply(x, weight, bias, residual, int(padding), int(dilation), float(eps), bool(relu))

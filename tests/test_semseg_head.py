@@ -170,3 +170,40 @@ def test_conv_instancenorm_vs_torch(C, Cout, res, relu):
         ref = ref.relu()
     y = ops.conv_in(x.cuda(), ops.conv2d_pack(w.cuda()), b.cuda(), 3, 1, 1, 1, residual=None if r is None else r.cuda(), relu=relu)
     assert float((y.cpu().double() - ref).abs().max()) < 1e-2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,Cout,res,relu", [(64, 64, True, False), (32, 64, False, True), (64, 32, True, True)])
+def test_conv_instancenorm_autograd_vs_torch(C, Cout, res, relu):
+    """Training block of the SemSegE2VID trunk (conv -> InstanceNorm -> (+x) -> ReLU) forward AND backward on the
+    hand-written kernels (tcgen05 conv / dgrad / wgrad + InstanceNorm Jacobian) against torch autograd in float64."""
+    import torch.nn.functional as F
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(C + 2 * Cout)
+    B, H, W = 2, 12, 20
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    w = (torch.randn(Cout, C, 3, 3, generator=g, dtype=torch.float64) / (9 * C) ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, generator=g, dtype=torch.float64, requires_grad=True)
+    r = torch.randn(B, Cout, H, W, generator=g, dtype=torch.float64, requires_grad=True) if res else None
+    xg = x.detach().float().cuda().requires_grad_(True)
+    wg = w.detach().float().cuda().requires_grad_(True)
+    bg = b.detach().float().cuda().requires_grad_(True)
+    rg = r.detach().float().cuda().requires_grad_(True) if res else None
+    yg = ops.conv_in_autograd(xg, wg, bg, rg, padding=1, relu=relu)
+    y = F.instance_norm(F.conv2d(x, w, b, padding=1), eps=1e-5)
+    if res:
+        y = y + r
+    if relu:
+        # ReLU is discontinuous: a pre-activation within TF32 rounding of zero may land on the other side.  The reference
+        # uses the kernel's own active set (the two forwards differ by < 1e-2 there), which makes the gradients comparable.
+        y = y * (yg.detach().cpu() > 0).double()
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    yg.backward(dy.float().cuda())
+    assert float((yg.detach().cpu().double() - y.detach()).abs().max()) < 1e-2
+    for got, ref, name in ((xg.grad, x.grad, "dx"), (wg.grad, w.grad, "dW")):
+        err = float((got.cpu().double() - ref).abs().max())
+        assert err < 1e-2 * float(ref.abs().max()) + 1e-4, (name, err, float(ref.abs().max()))
+    if res:
+        assert float((rg.grad.cpu().double() - r.grad).abs().max()) < 1e-6
+    assert float(bg.grad.abs().max()) < 1e-2 * float(w.grad.abs().max())      # mathematically zero
