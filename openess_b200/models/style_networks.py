@@ -12,8 +12,10 @@ superpixel-pooled contrastive features k directly (pool the 32-channel map, then
 means -- exact by linearity), so the 2.3 GB x_ch256 map never exists either.
 Forward-only uses (validation / test.py under no_grad, linear probing with the trunk frozen) run the trunk on the tensor
 cores: conv + InstanceNorm (+ residual) (+ ReLU) = `oess_conv2d_nhwc_tf32_instats` (per-sample statistics in the TMEM
-epilogue) + `oess_instancenorm_nhwc_sums`.  Under autograd (pretraining: the trunk trains) the 3x3 convolutions +
-InstanceNorm of decoder_scale_1..4 still run on cuDNN (backward kernels: DESIGN.md 8)."""
+epilogue) + `oess_instancenorm_nhwc_sums`.  Under autograd (pretraining: the trunk trains) every block is `ops.conv_in_autograd`: tcgen05 forward conv with
+per-sample statistics, InstanceNorm Jacobian kernels, tcgen05 backward-data (forward kernel on rotated weights) and
+backward-weight (split-K MN-major GEMM) convolutions -- no cuDNN call is left in the module
+(`TRAIN_ON_TENSOR_CORES = False` / OESS_SEMSEG_TC_TRAIN=0 restores the strict-fp32 torch path)."""
 import os
 
 import torch
@@ -24,6 +26,7 @@ from .. import ops as _ops
 from ..losses import segpool_forward, superpixel_pool  # noqa: F401
 
 USE_TENSOR_CORES = os.environ.get("OESS_SEMSEG_TC", "1") != "0"
+TRAIN_ON_TENSOR_CORES = os.environ.get("OESS_SEMSEG_TC_TRAIN", "1") != "0"   # training trunk (fwd + bwd) on own kernels
 
 
 def skip_concat(x1, x2):
@@ -122,6 +125,8 @@ class SemSegE2VID(nn.Module):
     def trunk(self, input_dict, out):
         if self._tc_trunk_ok(input_dict):
             return self.trunk_tc(input_dict, out)
+        if self._tc_train_ok(input_dict):
+            return self.trunk_tc(input_dict, out, train=True)
         sz_in = input_dict[1].shape[3]
         x = self.decoder_scale_1(input_dict[8])
         x = f.interpolate(x, scale_factor=2, mode='nearest')
@@ -152,37 +157,51 @@ class SemSegE2VID(nn.Module):
             self._pack_cache[id(conv)] = hit
         return hit[1], hit[2]
 
-    def _conv_in(self, x, conv, norm, relu, residual=None):
+    def _conv_in(self, x, conv, norm, relu, residual=None, train=False):
+        if train:                                                 # differentiable: fwd + dgrad + wgrad + IN Jacobian
+            return _ops.conv_in_autograd(x, conv.weight, conv.bias, residual, padding=conv.padding[0],
+                                         dilation=conv.dilation[0], eps=norm.eps, relu=relu)
         wp, b = self._packed(conv)
         return _ops.conv_in(x, wp, b, conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0], eps=norm.eps,
                             residual=residual, relu=relu)
 
-    def _seq_tc(self, seq, x):
+    def _seq_tc(self, seq, x, train=False):
         for blk in seq:
             if isinstance(blk, INSResBlock):                      # conv-IN-ReLU-conv-IN, + x (style_networks.py:266-289)
                 m = blk.model
-                h = self._conv_in(x, m[0], m[1], True)
-                x = self._conv_in(h, m[3], m[4], False, residual=x)
+                h = self._conv_in(x, m[0], m[1], True, train=train)
+                x = self._conv_in(h, m[3], m[4], False, residual=x, train=train)
             else:                                                 # ReLUINSConv2d: conv-IN-ReLU (:252-263)
                 m = blk.model
-                x = self._conv_in(x, m[0], m[1], True)
+                x = self._conv_in(x, m[0], m[1], True, train=train)
         return x
 
-    def trunk_tc(self, input_dict, out):
-        """`trunk` with every conv + InstanceNorm (+ residual) (+ ReLU) on `oess_conv2d_nhwc_tf32_instats` /
-        `oess_instancenorm_nhwc_sums`; nearest x2 upsampling and the skip concatenations stay (channels-last) torch ops."""
-        with torch.no_grad():
+    def trunk_tc(self, input_dict, out, train=False):
+        """`trunk` with every conv + InstanceNorm (+ residual) (+ ReLU) on the hand-written kernels; nearest x2 upsampling
+        and the skip concatenations stay (channels-last) torch ops.  train=False: forward only (no autograd graph);
+        train=True: differentiable blocks (`ops.conv_in_autograd`)."""
+        with torch.set_grad_enabled(train and torch.is_grad_enabled()):
             cl = torch.channels_last
             sz_in = input_dict[1].shape[3]
-            x = self._seq_tc(self.decoder_scale_1, input_dict[8])
+            x = self._seq_tc(self.decoder_scale_1, input_dict[8], train)
             x = torch.cat([f.interpolate(x, scale_factor=2, mode='nearest'), input_dict[4]], dim=1).contiguous(memory_format=cl)
-            x = self._seq_tc(self.decoder_scale_2, x)
+            x = self._seq_tc(self.decoder_scale_2, x, train)
             self.update_skip_dict(out, x, sz_in)
             x = torch.cat([f.interpolate(x, scale_factor=2, mode='nearest'), input_dict[2]], dim=1).contiguous(memory_format=cl)
-            x = self._seq_tc(self.decoder_scale_3, x)
+            x = self._seq_tc(self.decoder_scale_3, x, train)
             self.update_skip_dict(out, x, sz_in)
             x = f.interpolate(x, scale_factor=2, mode='nearest').contiguous(memory_format=cl)
-            return self._seq_tc(self.decoder_scale_4, x)
+            return self._seq_tc(self.decoder_scale_4, x, train)
+
+    def _tc_train_ok(self, input_dict):
+        x = input_dict[8]
+        convs = [m for blk in (self.decoder_scale_1, self.decoder_scale_2, self.decoder_scale_3, self.decoder_scale_4)
+                 for m in blk.modules() if isinstance(m, nn.Conv2d)]
+        return (USE_TENSOR_CORES and TRAIN_ON_TENSOR_CORES and x.is_cuda and x.dtype == torch.float32
+                and self.skip_type == 'concat' and torch.is_grad_enabled()
+                and all(v.shape[1] % 4 == 0 for v in input_dict.values())
+                and all(c.stride == (1, 1) and c.kernel_size[0] == c.kernel_size[1] and c.out_channels % 4 == 0
+                        and (256 % (c.out_channels // 4) == 0 or (c.out_channels // 4) % 256 == 0) for c in convs))
 
     # ---- collapsed head weights (tiny, differentiable w.r.t. decoder_ch256 / decoder_ch512 / text_embeddings / linear_probe)
     def collapsed_head(self):

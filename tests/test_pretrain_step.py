@@ -92,7 +92,9 @@ def test_pretrain_step_matches_literal_reference_formulation():
     sd_back = {k: v.clone() for k, v in back.state_dict().items()}
     sd_teacher = {k: v.clone() for k, v in teacher.state_dict().items()}
 
+    from openess_b200.models import style_networks as sn
     im.USE_TENSOR_CORES = False                       # identical fp32 modules on both sides: pins the composition
+    sn.TRAIN_ON_TENSOR_CORES = False
     try:
         teacher.train(); back.train()
         ref_total, ref_nce, ref_dense = _literal_step(e2vid, back, teacher, event, frame, pl, sp, S, steps)
@@ -135,11 +137,12 @@ def test_pretrain_step_matches_literal_reference_formulation():
             assert torch.equal(p, before[n]) == (not n.startswith("decoder")), n
     finally:
         im.USE_TENSOR_CORES = True
+        sn.TRAIN_ON_TENSOR_CORES = True
 
-    # tensor-core teacher (the production configuration): same step, loss in the same noise class
+    # tensor-core teacher and task decoder (the production configuration): same step, losses in the TF32 noise class
     back.load_state_dict(sd_back); teacher.load_state_dict(sd_teacher)
     total_tc, losses_tc, _ = step.task_train_step((event, None, frame, pl, sp))
-    assert float(losses_tc["dense_clip_loss"]) == pytest.approx(float(ref_dense), rel=2e-4)     # event branch: no TF32 here
+    assert float(losses_tc["dense_clip_loss"]) == pytest.approx(float(ref_dense), rel=2e-2)
     assert float(losses_tc["contrastive_nce_loss"]) == pytest.approx(float(ref_nce), rel=5e-2)
 
 
