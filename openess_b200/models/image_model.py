@@ -127,5 +127,11 @@ class DilationFeatureExtractor(nn.Module):
         without materialising the [B, 256, H, W] map: encoder -> decoder 1x1 conv (autograd) -> `oess_upnorm_pool`."""
         if self.preprocessing:
             x = self.preprocessing(x)
-        d = self.decoder[0](self.encoder(x))                  # [B, 256, H/4, W/4]
+        feats = self.encoder(x)                               # [B, 2048, H/4, W/4]
+        conv = self.decoder[0]
+        if USE_TENSOR_CORES and feats.is_cuda and feats.dtype == torch.float32:
+            # trainable 1x1 conv 2048 -> 256: tcgen05 forward + backward-weight (the frozen encoder needs no backward-data)
+            d = _tc.conv2d_tc_autograd(feats, conv.weight, conv.bias, 0, 1)
+        else:
+            d = conv(feats)                                   # [B, 256, H/4, W/4]
         return _tc.upnorm_pool(d, superpixels, superpixel_size, M, scale=4)
