@@ -265,6 +265,15 @@ int oess_instancenorm_nhwc_bwd(const float* dy, const float* y, const float* xha
                                const double* fwd_sums, double* bwd_sums, float eps, float* dz, float* d_res,
                                oess_stream_t stream);
 
+/* Training variants of conv -> BatchNorm (batch statistics from oess_conv2d_nhwc_tf32_stats in the first 2 C doubles of ws):
+ * the forward keeps z (conv output) and writes y = act(BN(z) + residual) to y_out; the backward produces the gradient dz of
+ * the conv output, d_res, and (d_beta, d_gamma) in bwd_sums [2 C] doubles.  models/deeplabv3.py head / ASPP blocks. */
+int oess_batchnorm_nhwc_sums_train(float* z, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
+                                   float* running_var, float eps, float momentum, const float* residual, int relu,
+                                   float* y_out, void* ws, size_t ws_bytes, oess_stream_t stream);
+int oess_batchnorm_nhwc_bwd(const float* dy, const float* y, const float* z, int64_t R, int C, const double* fwd_sums,
+                            const float* gamma, double* bwd_sums, float eps, float* dz, float* d_res, oess_stream_t stream);
+
 /* BatchNorm2d (torch.nn.BatchNorm2d semantics) over channels-last rows x [R = B*H*W, C], IN PLACE, with optional residual
  * add and ReLU: the normalisation between the teacher's tensor-core convolutions.  The OpenESS trainers call `.train()`
  * on the frozen ResNet-50 teacher every step (training/pretrain_trainer.py:370-371; models/image_model.py:116-117), so

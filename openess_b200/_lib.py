@@ -68,6 +68,8 @@ SIGNATURES = {
     "oess_conv2d_wgrad_nhwc_tf32": [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, _vp],
     "oess_instancenorm_nhwc_sums_train": [_vp, _int, _i64, _int, _vp, _f32, _vp, _int, _vp, _vp],
     "oess_instancenorm_nhwc_bwd": [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _f32, _vp, _vp, _vp],
+    "oess_batchnorm_nhwc_sums_train": [_vp, _i64, _int, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _int, _vp, _vp, _sz, _vp],
+    "oess_batchnorm_nhwc_bwd": [_vp, _vp, _vp, _i64, _int, _vp, _vp, _vp, _f32, _vp, _vp, _vp],
     "oess_bn_ws_bytes": [_int, ctypes.POINTER(_sz)],
     "oess_batchnorm_nhwc": [_vp, _i64, _int, _vp, _vp, _vp, _vp, _f32, _f32, _int, _vp, _int, _vp, _sz, _vp],
     "oess_conv2d_nhwc_tf32": [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _vp],

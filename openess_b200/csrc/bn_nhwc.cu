@@ -86,7 +86,7 @@ __global__ void k_bn_finalize(const double* __restrict__ sums, const float* __re
 
 __global__ void __launch_bounds__(256)
 k_bn_apply(float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-           const float* __restrict__ residual, int64_t total4, int C4, int relu) {
+           const float* __restrict__ residual, int64_t total4, int C4, int relu, float* __restrict__ y_out) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
         const int q = (int)(i % C4);
@@ -99,7 +99,7 @@ k_bn_apply(float* __restrict__ x, const float* __restrict__ scale, const float* 
             v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
         }
         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        reinterpret_cast<float4*>(x)[i] = v;
+        reinterpret_cast<float4*>(y_out ? y_out : x)[i] = v;
     }
 }
 
@@ -139,7 +139,7 @@ k_in_apply(float* __restrict__ x, const double* __restrict__ sums, const float* 
 // ReLU).  grid (row blocks, channel-quad blocks, B); same thread layout as k_bn_stats.
 __global__ void __launch_bounds__(256)
 k_in_bwd_stats(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ xhat, int64_t HW, int C,
-               int rows_per_block, double* __restrict__ sums) {
+               int rows_per_block, double* __restrict__ sums, const double* __restrict__ fwd_sums, float eps, int raw) {
     const int C4 = C >> 2;
     const int qpb = min(C4, 256);
     const int lanes = 256 / qpb;
@@ -150,6 +150,18 @@ k_in_bwd_stats(const float* __restrict__ dy, const float* __restrict__ y, const 
     const int64_t base = (int64_t)b * HW;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f), ss = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q < C4) {
+        float mu[4] = {0.f, 0.f, 0.f, 0.f}, iv[4] = {1.f, 1.f, 1.f, 1.f};     // raw: xhat holds the un-normalised conv output
+        if (raw) {
+            const double* fs = fwd_sums + (int64_t)b * 2 * C;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double mean = fs[q * 4 + j] / (double)HW;
+                double var = fs[C + q * 4 + j] / (double)HW - mean * mean;
+                if (var < 0) var = 0;
+                mu[j] = (float)mean;
+                iv[j] = (float)rsqrt(var + (double)eps);
+            }
+        }
         for (int64_t r = r0 + rl; r < r1; r += lanes) {
             const int64_t i = (base + r) * C4 + q;
             float4 g = __ldg(reinterpret_cast<const float4*>(dy) + i);
@@ -157,7 +169,8 @@ k_in_bwd_stats(const float* __restrict__ dy, const float* __restrict__ y, const 
                 const float4 yy = __ldg(reinterpret_cast<const float4*>(y) + i);
                 g.x = yy.x > 0.f ? g.x : 0.f; g.y = yy.y > 0.f ? g.y : 0.f; g.z = yy.z > 0.f ? g.z : 0.f; g.w = yy.w > 0.f ? g.w : 0.f;
             }
-            const float4 xh = __ldg(reinterpret_cast<const float4*>(xhat) + i);
+            float4 xh = __ldg(reinterpret_cast<const float4*>(xhat) + i);
+            if (raw) { xh.x = (xh.x - mu[0]) * iv[0]; xh.y = (xh.y - mu[1]) * iv[1]; xh.z = (xh.z - mu[2]) * iv[2]; xh.w = (xh.w - mu[3]) * iv[3]; }
             s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
             ss.x += g.x * xh.x; ss.y += g.y * xh.y; ss.z += g.z * xh.z; ss.w += g.w * xh.w;
         }
@@ -186,7 +199,7 @@ k_in_bwd_stats(const float* __restrict__ dy, const float* __restrict__ y, const 
 __global__ void __launch_bounds__(256)
 k_in_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ xhat,
                const double* __restrict__ fwd_sums, const double* __restrict__ bwd_sums, int64_t HW, int C, int64_t total4,
-               float eps, float* __restrict__ dz, float* __restrict__ d_res) {
+               float eps, float* __restrict__ dz, float* __restrict__ d_res, const float* __restrict__ gamma, int raw) {
     const int C4 = C >> 2;
     const int64_t per_sample4 = HW * C4;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -210,7 +223,9 @@ k_in_bwd_apply(const float* __restrict__ dy, const float* __restrict__ y, const 
             double var = fs[C + c] / (double)HW - mean * mean;
             if (var < 0) var = 0;
             const double inv = rsqrt(var + (double)eps);
-            o[j] = (float)(inv * ((double)gg[j] - bs[c] / (double)HW - (double)xx[j] * (bs[C + c] / (double)HW)));
+            const double xhj = raw ? ((double)xx[j] - mean) * inv : (double)xx[j];
+            const double gam = gamma ? (double)gamma[c] : 1.0;
+            o[j] = (float)(gam * inv * ((double)gg[j] - bs[c] / (double)HW - xhj * (bs[C + c] / (double)HW)));
         }
         reinterpret_cast<float4*>(dz)[i] = make_float4(o[0], o[1], o[2], o[3]);
         if (d_res) reinterpret_cast<float4*>(d_res)[i] = g;
@@ -238,10 +253,10 @@ OESS_API int oess_instancenorm_nhwc_bwd(const float* dy, const float* y, const f
     int64_t rpb = (HW * B + (int64_t)kNumSMs * 16 - 1) / ((int64_t)kNumSMs * 16);
     if (rpb < (int64_t)lanes * 16) rpb = (int64_t)lanes * 16;
     const dim3 grid((unsigned)((HW + rpb - 1) / rpb), (unsigned)((C4 + qpb - 1) / qpb), (unsigned)B);
-    OESS_KERNEL("in_bwd_stats", st, k_in_bwd_stats<<<grid, 256, 0, st>>>(dy, y, xhat, HW, C, (int)rpb, bwd_sums));
+    OESS_KERNEL("in_bwd_stats", st, k_in_bwd_stats<<<grid, 256, 0, st>>>(dy, y, xhat, HW, C, (int)rpb, bwd_sums, fwd_sums, eps, 0));
     const int64_t total4 = (int64_t)B * HW * C4;
     const unsigned blocks = (unsigned)((total4 + 255) / 256 < (int64_t)kNumSMs * 16 ? (total4 + 255) / 256 : (int64_t)kNumSMs * 16);
-    OESS_KERNEL("in_bwd_apply", st, k_in_bwd_apply<<<blocks, 256, 0, st>>>(dy, y, xhat, fwd_sums, bwd_sums, HW, C, total4, eps, dz, d_res));
+    OESS_KERNEL("in_bwd_apply", st, k_in_bwd_apply<<<blocks, 256, 0, st>>>(dy, y, xhat, fwd_sums, bwd_sums, HW, C, total4, eps, dz, d_res, nullptr, 0));
     return OESS_OK;
 }
 
@@ -278,7 +293,7 @@ OESS_API int oess_bn_ws_bytes(int C, size_t* ws_bytes) {
 
 static int batchnorm_impl(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
                           float* running_var, float eps, float momentum, int training, const float* residual,
-                          int relu, void* ws, size_t ws_bytes, int have_sums, oess_stream_t stream) {
+                          int relu, void* ws, size_t ws_bytes, int have_sums, oess_stream_t stream, float* y_out = nullptr) {
     size_t need = 0;
     if (oess_bn_ws_bytes(C, &need)) return OESS_E_ARG;
     if (!x || R < 0 || (C & 3)) return OESS_E_ARG;
@@ -306,7 +321,7 @@ static int batchnorm_impl(float* x, int64_t R, int C, const float* gamma, const 
         sums, gamma, beta, running_mean, running_var, C, (double)R, eps, momentum, training ? 1 : 0, scale, shift));
     const int64_t total4 = R * C4;
     const unsigned blocks = (unsigned)((total4 + 255) / 256 < (int64_t)kNumSMs * 16 ? (total4 + 255) / 256 : (int64_t)kNumSMs * 16);
-    OESS_KERNEL("bn_apply", st, k_bn_apply<<<blocks, 256, 0, st>>>(x, scale, shift, residual, total4, C4, relu ? 1 : 0));
+    OESS_KERNEL("bn_apply", st, k_bn_apply<<<blocks, 256, 0, st>>>(x, scale, shift, residual, total4, C4, relu ? 1 : 0, y_out));
     return OESS_OK;
 }
 
@@ -324,4 +339,38 @@ OESS_API int oess_batchnorm_nhwc_sums(float* x, int64_t R, int C, const float* g
                                       void* ws, size_t ws_bytes, oess_stream_t stream) {
     return batchnorm_impl(x, R, C, gamma, beta, running_mean, running_var, eps, momentum, 1, residual, relu, ws, ws_bytes,
                           1, stream);
+}
+
+// Training forward of conv -> BatchNorm (batch statistics already in the first 2 C doubles of `ws`): z (the conv output) is
+// KEPT for the backward pass, y_out receives act(BN(z) + residual); running statistics are updated.
+OESS_API int oess_batchnorm_nhwc_sums_train(float* z, int64_t R, int C, const float* gamma, const float* beta,
+                                            float* running_mean, float* running_var, float eps, float momentum,
+                                            const float* residual, int relu, float* y_out, void* ws, size_t ws_bytes,
+                                            oess_stream_t stream) {
+    if (!y_out) return OESS_E_ARG;
+    return batchnorm_impl(z, R, C, gamma, beta, running_mean, running_var, eps, momentum, 1, residual, relu, ws, ws_bytes, 1,
+                          stream, y_out);
+}
+
+// Backward of y = act(gamma * (z - mean) / sqrt(var + eps) + beta + residual) with batch statistics (fwd_sums [2 C]):
+//   g = dy * [y > 0];  d_beta = sum g;  d_gamma = sum g x_hat;  dz = gamma inv_std (g - mean(g) - x_hat mean(g x_hat))
+// bwd_sums [2 C] doubles receive (d_beta, d_gamma); dz and optionally d_res (= g) are written.  y = NULL: no ReLU.
+OESS_API int oess_batchnorm_nhwc_bwd(const float* dy, const float* y, const float* z, int64_t R, int C, const double* fwd_sums,
+                                     const float* gamma, double* bwd_sums, float eps, float* dz, float* d_res,
+                                     oess_stream_t stream) {
+    if (!dy || !z || !fwd_sums || !bwd_sums || !dz || R <= 0 || C <= 0 || (C & 3)) return OESS_E_ARG;
+    const int C4 = C >> 2;
+    if (C4 > 256 ? (C4 % 256) != 0 : (256 % C4) != 0) return OESS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    OESS_CUDA(cudaMemsetAsync(bwd_sums, 0, sizeof(double) * 2 * (size_t)C, st));
+    const int qpb = C4 < 256 ? C4 : 256;
+    const int lanes = 256 / qpb;
+    int64_t rpb = (R + (int64_t)kNumSMs * 16 - 1) / ((int64_t)kNumSMs * 16);
+    if (rpb < (int64_t)lanes * 16) rpb = (int64_t)lanes * 16;
+    const dim3 grid((unsigned)((R + rpb - 1) / rpb), (unsigned)((C4 + qpb - 1) / qpb), 1);
+    OESS_KERNEL("bn_bwd_stats", st, k_in_bwd_stats<<<grid, 256, 0, st>>>(dy, y, z, R, C, (int)rpb, bwd_sums, fwd_sums, eps, 1));
+    const int64_t total4 = R * C4;
+    const unsigned blocks = (unsigned)((total4 + 255) / 256 < (int64_t)kNumSMs * 16 ? (total4 + 255) / 256 : (int64_t)kNumSMs * 16);
+    OESS_KERNEL("bn_bwd_apply", st, k_in_bwd_apply<<<blocks, 256, 0, st>>>(dy, y, z, fwd_sums, bwd_sums, R, C, total4, eps, dz, d_res, gamma, 1));
+    return OESS_OK;
 }

@@ -398,3 +398,71 @@ class _ConvINAct(torch.autograd.Function):
 def conv_in_autograd(x, weight, bias=None, residual=None, padding=0, dilation=1, eps=1e-5, relu=False):
     """Differentiable act(InstanceNorm2d(conv(x) + bias) + residual) on hand-written kernels (see _ConvINAct)."""
     return _ConvINAct.apply(x, weight, bias, residual, int(padding), int(dilation), float(eps), bool(relu))
+
+
+class _ConvBNAct(torch.autograd.Function):
+    """y = act(BatchNorm2d_train(conv(x)) + residual), stride 1, bias-free conv: tcgen05 conv with batch statistics in its
+    epilogue, fused normalise kernel (running statistics updated), and in the backward pass the BatchNorm Jacobian kernels
+    + tcgen05 backward-data / backward-weight convolutions.  `bn` is the nn.BatchNorm2d module (buffers updated in place)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, residual, bn, padding, dilation, relu):
+        B, Cin, H, W = x.shape
+        Cout, _, K, _ = weight.shape
+        cl = torch.channels_last
+        xc = x.float().contiguous(memory_format=cl)
+        Ho = H + 2 * padding - dilation * (K - 1)
+        Wo = W + 2 * padding - dilation * (K - 1)
+        z = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=cl)
+        y = torch.empty_like(z)
+        res = None if residual is None else residual.float().contiguous(memory_format=cl)
+        mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        track = bn.track_running_stats and bn.running_mean is not None
+        nb = ctypes.c_size_t(0)
+        check(lib().oess_bn_ws_bytes(Cout, ctypes.byref(nb)), "oess_bn_ws_bytes")
+        wp = conv2d_pack(weight)
+        with torch.cuda.device(x.device):
+            ws = _lib.workspace(nb.value, x.device)
+            st = stream_ptr(x.device)
+            check(lib().oess_conv2d_nhwc_tf32_stats(ptr(xc), ptr(wp), None, ptr(z), B, H, W, Cin, Cout, K, K, 1, padding,
+                                                    dilation, ptr(ws), st), "oess_conv2d_nhwc_tf32_stats")
+            sums = ws[:16 * Cout].view(torch.float64).clone()
+            check(lib().oess_batchnorm_nhwc_sums_train(ptr(z), B * Ho * Wo, Cout, ptr(gamma), ptr(beta),
+                                                       ptr(bn.running_mean) if track else None,
+                                                       ptr(bn.running_var) if track else None, float(bn.eps), mom, ptr(res),
+                                                       1 if relu else 0, ptr(y), ptr(ws), ws.numel(), st),
+                  "oess_batchnorm_nhwc_sums_train")
+            if track and bn.num_batches_tracked is not None:
+                bn.num_batches_tracked += 1
+        ctx.save_for_backward(xc, weight, z, y if relu else None, sums, gamma)
+        ctx.meta = (K, padding, dilation, float(bn.eps), residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, weight, z, y, sums, gamma = ctx.saved_tensors
+        K, padding, dilation, eps, has_res = ctx.meta
+        B, Cout, Ho, Wo = z.shape
+        dyc = dy.float().contiguous(memory_format=torch.channels_last)
+        dz = torch.empty_like(z)
+        d_res = torch.empty_like(z) if (has_res and ctx.needs_input_grad[4]) else None
+        bsums = torch.empty(2 * Cout, dtype=torch.float64, device=dy.device)
+        with torch.cuda.device(dy.device):
+            check(lib().oess_batchnorm_nhwc_bwd(ptr(dyc), ptr(y), ptr(z), B * Ho * Wo, Cout, ptr(sums), ptr(gamma), ptr(bsums),
+                                                eps, ptr(dz), ptr(d_res), stream_ptr(dy.device)), "oess_batchnorm_nhwc_bwd")
+        dx = dW = None
+        if ctx.needs_input_grad[0]:
+            wpd, pad = conv2d_dgrad_pack(weight, padding, dilation)
+            dx = conv2d_tc(dz, wpd, None, K, 1, pad, dilation)
+        if ctx.needs_input_grad[1]:
+            dW = conv2d_wgrad(xc, dz, K, padding, dilation)
+        dgamma = bsums[Cout:].float() if ctx.needs_input_grad[2] else None
+        dbeta = bsums[:Cout].float() if ctx.needs_input_grad[3] else None
+        return dx, dW, dgamma, dbeta, d_res, None, None, None, None
+
+
+def conv_bn_autograd(x, conv, bn, residual=None, relu=False):
+    """Differentiable act(bn(conv(x)) + residual) for a bias-free stride-1 `conv` and a train-mode nn.BatchNorm2d `bn`."""
+    if conv.bias is not None or conv.stride != (1, 1):
+        raise ValueError("conv_bn_autograd: bias-free stride-1 convolutions only")
+    return _ConvBNAct.apply(x, conv.weight, bn.weight, bn.bias, residual, bn, conv.padding[0], conv.dilation[0], bool(relu))

@@ -86,3 +86,46 @@ def test_deeplab_frozen_backbone_tensor_cores_train_and_eval():
           % (scale, err_tc.mean(), err_lib.mean()))
     assert err_tc.mean() < 2.0 * err_lib.mean() + 1e-4 * scale
     np.testing.assert_allclose(m.state_dict()["backbone.layer4.2.bn3.running_mean"].cpu().numpy(), z["rm_l4"], atol=5e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,Cout,k,p,d,res,relu", [(64, 64, 3, 1, 1, False, True), (256, 64, 1, 0, 1, False, True),
+                                                   (32, 128, 3, 2, 2, True, True), (64, 32, 3, 1, 1, True, False)])
+def test_conv_batchnorm_autograd_vs_torch(C, Cout, k, p, d, res, relu):
+    """conv -> train-mode BatchNorm (-> + residual) (-> ReLU), forward and backward on hand-written kernels, against torch
+    autograd in float64 (ReLU active set taken from the kernel's forward, see test_conv_instancenorm_autograd_vs_torch)."""
+    import torch.nn.functional as F
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(C + Cout + k)
+    B, H, W = 2, 12, 20
+    x = torch.randn(B, C, H, W, generator=g, dtype=torch.float64, requires_grad=True)
+    conv_ref = torch.nn.Conv2d(C, Cout, k, padding=p, dilation=d, bias=False).double()
+    bn_ref = torch.nn.BatchNorm2d(Cout).double().train()
+    with torch.no_grad():
+        conv_ref.weight.copy_(torch.randn(conv_ref.weight.shape, generator=g, dtype=torch.float64) / (C * k * k) ** 0.5)
+        bn_ref.weight.uniform_(0.5, 1.5)
+        bn_ref.bias.normal_(0, 0.3)
+    r = torch.randn(B, Cout, H, W, generator=g, dtype=torch.float64, requires_grad=True) if res else None
+    conv = torch.nn.Conv2d(C, Cout, k, padding=p, dilation=d, bias=False).cuda()
+    bn = torch.nn.BatchNorm2d(Cout).cuda().train()
+    conv.load_state_dict({k_: v.float() for k_, v in conv_ref.state_dict().items()})
+    bn.load_state_dict({k_: (v.float() if v.is_floating_point() else v) for k_, v in bn_ref.state_dict().items()})
+    xg = x.detach().float().cuda().requires_grad_(True)
+    rg = r.detach().float().cuda().requires_grad_(True) if res else None
+    yg = ops.conv_bn_autograd(xg, conv, bn, residual=rg, relu=relu)
+    y = bn_ref(conv_ref(x))
+    if res:
+        y = y + r
+    if relu:
+        y = y * (yg.detach().cpu() > 0).double()
+    dy = torch.randn(y.shape, generator=g, dtype=torch.float64)
+    y.backward(dy)
+    yg.backward(dy.float().cuda())
+    assert float((yg.detach().cpu().double() - y.detach()).abs().max()) < 1e-2
+    for got, ref, name in ((xg.grad, x.grad, "dx"), (conv.weight.grad, conv_ref.weight.grad, "dW"),
+                           (bn.weight.grad, bn_ref.weight.grad, "dgamma"), (bn.bias.grad, bn_ref.bias.grad, "dbeta")):
+        err = float((got.cpu().double() - ref).abs().max())
+        assert err < 1e-2 * float(ref.abs().max()) + 1e-4, (name, err, float(ref.abs().max()))
+    if res:
+        assert float((rg.grad.cpu().double() - r.grad).abs().max()) < 1e-6
+    torch.testing.assert_close(bn.running_var.cpu().double(), bn_ref.running_var, atol=1e-3, rtol=2e-3)
