@@ -12,7 +12,9 @@ What changes on the B200:
     running-stat updates in train mode, folded in eval mode);
   * eval + no-grad (validation, test.py): the head also runs on the tensor cores -- ASPP branches, projection and the
     3x3 classifier conv with folded BN + ReLU epilogues;
-  * the trainable head under autograd stays torch ops (backward kernels are future work).
+  * the trainable head under autograd (fine-tuning, BASELINE config 4): every conv -> BatchNorm -> ReLU block is
+    `ops.conv_bn_autograd` (tcgen05 forward / backward-data / backward-weight + BatchNorm Jacobian kernels); the one-pixel
+    image-pooling branch, Dropout and the K-class text-embedding conv stay torch ops.
 """
 import os
 
@@ -25,6 +27,7 @@ from torchvision.models.resnet import Bottleneck, ResNet
 from . import _tc_resnet as _tcr
 
 USE_TENSOR_CORES = os.environ.get("OESS_DEEPLAB_TC", "1") != "0"
+TRAIN_ON_TENSOR_CORES = os.environ.get("OESS_DEEPLAB_TC_TRAIN", "1") != "0"     # trainable head (fwd + bwd) on own kernels
 
 
 class ASPPConv(nn.Sequential):
@@ -89,11 +92,29 @@ class DeepLabHead(nn.Module):
                 and x.dtype == torch.float32):
             feature = self._aspp_tc(x)
             cls = _tcr.conv_bn(self._cache, feature, self.classifier[0], self.classifier[1], True)
+        elif (USE_TENSOR_CORES and TRAIN_ON_TENSOR_CORES and x.is_cuda and torch.is_grad_enabled() and self.training
+              and x.dtype == torch.float32):
+            feature, cls = self._train_tc(x)
         else:
             feature = self.ASPP(x)
             cls = self.classifier(feature)
         logits = F.conv2d(cls, self.text_embeddings[:, :, None, None])
         return logits, feature
+
+    def _train_tc(self, x):
+        """Training forward (fine-tuning / pretraining of the head) with every conv -> BatchNorm -> ReLU block as
+        `ops.conv_bn_autograd`: tcgen05 forward / backward-data / backward-weight convolutions + BatchNorm Jacobian kernels.
+        The image-pooling branch (one pixel), Dropout and the K-class text-embedding conv stay torch ops."""
+        from .. import ops as _ops
+        a = self.ASPP
+        cl = torch.channels_last
+        x = x.contiguous(memory_format=cl)
+        res = [_ops.conv_bn_autograd(x, a.convs[i][0], a.convs[i][1], relu=True) for i in range(4)]
+        res.append(a.convs[4](x))
+        cat = torch.cat(res, dim=1).contiguous(memory_format=cl)
+        feature = a.project[3](_ops.conv_bn_autograd(cat, a.project[0], a.project[1], relu=True))      # Dropout(0.1)
+        cls = _ops.conv_bn_autograd(feature, self.classifier[0], self.classifier[1], relu=True)
+        return feature, cls
 
     def _aspp_tc(self, x):
         """ASPP.forward in eval mode on the tensor cores (folded BN + ReLU epilogues; Dropout is the identity in eval)."""

@@ -61,12 +61,20 @@ def test_deeplab_frozen_backbone_tensor_cores_train_and_eval():
     assert prof.kernels["tc_conv2d"][0] == 52 + 4 + 1 + 1 and "bn_apply" not in prof.kernels
     for got, key in ((lo, "eval_logits_sub"), (fe, "eval_feats_sub")):
         assert float(np.abs(got - z[key]).max()) < 2e-2 * float(np.abs(z[key]).max()), key
-    # ---- train mode (fine-tuning step): frozen backbone on the tensor cores with batch-statistics BN, head under autograd
+    # ---- train mode (fine-tuning step, BASELINE config 4): frozen backbone on the tensor cores with batch-statistics BN,
+    #      trainable head as conv_bn_autograd blocks (6 more tcgen05 convs forward; dgrad / wgrad / BN Jacobian backward)
     m.train()
+    n0 = _lib.launch_count()
     with _lib.profile() as prof:
         lt, ft = m(x)
-    assert prof.kernels["tc_conv2d"][0] == 52 and "bn_stats" not in prof.kernels and prof.kernels["bn_apply"][0] == 52
+    assert prof.kernels["tc_conv2d"][0] == 52 + 6 and "bn_stats" not in prof.kernels and prof.kernels["bn_apply"][0] == 52 + 6
+    n1 = _lib.launch_count()
     (lt.square().mean() + ft.square().mean()).backward()
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - n1 >= 6 * 3 + 2          # per block: BN bwd stats + apply + wgrad (+ dgrad past the first)
+    np.testing.assert_allclose(m.classifier.text_embeddings.grad.cpu().numpy(), z["grad_text"],
+                               atol=0.25 * float(np.abs(z["grad_text"]).max()))
+    assert m.classifier.pixel_feature.weight.grad is None
     assert m.classifier.text_embeddings.grad is not None and not any(p.grad is not None for p in m.backbone.parameters())
     err_tc = np.abs(_sub(lt, ft)[0] - z["train_logits_sub"])
     # noise class: the same mirror through torch's default cuDNN-TF32 convolutions

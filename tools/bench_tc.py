@@ -143,10 +143,37 @@ def semseg():
                       "ms_torch_cudnn_tf32": res[False], "torch_tflops": fl / res[False] / 1e9}))
 
 
+def deeplab():
+    """BASELINE config 4: DeepLabv3-R50 head fine-tune step (frozen backbone, K = 11) forward + backward, 440 x 640."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from seeded_weights import seeded_state_dict
+    from openess_b200.models import deeplabv3 as dl
+    m = dl.deeplabv3_resnet50(num_classes=11, text_embeddings_path=None, output_stride=32, pretrained_backbone='',
+                              if_finetuning=True, frozen_backbone=True)
+    m.load_state_dict(seeded_state_dict(m, 4), strict=True)
+    m = m.cuda().train()
+    B = 4
+    x = torch.rand(B, 3, 440, 640, device="cuda")
+
+    def step():
+        m.zero_grad(set_to_none=True)
+        lo, fe = m(x)
+        (lo.square().mean() + fe.square().mean()).backward()
+
+    res = {}
+    for mode in ("own", "torch"):
+        dl.USE_TENSOR_CORES = mode == "own"
+        res[mode] = timeit(step, iters=5, warm=2)
+    dl.USE_TENSOR_CORES = True
+    print(json.dumps({"op": "deeplabv3_r50_head_finetune_fwd_bwd", "B": B, "ms_own_kernels": res["own"],
+                      "ms_torch_cudnn_tf32": res["torch"], "samples_per_s_own": B / res["own"] * 1e3}))
+
+
 if __name__ == "__main__":
     if "--teacher" in sys.argv:
         teacher()
         semseg()
+        deeplab()
         sys.exit(0)
     main()
     convlstm()
