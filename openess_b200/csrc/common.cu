@@ -113,9 +113,13 @@ k_seg_exscan_u32(uint32_t* __restrict__ data, int64_t stride, int64_t len) {
 namespace radix {
 
 __global__ void k_prefix_chunks(uint32_t* __restrict__ hist, const int* __restrict__ chunk_start,
-                                uint32_t* __restrict__ tot) {
+                                uint32_t* __restrict__ tot, int nb) {
     const int f = blockIdx.x;
     const int b = blockIdx.y * 128 + threadIdx.x;
+    if (b >= nb) {                                   // bins that cannot occur in this pass: never histogrammed
+        tot[(int64_t)f * kBins + b] = 0;
+        return;
+    }
     const int c0 = chunk_start[f], c1 = chunk_start[f + 1];
     uint32_t run = 0;
     int c = c0;

@@ -36,7 +36,7 @@ template <class Src>
 __global__ void __launch_bounds__(kThreads)
 k_hist(Src src, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start, int F,
        int shift, uint32_t mask, uint32_t* __restrict__ hist, uint32_t* __restrict__ pix,
-       int64_t pix_stride) {
+       int64_t pix_stride, int nb) {
     __shared__ uint32_t s_hist[kBins];
     const int g = blockIdx.x;
     const int f = find_frame(chunk_start, F, g);
@@ -44,7 +44,7 @@ k_hist(Src src, const int64_t* __restrict__ frame_offsets, const int* __restrict
     const int c = g - chunk_start[f];
     const int64_t fbeg = frame_offsets[f];
     const uint32_t nf = (uint32_t)(frame_offsets[f + 1] - fbeg);
-    for (int b = threadIdx.x; b < kBins; b += kThreads) s_hist[b] = 0;
+    for (int b = threadIdx.x; b < nb; b += kThreads) s_hist[b] = 0;      // nb = bins that can occur (multiple of 128)
     __syncthreads();
     const uint32_t cbeg = (uint32_t)c * kChunk;
 #pragma unroll
@@ -58,13 +58,13 @@ k_hist(Src src, const int64_t* __restrict__ frame_offsets, const int* __restrict
     }
     __syncthreads();
     uint32_t* h = hist + (int64_t)g * kBins;
-    for (int b = threadIdx.x; b < kBins; b += kThreads) h[b] = s_hist[b];
+    for (int b = threadIdx.x; b < nb; b += kThreads) h[b] = s_hist[b];
 }
 
 // Exclusive prefix over the chunks of each frame, per bin (in place); per-frame bin totals to tot.
 // grid (F, kBins / 128), 128 threads.
 __global__ void k_prefix_chunks(uint32_t* __restrict__ hist, const int* __restrict__ chunk_start,
-                                uint32_t* __restrict__ tot);
+                                uint32_t* __restrict__ tot, int nb);
 // Exclusive scan over the kBins totals of each frame (in place).  grid F, kBins threads.
 __global__ void k_bin_scan(uint32_t* __restrict__ tot);
 
@@ -72,7 +72,7 @@ template <class Src>
 __global__ void __launch_bounds__(kThreads, 4)
 k_scatter(Src src, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start, int F,
           int shift, uint32_t mask, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ binbase,
-          typename Src::Item* __restrict__ dst) {
+          typename Src::Item* __restrict__ dst, int nb) {
     __shared__ uint32_t s_cnt[kWarps][kBins];
     const int g = blockIdx.x;
     const int f = find_frame(chunk_start, F, g);
@@ -80,7 +80,10 @@ k_scatter(Src src, const int64_t* __restrict__ frame_offsets, const int* __restr
     const int c = g - chunk_start[f];
     const int64_t fbeg = frame_offsets[f];
     const uint32_t nf = (uint32_t)(frame_offsets[f + 1] - fbeg);
-    for (int b = threadIdx.x; b < kWarps * kBins; b += kThreads) (&s_cnt[0][0])[b] = 0;
+    for (int b = threadIdx.x; b < nb; b += kThreads) {
+#pragma unroll
+        for (int ww = 0; ww < kWarps; ++ww) s_cnt[ww][b] = 0;
+    }
     __syncthreads();
 
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -116,7 +119,7 @@ k_scatter(Src src, const int64_t* __restrict__ frame_offsets, const int* __restr
     // warp-major exclusive prefix per bin, seeded with the global base of (frame, bin, chunk)
     const uint32_t* h = hist + (int64_t)g * kBins;
     const uint32_t* bb = binbase + (int64_t)f * kBins;
-    for (int b = threadIdx.x; b < kBins; b += kThreads) {
+    for (int b = threadIdx.x; b < nb; b += kThreads) {
         uint32_t run = bb[b] + h[b];
 #pragma unroll
         for (int ww = 0; ww < kWarps; ++ww) {
@@ -136,14 +139,18 @@ k_scatter(Src src, const int64_t* __restrict__ frame_offsets, const int* __restr
 template <class Src>
 static inline int run_pass(const Src& src, const int64_t* frame_offsets, const int* chunk_start, int F,
                            int64_t n_chunks_ub, int shift, uint32_t mask, uint32_t* hist, uint32_t* tot,
-                           uint32_t* pix, int64_t pix_stride, typename Src::Item* dst, cudaStream_t st) {
+                           uint32_t* pix, int64_t pix_stride, typename Src::Item* dst, cudaStream_t st, int n_keys = kBins) {
+    // bins that can occur in this pass, rounded up to the 128-bin granularity of k_prefix_chunks: the per-CTA zeroing /
+    // prefix loops and the chunk-histogram traffic shrink with it (482 of 1024 bins for the 480-row DSEC sensor)
+    int nb = (int)(((int64_t)(n_keys < (int)(mask + 1) ? n_keys : (int)(mask + 1)) + 127) / 128 * 128);
+    if (nb > kBins) nb = kBins;
     if (n_chunks_ub <= 0 || F <= 0) return 0;
     OESS_KERNEL("k_hist", st, k_hist<Src><<<(unsigned)n_chunks_ub, kThreads, 0, st>>>(src, frame_offsets, chunk_start, F, shift, mask,
-                                                          hist, pix, pix_stride));
-    OESS_KERNEL("k_prefix_chunks", st, k_prefix_chunks<<<dim3((unsigned)F, kBins / 128), 128, 0, st>>>(hist, chunk_start, tot));
+                                                          hist, pix, pix_stride, nb));
+    OESS_KERNEL("k_prefix_chunks", st, k_prefix_chunks<<<dim3((unsigned)F, kBins / 128), 128, 0, st>>>(hist, chunk_start, tot, nb));
     OESS_KERNEL("k_bin_scan", st, k_bin_scan<<<(unsigned)F, kBins, 0, st>>>(tot));
     OESS_KERNEL("k_scatter", st, k_scatter<Src><<<(unsigned)n_chunks_ub, kThreads, 0, st>>>(src, frame_offsets, chunk_start, F, shift,
-                                                             mask, hist, tot, dst));
+                                                             mask, hist, tot, dst, nb));
     return 0;
 }
 

@@ -305,7 +305,7 @@ OESS_API int oess_voxel_trilinear(const float* x, const float* y, const float* p
             const tri::Geom g{C, H, W, 0};
             tri::SrcSoA src{x, y, pol, t, frame_offsets, g, 1};
             rc = radix::run_pass(src, frame_offsets, w.chunk_start, F, nch, 0, radix::kBins - 1, w.hist, w.tot,
-                                 (uint32_t*)nullptr, 0, w.a, st);
+                                 (uint32_t*)nullptr, 0, w.a, st, H + 2);
             if (rc) return rc;
             OESS_CUDA(cudaFuncSetAttribute(tri::k_rowsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.row_smem));
             OESS_KERNEL("tri_rowsort", st, tri::k_rowsort<<<dim3((unsigned)F, (unsigned)((H + 1 + tri::kRowWarps - 1) / tri::kRowWarps)),
