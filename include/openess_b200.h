@@ -210,6 +210,35 @@ int oess_pixel_linear_wgrad(const float* dy, const float* x, int B, int Cin, int
  * Requirements: K % 4 == 0 and 16-byte aligned pointers (TMA). */
 int oess_gemm_tf32(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int K,
                    oess_stream_t stream);
+/* Same GEMM with the epilogue the ViT blocks of models/maskclip_model.py:519-541 need:
+ *   C = act(A * B^T + bias) + residual      act: 0 = identity, 1 = GELU (erf form, mmcv FFN :507-513)
+ * residual: [M, N] or NULL; may alias C (the `identity + dropout_layer(out)` residual of mmcv's MultiheadAttention / FFN). */
+int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M,
+                      int N, int K, int act, oess_stream_t stream);
+
+/* ---- MaskCLIP ViT-B/16 forward (models/maskclip_model.py) -- the non-GEMM kernels ------------------
+ * Tokens are row-major [rows, D] float32 (rows = B * T, T = 1 + h * w); D % 128 == 0, D <= 1024.
+ *
+ * oess_vit_patchify: PatchEmbed input side (maskclip_model.py:427-441): 'corner' AdaptivePadding (zeros at the bottom /
+ *   right up to a multiple of P) + non-overlapping P x P patches -> rows [B * h * w, C * P * P] in the column order
+ *   (c, ky, kx) of projection.weight.view(D, -1), so that the strided conv is one oess_gemm_tf32 call.
+ * oess_vit_assemble: x[b, 0] = cls + pos[0]; x[b, 1 + i] = tok[b, i] + pos[1 + i] (VisionTransformer.forward :799-806).
+ * oess_layernorm_rows: y = LayerNorm(x) * gamma + beta over the last dim (biased variance, eps inside the sqrt).
+ * oess_mha_fwd: softmax(Q K^T / sqrt(64)) V per (sample, head) on the packed in_proj output qkv [B, T, 3 * Hh * 64]
+ *   (nn.MultiheadAttention layout: q | k | v, head-major inside each) -> out [B, T, Hh * 64]; head dim is 64 (ViT-B/16);
+ *   fp32 online softmax, no attention matrix in memory.
+ * oess_l2norm_rows: x /= ||x||_2 per row (MaskClipHead.cls_seg :218-219; no eps, as the reference).
+ * oess_bilinear_tokens_to_nchw: bilinear resize (align_corners = False, mmseg.ops.resize = F.interpolate, :909-913) of a
+ *   channels-last token map [B, h, w, K] to planes [B, K, H, W]. */
+int oess_vit_patchify(const float* img, int B, int C, int H, int W, int P, float* rows, oess_stream_t stream);
+int oess_vit_assemble(const float* tok, const float* cls, const float* pos, int B, int T, int D, float* x,
+                      oess_stream_t stream);
+int oess_layernorm_rows(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int D, float* y,
+                        oess_stream_t stream);
+int oess_mha_fwd(const float* qkv, int B, int T, int heads, float* out, oess_stream_t stream);
+int oess_l2norm_rows(float* x, int64_t rows, int D, oess_stream_t stream);
+int oess_bilinear_tokens_to_nchw(const float* tok, int B, int h, int w, int K, int H, int W, float* out,
+                                 oess_stream_t stream);
 
 /* One ConvLSTM step of the E2VID recurrent encoder as one tensor-core kernel (tcgen05 implicit GEMM, TMA 4-D boxes
  * supply the 9 shifted taps with hardware zero padding, LSTM pointwise math fused into the TMEM epilogue).

@@ -57,6 +57,13 @@ SIGNATURES = {
     "oess_pixel_linear_wgrad_ws_bytes": [_int, _int, ctypes.POINTER(_sz)],
     "oess_pixel_linear_wgrad": [_vp, _vp, _int, _int, _int, _i64, _vp, _vp, _vp, _sz, _vp],
     "oess_gemm_tf32": [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp],
+    "oess_gemm_tf32_ex": [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp],
+    "oess_vit_patchify": [_vp, _int, _int, _int, _int, _int, _vp, _vp],
+    "oess_vit_assemble": [_vp, _vp, _vp, _int, _int, _int, _vp, _vp],
+    "oess_layernorm_rows": [_vp, _vp, _vp, _f32, _i64, _int, _vp, _vp],
+    "oess_mha_fwd": [_vp, _int, _int, _int, _vp, _vp],
+    "oess_l2norm_rows": [_vp, _i64, _int, _vp],
+    "oess_bilinear_tokens_to_nchw": [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp],
     "oess_convlstm_step_nhwc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp],
     "oess_upnorm_pool_fwd": [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _i64, _vp, _vp, _vp, _vp],
     "oess_upnorm_pool_bwd": [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _i64, _vp, _vp],

@@ -34,6 +34,7 @@ SOURCES = {
     "tc_wgrad.cu": [],
     "bn_nhwc.cu": [],
     "upnorm_pool.cu": [],
+    "vit.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--threads", "0"]

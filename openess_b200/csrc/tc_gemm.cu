@@ -60,6 +60,9 @@ constexpr int kBM = 128;
 constexpr int kStages = 4;
 constexpr int kGemmThreads = 192;
 
+// nn.GELU() (erf form), the activation of mmcv's FFN in models/maskclip_model.py:507-513
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
 template <int BN>
 struct GemmSmem {
     static constexpr int kABytes = kBM * kBlockK * 4;      // 16 KB
@@ -70,7 +73,7 @@ struct GemmSmem {
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const float* __restrict__ bias, float* __restrict__ C, int64_t M, int N, int K) {
+            const float* __restrict__ bias, const float* residual, float* C, int64_t M, int N, int K, int act) {
     extern __shared__ uint8_t smem_raw[];
     using S = GemmSmem<BN>;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned tiles
@@ -134,6 +137,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const int64_t row = m0 + q * 32 + lane;
         float* crow = C + row * (int64_t)N;
+        const float* rrow = residual ? residual + row * (int64_t)N : nullptr;   // may alias C (same element, same thread)
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             float v[32];
@@ -148,10 +152,20 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             const float4 b = *reinterpret_cast<const float4*>(bias + col + j);
                             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                         }
+                        if (act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
+                        if (rrow) {
+                            const float4 r = *reinterpret_cast<const float4*>(rrow + col + j);
+                            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                        }
                         *reinterpret_cast<float4*>(crow + col + j) = o;
                     }
                 } else {
-                    for (int j = 0; j < 32 && col + j < N; ++j) crow[col + j] = v[j] + (bias ? bias[col + j] : 0.0f);
+                    for (int j = 0; j < 32 && col + j < N; ++j) {
+                        float o = v[j] + (bias ? bias[col + j] : 0.0f);
+                        if (act == 1) o = gelu_erf(o);
+                        if (rrow) o += rrow[col + j];
+                        crow[col + j] = o;
+                    }
                 }
             }
         }
@@ -162,7 +176,8 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 template <int BN>
-static int launch_gemm(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int K, cudaStream_t st) {
+static int launch_gemm(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M, int N,
+                       int K, int act, cudaStream_t st) {
     CUtensorMap tmA, tmB;
     const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)K * 4};
     const uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)K * 4};
@@ -174,7 +189,7 @@ static int launch_gemm(const float* A, const float* B, const float* bias, float*
     auto kern = k_gemm_tf32<BN>;
     OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kBytes));
     const dim3 grid((unsigned)((M + kBM - 1) / kBM), (unsigned)((N + BN - 1) / BN));
-    OESS_KERNEL("tc_gemm_tf32", st, kern<<<grid, kGemmThreads, GemmSmem<BN>::kBytes, st>>>(tmA, tmB, bias, C, M, N, K));
+    OESS_KERNEL("tc_gemm_tf32", st, kern<<<grid, kGemmThreads, GemmSmem<BN>::kBytes, st>>>(tmA, tmB, bias, residual, C, M, N, K, act));
     return 0;
 }
 
@@ -185,14 +200,20 @@ using namespace oess;
 
 OESS_API int oess_gemm_tf32(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int K,
                             oess_stream_t stream) {
-    if (M < 0 || N <= 0 || K <= 0) return OESS_E_ARG;
+    return oess_gemm_tf32_ex(A, B, bias, nullptr, C, M, N, K, 0, stream);
+}
+
+OESS_API int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M,
+                               int N, int K, int act, oess_stream_t stream) {
+    if (M < 0 || N <= 0 || K <= 0 || act < 0 || act > 1) return OESS_E_ARG;
     if (M == 0) return OESS_OK;
     if (!A || !B || !C) return OESS_E_ARG;
     // TMA: 16-byte aligned bases and row strides
-    if ((K & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15) || ((uintptr_t)bias & 15)) return OESS_E_ARG;
+    if ((K & 3) || ((uintptr_t)A & 15) || ((uintptr_t)B & 15) || ((uintptr_t)C & 15) || ((uintptr_t)bias & 15) ||
+        ((uintptr_t)residual & 15)) return OESS_E_ARG;
     if (M >= (1ll << 31)) return OESS_E_RANGE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (N > 128) return tc::launch_gemm<256>(A, B, bias, C, M, N, K, st);
-    if (N > 64) return tc::launch_gemm<128>(A, B, bias, C, M, N, K, st);
-    return tc::launch_gemm<64>(A, B, bias, C, M, N, K, st);
+    if (N > 128) return tc::launch_gemm<256>(A, B, bias, residual, C, M, N, K, act, st);
+    if (N > 64) return tc::launch_gemm<128>(A, B, bias, residual, C, M, N, K, act, st);
+    return tc::launch_gemm<64>(A, B, bias, residual, C, M, N, K, act, st);
 }

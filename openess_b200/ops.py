@@ -84,6 +84,108 @@ def gemm_tf32(a, b, bias=None, out=None):
     return out
 
 
+def gemm_tf32_ex(a, b, bias=None, residual=None, act=None, out=None):
+    """out = act(a @ b.T + bias) + residual on the tensor cores (oess_gemm_tf32_ex): act in (None, "gelu"); `out` may be
+    `residual` (the residual add of a transformer block, maskclip_model.py:538-539)."""
+    _lib.require_cuda(a, b, bias, residual)
+    a, b = _f32c(a), _f32c(b)
+    if a.ndim != 2 or b.ndim != 2 or a.shape[1] != b.shape[1]:
+        raise ValueError("gemm_tf32_ex: a must be [M, K] and b [N, K]")
+    M, K = a.shape
+    N = b.shape[0]
+    if bias is not None:
+        bias = _f32c(bias)
+        if bias.numel() != N:
+            raise ValueError("gemm_tf32_ex: bias must have N elements")
+    if residual is not None:
+        if residual.shape != (M, N) or residual.dtype != torch.float32 or not residual.is_contiguous():
+            raise ValueError("gemm_tf32_ex: residual must be a contiguous float32 [M, N] tensor")
+    if act not in (None, "gelu"):
+        raise ValueError("gemm_tf32_ex: act must be None or 'gelu'")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib().oess_gemm_tf32_ex(ptr(a), ptr(b), ptr(bias), ptr(residual), ptr(out), M, N, K, 1 if act == "gelu" else 0,
+                                      stream_ptr(a.device)), "oess_gemm_tf32_ex")
+    return out
+
+
+def vit_patchify(img, patch):
+    """[B, C, H, W] -> [B * ceil(H / P) * ceil(W / P), C * P * P] rows in projection.weight.view(D, -1) column order, zero
+    'corner' padding (maskclip_model.py:303-312, 427-441)."""
+    _lib.require_cuda(img)
+    img = _f32c(img)
+    B, C, H, W = img.shape
+    h, w = -(-H // patch), -(-W // patch)
+    rows = torch.empty(B * h * w, C * patch * patch, dtype=torch.float32, device=img.device)
+    with torch.cuda.device(img.device):
+        check(lib().oess_vit_patchify(ptr(img), B, C, H, W, patch, ptr(rows), stream_ptr(img.device)), "oess_vit_patchify")
+    return rows, (h, w)
+
+
+def vit_assemble(tok, cls, pos, B, T):
+    """x[b, 0] = cls + pos[0], x[b, 1 + i] = tok[b, i] + pos[1 + i]  ->  [B * T, D] (maskclip_model.py:799-806)."""
+    _lib.require_cuda(tok, cls, pos)
+    tok, cls, pos = _f32c(tok), _f32c(cls), _f32c(pos)
+    D = cls.numel()
+    if tok.shape != (B * (T - 1), D) or pos.numel() != T * D:
+        raise ValueError("vit_assemble: tok must be [B * (T - 1), D] and pos [T, D]")
+    x = torch.empty(B * T, D, dtype=torch.float32, device=tok.device)
+    with torch.cuda.device(tok.device):
+        check(lib().oess_vit_assemble(ptr(tok), ptr(cls), ptr(pos), B, T, D, ptr(x), stream_ptr(tok.device)), "oess_vit_assemble")
+    return x
+
+
+def layernorm_rows(x, weight, bias, eps):
+    """nn.LayerNorm over the last dim of a [rows, D] tensor (D % 128 == 0, D <= 1024)."""
+    _lib.require_cuda(x, weight, bias)
+    x, weight, bias = _f32c(x), _f32c(weight), _f32c(bias)
+    rows, D = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib().oess_layernorm_rows(ptr(x), ptr(weight), ptr(bias), float(eps), rows, D, ptr(y), stream_ptr(x.device)),
+              "oess_layernorm_rows")
+    return y
+
+
+def mha_fwd(qkv, B, T, heads):
+    """softmax(q k^T / 8) v per head on the packed in_proj output [B * T, 3 * heads * 64] -> [B * T, heads * 64]."""
+    _lib.require_cuda(qkv)
+    qkv = _f32c(qkv)
+    D = heads * 64
+    if qkv.shape != (B * T, 3 * D):
+        raise ValueError("mha_fwd: qkv must be [B * T, 3 * heads * 64] (head dim 64)")
+    out = torch.empty(B * T, D, dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(lib().oess_mha_fwd(ptr(qkv), B, T, heads, ptr(out), stream_ptr(qkv.device)), "oess_mha_fwd")
+    return out
+
+
+def l2norm_rows_(x):
+    """x /= ||x||_2 per row, in place (maskclip_model.py:218-219)."""
+    _lib.require_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.ndim != 2:
+        raise ValueError("l2norm_rows_: contiguous float32 [rows, D]")
+    with torch.cuda.device(x.device):
+        check(lib().oess_l2norm_rows(ptr(x), x.shape[0], x.shape[1], stream_ptr(x.device)), "oess_l2norm_rows")
+    return x
+
+
+def bilinear_tokens_to_nchw(tok, B, h, w, size):
+    """F.interpolate(bilinear, align_corners=False) of a channels-last token map [B * h * w, K] -> [B, K, H, W]."""
+    _lib.require_cuda(tok)
+    tok = _f32c(tok)
+    K = tok.shape[1]
+    if tok.shape[0] != B * h * w:
+        raise ValueError("bilinear_tokens_to_nchw: tok must be [B * h * w, K]")
+    H, W = size
+    out = torch.empty(B, K, H, W, dtype=torch.float32, device=tok.device)
+    with torch.cuda.device(tok.device):
+        check(lib().oess_bilinear_tokens_to_nchw(ptr(tok), B, h, w, K, H, W, ptr(out), stream_ptr(tok.device)),
+              "oess_bilinear_tokens_to_nchw")
+    return out
+
+
 def convlstm_pack(weight, bias, hidden):
     """Repack ConvLSTM.Gates (e2vid/model/submodules.py:186: Conv2d(2C, 4C, 3, padding=1), input = cat(x, h)) for
     oess_convlstm_step_nhwc: rows (chunk, gate, c) so one 256-column tile holds all four gates of 64 hidden channels,
