@@ -98,6 +98,20 @@ int oess_voxel_histogram_f64(double* ev4, const int64_t* frame_offsets, int64_t 
                              int n_frames, int H, int W, int mutate_p, float* out, int32_t* status,
                              oess_stream_t stream);
 
+/* The same two kernels on the DDD17 ON-DISK records (datasets/extract_data_tools/
+ * example_loader_ddd17.py:32-38): t = `events.dat.t` int64 [n], xyp = `events.dat.xyp` int16 [n, 3] (x, y, p), staged
+ * to the device as they are -- 14 B / event instead of the 32 B / event int64 rows extract_events_from_memmap (:41-54)
+ * assembles on the host (np.concatenate + astype(int64) + column reorder).  Values are identical after widening, so
+ * the outputs are bit-identical to oess_voxel_tbilinear_i64 / oess_voxel_histogram_i64 on the assembled rows.  The
+ * reference's in-place p == 0 -> -1 lands on that temporary host copy, never on the memory map: nothing is written
+ * back here.  Workspace: oess_voxel_ws_bytes(OESS_KIND_TBILINEAR, ...). */
+int oess_voxel_tbilinear_ddd17(const int64_t* t, const int16_t* xyp, const int64_t* frame_offsets,
+                               int64_t n_events_total, int n_frames, int C, int H, int W, int separate_pol, int mode,
+                               float* out, void* ws, size_t ws_bytes, oess_stream_t stream);
+int oess_voxel_histogram_ddd17(const int64_t* t, const int16_t* xyp, const int64_t* frame_offsets,
+                               int64_t n_events_total, int n_frames, int H, int W, float* out, int32_t* status,
+                               oess_stream_t stream);
+
 /* Replaces DSEC/dataset/sequence_ov.py:204-210 rectify_events (gather rectify_map[y, x]) fused with the
  * per-chunk pre-step of sequence_ov.py:154-159 events_to_voxel_grid (t = f32(t - t[0]); t /= t[-1];
  * pol = f32(p)), per frame.  Raw DSEC records: x, y uint16, t int64 microseconds (t_offset already added,
@@ -216,6 +230,12 @@ int oess_gemm_tf32(const float* A, const float* B, const float* bias, float* C, 
 int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M,
                       int N, int K, int act, oess_stream_t stream);
 
+/* Pooling layers of the torchvision-style ResNets (models/_resnet.py:137 MaxPool2d(kernel_size=3, stride=2, padding=1);
+ * :149 AdaptiveAvgPool2d((1, 1))) on channels-last float32 tensors.  x: [B, H, W, C]; max pool y: [B, Ho, Wo, C] with
+ * Ho = (H - 1) / 2 + 1 (C % 4 == 0); average pool y: [B, C] (mean over the HW pixels). */
+int oess_maxpool3x3s2_nhwc(const float* x, int B, int H, int W, int C, float* y, oess_stream_t stream);
+int oess_global_avgpool_nhwc(const float* x, int B, int64_t HW, int C, float* y, oess_stream_t stream);
+
 /* ---- MaskCLIP ViT-B/16 forward (models/maskclip_model.py) -- the non-GEMM kernels ------------------
  * Tokens are row-major [rows, D] float32 (rows = B * T, T = 1 + h * w); D % 128 == 0, D <= 1024.
  *
@@ -260,7 +280,10 @@ int oess_convlstm_step_nhwc(const float* x, const float* h_prev, const float* c_
  * x: [B, H, W, Cin] channels-last, Cin % 4 == 0; w_packed: [Cout, KH * KW * Cin_p] with Cin_p = Cin rounded up to 32
  * (zero padded), column (tap = ky * KW + kx, channel) -- openess_b200/ops.py:conv2d_pack; bias: [Cout] or NULL;
  * residual: [B, Ho, Wo, Cout] or NULL; y: [B, Ho, Wo, Cout], Ho = (H + 2 pad - dil (KH - 1) - 1) / stride + 1.
- * Zero padding is the TMA unit's out-of-bounds fill; stride is a strided TMA box traversal. */
+ * Zero padding is the TMA unit's out-of-bounds fill; stride is a strided TMA box traversal.
+ * relu is a flag word: bit 0 = ReLU, bit 1 = store y rounded to TF32 (round-to-nearest, cvt.rna) -- for activations
+ * that feed another tensor-core layer: the tensor core truncates fp32 operands to TF32, a systematic -2^-12 relative
+ * bias per layer that accumulates when nothing re-normalises (eval-mode ResNets); rounding at the producer removes it. */
 int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
                           int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                           int relu, oess_stream_t stream);

@@ -35,6 +35,8 @@ SIGNATURES = {
     "oess_voxel_tbilinear_f64": [_vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _int, _vp, _vp, _sz, _vp],
     "oess_voxel_histogram_i64": [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp],
     "oess_voxel_histogram_f64": [_vp, _vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp],
+    "oess_voxel_tbilinear_ddd17": [_vp, _vp, _vp, _i64, _int, _int, _int, _int, _int, _int, _vp, _vp, _sz, _vp],
+    "oess_voxel_histogram_ddd17": [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp],
     "oess_dsec_rectify_tnorm": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "oess_dsec_rectify_tnorm_u32": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp],
     "oess_nonzero_standardize": [_vp, _i64, _int, _vp, _int, _int, _vp],
@@ -58,6 +60,8 @@ SIGNATURES = {
     "oess_pixel_linear_wgrad": [_vp, _vp, _int, _int, _int, _i64, _vp, _vp, _vp, _sz, _vp],
     "oess_gemm_tf32": [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp],
     "oess_gemm_tf32_ex": [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp],
+    "oess_maxpool3x3s2_nhwc": [_vp, _int, _int, _int, _int, _vp, _vp],
+    "oess_global_avgpool_nhwc": [_vp, _int, _i64, _int, _vp, _vp],
     "oess_vit_patchify": [_vp, _int, _int, _int, _int, _int, _vp, _vp],
     "oess_vit_assemble": [_vp, _vp, _vp, _int, _int, _int, _vp, _vp],
     "oess_layernorm_rows": [_vp, _vp, _vp, _f32, _i64, _int, _vp, _vp],

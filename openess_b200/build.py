@@ -35,6 +35,7 @@ SOURCES = {
     "bn_nhwc.cu": [],
     "upnorm_pool.cu": [],
     "vit.cu": [],
+    "pool_nhwc.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--threads", "0"]

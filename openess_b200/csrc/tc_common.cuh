@@ -75,6 +75,14 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
+// fp32 -> TF32 with round-to-nearest (ties away), kept in an fp32 register: tcgen05.mma.kind::tf32 TRUNCATES the low 13
+// mantissa bits of its operands, a bias of -2^-12 relative per operand that adds up layer after layer when nothing
+// re-normalises (eval-mode ResNets); producers that feed another tensor-core layer round their output instead.
+__device__ __forceinline__ float rna_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

@@ -160,7 +160,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                         const float4 rr = *reinterpret_cast<const float4*>(residual + pix + col + j);
                         o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
                     }
-                    if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (a.relu & 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                    if (a.relu & 2) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
                     *reinterpret_cast<float4*>(y + pix + col + j) = o;
                 }
             } else {
@@ -168,7 +169,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                 for (int j = 0; j < 16; ++j) {
                     if (col + j < a.Cout) {
                         float o = v[j] + (bias ? bias[col + j] : 0.f) + (residual ? residual[pix + col + j] : 0.f);
-                        y[pix + col + j] = a.relu ? fmaxf(o, 0.f) : o;
+                        if (a.relu & 1) o = fmaxf(o, 0.f);
+                        y[pix + col + j] = (a.relu & 2) ? rna_tf32(o) : o;
                     }
                 }
             }
@@ -255,7 +257,7 @@ static int conv2d_impl(const float* x, const float* w_packed, const float* bias,
     const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     int rc = tc::make_tmap_f32_strided(&tmX, x, 4, dims, strides, box, estr);
     if (rc) return rc;
-    tc::ConvArgs a{Ho, Wo, Cout, KW, KH * KW, chunks, stride, pad, dil, relu ? 1 : 0, (Wo + tc::kVW - 1) / tc::kVW,
+    tc::ConvArgs a{Ho, Wo, Cout, KW, KH * KW, chunks, stride, pad, dil, relu & 3, (Wo + tc::kVW - 1) / tc::kVW,
                    per_sample ? 2 * Cout : 0};
     if (bn_sums) OESS_CUDA(cudaMemsetAsync(bn_sums, 0, sizeof(double) * 2 * (size_t)Cout * (per_sample ? B : 1), st));
     if (Cout > 128) return tc::launch_conv<256>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);

@@ -37,22 +37,53 @@ struct FrameTime {
     double dT;
 };
 
+// Event rows as the reference holds them: an [N, 4] array (x, y, t, p) of int64 or float64 ...
 template <class T>
-__device__ __forceinline__ FrameTime<T> frame_time(const T* __restrict__ ev4, int64_t fbeg, int64_t nf) {
+struct RowsAoS {
+    typedef T V;
+    T* ev4;
+    __device__ __forceinline__ V x(int64_t i) const { return ev4[i * 4 + 0]; }
+    __device__ __forceinline__ V y(int64_t i) const { return ev4[i * 4 + 1]; }
+    __device__ __forceinline__ V t(int64_t i) const { return ev4[i * 4 + 2]; }
+    __device__ __forceinline__ V p(int64_t i) const { return ev4[i * 4 + 3]; }
+    __device__ __forceinline__ void set_p(int64_t i, V v) const { ev4[i * 4 + 3] = v; }
+    __host__ bool null() const { return ev4 == nullptr; }
+};
+// ... or the DDD17 on-disk records themselves (example_loader_ddd17.py:32-38: `events.dat.t` int64 [N, 1] and
+// `events.dat.xyp` int16 [N, 3]), 14 B / event instead of the 32 B / event int64 rows that
+// extract_events_from_memmap (:41-54) builds from them with np.concatenate(...).astype(int64)[:, [1, 2, 0, 3]]: the
+// values are identical after the widening, so every kernel below computes the same bits.  The reference's in-place
+// p == 0 -> -1 happens on that temporary copy, never on the memory map: set_p is a no-op.
+struct RowsDDD17 {
+    typedef int64_t V;
+    const int64_t* ts;
+    const int16_t* xyp;
+    __device__ __forceinline__ V x(int64_t i) const { return (V)xyp[i * 3 + 0]; }
+    __device__ __forceinline__ V y(int64_t i) const { return (V)xyp[i * 3 + 1]; }
+    __device__ __forceinline__ V t(int64_t i) const { return ts[i]; }
+    __device__ __forceinline__ V p(int64_t i) const { return (V)xyp[i * 3 + 2]; }
+    __device__ __forceinline__ void set_p(int64_t, V) const {}
+    __host__ bool null() const { return ts == nullptr || xyp == nullptr; }
+};
+
+template <class R>
+__device__ __forceinline__ FrameTime<typename R::V> frame_time(const R& rows, int64_t fbeg, int64_t nf) {
+    typedef typename R::V T;
     FrameTime<T> ft;
-    ft.first = ev4[fbeg * 4 + 2];                          // data_util.py:68
-    const T draw = ev4[(fbeg + nf - 1) * 4 + 2] - ft.first;  // :67,69
+    ft.first = rows.t(fbeg);                               // data_util.py:68
+    const T draw = rows.t(fbeg + nf - 1) - ft.first;       // :67,69
     ft.dT = (draw == (T)0) ? 1.0 : (double)draw;           // :71-72
     return ft;
 }
 
-template <class T>
-__device__ __forceinline__ Decoded decode(const T* __restrict__ row, const FrameTime<T>& ft, const Geom& g,
-                                          T* p_out) {
+template <class R>
+__device__ __forceinline__ Decoded decode(const R& rows, int64_t i, const FrameTime<typename R::V>& ft, const Geom& g,
+                                          bool mutate_p) {
+    typedef typename R::V T;
     Decoded r;
-    const T rx = row[0], ry = row[1], rt = row[2];
-    T p = row[3];
-    if (p == (T)0) { p = (T)-1; if (p_out) *p_out = p; }   // :78-79 (in place on the caller's array)
+    const T rx = rows.x(i), ry = rows.y(i), rt = rows.t(i);
+    T p = rows.p(i);
+    if (p == (T)0) { p = (T)-1; if (mutate_p) rows.set_p(i, p); }   // :78-79 (in place on the caller's array)
     const T num = (T)(g.C - 1) * (rt - ft.first);           // :76, array dtype arithmetic
     const double ts = __ddiv_rn((double)num, ft.dT);        //      then float64 true division
     r.x = is_int<T>::value ? (long long)rx : cvtt_f64_i64((double)rx);  // :74-75
@@ -75,9 +106,9 @@ struct SrcPairs {
     __device__ __forceinline__ uint32_t key_at(int, int64_t fbeg, uint32_t li) const { return items[fbeg + li].x; }
 };
 
-template <class T>
+template <class R>
 __global__ void __launch_bounds__(256)
-k_keygen(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start,
+k_keygen(R rows, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start,
          int F, Geom g, int mutate_p, uint2* __restrict__ pairs) {
     const int gch = blockIdx.x;
     const int f = find_frame(chunk_start, F, gch);
@@ -85,13 +116,12 @@ k_keygen(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, const i
     const int c = gch - chunk_start[f];
     const int64_t fbeg = frame_offsets[f];
     const int64_t nf = frame_offsets[f + 1] - fbeg;
-    const FrameTime<T> ft = frame_time(ev4, fbeg, nf);
+    const FrameTime<typename R::V> ft = frame_time(rows, fbeg, nf);
 #pragma unroll 2
     for (int s = 0; s < radix::kItemsPerThread; ++s) {
         const int64_t li = (int64_t)c * radix::kChunk + s * radix::kThreads + threadIdx.x;
         if (li >= nf) break;
-        T* row = ev4 + (fbeg + li) * 4;
-        const Decoded d = decode(row, ft, g, mutate_p ? row + 3 : (T*)nullptr);
+        const Decoded d = decode(rows, fbeg + li, ft, g, mutate_p != 0);
         const uint32_t key = d.valid ? (uint32_t)(d.y * g.W + d.x) : g.invalid_key;
         pairs[fbeg + li] = make_uint2(key, (uint32_t)li);
     }
@@ -103,9 +133,9 @@ __device__ __forceinline__ float add_at(float acc, double w) {  // np.add.at(f32
 
 // One thread per sorted {key, index} pair; the head of each pixel run replays the run.
 // CT > 0: all CT bins at once (2*CT register accumulators).  CT == 0: any C, one bin at a time.
-template <class T, int CT>
+template <class R, int CT>
 __global__ void __launch_bounds__(256)
-k_runs(const T* __restrict__ ev4, const uint2* __restrict__ pairs, const int64_t* __restrict__ frame_offsets,
+k_runs(R rows, const uint2* __restrict__ pairs, const int64_t* __restrict__ frame_offsets,
        const int* __restrict__ chunk_start, int F, Geom g, int separate_pol, float* __restrict__ out) {
     const int gch = blockIdx.x;
     const int f = find_frame(chunk_start, F, gch);
@@ -113,7 +143,7 @@ k_runs(const T* __restrict__ ev4, const uint2* __restrict__ pairs, const int64_t
     const int c = gch - chunk_start[f];
     const int64_t fbeg = frame_offsets[f];
     const int64_t nf = frame_offsets[f + 1] - fbeg;
-    const FrameTime<T> ft = frame_time(ev4, fbeg, nf);
+    const FrameTime<typename R::V> ft = frame_time(rows, fbeg, nf);
     const int64_t HW = (int64_t)g.H * g.W;
     const int planes = separate_pol ? 2 * g.C : g.C;
     const uint2* pr = pairs + fbeg;
@@ -128,7 +158,7 @@ k_runs(const T* __restrict__ ev4, const uint2* __restrict__ pairs, const int64_t
         if (i + 1 >= nf || pr[i + 1].x != me.x) {
             // single-event pixel (the common case): one decode; acc = f32(f64(0) + w) = f32(w) per touched bin,
             // the other bins stay at the memset zero; pos - neg = +-f32(w) exactly (data_util.py:91-116)
-            const Decoded d = decode(ev4 + (fbeg + me.y) * 4, ft, g, (T*)nullptr);
+            const Decoded d = decode(rows, fbeg + me.y, ft, g, false);
             const int64_t plane0 = (separate_pol && !d.pos) ? g.C : 0;
             const bool negate = !separate_pol && !d.pos;
             if (d.ti < g.C) {
@@ -152,7 +182,7 @@ k_runs(const T* __restrict__ ev4, const uint2* __restrict__ pairs, const int64_t
                 for (int64_t j = i; j < nf; ++j) {
                     const uint2 pj = (j == i) ? me : pr[j];
                     if (pj.x != me.x) break;
-                    const Decoded d = decode(ev4 + (fbeg + pj.y) * 4, ft, g, (T*)nullptr);
+                    const Decoded d = decode(rows, fbeg + pj.y, ft, g, false);
                     const long long tbin = d.ti + right;
                     if (!(tbin < g.C)) continue;                  // :87 / :94
                     if (CT == 0 && tbin != bin) continue;
@@ -183,9 +213,9 @@ k_runs(const T* __restrict__ ev4, const uint2* __restrict__ pairs, const int64_t
     }
 }
 
-template <class T>
+template <class R>
 __global__ void __launch_bounds__(256)
-k_atomic(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start,
+k_atomic(R rows, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start,
          int F, Geom g, int separate_pol, int mutate_p, float* __restrict__ out) {
     const int gch = blockIdx.x;
     const int f = find_frame(chunk_start, F, gch);
@@ -193,7 +223,7 @@ k_atomic(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, const i
     const int c = gch - chunk_start[f];
     const int64_t fbeg = frame_offsets[f];
     const int64_t nf = frame_offsets[f + 1] - fbeg;
-    const FrameTime<T> ft = frame_time(ev4, fbeg, nf);
+    const FrameTime<typename R::V> ft = frame_time(rows, fbeg, nf);
     const int64_t HW = (int64_t)g.H * g.W;
     const int planes = separate_pol ? 2 * g.C : g.C;
     float* o = out + (int64_t)f * planes * HW;
@@ -201,8 +231,7 @@ k_atomic(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, const i
     for (int s = 0; s < radix::kItemsPerThread; ++s) {
         const int64_t li = (int64_t)c * radix::kChunk + s * radix::kThreads + threadIdx.x;
         if (li >= nf) break;
-        T* row = ev4 + (fbeg + li) * 4;
-        const Decoded d = decode(row, ft, g, mutate_p ? row + 3 : (T*)nullptr);
+        const Decoded d = decode(rows, fbeg + li, ft, g, mutate_p != 0);
         if (!d.valid) continue;
         const int64_t pixel = d.y * g.W + d.x;
         const float sign = (separate_pol || d.pos) ? 1.0f : -1.0f;
@@ -216,9 +245,9 @@ k_atomic(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, const i
 
 // data_util.py:17-35: out[f, 0] = neg counts, out[f, 1] = pos counts; flat index x + W*y.
 // One thread per event over the flat event range; the frame is found by binary search in frame_offsets.
-template <class T>
+template <class R>
 __global__ void __launch_bounds__(256)
-k_histogram(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, int64_t n, int F, int H, int W,
+k_histogram(R rows, const int64_t* __restrict__ frame_offsets, int64_t n, int F, int H, int W,
             int mutate_p, float* __restrict__ out, int32_t* __restrict__ status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -229,12 +258,13 @@ k_histogram(T* __restrict__ ev4, const int64_t* __restrict__ frame_offsets, int6
     }
     const int64_t HW = (int64_t)H * W;
     float* o = out + (int64_t)lo * 2 * HW;
-    T* row = ev4 + i * 4;
-    T p = row[3];
-    if (p == (T)0) { p = (T)-1; if (mutate_p) row[3] = p; }   // :26
+    typedef typename R::V T;
+    T p = rows.p(i);
+    if (p == (T)0) { p = (T)-1; if (mutate_p) rows.set_p(i, p); }   // :26
     if (p != (T)1 && p != (T)-1) return;                       // :30-31 boolean masks
-    const long long x = is_int<T>::value ? (long long)row[0] : cvtt_f64_i64((double)row[0]);  // :23-24
-    const long long y = is_int<T>::value ? (long long)row[1] : cvtt_f64_i64((double)row[1]);
+    const T rx = rows.x(i), ry = rows.y(i);
+    const long long x = is_int<T>::value ? (long long)rx : cvtt_f64_i64((double)rx);  // :23-24
+    const long long y = is_int<T>::value ? (long long)ry : cvtt_f64_i64((double)ry);
     const long long idx = x + (long long)W * y;
     if (idx < 0 || idx >= HW) { if (status) *status = 1; return; }
     atomicAdd(o + (p == (T)1 ? HW : 0) + idx, 1.0f);            // :33 stack([neg, pos])
@@ -261,14 +291,14 @@ static Ws carve(void* ws, int mode, int64_t n, int F, int H, int W) {
     return r;
 }
 
-template <class T>
-static int run(T* ev4, const int64_t* frame_offsets, int64_t n, int F, int C, int H, int W, int separate_pol,
+template <class R>
+static int run(R rows, const int64_t* frame_offsets, int64_t n, int F, int C, int H, int W, int separate_pol,
                int mode, int mutate_p, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (n < 0 || F < 0 || C <= 0 || H <= 0 || W <= 0) return OESS_E_ARG;   // data_util.py:59-62 asserts
     if (mode != OESS_MODE_ORDERED && mode != OESS_MODE_ATOMIC) return OESS_E_ARG;
     if ((int64_t)H * W + 2 >= (1ll << 31) || n >= (1ll << 31)) return OESS_E_RANGE;
     if (F == 0) return OESS_OK;
-    if (!frame_offsets || !out || (n > 0 && !ev4)) return OESS_E_ARG;
+    if (!frame_offsets || !out || (n > 0 && rows.null())) return OESS_E_ARG;
     const Ws w = carve(ws, mode, n, F, H, W);
     if (!ws || ws_bytes < w.bytes) return OESS_E_WORKSPACE;
     const Geom g{C, H, W, (uint32_t)(H * W)};
@@ -281,7 +311,7 @@ static int run(T* ev4, const int64_t* frame_offsets, int64_t n, int F, int C, in
     if (mode == OESS_MODE_ATOMIC) {
         OESS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)F * planes * HW, st));
         if (n > 0) {
-            OESS_KERNEL("tb_atomic", st, k_atomic<T><<<(unsigned)nch, radix::kThreads, 0, st>>>(ev4, frame_offsets, w.chunk_start, F, g,
+            OESS_KERNEL("tb_atomic", st, k_atomic<R><<<(unsigned)nch, radix::kThreads, 0, st>>>(rows, frame_offsets, w.chunk_start, F, g,
                                                                   separate_pol, mutate_p, out));
         }
         return OESS_OK;
@@ -289,8 +319,8 @@ static int run(T* ev4, const int64_t* frame_offsets, int64_t n, int F, int C, in
     OESS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)F * planes * HW, st));
     if (n == 0) return OESS_OK;
     uint2* cur = w.a;
-    OESS_KERNEL("tb_keygen", st, k_keygen<T><<<(unsigned)nch, radix::kThreads, 0, st>>>(
-        ev4, frame_offsets, w.chunk_start, F, g, mutate_p, w.a));
+    OESS_KERNEL("tb_keygen", st, k_keygen<R><<<(unsigned)nch, radix::kThreads, 0, st>>>(
+        rows, frame_offsets, w.chunk_start, F, g, mutate_p, w.a));
     const int bits = radix::key_bits(g.invalid_key + 1);
     const int passes = (bits + radix::kBits - 1) / radix::kBits;
     const int pbits = (bits + passes - 1) / passes;
@@ -304,25 +334,25 @@ static int run(T* ev4, const int64_t* frame_offsets, int64_t n, int F, int C, in
         cur = dst;
     }
     if (C == 5) {
-        OESS_KERNEL("tb_runs", st, k_runs<T, 5><<<(unsigned)nch, radix::kThreads, 0, st>>>(
-            ev4, cur, frame_offsets, w.chunk_start, F, g, separate_pol, out));
+        OESS_KERNEL("tb_runs", st, k_runs<R, 5><<<(unsigned)nch, radix::kThreads, 0, st>>>(
+            rows, cur, frame_offsets, w.chunk_start, F, g, separate_pol, out));
     } else {
-        OESS_KERNEL("tb_runs", st, k_runs<T, 0><<<(unsigned)nch, radix::kThreads, 0, st>>>(
-            ev4, cur, frame_offsets, w.chunk_start, F, g, separate_pol, out));
+        OESS_KERNEL("tb_runs", st, k_runs<R, 0><<<(unsigned)nch, radix::kThreads, 0, st>>>(
+            rows, cur, frame_offsets, w.chunk_start, F, g, separate_pol, out));
     }
     return OESS_OK;
 }
 
-template <class T>
-static int run_hist(T* ev4, const int64_t* frame_offsets, int64_t n, int F, int H, int W, int mutate_p,
+template <class R>
+static int run_hist(R rows, const int64_t* frame_offsets, int64_t n, int F, int H, int W, int mutate_p,
                     float* out, int32_t* status, cudaStream_t st) {
     if (n < 0 || F < 0 || H <= 0 || W <= 0) return OESS_E_ARG;
     if (F == 0) return OESS_OK;
-    if (!frame_offsets || !out || (n > 0 && !ev4)) return OESS_E_ARG;
+    if (!frame_offsets || !out || (n > 0 && rows.null())) return OESS_E_ARG;
     OESS_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)F * 2 * H * W, st));
     if (status) OESS_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
     if (n == 0) return OESS_OK;
-    OESS_KERNEL("k_histogram", st, k_histogram<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ev4, frame_offsets, n, F, H, W, mutate_p, out,
+    OESS_KERNEL("k_histogram", st, k_histogram<R><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows, frame_offsets, n, F, H, W, mutate_p, out,
                                                                status));
     return OESS_OK;
 }
@@ -343,23 +373,34 @@ int oess_voxel_tbilinear_ws_bytes_impl(int mode, int64_t n, int F, int C, int H,
 OESS_API int oess_voxel_tbilinear_i64(int64_t* ev4, const int64_t* frame_offsets, int64_t n, int F, int C, int H,
                                       int W, int separate_pol, int mode, int mutate_p, float* out, void* ws,
                                       size_t ws_bytes, oess_stream_t stream) {
-    return tb::run<int64_t>(ev4, frame_offsets, n, F, C, H, W, separate_pol, mode, mutate_p, out, ws, ws_bytes,
+    return tb::run(tb::RowsAoS<int64_t>{ev4}, frame_offsets, n, F, C, H, W, separate_pol, mode, mutate_p, out, ws, ws_bytes,
                             (cudaStream_t)stream);
 }
 OESS_API int oess_voxel_tbilinear_f64(double* ev4, const int64_t* frame_offsets, int64_t n, int F, int C, int H,
                                       int W, int separate_pol, int mode, int mutate_p, float* out, void* ws,
                                       size_t ws_bytes, oess_stream_t stream) {
-    return tb::run<double>(ev4, frame_offsets, n, F, C, H, W, separate_pol, mode, mutate_p, out, ws, ws_bytes,
+    return tb::run(tb::RowsAoS<double>{ev4}, frame_offsets, n, F, C, H, W, separate_pol, mode, mutate_p, out, ws, ws_bytes,
                            (cudaStream_t)stream);
 }
 
 OESS_API int oess_voxel_histogram_i64(int64_t* ev4, const int64_t* frame_offsets, int64_t n, int F, int H, int W,
                                       int mutate_p, float* out, int32_t* status, oess_stream_t stream) {
-    return tb::run_hist<int64_t>(ev4, frame_offsets, n, F, H, W, mutate_p, out, status, (cudaStream_t)stream);
+    return tb::run_hist(tb::RowsAoS<int64_t>{ev4}, frame_offsets, n, F, H, W, mutate_p, out, status, (cudaStream_t)stream);
 }
 OESS_API int oess_voxel_histogram_f64(double* ev4, const int64_t* frame_offsets, int64_t n, int F, int H, int W,
                                       int mutate_p, float* out, int32_t* status, oess_stream_t stream) {
-    return tb::run_hist<double>(ev4, frame_offsets, n, F, H, W, mutate_p, out, status, (cudaStream_t)stream);
+    return tb::run_hist(tb::RowsAoS<double>{ev4}, frame_offsets, n, F, H, W, mutate_p, out, status, (cudaStream_t)stream);
+}
+
+OESS_API int oess_voxel_tbilinear_ddd17(const int64_t* t, const int16_t* xyp, const int64_t* frame_offsets, int64_t n, int F,
+                                        int C, int H, int W, int separate_pol, int mode, float* out, void* ws, size_t ws_bytes,
+                                        oess_stream_t stream) {
+    return tb::run(tb::RowsDDD17{t, xyp}, frame_offsets, n, F, C, H, W, separate_pol, mode, 0, out, ws, ws_bytes,
+                   (cudaStream_t)stream);
+}
+OESS_API int oess_voxel_histogram_ddd17(const int64_t* t, const int16_t* xyp, const int64_t* frame_offsets, int64_t n, int F,
+                                        int H, int W, float* out, int32_t* status, oess_stream_t stream) {
+    return tb::run_hist(tb::RowsDDD17{t, xyp}, frame_offsets, n, F, H, W, 0, out, status, (cudaStream_t)stream);
 }
 
 int oess_voxel_trilinear_ws_bytes_impl(int mode, int64_t n, int F, int C, int H, int W, size_t* out);

@@ -19,7 +19,8 @@ class PackedConvCache:
     def __init__(self):
         self._packed = {}
 
-    def get(self, conv, bn):
+    def get(self, conv, bn, pad_cin=0):
+        """pad_cin: zero-pad the input channels to this count (the 3-channel stem runs on an 8-channel repack)."""
         fold = bn is not None and not bn.training
         key = (id(conv), fold)
         ver = (conv.weight.data_ptr(), conv.weight._version, conv.weight.device,
@@ -33,6 +34,10 @@ class PackedConvCache:
                 w = w * scale[:, None, None, None]
                 b0 = 0 if b is None else b
                 b = ((b0 - bn.running_mean) * scale + bn.bias.detach()).float().contiguous()
+            if pad_cin > w.shape[1]:
+                wp = torch.zeros(w.shape[0], pad_cin, w.shape[2], w.shape[3], dtype=w.dtype, device=w.device)
+                wp[:, :w.shape[1]] = w
+                w = wp
             hit = (ver, _tc.conv2d_pack(w), b)
             self._packed[key] = hit
         return hit[1], hit[2]
@@ -49,7 +54,9 @@ def conv_bn(cache, x, conv, bn, relu, residual=None):
     wp, b = cache.get(conv, bn)
     k, s, p, d = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
     if bn is None or not bn.training:
-        return _tc.conv2d_tc(x, wp, b, k, s, p, d, relu=relu, residual=residual)
+        # eval mode: nothing re-normalises between the layers, so the activation is stored TF32-rounded (round-to-nearest)
+        # instead of being truncated by the next conv's tensor-core read (a -2^-12 relative bias per layer otherwise)
+        return _tc.conv2d_tc(x, wp, b, k, s, p, d, relu=relu, residual=residual, round_out=True)
     if FUSE_BN_STATS and bn.weight.numel() % 4 == 0:
         return _tc.conv_bn_train(x, wp, b, k, s, p, d, bn, residual=residual, relu=relu)
     y = _tc.conv2d_tc(x, wp, b, k, s, p, d)
@@ -66,13 +73,48 @@ def bottleneck(cache, blk, x):
     return conv_bn(cache, out, blk.conv3, blk.bn3, True, residual=identity)
 
 
+def basic_block(cache, blk, x):
+    """torchvision.models.resnet.BasicBlock.forward / models/_resnet.py:55-71 (ResNet-18 / 34)."""
+    out = conv_bn(cache, x, blk.conv1, blk.bn1, True)
+    identity = x
+    if blk.downsample is not None:
+        identity = conv_bn(cache, x, blk.downsample[0], blk.downsample[1], False)
+    return conv_bn(cache, out, blk.conv2, blk.bn2, True, residual=identity)
+
+
+STEM_TC = True            # False: conv1 / bn1 / relu / maxpool as torch ops (the round-1c formulation)
+
+
+def stem(cache, net, x):
+    """conv1 (7x7 stride 2, Cin = 3) + bn1 + relu + maxpool (models/_resnet.py:134-137, 199-202) -> channels-last.
+    Cin = 3 is too thin for a 16-byte TMA pixel: the planes are repacked to 8 zero-padded channels-last channels
+    (`oess_planes_to_nhwc_padded`) and run through the same tcgen05 conv kernel (BN folded or batch statistics in the
+    epilogue, ReLU fused); the max pool is `oess_maxpool3x3s2_nhwc`."""
+    conv, bn = net.conv1, net.bn1
+    if not (STEM_TC and conv.in_channels <= 8 and conv.groups == 1 and conv.kernel_size[0] == conv.kernel_size[1]
+            and conv.kernel_size[0] ** 2 <= 64 and isinstance(bn, torch.nn.BatchNorm2d)
+            and type(net.maxpool) is torch.nn.MaxPool2d and net.maxpool.kernel_size == 3 and net.maxpool.stride == 2
+            and net.maxpool.padding == 1 and net.maxpool.dilation == 1 and not net.maxpool.ceil_mode):
+        x = net.relu(net.bn1(net.conv1(x)))
+        return net.maxpool(x).contiguous(memory_format=torch.channels_last)
+    wp, b = cache.get(conv, bn, pad_cin=8)
+    x8 = _tc.planes_to_nhwc_padded(x, 8)
+    k, s, p, d = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
+    if not bn.training:
+        y = _tc.conv2d_tc(x8, wp, b, k, s, p, d, relu=True, round_out=True)
+    elif FUSE_BN_STATS:
+        y = _tc.conv_bn_train(x8, wp, b, k, s, p, d, bn, relu=True)
+    else:
+        y = _tc.batchnorm_nhwc_(_tc.conv2d_tc(x8, wp, b, k, s, p, d), bn, relu=True)
+    return _tc.maxpool3x3s2_nhwc(y)
+
+
 def resnet_stages(cache, net, x):
-    """conv1 / bn1 / relu / maxpool as torch ops (Cin = 3), layer1..4 on the tensor cores; returns layer4 channels-last."""
-    x = net.relu(net.bn1(net.conv1(x)))
-    x = net.maxpool(x).contiguous(memory_format=torch.channels_last)
+    """Stem + layer1..4 on hand-written kernels (tcgen05 convs, fused BN, own max pool); returns layer4 channels-last."""
+    x = stem(cache, net, x)
     for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
         for blk in layer:
-            x = bottleneck(cache, blk, x)
+            x = bottleneck(cache, blk, x) if hasattr(blk, "conv3") else basic_block(cache, blk, x)
     return x
 
 

@@ -225,12 +225,20 @@ def conv2d_pack(weight):
     cin_p = (Cin + 31) // 32 * 32
     w = torch.zeros(Cout, KH * KW, cin_p, dtype=torch.float32, device=weight.device)
     w[:, :, :Cin] = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin)
-    return w.reshape(Cout, KH * KW * cin_p).contiguous()
+    return round_tf32(w.reshape(Cout, KH * KW * cin_p).contiguous())
 
 
-def conv2d_tc(x, w_packed, bias, kernel_size, stride=1, padding=0, dilation=1, relu=False, residual=None):
+def round_tf32(t):
+    """fp32 -> nearest TF32 value (ties away from zero, = cvt.rna.tf32.f32), kept as fp32.  tcgen05.mma.kind::tf32 truncates
+    its operands; rounding the packed weights once removes the weight half of that systematic bias."""
+    bits = t.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & -8192).view(torch.float32)
+
+
+def conv2d_tc(x, w_packed, bias, kernel_size, stride=1, padding=0, dilation=1, relu=False, residual=None, round_out=False):
     """Convolution on the tensor cores (tcgen05 implicit GEMM, TF32 operands, fp32 accumulate).
-    x: [B, Cin, H, W] (any memory format; handled channels-last), Cin % 4 == 0; returns [B, Cout, Ho, Wo] channels-last."""
+    x: [B, Cin, H, W] (any memory format; handled channels-last), Cin % 4 == 0; returns [B, Cout, Ho, Wo] channels-last.
+    round_out: store the output rounded to TF32 (for activations that feed the next tensor-core conv, see round_tf32)."""
     _lib.require_cuda(x, w_packed, bias, residual)
     B, Cin, H, W = x.shape
     KH, KW = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
@@ -244,8 +252,8 @@ def conv2d_tc(x, w_packed, bias, kernel_size, stride=1, padding=0, dilation=1, r
     bc = None if bias is None else _f32c(bias)
     with torch.cuda.device(x.device):
         check(lib().oess_conv2d_nhwc_tf32(ptr(xc), ptr(w_packed), ptr(bc), ptr(rc), ptr(y), B, H, W, Cin, Cout, KH, KW,
-                                          stride, padding, dilation, 1 if relu else 0, stream_ptr(x.device)),
-              "oess_conv2d_nhwc_tf32")
+                                          stride, padding, dilation, (1 if relu else 0) | (2 if round_out else 0),
+                                          stream_ptr(x.device)), "oess_conv2d_nhwc_tf32")
     return y
 
 
@@ -345,6 +353,29 @@ def conv_bn_train(x, w_packed, bias, kernel_size, stride, padding, dilation, bn,
               "oess_batchnorm_nhwc_sums")
         if track and bn.num_batches_tracked is not None:
             bn.num_batches_tracked += 1
+    return y
+
+
+def maxpool3x3s2_nhwc(x):
+    """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (models/_resnet.py:137) on a channels-last [B, C, H, W] tensor."""
+    _lib.require_cuda(x)
+    B, C, H, W = x.shape
+    cl = torch.channels_last
+    xc = x.float().contiguous(memory_format=cl)
+    y = torch.empty((B, C, (H - 1) // 2 + 1, (W - 1) // 2 + 1), dtype=torch.float32, device=x.device, memory_format=cl)
+    with torch.cuda.device(x.device):
+        check(lib().oess_maxpool3x3s2_nhwc(ptr(xc), B, H, W, C, ptr(y), stream_ptr(x.device)), "oess_maxpool3x3s2_nhwc")
+    return y
+
+
+def global_avgpool_nhwc(x):
+    """nn.AdaptiveAvgPool2d((1, 1)) + flatten (models/_resnet.py:149, 207-208): channels-last [B, C, H, W] -> [B, C]."""
+    _lib.require_cuda(x)
+    B, C, H, W = x.shape
+    xc = x.float().contiguous(memory_format=torch.channels_last)
+    y = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().oess_global_avgpool_nhwc(ptr(xc), B, H * W, C, ptr(y), stream_ptr(x.device)), "oess_global_avgpool_nhwc")
     return y
 
 

@@ -106,6 +106,47 @@ def voxel_histogram(ev4, H, W, frame_offsets=None, mutate_p=True, out=None, stat
     return out
 
 
+def _ddd17_check(t, xyp):
+    require_cuda(t, xyp)
+    if t.dtype != torch.int64 or xyp.dtype != torch.int16:
+        raise TypeError("DDD17 records are t int64 [N] / [N, 1] and xyp int16 [N, 3] (events.dat.t / events.dat.xyp)")
+    n = xyp.shape[0]
+    if xyp.ndim != 2 or xyp.shape[1] != 3 or t.numel() != n or not t.is_contiguous() or not xyp.is_contiguous():
+        raise ValueError("DDD17 records: contiguous t with N elements and contiguous xyp [N, 3]")
+    return n
+
+
+def voxel_tbilinear_ddd17(t, xyp, C, H, W, frame_offsets=None, separate_pol=True, mode=None, out=None):
+    """generate_voxel_grid (datasets/data_util.py:51-117) straight from the DDD17 on-disk records (14 B / event): bit-equal
+    to voxel_tbilinear on the int64 rows example_loader_ddd17.py:41-54 assembles from them."""
+    n = _ddd17_check(t, xyp)
+    dev = xyp.device
+    fo = _offsets(frame_offsets, n, dev)
+    F = fo.numel() - 1
+    m = resolve_mode(mode)
+    if out is None:
+        out = torch.empty((F, 2 * C if separate_pol else C, H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _lib.workspace(_lib.voxel_ws_bytes(KIND_TBILINEAR, m, n, F, C, H, W), dev)
+        check(lib().oess_voxel_tbilinear_ddd17(ptr(t), ptr(xyp), ptr(fo), n, F, C, H, W, int(bool(separate_pol)), m, ptr(out),
+                                               ptr(ws), ws.numel(), stream_ptr(dev)), "oess_voxel_tbilinear_ddd17")
+    return out
+
+
+def voxel_histogram_ddd17(t, xyp, H, W, frame_offsets=None, out=None, status=None):
+    """generate_event_histogram (datasets/data_util.py:17-35) from the DDD17 on-disk records -> [F, 2, H, W] (neg, pos)."""
+    n = _ddd17_check(t, xyp)
+    dev = xyp.device
+    fo = _offsets(frame_offsets, n, dev)
+    F = fo.numel() - 1
+    if out is None:
+        out = torch.empty((F, 2, H, W), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().oess_voxel_histogram_ddd17(ptr(t), ptr(xyp), ptr(fo), n, F, H, W, ptr(out), ptr(status), stream_ptr(dev)),
+              "oess_voxel_histogram_ddd17")
+    return out
+
+
 def dsec_rectify_tnorm(x, y, t, p, rectify_map, frame_offsets=None, status=None, out=None):
     """sequence_ov.py:204-210 + :154-159 for F frames: raw (u16 x, u16 y, i64|u32 t, u8 p) -> f32 x', y', pol, t.
 

@@ -308,8 +308,65 @@ def golden_losses():
          **{f"met__{k_}": v for k_, v in met.items()})
 
 
+def _extract_functions(rel, names):
+    """Compile selected module-level functions of an unmodified reference file without importing it (the module imports
+    matplotlib / cv2 at the top)."""
+    src = open(os.path.join(REF, rel)).read()
+    ns = {"np": np, "os": os}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(textwrap.dedent(ast.get_source_segment(src, node)), rel, "exec"), ns)
+    return {n: ns[n] for n in names}
+
+
+def golden_ddd17_ingest(du):
+    """SURVEY 8f row 1 (DDD17 half): the reference's own load_events / extract_events_from_memmap
+    (datasets/extract_data_tools/example_loader_ddd17.py:32-54) on a synthetic recording directory, followed by the
+    chunking of DDD17Events.__getitem__ (datasets/ddd17_events_loader.py:153-177) and generate_voxel_grid."""
+    import tempfile
+    fns = _extract_functions("datasets/extract_data_tools/example_loader_ddd17.py", ["load_events", "extract_events_from_memmap"])
+    rng = np.random.default_rng(1717)
+    n, W, H = 24000, 346, 260
+    t = (np.sort(rng.integers(0, 400_000, n)) + 1_500_000_000).astype(np.int64).reshape(n, 1)
+    xyp = np.stack([rng.integers(0, W, n), rng.integers(0, H, n), rng.integers(0, 2, n)], 1).astype(np.int16)
+    xyp[rng.random(n) < 0.01, 0] = W + 3                       # a few out-of-sensor records
+    idx = np.array([[int(t[8000, 0]), 8000, 5000], [int(t[16000, 0]), 16000, 12500], [int(t[23999, 0]), 23999, 20000],
+                    [int(t[3000, 0]), 3000, -40]], dtype=np.int64)     # (timestamp, event_idx, event_idx_before)
+    out = {"t": t, "xyp": xyp, "index": idx}
+    with tempfile.TemporaryDirectory() as d:
+        t.tofile(os.path.join(d, "events.dat.t"))
+        xyp.tofile(os.path.join(d, "events.dat.xyp"))
+        tm, xm = fns["load_events"](os.path.join(d, "events.dat.t"), os.path.join(d, "events.dat.xyp"))
+        assert tm.shape == (n, 1) and xm.shape == (n, 3)
+        for img_idx in range(4):
+            for fixed in (False, True):
+                ev = fns["extract_events_from_memmap"](tm, xm, img_idx, idx, fixed, 6000)
+                tag = f"s{img_idx}_{int(fixed)}"
+                out[tag + "__sha_events"] = np.array(sha(ev))
+                out[tag + "__n"] = np.array(ev.shape[0])
+                # DDD17Events.__getitem__ :153-177 with nr_events_data = 4, voxel_grid, C = 5, separate_pol False
+                nd = 4
+                t_ns = ev[:, 2]
+                delta = int((t_ns[-1] - t_ns[0]) / nd)
+                per = ev.shape[0] // nd
+                id_end, grids, cuts = 0, [], [0]
+                for i in range(nd):
+                    id_start = id_end
+                    id_end = int(np.searchsorted(t_ns, t_ns[0] + (i + 1) * delta)) if fixed else id_end + per
+                    id_end = min(id_end, ev.shape[0])
+                    cuts.append(id_end)
+                    grids.append(du.generate_input_representation(ev[id_start:id_end], "voxel_grid", (H, W),
+                                                                  nr_temporal_bins=5, separate_pol=False))
+                out[tag + "__cuts"] = np.array(cuts)
+                out[tag + "__sha_grid"] = np.array(sha(np.concatenate(grids, 0)))
+                out[tag + "__sum"] = np.array([float(np.abs(g).astype(np.float64).sum()) for g in grids])
+    save("ddd17_ingest", **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--ddd17" in sys.argv:
+        return golden_ddd17_ingest(_load("ref_data_util", "datasets/data_util.py"))
     du = _load("ref_data_util", "datasets/data_util.py")
     rp = _load("ref_representations", "DSEC/dataset/representations.py")
     golden_tbilinear(du)

@@ -202,8 +202,46 @@ def golden_deeplab():
     print("deeplab_r50.npz", os.path.getsize(os.path.join(OUT, "deeplab_r50.npz")) // 1024, "KiB")
 
 
+def golden_resnet18():
+    """models/_resnet.py:resnet18 (reference function, unmodified, pretrained='') -- row a14': eval-mode and train-mode
+    forward (logits + layer4 map + running statistics).  11.7 M weights regenerated from tests/seeded_weights.py."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+    from seeded_weights import seeded_state_dict
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_resnet", os.path.join(REF, "models", "_resnet.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    m = mod.resnet18(pretrained='')
+    sd0 = seeded_state_dict(m, 18)
+    m.load_state_dict(sd0, strict=True)
+    rng = np.random.default_rng(18)
+    x = rng.random((2, 3, 96, 160)).astype(np.float32)
+
+    def feats(net, t):
+        t = net.maxpool(net.relu(net.bn1(net.conv1(t))))
+        return net.layer4(net.layer3(net.layer2(net.layer1(t))))
+
+    out = {"seed": np.array(18), "x": x, "nkeys": np.array(len(sd0)), "nparams": np.array(sum(p.numel() for p in m.parameters()))}
+    m.eval()
+    with torch.no_grad():
+        out["eval_logits"] = m(torch.from_numpy(x)).numpy()
+        out["eval_feats"] = feats(m, torch.from_numpy(x)).numpy()
+    m.train()
+    with torch.no_grad():
+        out["train_logits"] = m(torch.from_numpy(x)).numpy()
+    sd = m.state_dict()
+    out["rm_l4"] = sd["layer4.1.bn2.running_mean"].numpy()
+    out["rv_stem"] = sd["bn1.running_var"].numpy()
+    out["nbt"] = sd["layer2.0.downsample.1.num_batches_tracked"].numpy()
+    np.savez_compressed(os.path.join(OUT, "resnet18.npz"), **out)
+    print("resnet18.npz", os.path.getsize(os.path.join(OUT, "resnet18.npz")) // 1024, "KiB")
+
+
 if __name__ == "__main__":
-    if "--deeplab" in sys.argv:
+    if "--resnet18" in sys.argv:
+        torch.set_num_threads(4)
+        golden_resnet18()
+    elif "--deeplab" in sys.argv:
         sys.path.insert(0, REF)
         torch.set_num_threads(4)
         golden_deeplab()

@@ -169,7 +169,62 @@ def deeplab():
                       "ms_torch_cudnn_tf32": res["torch"], "samples_per_s_own": B / res["own"] * 1e3}))
 
 
+def config2():
+    """BASELINE config 2 modules named by the north star: ResNet-18 (models/_resnet.py) and the MaskCLIP ViT-B/16
+    (models/maskclip_model.py) on a DSEC batch of frames (3 x 440 x 640), own kernels against torch's TF32 library path of
+    the same arithmetic for the ResNet (its torch formulation on cuDNN); the ViT mirror has no torch formulation in the
+    package (and tools/ may not import oracle/), so it is reported with its per-kernel breakdown only."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests"))
+    from seeded_weights import seeded_state_dict
+    from openess_b200 import _lib
+    from openess_b200.models._resnet import resnet18
+    from openess_b200.models import maskclip_model as mm
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    m = resnet18(pretrained='')
+    m.load_state_dict(seeded_state_dict(m, 18), strict=True)
+    m = m.cuda()
+    for p in m.parameters():
+        p.requires_grad = False
+    for B in (8, 32):
+        x = torch.rand(B, 3, 440, 640, device="cuda")
+        xcl = x.contiguous(memory_format=torch.channels_last)
+        for mode in ("train", "eval"):
+            m.train(mode == "train")
+            with torch.no_grad():
+                t_own = timeit(lambda: m(x), iters=10, warm=3)
+                t_lib = timeit(lambda: m.forward_torch(x), iters=10, warm=3)
+                m_cl = m.to(memory_format=torch.channels_last)
+                t_lib_cl = timeit(lambda: m_cl.forward_torch(xcl), iters=10, warm=3)
+                m.to(memory_format=torch.contiguous_format)
+            fl = 20.5e9 * B
+            print(json.dumps({"op": "resnet18_fwd", "B": B, "bn": mode, "ms_own_kernels": t_own, "tflops": fl / t_own / 1e9,
+                              "ms_torch_cudnn_tf32_nchw": t_lib, "ms_torch_cudnn_tf32_nhwc": t_lib_cl}))
+        del x, xcl
+    torch.manual_seed(1205)
+    v = mm.maskClipFeatureExtractor(None, None, 11, None)
+    with torch.no_grad():
+        v.encoder.pos_embed.normal_(0, 0.02)
+        v.encoder.cls_token.normal_(0, 0.02)
+    v = v.cuda().eval()
+    for B in (1, 8):
+        img = torch.rand(B, 3, 440, 640, device="cuda")
+        t_own = timeit(lambda: v(img), iters=10, warm=3)
+        with _lib.profile() as prof:
+            v(img)
+        T = 1121
+        fl = B * (12 * (2 * T * 768 * 9216 + 4 * T * T * 768) + 2 * (T - 1) * 768 * 768 + 2 * T * 768 * (3 * 768 + 6144))
+        print(json.dumps({"op": "maskclip_vit_b16_fwd", "B": B, "ms_own_kernels": t_own, "tflops": fl / t_own / 1e9,
+                          "kernel_ms": {k: round(val[1], 4) for k, val in prof.kernels.items()}}))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
 if __name__ == "__main__":
+    if "--config2" in sys.argv:
+        config2()
+        sys.exit(0)
     if "--teacher" in sys.argv:
         teacher()
         semseg()
