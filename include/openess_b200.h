@@ -225,7 +225,8 @@ int oess_pixel_linear_wgrad(const float* dy, const float* x, int B, int Cin, int
 int oess_gemm_tf32(const float* A, const float* B, const float* bias, float* C, int64_t M, int N, int K,
                    oess_stream_t stream);
 /* Same GEMM with the epilogue the ViT blocks of models/maskclip_model.py:519-541 need:
- *   C = act(A * B^T + bias) + residual      act: 0 = identity, 1 = GELU (erf form, mmcv FFN :507-513)
+ *   C = act(A * B^T + bias) + residual      act bit 0: GELU (erf form, mmcv FFN :507-513); bit 1: store C rounded to TF32
+ *   (round-to-nearest) for outputs that are tensor-core operands next (q, k, v of the attention; see oess_conv2d_nhwc_tf32)
  * residual: [M, N] or NULL; may alias C (the `identity + dropout_layer(out)` residual of mmcv's MultiheadAttention / FFN). */
 int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M,
                       int N, int K, int act, oess_stream_t stream);
@@ -256,6 +257,10 @@ int oess_vit_assemble(const float* tok, const float* cls, const float* pos, int 
 int oess_layernorm_rows(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int D, float* y,
                         oess_stream_t stream);
 int oess_mha_fwd(const float* qkv, int B, int T, int heads, float* out, oess_stream_t stream);
+/* The same attention on the tensor cores (tc_mha.cu): both products as tcgen05.mma.kind::tf32 with S and the O tile in
+ * TMEM, K / V tiles by TMA (V as an MN-major operand), fp32 online softmax in registers, P restaged through shared memory
+ * as the K-major A operand.  TF32 operands / fp32 accumulate; same arguments and layout as oess_mha_fwd. */
+int oess_mha_fwd_tc(const float* qkv, int B, int T, int heads, float* out, oess_stream_t stream);
 int oess_l2norm_rows(float* x, int64_t rows, int D, oess_stream_t stream);
 int oess_bilinear_tokens_to_nchw(const float* tok, int B, int h, int w, int K, int H, int W, float* out,
                                  oess_stream_t stream);

@@ -66,6 +66,7 @@ SIGNATURES = {
     "oess_vit_assemble": [_vp, _vp, _vp, _int, _int, _int, _vp, _vp],
     "oess_layernorm_rows": [_vp, _vp, _vp, _f32, _i64, _int, _vp, _vp],
     "oess_mha_fwd": [_vp, _int, _int, _int, _vp, _vp],
+    "oess_mha_fwd_tc": [_vp, _int, _int, _int, _vp, _vp],
     "oess_l2norm_rows": [_vp, _i64, _int, _vp],
     "oess_bilinear_tokens_to_nchw": [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp],
     "oess_convlstm_step_nhwc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp],

@@ -35,6 +35,7 @@ SOURCES = {
     "bn_nhwc.cu": [],
     "upnorm_pool.cu": [],
     "vit.cu": [],
+    "tc_mha.cu": [],
     "pool_nhwc.cu": [],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

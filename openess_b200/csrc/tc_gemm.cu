@@ -152,19 +152,20 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             const float4 b = *reinterpret_cast<const float4*>(bias + col + j);
                             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                         }
-                        if (act == 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
+                        if (act & 1) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
                         if (rrow) {
                             const float4 r = *reinterpret_cast<const float4*>(rrow + col + j);
                             o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                         }
+                        if (act & 2) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
                         *reinterpret_cast<float4*>(crow + col + j) = o;
                     }
                 } else {
                     for (int j = 0; j < 32 && col + j < N; ++j) {
                         float o = v[j] + (bias ? bias[col + j] : 0.0f);
-                        if (act == 1) o = gelu_erf(o);
+                        if (act & 1) o = gelu_erf(o);
                         if (rrow) o += rrow[col + j];
-                        crow[col + j] = o;
+                        crow[col + j] = (act & 2) ? rna_tf32(o) : o;
                     }
                 }
             }
@@ -205,7 +206,7 @@ OESS_API int oess_gemm_tf32(const float* A, const float* B, const float* bias, f
 
 OESS_API int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M,
                                int N, int K, int act, oess_stream_t stream) {
-    if (M < 0 || N <= 0 || K <= 0 || act < 0 || act > 1) return OESS_E_ARG;
+    if (M < 0 || N <= 0 || K <= 0 || act < 0 || act > 3) return OESS_E_ARG;
     if (M == 0) return OESS_OK;
     if (!A || !B || !C) return OESS_E_ARG;
     // TMA: 16-byte aligned bases and row strides

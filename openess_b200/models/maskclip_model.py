@@ -107,7 +107,8 @@ class TransformerEncoderLayer(nn.Module):
         D = x.shape[1]
         q = k = v = None
         y = _ops.layernorm_rows(x, self.ln1.weight, self.ln1.bias, self.ln1.eps)
-        qkv = _ops.gemm_tf32_ex(y, mha.in_proj_weight, mha.in_proj_bias)              # [B * T, 3 D]
+        # q, k, v are tensor-core operands next (attention, out_proj): stored TF32-rounded instead of truncated on read
+        qkv = _ops.gemm_tf32_ex(y, mha.in_proj_weight, mha.in_proj_bias, round_out=True)   # [B * T, 3 D]
         if return_qkv:
             # :524-533  y.view(N, L, 3, C).permute(2, 0, 1, 3) -> out_proj on each third; `v += x`; `v = ffn(norm2(v), identity=v)`
             thirds = qkv.view(B * T, 3, D).permute(1, 0, 2).contiguous()

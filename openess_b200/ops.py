@@ -1,5 +1,6 @@
 """Small dense ops over the C ABI with autograd: the per-pixel linear map used by the fused segmentation head."""
 import ctypes
+import os
 
 import torch
 
@@ -84,7 +85,7 @@ def gemm_tf32(a, b, bias=None, out=None):
     return out
 
 
-def gemm_tf32_ex(a, b, bias=None, residual=None, act=None, out=None):
+def gemm_tf32_ex(a, b, bias=None, residual=None, act=None, out=None, round_out=False):
     """out = act(a @ b.T + bias) + residual on the tensor cores (oess_gemm_tf32_ex): act in (None, "gelu"); `out` may be
     `residual` (the residual add of a transformer block, maskclip_model.py:538-539)."""
     _lib.require_cuda(a, b, bias, residual)
@@ -105,8 +106,9 @@ def gemm_tf32_ex(a, b, bias=None, residual=None, act=None, out=None):
     if out is None:
         out = torch.empty(M, N, dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
-        check(lib().oess_gemm_tf32_ex(ptr(a), ptr(b), ptr(bias), ptr(residual), ptr(out), M, N, K, 1 if act == "gelu" else 0,
-                                      stream_ptr(a.device)), "oess_gemm_tf32_ex")
+        check(lib().oess_gemm_tf32_ex(ptr(a), ptr(b), ptr(bias), ptr(residual), ptr(out), M, N, K,
+                                      (1 if act == "gelu" else 0) | (2 if round_out else 0), stream_ptr(a.device)),
+              "oess_gemm_tf32_ex")
     return out
 
 
@@ -148,8 +150,13 @@ def layernorm_rows(x, weight, bias, eps):
     return y
 
 
-def mha_fwd(qkv, B, T, heads):
-    """softmax(q k^T / 8) v per head on the packed in_proj output [B * T, 3 * heads * 64] -> [B * T, heads * 64]."""
+MHA_TENSOR_CORES = os.environ.get("OESS_MHA", "tc") != "simt"
+
+
+def mha_fwd(qkv, B, T, heads, tensor_cores=None):
+    """softmax(q k^T / 8) v per head on the packed in_proj output [B * T, 3 * heads * 64] -> [B * T, heads * 64].
+    tensor_cores (default: module switch MHA_TENSOR_CORES / env OESS_MHA=simt|tc): oess_mha_fwd_tc (tcgen05, TF32 operands)
+    or oess_mha_fwd (exact fp32 on the FMA pipes)."""
     _lib.require_cuda(qkv)
     qkv = _f32c(qkv)
     D = heads * 64
@@ -157,7 +164,8 @@ def mha_fwd(qkv, B, T, heads):
         raise ValueError("mha_fwd: qkv must be [B * T, 3 * heads * 64] (head dim 64)")
     out = torch.empty(B * T, D, dtype=torch.float32, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        check(lib().oess_mha_fwd(ptr(qkv), B, T, heads, ptr(out), stream_ptr(qkv.device)), "oess_mha_fwd")
+        fn = lib().oess_mha_fwd_tc if (MHA_TENSOR_CORES if tensor_cores is None else tensor_cores) else lib().oess_mha_fwd
+        check(fn(ptr(qkv), B, T, heads, ptr(out), stream_ptr(qkv.device)), "oess_mha_fwd")
     return out
 
 
