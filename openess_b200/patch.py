@@ -72,10 +72,21 @@ def patch_reference(ref_root, voxel_mode=None):
         done["e2vid.utils.inference_utils.EventPreprocessor"] = e
     # model mirrors (state_dict-compatible; tensor-core forward paths).  These reference modules import their
     # environment's optional packages (mmcv via models/__init__.py, cv2, ...): rebinding is best effort per module.
-    def try_rebind(ref_name, rel, names, src_mod):
+    def try_rebind(ref_name, rel, names, src_mod, stand_in=False):
+        """stand_in: if the reference module cannot be imported (its third-party imports are missing), register the
+        mirror module itself under the reference name -- `from models.maskclip_model import ...` then needs no mmcv."""
         try:
             src = __import__(src_mod, fromlist=["_"])
-            mod = _load(ref_root, ref_name, rel)
+            try:
+                mod = _load(ref_root, ref_name, rel)
+            except ImportError:
+                if not stand_in:
+                    raise
+                sys.modules.pop(ref_name, None)
+                sys.modules[ref_name] = mod = src
+                parent = sys.modules.get(ref_name.rpartition(".")[0])
+                if parent is not None:
+                    setattr(parent, ref_name.rpartition(".")[2], src)
             rebind(mod, names, src)
         except Exception as e:  # pragma: no cover - depends on the reference's optional imports
             for n in names:
@@ -89,5 +100,13 @@ def patch_reference(ref_root, voxel_mode=None):
     try_rebind("e2vid.model.model", "e2vid/model/model.py", ["E2VIDRecurrent"], "openess_b200.e2vid.model.model")
     try_rebind("e2vid.image_reconstructor", "e2vid/image_reconstructor.py", ["ImageReconstructor"],
                "openess_b200.e2vid.image_reconstructor")
+    # rows a14 / a14' (modules the trainers construct or BASELINE config 2 names) and the DDD17 record access (8f row 1)
+    try_rebind("models.maskclip_model", "models/maskclip_model.py",
+               ["maskClipFeatureExtractor", "VisionTransformer", "TransformerEncoderLayer", "MaskClipHead", "PatchEmbed"],
+               "openess_b200.models.maskclip_model", stand_in=True)
+    try_rebind("models._resnet", "models/_resnet.py", ["ResNet", "resnet18", "resnet34", "resnet50"], "openess_b200.models._resnet")
+    try_rebind("datasets.extract_data_tools.example_loader_ddd17", "datasets/extract_data_tools/example_loader_ddd17.py",
+               ["load_files_in_directory", "load_events", "extract_events_from_memmap"],
+               "openess_b200.datasets.extract_data_tools.example_loader_ddd17", stand_in=True)
     _PATCHED.update(done)
     return done

@@ -109,8 +109,12 @@ def test_patch_reference_rebinds_boundary_callables():
         "assert du.generate_voxel_grid.__module__.startswith('openess_b200')\n"
         "assert m.MetricsSemseg.__module__.startswith('openess_b200')\n"
         "assert hasattr(lf, 'make_one_hot')  # untouched reference symbols stay\n"
+        "import models._resnet as rn, models.maskclip_model as mc\n"
+        "assert rn.resnet18.__module__.startswith('openess_b200') and mc.maskClipFeatureExtractor.__module__.startswith('openess_b200')\n"
+        "from datasets.extract_data_tools.example_loader_ddd17 import extract_events_from_memmap as ex\n"
+        "assert ex.__module__.startswith('openess_b200')\n"
         "print('NDONE', len(done))\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     n = [int(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("NDONE")]
-    assert n and n[0] >= 11
+    assert n and n[0] >= 23
