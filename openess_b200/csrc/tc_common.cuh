@@ -66,6 +66,24 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// multicast variant: the box lands at the same shared-memory offset of every CTA in `mask` (cluster ranks), and each of
+// those CTAs' mbarrier at the offset of `bar` receives the complete_tx bytes
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {       // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- TMEM -----------------------------------------------------------------------------------
 // whole warp; writes the allocated TMEM base address to *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
@@ -151,6 +169,12 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 // mbarrier arrives once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// same, arriving on the mbarrier at this offset in every CTA of `mask` (stage release seen by all multicast producers)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
 // ---- host: tensor maps ------------------------------------------------------------------------

@@ -8,6 +8,8 @@
 // in TMEM), warps 2..5 = epilogue (tcgen05.ld -> + bias -> global).  Operands are fp32 in memory; the tensor core
 // reads them as TF32 (10-bit mantissa), accumulation is fp32 -- the same arithmetic class torch's default cuDNN /
 // cuBLAS-TF32 convolution path uses on the reference's GPU run.  Stated tolerance: 2e-3 relative to |A||B|.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace oess {
@@ -57,25 +59,30 @@ static int make_tmap_f32_sw(CUtensorMap* m, const void* base, int rank, const ui
 }
 
 constexpr int kBM = 128;
-constexpr int kStages = 4;
 constexpr int kGemmThreads = 192;
 
 // nn.GELU() (erf form), the activation of mmcv's FFN in models/maskclip_model.py:507-513
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN>
+// Ring depth: sized so that TWO CTAs share an SM (<= ~97 KB each): the TMEM epilogue of one tile (bias / GELU / residual,
+// 128 x BN global stores) runs under the main loop of the other CTA's tile -- same idea as the ConvLSTM kernel.
+template <int BN, int kStages>
 struct GemmSmem {
     static constexpr int kABytes = kBM * kBlockK * 4;      // 16 KB
     static constexpr int kBBytes = BN * kBlockK * 4;
     static constexpr int kBytes = 1024 + kStages * (kABytes + kBBytes) + 256;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+// MC: clusters of two CTAs with adjacent M tiles and the same N tile; each loads its own A tile and HALF of the B tile, which
+// TMA multicasts into both CTAs' shared memory: per-SM operand traffic from L2 drops from 16 + BN / 8 KB to 16 + BN / 16 KB per
+// K block (48 -> 32 KB at BN = 256) -- the L2 -> shared-memory stream, not the tensor pipe, bounds these kernels.  A stage is
+// released to BOTH producers (the commit arrives on the empty barrier of both CTAs, count 2).
+template <int BN, int kStages, bool MC>
+__global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, kStages>::kBytes <= 100 * 1024) ? 2 : 1)
 k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const float* __restrict__ bias, const float* residual, float* C, int64_t M, int N, int K, int act) {
     extern __shared__ uint8_t smem_raw[];
-    using S = GemmSmem<BN>;
+    using S = GemmSmem<BN, kStages>;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-byte aligned tiles
     uint8_t* sA = base;
     uint8_t* sB = base + kStages * S::kABytes;
@@ -88,20 +95,21 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int64_t m0 = (int64_t)blockIdx.x * kBM;
     const int n0 = blockIdx.y * BN;
     const int kblocks = (K + kBlockK - 1) / kBlockK;
+    const uint32_t crank = MC ? cluster_ctarank() : 0u;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], MC ? 2 : 1);
         }
         mbar_init(acc_full, 1);
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, BN);
     tc_fence_before();
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();      // peers' barriers exist before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 
@@ -112,7 +120,11 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 mbar_wait(&empty[s], ((kb / kStages) & 1) ^ 1);
                 mbar_expect_tx(&full[s], S::kABytes + S::kBBytes);
                 tma_load_2d(sA + s * S::kABytes, &tmA, &full[s], kb * kBlockK, (int)m0);
-                tma_load_2d(sB + s * S::kBBytes, &tmB, &full[s], kb * kBlockK, n0);
+                if (MC)
+                    tma_load_2d_mc(sB + s * S::kBBytes + crank * (S::kBBytes / 2), &tmB, &full[s], kb * kBlockK,
+                                   n0 + (int)crank * (BN / 2), (uint16_t)3);
+                else
+                    tma_load_2d(sB + s * S::kBBytes, &tmB, &full[s], kb * kBlockK, n0);
             }
         }
     } else if (warp == 1) {
@@ -127,7 +139,8 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
                 for (int k = 0; k < kBlockK / kUmmaK; ++k)   // +32 bytes (>> 4 = 2) per K = 8 step inside the swizzle line
                     umma_tf32(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                umma_commit(&empty[s]);                   // frees the smem stage once these MMAs have read it
+                if (MC) umma_commit_mc(&empty[s], (uint16_t)3);   // frees the stage in BOTH CTAs' producers' eyes
+                else umma_commit(&empty[s]);              // frees the smem stage once these MMAs have read it
             }
             umma_commit(acc_full);                        // accumulator complete
         }
@@ -161,36 +174,52 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         *reinterpret_cast<float4*>(crow + col + j) = o;
                     }
                 } else {
-                    for (int j = 0; j < 32 && col + j < N; ++j) {
-                        float o = v[j] + (bias ? bias[col + j] : 0.0f);
-                        if (act & 1) o = gelu_erf(o);
-                        if (rrow) o += rrow[col + j];
-                        crow[col + j] = (act & 2) ? rna_tf32(o) : o;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {        // fully unrolled + predicated: v[] stays in registers
+                        if (col + j < N) {
+                            float o = v[j] + (bias ? bias[col + j] : 0.0f);
+                            if (act & 1) o = gelu_erf(o);
+                            if (rrow) o += rrow[col + j];
+                            crow[col + j] = (act & 2) ? rna_tf32(o) : o;
+                        }
                     }
                 }
             }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();      // no CTA leaves while its peer can still write into it
     if (warp == 1) tmem_dealloc(tmem_acc, BN);
 }
 
-template <int BN>
+template <int BN, int kStages, bool MC>
 static int launch_gemm(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M, int N,
                        int K, int act, cudaStream_t st) {
     CUtensorMap tmA, tmB;
     const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)K * 4};
     const uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)K * 4};
-    const uint32_t bA[2] = {kBlockK, kBM}, bB[2] = {kBlockK, (uint32_t)BN};
+    const uint32_t bA[2] = {kBlockK, kBM}, bB[2] = {kBlockK, (uint32_t)(MC ? BN / 2 : BN)};
     int rc = make_tmap_f32(&tmA, A, 2, dA, sA, bA);
     if (rc) return rc;
     rc = make_tmap_f32(&tmB, B, 2, dB, sB, bB);
     if (rc) return rc;
-    auto kern = k_gemm_tf32<BN>;
-    OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN>::kBytes));
-    const dim3 grid((unsigned)((M + kBM - 1) / kBM), (unsigned)((N + BN - 1) / BN));
-    OESS_KERNEL("tc_gemm_tf32", st, kern<<<grid, kGemmThreads, GemmSmem<BN>::kBytes, st>>>(tmA, tmB, bias, residual, C, M, N, K, act));
+    auto kern = k_gemm_tf32<BN, kStages, MC>;
+    OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmSmem<BN, kStages>::kBytes));
+    unsigned gx = (unsigned)((M + kBM - 1) / kBM);
+    if (MC) gx = (gx + 1) & ~1u;                           // whole clusters: a padding CTA loads zeros and stores nothing
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, (unsigned)((N + BN - 1) / BN));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = GemmSmem<BN, kStages>::kBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = MC ? 2 : 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OESS_KERNEL("tc_gemm_tf32", st, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, bias, residual, C, M, N, K, act));
     return 0;
 }
 
@@ -214,7 +243,24 @@ OESS_API int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias
         ((uintptr_t)residual & 15)) return OESS_E_ARG;
     if (M >= (1ll << 31)) return OESS_E_RANGE;
     cudaStream_t st = (cudaStream_t)stream;
-    if (N > 128) return tc::launch_gemm<256>(A, B, bias, residual, C, M, N, K, act, st);
-    if (N > 64) return tc::launch_gemm<128>(A, B, bias, residual, C, M, N, K, act, st);
-    return tc::launch_gemm<64>(A, B, bias, residual, C, M, N, K, act, st);
+    // default: two CTAs per SM (ring depth 2-4).  OESS_GEMM=deep: one CTA per SM with a 4-stage ring; OESS_GEMM=mc: two CTAs
+    // per SM in clusters of two with the B tile multicast (measured: no gain -- at cluster size 2 the L2 already merges the two
+    // unicast requests, and the per-SM shared-memory fill rate, not the L2 request count, is what bounds the operand stream)
+    static const int variant = [] {
+        const char* e = getenv("OESS_GEMM");
+        return !e ? 1 : (e[0] == 'd' ? 0 : (e[0] == 'm' ? 2 : 1));
+    }();
+    if (variant == 0) {
+        if (N > 128) return tc::launch_gemm<256, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
+        if (N > 64) return tc::launch_gemm<128, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
+        return tc::launch_gemm<64, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
+    }
+    if (variant == 1) {
+        if (N > 128) return tc::launch_gemm<256, 2, false>(A, B, bias, residual, C, M, N, K, act, st);
+        if (N > 64) return tc::launch_gemm<128, 3, false>(A, B, bias, residual, C, M, N, K, act, st);
+        return tc::launch_gemm<64, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
+    }
+    if (N > 128) return tc::launch_gemm<256, 2, true>(A, B, bias, residual, C, M, N, K, act, st);
+    if (N > 64) return tc::launch_gemm<128, 3, true>(A, B, bias, residual, C, M, N, K, act, st);
+    return tc::launch_gemm<64, 4, true>(A, B, bias, residual, C, M, N, K, act, st);
 }
