@@ -250,7 +250,9 @@ OESS_API int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias
         const char* e = getenv("OESS_GEMM");
         return !e ? 1 : (e[0] == 'd' ? 0 : (e[0] == 'm' ? 2 : 1));
     }();
-    if (variant == 0) {
+    // fewer tiles than SMs: a second resident CTA has nothing to overlap with, the deeper ring hides the load latency instead
+    const int64_t tiles = ((M + 127) / 128) * (int64_t)((N + (N > 128 ? 255 : (N > 64 ? 127 : 63))) / (N > 128 ? 256 : (N > 64 ? 128 : 64)));
+    if (variant == 0 || (variant == 1 && tiles <= kNumSMs)) {
         if (N > 128) return tc::launch_gemm<256, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
         if (N > 64) return tc::launch_gemm<128, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
         return tc::launch_gemm<64, 4, false>(A, B, bias, residual, C, M, N, K, act, st);

@@ -38,6 +38,9 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_bmn(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// p >= 0: adding half a TF32 ulp to the bit pattern makes the tensor core's truncation a round-to-nearest (one IADD; the
+// sum of the row uses the same value the MMA sees up to the dropped bits)
+__device__ __forceinline__ float round_up_tf32(float p) { return __uint_as_float((__float_as_uint(p) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __global__ void __launch_bounds__(192, 2)
@@ -150,24 +153,27 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
             float s0[32], s1[32];
             tmem_ld32(tmem_s + lane_off, s0);
             tmem_ld32(tmem_s + lane_off + 32, s1);
-            float mx = -INFINITY;
+            if (k0 + kMhaK > T) {                          // ragged last tile only: keys past T drop out of max and sum
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                s0[i] = (k0 + i < T) ? s0[i] * kScale : -INFINITY;
-                s1[i] = (k0 + 32 + i < T) ? s1[i] * kScale : -INFINITY;
-                mx = fmaxf(mx, fmaxf(s0[i], s1[i]));
+                for (int i = 0; i < 32; ++i) {
+                    if (k0 + i >= T) s0[i] = -INFINITY;
+                    if (k0 + 32 + i >= T) s1[i] = -INFINITY;
+                }
             }
-            const float mn = fmaxf(m, mx);                 // finite: key k0 of every tile is valid
+            float mx = fmaxf(s0[0], s1[0]);
+#pragma unroll
+            for (int i = 1; i < 32; ++i) mx = fmaxf(mx, fmaxf(s0[i], s1[i]));
+            const float mn = fmaxf(m, mx * kScale);        // kScale > 0: scaling commutes with max; finite (key k0 is valid)
             const float alpha = exp2f(m - mn);             // first tile: exp2(-inf) = 0
             m = mn;
             float sum = 0.0f;
 #pragma unroll
             for (int c = 0; c < 8; ++c) {                  // 16-byte chunks of the two 128-byte lines of this row
                 float4 p0, p1;
-                p0.x = rna_tf32(exp2f(s0[4 * c + 0] - mn)); p0.y = rna_tf32(exp2f(s0[4 * c + 1] - mn));
-                p0.z = rna_tf32(exp2f(s0[4 * c + 2] - mn)); p0.w = rna_tf32(exp2f(s0[4 * c + 3] - mn));
-                p1.x = rna_tf32(exp2f(s1[4 * c + 0] - mn)); p1.y = rna_tf32(exp2f(s1[4 * c + 1] - mn));
-                p1.z = rna_tf32(exp2f(s1[4 * c + 2] - mn)); p1.w = rna_tf32(exp2f(s1[4 * c + 3] - mn));
+                p0.x = round_up_tf32(exp2f(fmaf(s0[4 * c + 0], kScale, -mn))); p0.y = round_up_tf32(exp2f(fmaf(s0[4 * c + 1], kScale, -mn)));
+                p0.z = round_up_tf32(exp2f(fmaf(s0[4 * c + 2], kScale, -mn))); p0.w = round_up_tf32(exp2f(fmaf(s0[4 * c + 3], kScale, -mn)));
+                p1.x = round_up_tf32(exp2f(fmaf(s1[4 * c + 0], kScale, -mn))); p1.y = round_up_tf32(exp2f(fmaf(s1[4 * c + 1], kScale, -mn)));
+                p1.z = round_up_tf32(exp2f(fmaf(s1[4 * c + 2], kScale, -mn))); p1.w = round_up_tf32(exp2f(fmaf(s1[4 * c + 3], kScale, -mn)));
                 sum += ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w));
                 *reinterpret_cast<float4*>(prow + ((c ^ sw) << 4)) = p0;                     // keys k0 + 4c .. (K block 0)
                 *reinterpret_cast<float4*>(prow + kPBytes / 2 + ((c ^ sw) << 4)) = p1;       // keys k0 + 32 + 4c .. (K block 1)
@@ -176,8 +182,10 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
             fence_proxy_async_smem();                      // generic-proxy writes of P -> visible to the tensor core
             tc_fence_before();                             // the TMEM reads of S are done before the next S product
             mbar_arrive(p_ready);
+            if (!__all_sync(0xffffffffu, alpha == 1.0f)) { // the running maxima settle after a few tiles
 #pragma unroll
-            for (int i = 0; i < kMhaD; ++i) o[i] *= alpha;
+                for (int i = 0; i < kMhaD; ++i) o[i] *= alpha;
+            }
             mbar_wait(o_full, j & 1);
             tc_fence_after();
             tmem_ld32(tmem_o + lane_off, s0);

@@ -77,5 +77,34 @@ ops.planes_to_nhwc_padded(torch.randn(2, 5, 9, 14, device=dev), 8)
 d = torch.randn(2, 256, 6, 9, device=dev, requires_grad=True)
 sp = torch.randint(0, 7, (2, 24, 36), device=dev)
 ops.upnorm_pool(d, sp, 7, 14).square().sum().backward()
+# rows added in the fourth session: ViT kernels (incl. the tcgen05 attention with ragged tails), GEMM epilogues, pooling,
+# the 7x7 stem through the padded repack, DDD17 native records
+qkv = torch.randn(2 * 150, 3 * 128, device=dev)
+ops.mha_fwd(qkv, 2, 150, 2, tensor_cores=True)
+ops.mha_fwd(qkv, 2, 150, 2, tensor_cores=False)
+ops.mha_fwd(qkv[:7].contiguous(), 1, 7, 2, tensor_cores=True)
+xr = torch.randn(2 * 36, 128, device=dev)
+ops.layernorm_rows(xr, torch.ones(128, device=dev), torch.zeros(128, device=dev), 1e-6)
+ops.l2norm_rows_(xr.clone())
+rows_, hw_ = ops.vit_patchify(torch.rand(2, 3, 72, 100, device=dev), 16)
+ops.vit_assemble(torch.randn(2 * 35, 128, device=dev), torch.randn(128, device=dev), torch.randn(36, 128, device=dev), 2, 36)
+ops.bilinear_tokens_to_nchw(torch.randn(2 * 35, 11, device=dev), 2, 5, 7, (72, 100))
+res_ = torch.randn(300, 200, device=dev)
+ops.gemm_tf32_ex(a, b, torch.randn(200, device=dev), residual=res_, act="gelu", out=res_, round_out=True)
+ops.gemm_tf32_ex(a, torch.randn(11, 96, device=dev))                       # N = 11: scalar epilogue tail
+xm = torch.randn(2, 64, 13, 17, device=dev).contiguous(memory_format=torch.channels_last)
+ops.maxpool3x3s2_nhwc(xm)
+ops.global_avgpool_nhwc(xm)
+w7 = torch.zeros(64, 8, 7, 7, device=dev)
+w7[:, :3] = torch.randn(64, 3, 7, 7, device=dev) * 0.05
+ops.conv2d_tc(ops.planes_to_nhwc_padded(torch.rand(2, 3, 37, 45, device=dev), 8), ops.conv2d_pack(w7), None, 7, 2, 3, 1, relu=True,
+              round_out=True)
+nd = 5000
+td = torch.from_numpy(np.sort(rng.integers(0, 50000, nd)).astype(np.int64) + 1_500_000_000).to(dev)
+xypd = torch.from_numpy(np.stack([rng.integers(0, 346, nd), rng.integers(0, 260, nd), rng.integers(0, 2, nd)], 1).astype(np.int16)).to(dev)
+fod = torch.tensor([0, 1200, 1200, nd], dtype=torch.int64)
+voxel.voxel_tbilinear_ddd17(td, xypd, 5, 260, 346, frame_offsets=fod, separate_pol=False)
+voxel.voxel_tbilinear_ddd17(td, xypd, 5, 260, 346, frame_offsets=fod, separate_pol=True, mode="atomic")
+voxel.voxel_histogram_ddd17(td, xypd, 260, 346, frame_offsets=fod)
 torch.cuda.synchronize()
 print("sanitize smoke done")
