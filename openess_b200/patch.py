@@ -108,5 +108,7 @@ def patch_reference(ref_root, voxel_mode=None):
     try_rebind("datasets.extract_data_tools.example_loader_ddd17", "datasets/extract_data_tools/example_loader_ddd17.py",
                ["load_files_in_directory", "load_events", "extract_events_from_memmap"],
                "openess_b200.datasets.extract_data_tools.example_loader_ddd17", stand_in=True)
+    try_rebind("DSEC.utils.eventslicer", "DSEC/utils/eventslicer.py", ["EventSlicer"], "openess_b200.DSEC.utils.eventslicer",
+               stand_in=True)
     _PATCHED.update(done)
     return done

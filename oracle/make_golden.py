@@ -363,8 +363,73 @@ def golden_ddd17_ingest(du):
     save("ddd17_ingest", **out)
 
 
+def synth_dsec_recording(seed=2024, n=60000, span_ms=700, t_offset=5_000_000):
+    """Synthetic stand-in for a DSEC events.h5 (dict of arrays with the file's dataset names and dtypes)."""
+    rng = np.random.default_rng(seed)
+    t = np.sort(rng.integers(3000, span_ms * 1000, n)).astype(np.uint32)          # first events after ms 3, bursts allowed
+    t[20000:20400] = t[20000]                                                     # 400 events on one microsecond
+    t = np.sort(t)
+    ms_to_idx = np.searchsorted(t, np.arange(span_ms + 1, dtype=np.int64) * 1000, side="left").astype(np.uint64)
+    return {"events/x": rng.integers(0, 640, n).astype(np.uint16), "events/y": rng.integers(0, 480, n).astype(np.uint16),
+            "events/t": t, "events/p": rng.integers(0, 2, n).astype(np.uint8), "ms_to_idx": ms_to_idx,
+            "t_offset": np.array(t_offset, dtype=np.int64)}
+
+
+def golden_dsec_slicer():
+    """SURVEY 8f row 1 (DSEC half): the reference's own EventSlicer (DSEC/utils/eventslicer.py, imported unmodified with
+    h5py / hdf5plugin stubbed -- they are only used for the type annotation / codec registration) on a dict stand-in for
+    events.h5, and the chunk selection of Sequence.__getitem__ (sequence_ov.py:247-254, 282-305) restated on top of it."""
+    import types
+    for name in ("h5py", "hdf5plugin"):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.File = object
+            sys.modules[name] = m
+    es = _load("ref_eventslicer", "DSEC/utils/eventslicer.py")
+    rec = synth_dsec_recording()
+    sl = es.EventSlicer(rec)
+    off = int(rec["t_offset"])
+    out = {"start": np.array(sl.get_start_time_us()), "final": np.array(sl.get_final_time_us())}
+    queries = [(off + 100_000, off + 150_000), (off + 3_000, off + 3_001), (off + 0, off + 10_000), (off + 250_123, off + 250_999),
+               (off + 699_000, off + 700_000), (off + 699_500, off + 700_500), (off + int(rec["events/t"][20000]), off + int(rec["events/t"][20000]) + 1)]
+    for i, (a, b) in enumerate(queries):
+        ev = sl.get_events(a, b)
+        out[f"w{i}__q"] = np.array([a, b])
+        out[f"w{i}__none"] = np.array(ev is None)
+        if ev is not None:
+            out[f"w{i}__n"] = np.array(ev["t"].size)
+            out[f"w{i}__sha"] = np.array(sha(np.concatenate([ev[k].astype(np.int64) for k in ("x", "y", "t", "p")])))
+    fq = [(off + 400_000, 20000), (off + 10_000, 5000), (off + 3_000, 100), (off + 700_000, 1000), (off + 700_001, 1000),
+          (off + int(rec["events/t"][20000]), 300), (off + 123_456, 40000)]
+    for i, (te, n) in enumerate(fq):
+        ev = sl.get_events_fixed_num(te, n)
+        out[f"f{i}__q"] = np.array([te, n])
+        out[f"f{i}__none"] = np.array(ev is None)
+        if ev is not None:
+            out[f"f{i}__n"] = np.array(ev["t"].size)
+            out[f"f{i}__sha"] = np.array(sha(np.concatenate([ev[k].astype(np.int64) for k in ("x", "y", "t", "p")])))
+            # sequence_ov.py:282-305: chunks of nr_events_data = 4
+            nd = 4
+            per = ev["t"].size // nd
+            out[f"f{i}__chunk_t0"] = np.array([int(ev["t"][j * per]) if per else -1 for j in range(nd)])
+            out[f"f{i}__per"] = np.array(per)
+    # duration mode, :247-254: delta_t_us = 40 000, 4 windows with FLOAT boundaries
+    ts_end, delta, nd = off + 300_001, 40_001, 4
+    per = delta / nd
+    ns = []
+    for i in range(nd):
+        ev = sl.get_events(ts_end - delta + i * per, ts_end - delta + (i + 1) * per)
+        ns.append(ev["t"].size)
+        out[f"d{i}__sha"] = np.array(sha(np.concatenate([ev[k].astype(np.int64) for k in ("x", "y", "t", "p")])))
+    out["d__n"] = np.array(ns)
+    out["d__q"] = np.array([ts_end, delta, nd])
+    save("dsec_slicer", **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--dsec-slicer" in sys.argv:
+        return golden_dsec_slicer()
     if "--ddd17" in sys.argv:
         return golden_ddd17_ingest(_load("ref_data_util", "datasets/data_util.py"))
     du = _load("ref_data_util", "datasets/data_util.py")
