@@ -231,6 +231,20 @@ int oess_gemm_tf32(const float* A, const float* B, const float* bias, float* C, 
 int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M,
                       int N, int K, int act, oess_stream_t stream);
 
+/* Training-time augmentation of a batch on the device (DSEC/dataset/sequence_ov.py:362-407).
+ * oess_hflip_rows: in-place horizontal flip (torch.flip along the last dim) of the samples whose flag is non-zero.
+ *   x: [B, rows_per_sample, W] of 4-byte (event tensor, frame) or 8-byte (label / pseudo-label / superpixel int64 maps)
+ *   elements; flip: uint8 [B] on the device.
+ * oess_frame_color_aug: frame [B, 3, H, W] float32 in [0, 1], in place, per sample b:
+ *   frame = clamp(brightness[b] * frame, 0, 1)                       (TF.adjust_brightness; 1.0 = off)
+ *   frame = clamp(contrast[b] * frame + (1 - contrast[b]) * mean(0.2989 r + 0.587 g + 0.114 b), 0, 1)   (TF.adjust_contrast)
+ *   frame = frame + noise                                            (noise: [B, 3, H, W] or NULL; the caller draws it)
+ *   gray_sums: float64 [B] scratch (zeroed here). */
+int oess_hflip_rows(void* x, int elem_bytes, int B, int64_t rows_per_sample, int W, const uint8_t* flip,
+                    oess_stream_t stream);
+int oess_frame_color_aug(float* frame, int B, int64_t HW, const float* brightness, const float* contrast,
+                         const float* noise, double* gray_sums, oess_stream_t stream);
+
 /* Pooling layers of the torchvision-style ResNets (models/_resnet.py:137 MaxPool2d(kernel_size=3, stride=2, padding=1);
  * :149 AdaptiveAvgPool2d((1, 1))) on channels-last float32 tensors.  x: [B, H, W, C]; max pool y: [B, Ho, Wo, C] with
  * Ho = (H - 1) / 2 + 1 (C % 4 == 0); average pool y: [B, C] (mean over the HW pixels). */

@@ -60,6 +60,8 @@ SIGNATURES = {
     "oess_pixel_linear_wgrad": [_vp, _vp, _int, _int, _int, _i64, _vp, _vp, _vp, _sz, _vp],
     "oess_gemm_tf32": [_vp, _vp, _vp, _vp, _i64, _int, _int, _vp],
     "oess_gemm_tf32_ex": [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp],
+    "oess_hflip_rows": [_vp, _int, _int, _i64, _int, _vp, _vp],
+    "oess_frame_color_aug": [_vp, _int, _i64, _vp, _vp, _vp, _vp, _vp],
     "oess_maxpool3x3s2_nhwc": [_vp, _int, _int, _int, _int, _vp, _vp],
     "oess_global_avgpool_nhwc": [_vp, _int, _i64, _int, _vp, _vp],
     "oess_vit_patchify": [_vp, _int, _int, _int, _int, _int, _vp, _vp],

@@ -37,6 +37,7 @@ SOURCES = {
     "vit.cu": [],
     "tc_mha.cu": [],
     "pool_nhwc.cu": [],
+    "augment.cu": ["--fmad=false"],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "--threads", "0"]
