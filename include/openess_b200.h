@@ -251,6 +251,16 @@ int oess_frame_color_aug(float* frame, int B, int64_t HW, const float* brightnes
 int oess_maxpool3x3s2_nhwc(const float* x, int B, int H, int W, int C, float* y, oess_stream_t stream);
 int oess_global_avgpool_nhwc(const float* x, int B, int64_t HW, int C, float* y, oess_stream_t stream);
 
+/* E2VID decoder helpers (online reconstruction; e2vid/model/unet.py:165-168, submodules.py:34-63).
+ * oess_zero_insert2x_nhwc: z[b, 2y, 2x, :] = x[b, y, x, :] + skip[b, y, x, :] (skip may be NULL), all other entries of the
+ *   [B, 2H, 2W, C] output zero: ConvTranspose2d(k, stride 2, padding p, output_padding 1) of (x + skip) is then
+ *   oess_conv2d_nhwc_tf32(z, rotated / transposed weights, stride 1, padding k - 1 - p).  C % 4 == 0.
+ * oess_pred_sigmoid_nhwc: out[p] = sigmoid(dot(w, x[p, :] + skip[p, :]) + bias), the 1x1 prediction conv to one channel
+ *   (eval BatchNorm folded into w / bias by the caller) + torch.sigmoid; C % 4 == 0, C <= 64; w 16-byte aligned. */
+int oess_zero_insert2x_nhwc(const float* x, const float* skip, int B, int H, int W, int C, float* z, oess_stream_t stream);
+int oess_pred_sigmoid_nhwc(const float* x, const float* skip, const float* w, float bias, int64_t pixels, int C,
+                           float* out, oess_stream_t stream);
+
 /* ---- MaskCLIP ViT-B/16 forward (models/maskclip_model.py) -- the non-GEMM kernels ------------------
  * Tokens are row-major [rows, D] float32 (rows = B * T, T = 1 + h * w); D % 128 == 0, D <= 1024.
  *

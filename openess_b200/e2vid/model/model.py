@@ -249,6 +249,57 @@ class UNetRecurrent(nn.Module):
         return _tc.conv2d_tc(x8, self._head_packed[1], self._head_packed[2], conv.kernel_size[0], conv.stride[0],
                              conv.padding[0], conv.dilation[0], relu=self.head.activation is not None)
 
+    # ---- image branch on own kernels (online reconstruction instead of precomputed PNGs) ----
+    def _decode_tc_ok(self, x):
+        chans = [d.transposed_conv2d.in_channels for d in self.decoders] + [d.transposed_conv2d.out_channels for d in self.decoders]
+        return (USE_TENSOR_CORES and x.is_cuda and not torch.is_grad_enabled() and not self.training and self.skip_type == 'sum'
+                and self.norm in (None, 'BN') and all(c % 4 == 0 for c in chans) and self.pred.conv2d.in_channels <= 64
+                and self.pred.conv2d.out_channels == 1 and self.activation is torch.sigmoid
+                and all(d.activation in (None, torch.relu) for d in self.decoders))
+
+    @staticmethod
+    def _bn_fold(bn, bias, n, device):
+        """(scale, shift) of an eval-mode BatchNorm (identity if bn is None), the conv bias folded in."""
+        if bn is None:
+            scale, shift = torch.ones(n, device=device), torch.zeros(n, device=device)
+        else:
+            scale = (bn.weight / torch.sqrt(bn.running_var + bn.eps)).detach().float()
+            shift = (bn.bias - bn.running_mean * scale).detach().float()
+        if bias is not None:
+            shift = shift + bias.detach().float() * scale
+        return scale, shift
+
+    def _decode_tc(self, x, blocks, head):
+        """resblocks -> decoders (skip sum fused into the zero insertion; ConvTranspose2d = tcgen05 conv over the zero-inserted
+        map with the rotated kernel, BN folded, ReLU in the epilogue) -> prediction layer + sigmoid (unet.py:165-168)."""
+        from ...models import _tc_resnet as _tcr
+        cache = self.__dict__.setdefault("_dec_cache", _tcr.PackedConvCache())
+        packed = self.__dict__.setdefault("_dec_packed", {})
+        for rb in self.resblocks:                          # submodules.py:140-172
+            bn1, bn2 = (rb.bn1, rb.bn2) if self.norm == 'BN' else (None, None)
+            out = _tcr.conv_bn(cache, x, rb.conv1, bn1, True)
+            x = _tcr.conv_bn(cache, out, rb.conv2, bn2, True, residual=x if rb.downsample is None else rb.downsample(x))
+        for i, dec in enumerate(self.decoders):            # submodules.py:34-63
+            tc = dec.transposed_conv2d
+            w = tc.weight
+            key = (w.data_ptr(), w._version, w.device)
+            hit = packed.get(i)
+            if hit is None or hit[0] != key:
+                scale, shift = self._bn_fold(dec.norm_layer if dec.norm == 'BN' else None, tc.bias, tc.out_channels, w.device)
+                hit = (key, _tc.conv_transpose2x_pack(w, scale), shift.contiguous())
+                packed[i] = hit
+            z = _tc.zero_insert2x_nhwc(x, blocks[self.num_encoders - i - 1])
+            k, p = tc.kernel_size[0], tc.padding[0]
+            x = _tc.conv2d_tc(z, hit[1], hit[2], k, 1, k - 1 - p, 1, relu=dec.activation is not None, round_out=True)
+        pc = self.pred.conv2d
+        key = (pc.weight.data_ptr(), pc.weight._version, pc.weight.device)
+        hit = packed.get("pred")
+        if hit is None or hit[0] != key:
+            scale, shift = self._bn_fold(self.pred.norm_layer if self.pred.norm == 'BN' else None, pc.bias, 1, pc.weight.device)
+            hit = (key, (pc.weight.detach().float().reshape(-1) * scale).contiguous(), float(shift))
+            packed["pred"] = hit
+        return _tc.pred_sigmoid_nhwc(x, head, hit[1], hit[2])
+
     def forward(self, x, prev_states, latent_only=True):
         hc = self.head.conv2d
         if (USE_TENSOR_CORES and x.is_cuda and not torch.is_grad_enabled() and self.head.norm is None
@@ -272,6 +323,8 @@ class UNetRecurrent(nn.Module):
             latent = {k: latent[k] for k in (1, 2, 4, 8)}
         if latent_only:
             return None, states, latent                 # resblocks + decoders + pred feed only the image
+        if self._decode_tc_ok(x):
+            return self._decode_tc(x, blocks, head), states, latent
         for resblock in self.resblocks:
             x = resblock(x)
         for i, decoder in enumerate(self.decoders):

@@ -364,6 +364,43 @@ def conv_bn_train(x, w_packed, bias, kernel_size, stride, padding, dilation, bn,
     return y
 
 
+def zero_insert2x_nhwc(x, skip=None):
+    """[B, C, H, W] (channels-last) -> [B, C, 2H, 2W] with (x + skip) at the even positions and zeros elsewhere: the input of
+    a stride-2 transposed convolution run as a stride-1 convolution (oess_zero_insert2x_nhwc)."""
+    _lib.require_cuda(x, skip)
+    B, C, H, W = x.shape
+    cl = torch.channels_last
+    xc = x.float().contiguous(memory_format=cl)
+    sc = None if skip is None else skip.float().contiguous(memory_format=cl)
+    z = torch.empty((B, C, 2 * H, 2 * W), dtype=torch.float32, device=x.device, memory_format=cl)
+    with torch.cuda.device(x.device):
+        check(lib().oess_zero_insert2x_nhwc(ptr(xc), ptr(sc), B, H, W, C, ptr(z), stream_ptr(x.device)), "oess_zero_insert2x_nhwc")
+    return z
+
+
+def conv_transpose2x_pack(weight, scale=None):
+    """nn.ConvTranspose2d weight [Cin, Cout, K, K] (stride 2) -> packed weights of the equivalent stride-1 convolution over the
+    zero-inserted input: W'[o, i, ky, kx] = W[i, o, K-1-ky, K-1-kx] (optionally scaled per output channel: folded BatchNorm)."""
+    wt = weight.detach().float().flip(2, 3).permute(1, 0, 2, 3)
+    if scale is not None:
+        wt = wt * scale.detach().float()[:, None, None, None]
+    return conv2d_pack(wt.contiguous())
+
+
+def pred_sigmoid_nhwc(x, skip, w, bias):
+    """sigmoid(1x1 conv to ONE channel of (x + skip)) -> [B, 1, H, W]; x, skip channels-last [B, C, H, W], w [C], bias float."""
+    _lib.require_cuda(x, skip, w)
+    B, C, H, W = x.shape
+    cl = torch.channels_last
+    xc = x.float().contiguous(memory_format=cl)
+    sc = None if skip is None else skip.float().contiguous(memory_format=cl)
+    out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().oess_pred_sigmoid_nhwc(ptr(xc), ptr(sc), ptr(_f32c(w)), float(bias), B * H * W, C, ptr(out), stream_ptr(x.device)),
+              "oess_pred_sigmoid_nhwc")
+    return out
+
+
 def maxpool3x3s2_nhwc(x):
     """nn.MaxPool2d(kernel_size=3, stride=2, padding=1) (models/_resnet.py:137) on a channels-last [B, C, H, W] tensor."""
     _lib.require_cuda(x)

@@ -134,8 +134,9 @@ def golden_e2vid_full_width():
     states = None
     with torch.no_grad():
         for i, s_ in enumerate(steps):
-            _, states, latent = m(torch.from_numpy(s_), states)
+            img, states, latent = m(torch.from_numpy(s_), states)
             out[f"in{i}"] = s_
+            out[f"img{i}"] = img.numpy()                   # reconstruction of every step (resblocks + decoders + pred + sigmoid)
     for kk, vv in latent.items():                          # outputs of the LAST step (they depend on all three)
         out[f"latent__{kk}"] = vv.numpy()
     for li, (h, c) in enumerate(states):

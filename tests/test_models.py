@@ -95,6 +95,51 @@ def test_e2vid_full_width_tensor_core_convlstm_vs_reference_golden():
 
 
 @pytest.mark.gpu
+def test_e2vid_online_reconstruction_on_own_kernels_vs_reference_golden():
+    """the image branch (resblocks, transposed-conv decoders with fused skip sums, prediction layer +
+    sigmoid) on hand-written kernels.  Golden = the reference E2VIDRecurrent's `img` of every step (CPU fp32).  Tolerance:
+    5e-3 on a sigmoid output in (0, 1) after TF32 convs (measured value printed); the torch formulation of the same mirror
+    on the GPU (strict fp32) 1e-4."""
+    from seeded_weights import seeded_state_dict
+    from openess_b200 import _lib, ops
+    from openess_b200.e2vid.model import model as mm
+    z = load_golden("e2vid_full_width")
+    dev = torch.device("cuda:0")
+    cfg = {}
+    for k, v in zip(z["cfg_keys"], z["cfg_vals"]):
+        cfg[str(k)] = (v == "True") if str(v) in ("True", "False") else (int(v) if str(v).isdigit() else str(v))
+    m = mm.E2VIDRecurrent(cfg, latent_only=False)
+    m.load_state_dict(seeded_state_dict(m, int(z["seed"])), strict=True)
+    m = m.eval().to(dev).fold_bn()
+    errs = {}
+    for use_tc in (False, True):
+        mm.USE_TENSOR_CORES = use_tc
+        try:
+            states, worst = None, 0.0
+            with _lib.profile() as prof, torch.no_grad():
+                for i in range(3):
+                    img, states, _ = m(torch.from_numpy(z[f"in{i}"]).to(dev), states)
+                    assert img.shape == (1, 1, 24, 40)
+                    worst = max(worst, float(np.abs(img.cpu().numpy() - z[f"img{i}"]).max()))
+            errs[use_tc] = worst
+            if use_tc:      # per step: 2 resblocks x 2 convs + 3 decoders (+ 1 head + 3 encoder convs) on the conv kernel
+                assert prof.kernels["tc_conv2d"][0] == 3 * (4 + 4 + 3) and prof.kernels["zero_insert2x_nhwc"][0] == 9
+                assert prof.kernels["pred_sigmoid_nhwc"][0] == 3
+        finally:
+            mm.USE_TENSOR_CORES = True
+    print("reconstruction max |err| vs reference: torch fp32 path %.2e, own kernels %.2e" % (errs[False], errs[True]))
+    assert errs[False] < 1e-4 and errs[True] < 5e-3
+    # the transposed convolution identity on its own: zero insertion + rotated kernel == F.conv_transpose2d
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = torch.randint(-3, 4, (2, 32, 5, 7), device=dev, generator=g).float()
+    sk = torch.randint(-3, 4, (2, 32, 5, 7), device=dev, generator=g).float()
+    w = torch.randint(-2, 3, (32, 16, 5, 5), device=dev, generator=g).float()
+    got = ops.conv2d_tc(ops.zero_insert2x_nhwc(x, sk), ops.conv_transpose2x_pack(w), None, 5, 1, 2, 1)
+    want = torch.nn.functional.conv_transpose2d(x + sk, w, stride=2, padding=2, output_padding=1)
+    assert torch.equal(got, want)                                    # small integers: exact in TF32
+
+
+@pytest.mark.gpu
 def test_convlstm_gates_kernel_vs_torch():
     from openess_b200 import losses
     dev = torch.device("cuda:0")
