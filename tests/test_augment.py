@@ -4,7 +4,6 @@ the reference's `random` call sequence.  Flips are exact; the colour chain agree
 instead of torch.mean's float32 cascade)."""
 import random
 
-import numpy as np
 import pytest
 import torch
 

@@ -6,7 +6,6 @@ reference's own outputs.  Tolerances: the fp32 kernels (LayerNorm, attention, L2
 to the value scale; the TF32 GEMM chain through 12 layers is compared with the noise torch's own TF32 matmuls show on the
 same network (printed), and the final cosine logits (|value| <= 1 x |text|) with 2e-3 absolute of the unit-cosine scale
 (measured 1.6e-4 on the full ViT-B/16 at 440 x 640; torch's TF32 matmuls 7.6e-5)."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
