@@ -12,9 +12,13 @@
 //   MMA   O_tile[128 x 64] = P V         (A K-major from the softmax threads, B MN-major from TMA)
 //   warps O = O * exp2(m_old - m_new) + O_tile in registers (one output row per thread)
 // K and V have separate full / empty barriers, so K of tile j + 1 streams in under the softmax of tile j and V under the
-// next S product; two CTAs share an SM (96 KB shared memory, 128 TMEM columns each) and fill each other's bubbles.
+// next S product; S is double-buffered in TMEM (S of tile j + 1 is issued before P V of tile j); two CTAs share an SM
+// (97 KB shared memory, 256 TMEM columns each) and fill each other's bubbles.
+// Measured (B = 8, T = 1121, 12 heads, per layer): 4 softmax warps + single S buffer 131 us; 8 softmax warps (two threads per
+// row) 132 us; + double-buffered S 132-135 us -- neither the per-thread softmax chain nor the S hand-off is what bounds it.
 // Tail handling: the tensor maps are 3-D {3 D, T, B}; rows past T are zero-filled by the TMA unit.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -26,7 +30,7 @@ constexpr int kQBytes = kMhaQ * kMhaD * 4;                 // 32 KB: 2 K blocks 
 constexpr int kKBytes = kMhaK * kMhaD * 4;                 // 16 KB: 2 K blocks of [64 x 32]
 constexpr int kVBytes = kMhaK * kMhaD * 4;                 // 16 KB: [2 key blocks][2 d groups][32 lines x 128 B]
 constexpr int kPBytes = kMhaQ * kMhaK * 4;                 // 32 KB: 2 K blocks of [128 x 32]
-constexpr int kMhaSmemBytes = 1024 + kQBytes + kKBytes + kVBytes + kPBytes + 128;
+constexpr int kMhaSmemBytes = 1024 + kQBytes + kKBytes + kVBytes + kPBytes + 128 + 1024;
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
@@ -43,7 +47,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_bmn(int M, int N) {
 __device__ __forceinline__ float round_up_tf32(float p) { return __uint_as_float((__float_as_uint(p) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__global__ void __launch_bounds__(192, 2)
+// SW = softmax warps (4 or 8).  With 8, two threads share a query row (32 of the tile's 64 keys / 32 of the 64 output
+// columns each; row maxima and sums meet in shared memory): half the dependent instruction chain per tile and twice the
+// warps per SM sub-partition to hide it -- the kernel is bound by that chain, not by the tensor pipe.
+template <int SW>
+__global__ void __launch_bounds__(64 + 32 * SW, 2)
 k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
          int T, int heads, float* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
@@ -54,8 +62,10 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
     uint8_t* sP = sV + kVBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBytes);
     uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4,
-             *s_full = bars + 5, *p_ready = bars + 6, *o_full = bars + 7;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+             *s_full = bars + 5, *p_ready = bars + 6, *o_full = bars + 7;      // s_full[0], and s_full[1] = bars + 8
+    uint64_t* s_full2[2] = {s_full, bars + 8};
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    float* s_x = reinterpret_cast<float*>(bars + 10);       // [2][128] exchange of row maxima / sums between the two halves
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kMhaQ;
@@ -72,17 +82,18 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
         mbar_init(k_empty, 1);
         mbar_init(v_full, 1);
         mbar_init(v_empty, 1);
-        mbar_init(s_full, 1);
-        mbar_init(p_ready, 128);
+        mbar_init(s_full2[0], 1);
+        mbar_init(s_full2[1], 1);
+        mbar_init(p_ready, 32 * SW);
         mbar_init(o_full, 1);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 128);
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_s = *tmem_slot;                    // columns [0, 64): S, [64, 128): O tile
-    const uint32_t tmem_o = tmem_s + 64;
+    const uint32_t tmem_s = *tmem_slot;                    // columns [0, 64) and [64, 128): S (double-buffered), [128, 192): O tile
+    const uint32_t tmem_o = tmem_s + 128;
 
     if (warp == 0) {
         if (lane == 0) {                                   // ===== TMA producer =====
@@ -109,18 +120,25 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
             constexpr uint32_t idesc_s = umma_idesc_tf32(kMhaQ, kMhaK);
             constexpr uint32_t idesc_o = umma_idesc_tf32_bmn(kMhaQ, kMhaD);
             mbar_wait(q_full, 0);
-            for (int j = 0; j < ntiles; ++j) {
-                mbar_wait(k_full, j & 1);
+            // S of tile j + 1 is issued BEFORE the P V product of tile j (into the other S buffer), so it runs -- and its
+            // completion reaches the softmax warps -- while they are still busy with tile j
+            auto issue_s = [&](int jj) {
+                mbar_wait(k_full, jj & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
                     const uint64_t da = umma_desc_k128(smem_u32(sQ + kb * (kQBytes / 2)));
                     const uint64_t db = umma_desc_k128(smem_u32(sK + kb * (kKBytes / 2)));
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) umma_tf32(tmem_s, da + 2 * k, db + 2 * k, idesc_s, (kb | k) != 0);
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_tf32(tmem_s + (uint32_t)((jj & 1) * 64), da + 2 * k, db + 2 * k, idesc_s, (kb | k) != 0);
                 }
                 umma_commit(k_empty);
-                umma_commit(s_full);
+                umma_commit(s_full2[jj & 1]);
+            };
+            issue_s(0);
+            for (int j = 0; j < ntiles; ++j) {
+                if (j + 1 < ntiles) issue_s(j + 1);
                 mbar_wait(p_ready, j & 1);
                 mbar_wait(v_full, j & 1);
                 tc_fence_after();
@@ -135,80 +153,96 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
                 umma_commit(o_full);                       // arrives last: the CTA outlives every pending arrive
             }
         }
-    } else {                                               // ===== softmax / output: warps 2..5 =====
+    } else {                                               // ===== softmax / output: warps 2 .. 2 + SW =====
+        constexpr int HV = SW / 4;                         // threads per query row
+        constexpr int NC = kMhaK / HV;                     // keys (and output columns) per thread: 64 or 32
         const int qd = warp & 3;                           // TMEM lane quarter this warp may access
+        const int hf = (warp - 2) >> 2;                    // which half of the columns (0 when SW == 4)
         const int row = qd * 32 + lane;                    // query row of the tile = TMEM lane
+        const int col0 = hf * NC;
         const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
         const float kScale = 0.125f * 1.4426950408889634f; // head_dim^-0.5 * log2(e)
-        float o[kMhaD];
+        float o[NC];
 #pragma unroll
-        for (int i = 0; i < kMhaD; ++i) o[i] = 0.0f;
+        for (int i = 0; i < NC; ++i) o[i] = 0.0f;
         float m = -INFINITY, l = 0.0f;
-        uint8_t* prow = sP + row * 128;
+        uint8_t* prow = sP + row * 128 + (col0 / 32) * (kPBytes / 2);
         const int sw = row & 7;
         for (int j = 0; j < ntiles; ++j) {
-            const int k0 = j * kMhaK;
-            mbar_wait(s_full, j & 1);
+            const int k0 = j * kMhaK + col0;               // first key of this thread's columns
+            mbar_wait(s_full2[j & 1], (j >> 1) & 1);
             tc_fence_after();
-            float s0[32], s1[32];
-            tmem_ld32(tmem_s + lane_off, s0);
-            tmem_ld32(tmem_s + lane_off + 32, s1);
-            if (k0 + kMhaK > T) {                          // ragged last tile only: keys past T drop out of max and sum
+            float sv[NC];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    if (k0 + i >= T) s0[i] = -INFINITY;
-                    if (k0 + 32 + i >= T) s1[i] = -INFINITY;
-                }
+            for (int blk = 0; blk < NC / 32; ++blk)
+                tmem_ld32(tmem_s + lane_off + (uint32_t)((j & 1) * 64 + col0 + 32 * blk), reinterpret_cast<float(&)[32]>(sv[32 * blk]));
+            if (j * kMhaK + kMhaK > T) {                   // ragged last tile only: keys past T drop out of max and sum
+#pragma unroll
+                for (int i = 0; i < NC; ++i)
+                    if (k0 + i >= T) sv[i] = -INFINITY;
             }
-            float mx = fmaxf(s0[0], s1[0]);
+            float mx = sv[0];
 #pragma unroll
-            for (int i = 1; i < 32; ++i) mx = fmaxf(mx, fmaxf(s0[i], s1[i]));
-            const float mn = fmaxf(m, mx * kScale);        // kScale > 0: scaling commutes with max; finite (key k0 is valid)
+            for (int i = 1; i < NC; ++i) mx = fmaxf(mx, sv[i]);
+            if (HV == 2) {                                 // the other half of the row lives in another warp
+                s_x[hf * 128 + row] = mx;
+                asm volatile("bar.sync 1, %0;" ::"r"(32 * SW) : "memory");
+                mx = fmaxf(s_x[row], s_x[128 + row]);
+            }
+            const float mn = fmaxf(m, mx * kScale);        // kScale > 0: scaling commutes with max; finite (key 0 of the tile is valid)
             const float alpha = exp2f(m - mn);             // first tile: exp2(-inf) = 0
             m = mn;
             float sum = 0.0f;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {                  // 16-byte chunks of the two 128-byte lines of this row
-                float4 p0, p1;
-                p0.x = round_up_tf32(exp2f(fmaf(s0[4 * c + 0], kScale, -mn))); p0.y = round_up_tf32(exp2f(fmaf(s0[4 * c + 1], kScale, -mn)));
-                p0.z = round_up_tf32(exp2f(fmaf(s0[4 * c + 2], kScale, -mn))); p0.w = round_up_tf32(exp2f(fmaf(s0[4 * c + 3], kScale, -mn)));
-                p1.x = round_up_tf32(exp2f(fmaf(s1[4 * c + 0], kScale, -mn))); p1.y = round_up_tf32(exp2f(fmaf(s1[4 * c + 1], kScale, -mn)));
-                p1.z = round_up_tf32(exp2f(fmaf(s1[4 * c + 2], kScale, -mn))); p1.w = round_up_tf32(exp2f(fmaf(s1[4 * c + 3], kScale, -mn)));
-                sum += ((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w));
-                *reinterpret_cast<float4*>(prow + ((c ^ sw) << 4)) = p0;                     // keys k0 + 4c .. (K block 0)
-                *reinterpret_cast<float4*>(prow + kPBytes / 2 + ((c ^ sw) << 4)) = p1;       // keys k0 + 32 + 4c .. (K block 1)
+            for (int blk = 0; blk < NC / 32; ++blk) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {              // 16-byte chunks of the 128-byte line of this row in K block blk
+                    float4 p4;
+                    p4.x = round_up_tf32(exp2f(fmaf(sv[32 * blk + 4 * c + 0], kScale, -mn)));
+                    p4.y = round_up_tf32(exp2f(fmaf(sv[32 * blk + 4 * c + 1], kScale, -mn)));
+                    p4.z = round_up_tf32(exp2f(fmaf(sv[32 * blk + 4 * c + 2], kScale, -mn)));
+                    p4.w = round_up_tf32(exp2f(fmaf(sv[32 * blk + 4 * c + 3], kScale, -mn)));
+                    sum += (p4.x + p4.y) + (p4.z + p4.w);
+                    *reinterpret_cast<float4*>(prow + blk * (kPBytes / 2) + ((c ^ sw) << 4)) = p4;
+                }
             }
-            l = l * alpha + sum;
+            l = l * alpha + sum;                           // partial sum over this thread's columns
             fence_proxy_async_smem();                      // generic-proxy writes of P -> visible to the tensor core
             tc_fence_before();                             // the TMEM reads of S are done before the next S product
             mbar_arrive(p_ready);
             if (!__all_sync(0xffffffffu, alpha == 1.0f)) { // the running maxima settle after a few tiles
 #pragma unroll
-                for (int i = 0; i < kMhaD; ++i) o[i] *= alpha;
+                for (int i = 0; i < NC; ++i) o[i] *= alpha;
             }
             mbar_wait(o_full, j & 1);
             tc_fence_after();
-            tmem_ld32(tmem_o + lane_off, s0);
-            tmem_ld32(tmem_o + lane_off + 32, s1);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                o[i] += s0[i];
-                o[32 + i] += s1[i];
+            for (int blk = 0; blk < NC / 32; ++blk) {
+                float t32[32];
+                tmem_ld32(tmem_o + lane_off + (uint32_t)(col0 + 32 * blk), t32);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[32 * blk + i] += t32[i];
             }
             tc_fence_before();
+        }
+        if (HV == 2) {                                     // total row sum = the two partial sums (same maxima history)
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * SW) : "memory");      // every read of the last maxima exchange is done
+            s_x[hf * 128 + row] = l;
+            asm volatile("bar.sync 1, %0;" ::"r"(32 * SW) : "memory");
+            l = s_x[row] + s_x[128 + row];
         }
         const int q = q0 + row;
         if (q < T) {
             const float inv = 1.0f / l;
-            float* dst = out + ((int64_t)b * T + q) * D + hh * kMhaD;
+            float* dst = out + ((int64_t)b * T + q) * D + hh * kMhaD + col0;
 #pragma unroll
-            for (int i = 0; i < kMhaD; i += 4)
+            for (int i = 0; i < NC; i += 4)
                 *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_s, 128);
+    if (warp == 1) tmem_dealloc(tmem_s, 256);
 }
 
 }  // namespace tc
@@ -232,8 +266,14 @@ OESS_API int oess_mha_fwd_tc(const float* qkv, int B, int T, int heads, float* o
     rc = tc::make_tmap_f32_atom32(&tmV, qkv, 3, dims, strides, bv);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    OESS_CUDA(cudaFuncSetAttribute(tc::k_mha_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMhaSmemBytes));
+    static const int sw = (getenv("OESS_MHA_WARPS") && atoi(getenv("OESS_MHA_WARPS")) == 4) ? 4 : 8;
     const dim3 grid((unsigned)((T + tc::kMhaQ - 1) / tc::kMhaQ), (unsigned)heads, (unsigned)B);
-    OESS_KERNEL("mha_fwd_tc", st, tc::k_mha_tc<<<grid, 192, tc::kMhaSmemBytes, st>>>(tmQ, tmK, tmV, T, heads, out));
+    if (sw == 8) {
+        OESS_CUDA(cudaFuncSetAttribute(tc::k_mha_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMhaSmemBytes));
+        OESS_KERNEL("mha_fwd_tc", st, tc::k_mha_tc<8><<<grid, 64 + 32 * 8, tc::kMhaSmemBytes, st>>>(tmQ, tmK, tmV, T, heads, out));
+    } else {
+        OESS_CUDA(cudaFuncSetAttribute(tc::k_mha_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMhaSmemBytes));
+        OESS_KERNEL("mha_fwd_tc", st, tc::k_mha_tc<4><<<grid, 64 + 32 * 4, tc::kMhaSmemBytes, st>>>(tmQ, tmK, tmV, T, heads, out));
+    }
     return OESS_OK;
 }
