@@ -68,6 +68,26 @@ def test_argument_errors_without_gpu(lib):
     assert lib.oess_infonce_ws_bytes(100, 256, ctypes.byref(sz)) == 0 and sz.value >= 800
 
 
+def test_argument_errors_of_later_rows_without_gpu(lib):
+    """Entry points added for rows a14 / a14' / 8f: shape and pointer checks come before any CUDA call."""
+    assert lib.oess_layernorm_rows(None, None, None, 1e-6, 10, 100, None, None) == -1          # D % 128 != 0
+    assert lib.oess_layernorm_rows(None, None, None, 1e-6, 10, 2048, None, None) == -1         # D > 1024
+    assert lib.oess_layernorm_rows(None, None, None, 1e-6, 0, 768, None, None) == 0            # empty: nothing to do
+    assert lib.oess_l2norm_rows(None, 5, 512, None) == -1                                      # null pointer
+    assert lib.oess_mha_fwd(None, 1, 0, 12, None, None) == -1 and lib.oess_mha_fwd_tc(None, 1, 0, 12, None, None) == -1
+    assert lib.oess_mha_fwd_tc(None, 0, 7, 12, None, None) == 0                                # B == 0
+    assert lib.oess_gemm_tf32_ex(None, None, None, None, None, 4, 4, 6, 0, None) == -1          # K % 4 != 0 / null
+    assert lib.oess_gemm_tf32_ex(None, None, None, None, None, 4, 4, 8, 7, None) == -1          # unknown epilogue flag
+    assert lib.oess_vit_patchify(None, 1, 3, 8, 8, 0, None, None) == -1                        # patch <= 0
+    assert lib.oess_maxpool3x3s2_nhwc(None, 1, 8, 8, 6, None, None) == -1                      # C % 4 != 0
+    assert lib.oess_zero_insert2x_nhwc(None, None, 1, 4, 4, 6, None, None) == -1
+    assert lib.oess_pred_sigmoid_nhwc(None, None, None, 0.0, 10, 128, None, None) == -1        # C > 64
+    assert lib.oess_hflip_rows(None, 2, 1, 4, 4, None, None) == -1                             # element size 2
+    assert lib.oess_frame_color_aug(None, 1, 16, None, None, None, None, None) == -1
+    assert lib.oess_voxel_tbilinear_ddd17(None, None, None, 10, 1, 5, 4, 4, 0, 0, None, None, 0, None) == -1
+    assert lib.oess_voxel_histogram_ddd17(None, None, None, 0, 0, 4, 4, None, None, None) == 0  # F == 0
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_product_path_fails_loudly_without_cuda():
     from openess_b200.datasets import data_util
@@ -77,6 +97,15 @@ def test_product_path_fails_loudly_without_cuda():
         data_util.generate_voxel_grid(ev, (4, 4), 5, False)
     with pytest.raises(RuntimeError):
         VoxelGrid(5, 4, 4, False).convert(*(torch.zeros(3) for _ in range(4)))
+    from openess_b200 import ops
+    from openess_b200.DSEC.dataset import augment
+    from openess_b200.datasets.extract_data_tools import example_loader_ddd17 as ld
+    for call in (lambda: ops.mha_fwd(torch.zeros(4, 384), 1, 4, 2), lambda: ops.layernorm_rows(torch.zeros(2, 128), torch.ones(128), torch.zeros(128), 1e-6),
+                 lambda: ops.maxpool3x3s2_nhwc(torch.zeros(1, 4, 4, 4)), lambda: ops.zero_insert2x_nhwc(torch.zeros(1, 4, 2, 2)),
+                 lambda: augment.frame_color_aug_(torch.zeros(1, 3, 2, 2), torch.ones(1), torch.ones(1)),
+                 lambda: ld.event_tensors(torch.zeros(4, dtype=torch.int64), torch.zeros((4, 3), dtype=torch.int16), None, (4, 4))):
+        with pytest.raises(RuntimeError):
+            call()
 
 
 def test_product_never_imports_oracle():

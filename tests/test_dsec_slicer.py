@@ -55,6 +55,39 @@ def test_eventslicer_mirror_matches_reference():
         m.DSECStager(16, device="cpu")                               # no CPU path
 
 
+def test_eventslicer_ranges_satisfy_their_definition():
+    """Size-independent property on random recordings: window_range is exactly {i : t_start <= t_i < t_end} inside the 1 kHz
+    index, fixed_num_range ends at the first record with t >= t_end and holds min(n, available) records, chunks tile it."""
+    from openess_b200.DSEC.utils.eventslicer import EventSlicer, sample_chunks
+    rng = np.random.default_rng(7)
+    for trial in range(20):
+        n, span_ms = int(rng.integers(50, 4000)), int(rng.integers(20, 200))
+        t = np.sort(rng.integers(0, span_ms * 1000, n)).astype(np.uint32)
+        if trial % 3 == 0:
+            t[n // 2: n // 2 + 30] = t[n // 2]                      # bursts on one microsecond
+            t = np.sort(t)
+        off = int(rng.integers(0, 10_000_000))
+        rec = {"events/x": np.zeros(n, np.uint16), "events/y": np.zeros(n, np.uint16), "events/t": t, "events/p": np.zeros(n, np.uint8),
+               "ms_to_idx": np.searchsorted(t, np.arange(span_ms + 1, dtype=np.int64) * 1000, side="left").astype(np.uint64),
+               "t_offset": np.array(off)}
+        sl = EventSlicer(rec)
+        for _ in range(30):
+            a = int(rng.integers(0, span_ms * 1000 - 1))
+            b = int(rng.integers(a + 1, span_ms * 1000 + 1))
+            r = sl.window_range(off + a, off + b)
+            assert r is not None
+            idx = np.nonzero((t >= a) & (t < b))[0]
+            assert (r[1] - r[0]) == idx.size and (idx.size == 0 or (r[0] == idx[0] and r[1] == idx[-1] + 1))
+            te, k = int(rng.integers(0, span_ms * 1000 + 1)), int(rng.integers(1, n + 50))
+            r = sl.fixed_num_range(off + te, k)
+            end = int(np.searchsorted(t, te, side="left"))
+            assert r == (max(end - k, 0), end)
+            ch = sample_chunks(sl, off + te, nr_events_data=4, nr_events_per_data=max(k // 4, 1))
+            per = (ch[0][1] - ch[0][0])
+            assert all(e - b_ == per for b_, e in ch) and all(ch[i][1] == ch[i + 1][0] for i in range(3)) and ch[-1][1] <= end
+        assert sl.window_range(off + span_ms * 1000, off + span_ms * 1000 + 2000) is None      # past the index
+
+
 @pytest.mark.gpu
 def test_staged_raw_events_voxelise_like_the_reference_path(oracle):
     """Two samples x 4 chunks staged from the recording -> RawEvents -> device voxel grids == oracle on the host arrays the
