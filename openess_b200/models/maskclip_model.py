@@ -15,7 +15,8 @@ B200 forward (frozen, no grad): tokens stay row-major [B * T, D] end to end (no 
   * every linear (in_proj, out_proj, fc1 + GELU, fc2, head proj, text classifier) = `oess_gemm_tf32_ex` with bias / GELU /
     residual in the TMEM epilogue -- the residual stream is updated in place by the GEMM that produces the branch;
   * LayerNorm = `oess_layernorm_rows` (one warp per token, the row read once);
-  * attention = `oess_mha_fwd` (flash-style fp32, no [T, T] matrix in memory);
+  * attention = `oess_mha_fwd_tc` (tcgen05 flash attention: S and the O tile in TMEM, fp32 online softmax, no [T, T] matrix in
+    memory; `OESS_MHA=simt` selects the exact-fp32 FMA kernel `oess_mha_fwd`);
   * the last layer's extra value path (`v = out_proj(v_proj(ln1(x))) + x; v = ffn(ln2(v)) + v`, :522-536) reuses the v third
     of the in_proj output the attention needs anyway;
   * head: proj GEMM -> `oess_l2norm_rows` -> classifier GEMM against the text embeddings -> `oess_bilinear_tokens_to_nchw`.
