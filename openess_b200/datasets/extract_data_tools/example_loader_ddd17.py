@@ -145,6 +145,9 @@ def load_event_tensors(stager, t_events, xyp_events, img_indices, img_timestamp_
     for i in img_indices:
         b, e = event_range(i, img_timestamp_event_idx, fixed_duration, nr_events)
         cuts = chunk_cuts(t_events, b, e, nr_events_data, fixed_duration)
+        if event_representation == "voxel_grid" and np.any(np.diff(cuts) <= 0):
+            # generate_voxel_grid reads events[-1, 2] of every chunk (data_util.py:67): an empty chunk is an IndexError there
+            raise IndexError("index -1 is out of bounds for axis 0 with size 0")
         ranges.append((b, b + int(cuts[-1])))
         fo.extend((fo[-1] + cuts[1:]).tolist())
     t_dev, xyp_dev, _ = stager.stage(t_events, xyp_events, ranges)

@@ -39,6 +39,22 @@ def test_loader_mirror_host_functions_match_reference(tmp_path):
             np.testing.assert_array_equal(ld.chunk_cuts(t_ev, b, e, 4, fixed), z[tag + "__cuts"])
     with pytest.raises(IndexError):
         ld.chunk_cuts(t_ev, 5, 5, 4, False)
+    # chunk boundaries: count mode tiles the first n - n % chunks records; duration mode is monotone and ends before the
+    # records of the final timestamp
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        b = int(rng.integers(0, 20000))
+        e = int(rng.integers(b + 1, 24001))
+        nd = int(rng.integers(1, 9))
+        c = ld.chunk_cuts(t_ev, b, e, nd, False)
+        assert c[0] == 0 and np.all(np.diff(c) == (e - b) // nd) and c[-1] == (e - b) // nd * nd
+        d = ld.chunk_cuts(t_ev, b, e, nd, True)
+        assert d[0] == 0 and np.all(np.diff(d) >= 0) and d[-1] <= e - b
+        ts = t_ev[b:e, 0]
+        delta = int((ts[-1] - ts[0]) / nd)
+        assert all(int(np.searchsorted(ts, ts[0] + (i + 1) * delta)) == d[i + 1] for i in range(nd))
+    with pytest.raises(IndexError):        # fewer records than chunks: an empty chunk is an IndexError in the reference too
+        ld.load_event_tensors(None, t_ev, xyp_ev, [3], np.array([[0, 2, 0]] * 4), (260, 346), nr_events_data=4, nr_events=2)
     with pytest.raises(RuntimeError):
         ld.DDD17Stager(16, device="cpu")                       # no CPU path
 
