@@ -50,7 +50,21 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 // SW = softmax warps (4 or 8).  With 8, two threads share a query row (32 of the tile's 64 keys / 32 of the 64 output
 // columns each; row maxima and sums meet in shared memory): half the dependent instruction chain per tile and twice the
 // warps per SM sub-partition to hide it -- the kernel is bound by that chain, not by the tensor pipe.
-template <int SW>
+// FAST_EX2: ex2.approx.ftz.f32 instead of exp2f() (whose denormal-range handling costs ~5 extra instructions per element:
+// the ncu instruction mix of this kernel is 15 % FMUL / 7 % FSETP / 4 % FSEL around 4 % MUFU.EX2, and issue slots -- half
+// of them also burnt by barrier polling -- are what it runs out of).  Arguments are <= 0 here, results in [0, 1]; values
+// below 2^-126 flush to zero.  Opt-in (OESS_MHA_EX2=approx) until it has been through the parity tests on a GPU.
+template <bool FAST>
+__device__ __forceinline__ float ex2(float x) {
+    if (FAST) {
+        float r;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+        return r;
+    }
+    return exp2f(x);
+}
+
+template <int SW, bool FAST_EX2>
 __global__ void __launch_bounds__(64 + 32 * SW, 2)
 k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
          int T, int heads, float* __restrict__ out) {
@@ -190,7 +204,7 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
                 mx = fmaxf(s_x[row], s_x[128 + row]);
             }
             const float mn = fmaxf(m, mx * kScale);        // kScale > 0: scaling commutes with max; finite (key 0 of the tile is valid)
-            const float alpha = exp2f(m - mn);             // first tile: exp2(-inf) = 0
+            const float alpha = ex2<FAST_EX2>(m - mn);      // first tile: exp2(-inf) = 0
             m = mn;
             float sum = 0.0f;
 #pragma unroll
@@ -198,10 +212,10 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {              // 16-byte chunks of the 128-byte line of this row in K block blk
                     float4 p4;
-                    p4.x = round_up_tf32(exp2f(fmaf(sv[32 * blk + 4 * c + 0], kScale, -mn)));
-                    p4.y = round_up_tf32(exp2f(fmaf(sv[32 * blk + 4 * c + 1], kScale, -mn)));
-                    p4.z = round_up_tf32(exp2f(fmaf(sv[32 * blk + 4 * c + 2], kScale, -mn)));
-                    p4.w = round_up_tf32(exp2f(fmaf(sv[32 * blk + 4 * c + 3], kScale, -mn)));
+                    p4.x = round_up_tf32(ex2<FAST_EX2>(fmaf(sv[32 * blk + 4 * c + 0], kScale, -mn)));
+                    p4.y = round_up_tf32(ex2<FAST_EX2>(fmaf(sv[32 * blk + 4 * c + 1], kScale, -mn)));
+                    p4.z = round_up_tf32(ex2<FAST_EX2>(fmaf(sv[32 * blk + 4 * c + 2], kScale, -mn)));
+                    p4.w = round_up_tf32(ex2<FAST_EX2>(fmaf(sv[32 * blk + 4 * c + 3], kScale, -mn)));
                     sum += (p4.x + p4.y) + (p4.z + p4.w);
                     *reinterpret_cast<float4*>(prow + blk * (kPBytes / 2) + ((c ^ sw) << 4)) = p4;
                 }
@@ -268,12 +282,17 @@ OESS_API int oess_mha_fwd_tc(const float* qkv, int B, int T, int heads, float* o
     cudaStream_t st = (cudaStream_t)stream;
     static const int sw = (getenv("OESS_MHA_WARPS") && atoi(getenv("OESS_MHA_WARPS")) == 4) ? 4 : 8;
     const dim3 grid((unsigned)((T + tc::kMhaQ - 1) / tc::kMhaQ), (unsigned)heads, (unsigned)B);
+    static const bool fast = getenv("OESS_MHA_EX2") && getenv("OESS_MHA_EX2")[0] == 'a';
+#define OESS_MHA_LAUNCH(SWV, FV)                                                                                                   \
+    do {                                                                                                                           \
+        OESS_CUDA(cudaFuncSetAttribute(tc::k_mha_tc<SWV, FV>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMhaSmemBytes));       \
+        OESS_KERNEL("mha_fwd_tc", st, tc::k_mha_tc<SWV, FV><<<grid, 64 + 32 * SWV, tc::kMhaSmemBytes, st>>>(tmQ, tmK, tmV, T, heads, out)); \
+    } while (0)
     if (sw == 8) {
-        OESS_CUDA(cudaFuncSetAttribute(tc::k_mha_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMhaSmemBytes));
-        OESS_KERNEL("mha_fwd_tc", st, tc::k_mha_tc<8><<<grid, 64 + 32 * 8, tc::kMhaSmemBytes, st>>>(tmQ, tmK, tmV, T, heads, out));
+        if (fast) OESS_MHA_LAUNCH(8, true); else OESS_MHA_LAUNCH(8, false);
     } else {
-        OESS_CUDA(cudaFuncSetAttribute(tc::k_mha_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kMhaSmemBytes));
-        OESS_KERNEL("mha_fwd_tc", st, tc::k_mha_tc<4><<<grid, 64 + 32 * 4, tc::kMhaSmemBytes, st>>>(tmQ, tmK, tmV, T, heads, out));
+        if (fast) OESS_MHA_LAUNCH(4, true); else OESS_MHA_LAUNCH(4, false);
     }
+#undef OESS_MHA_LAUNCH
     return OESS_OK;
 }
