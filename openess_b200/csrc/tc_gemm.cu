@@ -74,9 +74,9 @@ struct GemmSmem {
 };
 
 // MC: clusters of two CTAs with adjacent M tiles and the same N tile; each loads its own A tile and HALF of the B tile, which
-// TMA multicasts into both CTAs' shared memory: per-SM operand traffic from L2 drops from 16 + BN / 8 KB to 16 + BN / 16 KB per
-// K block (48 -> 32 KB at BN = 256) -- the L2 -> shared-memory stream, not the tensor pipe, bounds these kernels.  A stage is
-// released to BOTH producers (the commit arrives on the empty barrier of both CTAs, count 2).
+// TMA multicasts into both CTAs' shared memory (a stage is released to BOTH producers: the commit arrives on the empty barrier
+// of both CTAs, count 2).  Measured: no gain (122 vs 114 us at M = 8968, N = 2304, K = 768) -- the L2 -> SM read path is only
+// 20 % utilised in this kernel (ncu), so halving the requests does not help; kept as OESS_GEMM=mc.
 template <int BN, int kStages, bool MC>
 __global__ void __launch_bounds__(kGemmThreads, (GemmSmem<BN, kStages>::kBytes <= 100 * 1024) ? 2 : 1)
 k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -244,8 +244,7 @@ OESS_API int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias
     if (M >= (1ll << 31)) return OESS_E_RANGE;
     cudaStream_t st = (cudaStream_t)stream;
     // default: two CTAs per SM (ring depth 2-4).  OESS_GEMM=deep: one CTA per SM with a 4-stage ring; OESS_GEMM=mc: two CTAs
-    // per SM in clusters of two with the B tile multicast (measured: no gain -- at cluster size 2 the L2 already merges the two
-    // unicast requests, and the per-SM shared-memory fill rate, not the L2 request count, is what bounds the operand stream)
+    // per SM in clusters of two with the B tile multicast (measured: no gain, see the kernel comment)
     static const int variant = [] {
         const char* e = getenv("OESS_GEMM");
         return !e ? 1 : (e[0] == 'd' ? 0 : (e[0] == 'm' ? 2 : 1));
