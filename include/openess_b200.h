@@ -245,6 +245,14 @@ int oess_hflip_rows(void* x, int elem_bytes, int B, int64_t rows_per_sample, int
 int oess_frame_color_aug(float* frame, int B, int64_t HW, const float* brightness, const float* contrast,
                          const float* noise, double* gray_sums, oess_stream_t stream);
 
+/* Post-processing of reconstructed images (e2vid/image_reconstructor.py:126-140 PostProcessor =
+ * e2vid/utils/inference_utils.py:234-252 UnsharpMaskFilter + :90-129 IntensityRescaler), img / out: [B, 1, H, W] float32
+ * (out must not alias img), kernel5x5: the 25 taps of gkern(5, sigma) on the device:
+ *   sharp = (1 + amount) * img - amount * conv2d(img, kernel5x5, padding = 2)          (amount <= 0: sharp = img)
+ *   quantize != 0: out = float(uint8(clamp(255 * (sharp - imin) / (imax - imin), 0, 255))) / 255;   else out = sharp. */
+int oess_unsharp_rescale(const float* img, const float* kernel5x5, int B, int H, int W, float amount, float imin,
+                         float imax, int quantize, float* out, oess_stream_t stream);
+
 /* Pooling layers of the torchvision-style ResNets (models/_resnet.py:137 MaxPool2d(kernel_size=3, stride=2, padding=1);
  * :149 AdaptiveAvgPool2d((1, 1))) on channels-last float32 tensors.  x: [B, H, W, C]; max pool y: [B, Ho, Wo, C] with
  * Ho = (H - 1) / 2 + 1 (C % 4 == 0); average pool y: [B, C] (mean over the HW pixels). */

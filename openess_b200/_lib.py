@@ -62,6 +62,7 @@ SIGNATURES = {
     "oess_gemm_tf32_ex": [_vp, _vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp],
     "oess_hflip_rows": [_vp, _int, _int, _i64, _int, _vp, _vp],
     "oess_frame_color_aug": [_vp, _int, _i64, _vp, _vp, _vp, _vp, _vp],
+    "oess_unsharp_rescale": [_vp, _vp, _int, _int, _int, _f32, _f32, _f32, _int, _vp, _vp],
     "oess_zero_insert2x_nhwc": [_vp, _vp, _int, _int, _int, _int, _vp, _vp],
     "oess_pred_sigmoid_nhwc": [_vp, _vp, _vp, _f32, _i64, _int, _vp, _vp],
     "oess_maxpool3x3s2_nhwc": [_vp, _int, _int, _int, _int, _vp, _vp],

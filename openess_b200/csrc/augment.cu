@@ -72,10 +72,60 @@ k_contrast_noise(float* __restrict__ frame, int64_t HW, const float* __restrict_
     }
 }
 
+// Post-processing of a reconstructed image (e2vid/utils/inference_utils.py:234-252 UnsharpMaskFilter, :90-129 IntensityRescaler):
+//   sharp = (1 + amount) * img - amount * conv2d(img, gauss5x5, padding 2);
+//   quantize: out = float(uint8(clamp(255 * (sharp - Imin) / (Imax - Imin), 0, 255))) / 255      else: out = sharp
+__global__ void __launch_bounds__(256)
+k_unsharp_rescale(const float* __restrict__ img, const float* __restrict__ kern, int H, int W, float amount, float imin,
+                  float imax, int quantize, float* __restrict__ out) {
+    __shared__ float s_k[25];
+    if (threadIdx.x < 25) s_k[threadIdx.x] = kern[threadIdx.x];
+    __syncthreads();
+    const int64_t HW = (int64_t)H * W;
+    const float* im = img + (int64_t)blockIdx.y * HW;
+    float* o = out + (int64_t)blockIdx.y * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / W), x = (int)(i - (int64_t)y * W);
+        float blur = 0.0f;
+#pragma unroll
+        for (int dy = -2; dy <= 2; ++dy) {
+            const int yy = y + dy;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int dx = -2; dx <= 2; ++dx) {
+                const int xx = x + dx;
+                if (xx < 0 || xx >= W) continue;
+                blur = __fadd_rn(blur, __fmul_rn(im[(int64_t)yy * W + xx], s_k[(dy + 2) * 5 + dx + 2]));
+            }
+        }
+        float v = im[i];
+        if (amount > 0.0f) v = __fsub_rn(__fmul_rn(1.0f + amount, v), __fmul_rn(amount, blur));
+        if (quantize) {
+            v = __fdiv_rn(__fmul_rn(255.0f, __fsub_rn(v, imin)), __fsub_rn(imax, imin));
+            v = fminf(fmaxf(v, 0.0f), 255.0f);
+            v = __fdiv_rn((float)(unsigned char)__float2int_rz(v), 255.0f);
+        }
+        o[i] = v;
+    }
+}
+
 }  // namespace aug
 }  // namespace oess
 
 using namespace oess;
+
+OESS_API int oess_unsharp_rescale(const float* img, const float* kernel5x5, int B, int H, int W, float amount, float imin,
+                                  float imax, int quantize, float* out, oess_stream_t stream) {
+    if (B < 0 || H <= 0 || W <= 0 || B > 65535) return OESS_E_ARG;
+    if (B == 0) return OESS_OK;
+    if (!img || !kernel5x5 || !out || img == out) return OESS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t g = ((int64_t)H * W + 255) / 256;
+    if (g > 4 * kNumSMs) g = 4 * kNumSMs;
+    OESS_KERNEL("unsharp_rescale", st, aug::k_unsharp_rescale<<<dim3((unsigned)g, (unsigned)B), 256, 0, st>>>(
+        img, kernel5x5, H, W, amount, imin, imax, quantize, out));
+    return OESS_OK;
+}
 
 OESS_API int oess_hflip_rows(void* x, int elem_bytes, int B, int64_t rows_per_sample, int W, const uint8_t* flip,
                              oess_stream_t stream) {

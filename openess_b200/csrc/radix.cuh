@@ -69,11 +69,7 @@ __global__ void k_prefix_chunks(uint32_t* __restrict__ hist, const int* __restri
 // Exclusive scan over the kBins totals of each frame (in place).  grid F, kBins threads.
 __global__ void k_bin_scan(uint32_t* __restrict__ tot);
 
-// PRELOAD: issue the kItemsPerThread global loads of a thread back to back BEFORE the ranking loop.  In the default form every
-// step's load sits behind the previous step's __match_any_sync / __syncwarp (which order memory operations), so a warp pays
-// eight dependent memory latencies per chunk -- ncu: issue slots 21 % busy, long-scoreboard stall 19 per issued instruction,
-// DRAM 21 %.  Same ranks, same output; opt-in (OESS_RADIX_PRELOAD=1) until it has been through the parity tests on a GPU.
-template <class Src, bool PRELOAD>
+template <class Src>
 __global__ void __launch_bounds__(kThreads, 4)
 k_scatter(Src src, const int64_t* __restrict__ frame_offsets, const int* __restrict__ chunk_start, int F,
           int shift, uint32_t mask, const uint32_t* __restrict__ hist, const uint32_t* __restrict__ binbase,
@@ -99,20 +95,13 @@ k_scatter(Src src, const int64_t* __restrict__ frame_offsets, const int* __restr
     uint32_t rk[kItemsPerThread];
     // Warp w owns items [wbeg, wbeg + 256) of the frame; step s covers 32 consecutive items, so
     // (step, lane) order == event order and the ranking below is stable.
-    if (PRELOAD) {
-#pragma unroll
-        for (int s = 0; s < kItemsPerThread; ++s) {
-            const uint32_t li = wbeg + s * 32 + lane;
-            if (li < nf) it[s] = src.load(f, fbeg, li);
-        }
-    }
 #pragma unroll
     for (int s = 0; s < kItemsPerThread; ++s) {
         const uint32_t li = wbeg + s * 32 + lane;
         const bool act = li < nf;
         uint32_t d = kBins;  // sentinel digit for the ragged tail
         if (act) {
-            if (!PRELOAD) it[s] = src.load(f, fbeg, li);
+            it[s] = src.load(f, fbeg, li);
             d = (src.key(it[s]) >> shift) & mask;
         }
         const unsigned peers = __match_any_sync(0xffffffffu, d);
@@ -161,13 +150,8 @@ static inline int run_pass(const Src& src, const int64_t* frame_offsets, const i
                                                           hist, pix, pix_stride, nb));
     OESS_KERNEL("k_prefix_chunks", st, k_prefix_chunks<<<dim3((unsigned)F, kBins / 128), 128, 0, st>>>(hist, chunk_start, tot, nb));
     OESS_KERNEL("k_bin_scan", st, k_bin_scan<<<(unsigned)F, kBins, 0, st>>>(tot));
-    static const bool preload = getenv("OESS_RADIX_PRELOAD") && getenv("OESS_RADIX_PRELOAD")[0] == '1';
-    if (preload)
-        OESS_KERNEL("k_scatter", st, k_scatter<Src, true><<<(unsigned)n_chunks_ub, kThreads, 0, st>>>(src, frame_offsets, chunk_start, F,
-                                                                   shift, mask, hist, tot, dst, nb));
-    else
-        OESS_KERNEL("k_scatter", st, k_scatter<Src, false><<<(unsigned)n_chunks_ub, kThreads, 0, st>>>(src, frame_offsets, chunk_start, F,
-                                                                    shift, mask, hist, tot, dst, nb));
+    OESS_KERNEL("k_scatter", st, k_scatter<Src><<<(unsigned)n_chunks_ub, kThreads, 0, st>>>(src, frame_offsets, chunk_start, F,
+                                                             shift, mask, hist, tot, dst, nb));
     return 0;
 }
 

@@ -22,16 +22,6 @@ namespace tri {
 constexpr int kRowWarps = 8;
 constexpr float kCanonicalBadX = -8.0f;
 
-// REGS (opt-in, OESS_ROWSORT=regs; built but not yet run through the parity suite on a GPU): rows of <= 256 records -- every
-// row of a 100 k-event DSEC frame has ~208 -- are loaded ONCE into registers (8 float4 per lane, independent coalesced loads),
-// ranked from registers in event order, staged sorted in shared memory (4 KB per warp behind the bin counters), checked for
-// time monotonicity there and written out with coalesced 16-byte stores.  The default form reads the row from global memory
-// in the count pass and again in the scatter pass, scatters 16-byte global writes and re-reads them for the check: ~21
-// dependent memory latencies per row (ncu: issue 53 %, long scoreboard 9.7 per issue).  Same output by construction: the ranking
-// visits records in the same (step, lane) = event order.
-constexpr int kRowRegs = 8;                            // records per lane on the register path
-
-template <bool REGS>
 __global__ void __launch_bounds__(kRowWarps * 32)
 k_rowsort(const float4* __restrict__ src, float4* __restrict__ dst, const int64_t* __restrict__ frame_offsets,
           const uint32_t* __restrict__ rowoff, uint32_t* __restrict__ rowflag, int H, int W,
@@ -57,28 +47,7 @@ k_rowsort(const float4* __restrict__ src, float4* __restrict__ dst, const int64_
     float4* out = dst + frame_offsets[f];
     for (int b = lane; b < nb; b += 32) cnt[b] = 0;
     __syncwarp();
-    const bool regs = REGS && (e - s) <= (uint32_t)(32 * kRowRegs);      // warp-uniform
-    float4 rec[kRowRegs];
-    uint32_t rpx[kRowRegs];
-    if (regs) {
-#pragma unroll
-        for (int j = 0; j < kRowRegs; ++j) {
-            const uint32_t i = s + j * 32 + lane;
-            rpx[j] = 0xffffffffu;
-            if (i < e) rec[j] = in[i];
-        }
-#pragma unroll
-        for (int j = 0; j < kRowRegs; ++j) {
-            const uint32_t i = s + j * 32 + lane;
-            if (i < e) {
-                rpx[j] = cell_px(rec[j].x, W);
-                atomicAdd(&cnt[rpx[j]], 1u);
-                if (rpx[j] > (uint32_t)W) rec[j].x = kCanonicalBadX;
-            }
-        }
-    } else {
-        for (uint32_t i = s + lane; i < e; i += 32) atomicAdd(&cnt[cell_px(in[i].x, W)], 1u);
-    }
+    for (uint32_t i = s + lane; i < e; i += 32) atomicAdd(&cnt[cell_px(in[i].x, W)], 1u);
     __syncwarp();
     // exclusive scan of the W + 2 bins: each lane owns an odd-length (bank-conflict-free) segment of bins,
     // sums it serially, one warp scan of the 32 partials, then rewrites its segment
@@ -104,36 +73,6 @@ k_rowsort(const float4* __restrict__ src, float4* __restrict__ dst, const int64_
     if (T) for (int k = lane; k < KT; k += 32) T[k] = cnt[min((k >> 1) * WC, W) + (k & 1)];
     __syncwarp();
     const unsigned lt = lanemask_lt();
-    if (regs) {
-        // sorted row staged in shared memory: [kRowWarps][32 * kRowRegs] float4 behind the bin counters of all warps
-        float4* srow = reinterpret_cast<float4*>(s_cnt_all + (((size_t)kRowWarps * nb + 3) & ~(size_t)3)) + w * (32 * kRowRegs);
-        const uint32_t n = e - s;
-#pragma unroll
-        for (int j = 0; j < kRowRegs; ++j) {
-            if ((uint32_t)(j * 32) < n) {                                  // warp-uniform
-                const bool act = (uint32_t)(j * 32 + lane) < n;
-                const unsigned peers = __match_any_sync(0xffffffffu, rpx[j]);
-                const int leader = __ffs(peers) - 1;
-                uint32_t base = 0;
-                if (lane == leader && act) { base = cnt[rpx[j]]; cnt[rpx[j]] = base + __popc(peers); }
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (act) srow[base - s + __popc(peers & lt)] = rec[j];
-                __syncwarp();
-            }
-        }
-        bool bad = false;
-        for (uint32_t i = lane; i < n; i += 32) {
-            const float4 b = srow[i];
-            out[s + i] = b;
-            if (i > 0) {
-                const float4 a = srow[i - 1];
-                bad |= (__float2int_rz(a.x) == __float2int_rz(b.x)) && (__float2int_rz(b.z) < __float2int_rz(a.z));
-            }
-        }
-        const unsigned anybad = __ballot_sync(0xffffffffu, bad);
-        if (lane == 0) rowflag[(int64_t)f * radix::kBins + row] = anybad ? 1u : 0u;
-        return;
-    }
     for (uint32_t i0 = s; i0 < e; i0 += 32) {
         const uint32_t i = i0 + lane;
         const bool act = i < e;

@@ -309,18 +309,10 @@ OESS_API int oess_voxel_trilinear(const float* x, const float* y, const float* p
             rc = radix::run_pass(src, frame_offsets, w.chunk_start, F, nch, 0, radix::kBins - 1, w.hist, w.tot,
                                  (uint32_t*)nullptr, 0, w.a, st, H + 2);
             if (rc) return rc;
-            static const bool row_regs = getenv("OESS_ROWSORT") && getenv("OESS_ROWSORT")[0] == 'r';
             const dim3 rgrid((unsigned)F, (unsigned)((H + 1 + tri::kRowWarps - 1) / tri::kRowWarps));
-            if (row_regs) {     // sorted rows staged in shared memory behind the bin counters (16-byte aligned)
-                const size_t smem = ((plan.row_smem + 15) & ~(size_t)15) + sizeof(float4) * tri::kRowWarps * 32 * tri::kRowRegs;
-                OESS_CUDA(cudaFuncSetAttribute(tri::k_rowsort<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                OESS_KERNEL("tri_rowsort", st, tri::k_rowsort<true><<<rgrid, tri::kRowWarps * 32, smem, st>>>(
+            OESS_CUDA(cudaFuncSetAttribute(tri::k_rowsort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.row_smem));
+            OESS_KERNEL("tri_rowsort", st, tri::k_rowsort<<<rgrid, tri::kRowWarps * 32, plan.row_smem, st>>>(
                 w.a, w.b, frame_offsets, w.tot, w.rowflag, H, W, plan.strip ? w.coloff : nullptr, plan.NS, tri::kStripWC));
-            } else {
-                OESS_CUDA(cudaFuncSetAttribute(tri::k_rowsort<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.row_smem));
-                OESS_KERNEL("tri_rowsort", st, tri::k_rowsort<false><<<rgrid, tri::kRowWarps * 32, plan.row_smem, st>>>(
-                w.a, w.b, frame_offsets, w.tot, w.rowflag, H, W, plan.strip ? w.coloff : nullptr, plan.NS, tri::kStripWC));
-            }
             if (plan.strip) {
                 rc = tri::launch_strip(plan, w.b, frame_offsets, w.coloff, w.rowflag, g, F, out, st);
                 if (rc) return rc;

@@ -644,3 +644,22 @@ def conv_bn_autograd(x, conv, bn, residual=None, relu=False):
     if conv.bias is not None or conv.stride != (1, 1):
         raise ValueError("conv_bn_autograd: bias-free stride-1 convolutions only")
     return _ConvBNAct.apply(x, conv.weight, bn.weight, bn.bias, residual, bn, conv.padding[0], conv.dilation[0], bool(relu))
+
+
+def unsharp_rescale(img, kernel5x5, amount, imin, imax, quantize=True):
+    """PostProcessor of the reconstruction (e2vid/image_reconstructor.py:126-140): unsharp mask + intensity rescaling +
+    8-bit quantisation in one kernel.  img: [B, 1, H, W] float32 CUDA; kernel5x5: 25 float32 taps on the device."""
+    _lib.require_cuda(img, kernel5x5)
+    if img.ndim != 4 or img.shape[1] != 1 or img.dtype != torch.float32:
+        raise ValueError("unsharp_rescale: img must be float32 [B, 1, H, W]")
+    img = img.contiguous()
+    k = kernel5x5.to(img.device, torch.float32).contiguous()
+    if k.numel() != 25:
+        raise ValueError("unsharp_rescale: the Gaussian kernel must have 5 x 5 taps")
+    B, _, H, W = img.shape
+    out = torch.empty_like(img)
+    with torch.cuda.device(img.device):
+        _lib.check(_lib.lib().oess_unsharp_rescale(_lib.ptr(img), _lib.ptr(k), B, H, W, float(amount), float(imin), float(imax),
+                                                   int(bool(quantize)), _lib.ptr(out), _lib.stream_ptr(img.device)),
+                   "oess_unsharp_rescale")
+    return out
