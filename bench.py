@@ -3,27 +3,29 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode ordered|atomic]
 
-Unit of work: one event-frame = one [5,480,640] float32 voxel grid built from one 50 ms window
-of N = 100 000 events = one call of VoxelGrid.convert (DSEC/dataset/representations.py:15-55).
-One step = one batch of F = 160 event-frames (8 DSEC samples x 20 frames, config `batch_size_b: 8`,
-`nr_events_data: 20`) through ONE batched C-ABI call (oess_voxel_trilinear).
+WORKLOAD (identical in both arms, `config`): raw DSEC records (u16 x, u16 y, u32 t, u8 p: the on-disk layout, 9 B / event) of
+F = 160 event-frames (8 samples x 20 frames; 100 000 events per 50 ms frame; every second frame edge-clustered) go through
+  rectify_events (DSEC/dataset/sequence_ov.py:204-210) -> per-frame time normalisation (:154-159) -> VoxelGrid.convert, the
+  trilinear splat (DSEC/dataset/representations.py:15-55)  ->  [F, 5, 480, 640] float32 voxel grids.
+One event-frame = one [5, 480, 640] grid.  One bench STEP = `--inner` consecutive batches of F frames, so that
+the K timed steps last about a second.
 
- value : frames/s of VoxelGrid.convert, its four float32 input arrays resident in HBM, CUDA-event timed over
-         exactly K steps, max over ranks.
- e2e   : same metric from PINNED HOST buffers holding the raw DSEC records (u16 x, u16 y, u32 t, u8 p = 9 B/event,
-         the on-disk layout): per step H2D of the records, rectification + per-frame time normalisation
-         (oess_dsec_rectify_tnorm_u32 = sequence_ov.py:204-210,154-159), voxelisation, and a D2H read of one grid
-         row per frame (the grids stay on the device because their consumer, the event encoder, runs there).
-         The batch goes as two sub-batches on two streams (one contiguous 72 MB host->device copy each); measured
-         alternatives (sub-batches of 10..160 frames, 2-4 streams) are within -25 % .. +0 % of this setting: the leg
-         is PCIe-bound (144 MB / step at ~53 GB/s), the 1.5 ms of GPU work hides behind the transfer.
-         `e2e_host_output` additionally copies every grid back to pinned host memory (what VoxelGrid.convert
-         returns for CPU inputs; PCIe-bound by the 6.1 MB/frame output).
- roofline : dominant kernel, algorithmic bytes (16 N + 4 C H W per frame) / its CUDA-event duration.
- cpu_baseline : the C oracle port of the same work (rectify + normalise + trilinear splat) on the host cores.
- --impl reference : the CPU arm alone (the reference is pure Python and cannot travel to the GPU box; the
-         oracle port restates it in C and is a *stronger* baseline than the reference's numpy/torch code).
-Multi-GPU: frames are sharded over ranks (independent units, no data-path collective) -> weak scaling.
+ value : frames/s with the raw records resident in HBM, ONE CUDA stream, CUDA-event timed over exactly K steps, max over ranks
+         (`value_streams3`: the same steps alternating over three streams, for the record).
+ e2e   : frames/s from PINNED HOST memory through the public API, every batch: H2D of the raw records -> rectify + normalise +
+         voxelise -> the grids' first consumer on the device: `EventPreprocessor` (e2vid/utils/inference_utils.py:70-87) and the
+         FIRST recurrent step of the E2VID encoder (tcgen05 kernels) on the first 5-bin slice of every sample -> D2H of the
+         latent's checksum.  The voxel grids are consumed where they are produced (no trainer reads them on the host), so the
+         read-back is the checksum, not 983 MB of grids; `e2e_host_output` (every grid copied back to pinned host memory, what
+         VoxelGrid.convert returns for CPU inputs) and `e2e_voxel_only` (no consumer) are reported next to it.
+ roofline : dominant kernel, algorithmic bytes (16 N + 4 C H W per frame, SURVEY.md 8d) / its CUDA-event duration.
+ train_step : the end-to-end OpenESS pretraining step with the NCCL gradient all-reduce overlapped with
+         backward, next to the literal torch / cuDNN formulation of training/pretrain_trainer.py:427-472 on the same GPU.
+ cpu_baseline : the C oracle port of the same workload on the host cores (rank 0, N = 1).
+ --impl reference : the CPU arm alone, same `config` (the reference is pure Python and cannot travel to the GPU box; the oracle
+         port restates it in C and is a *stronger* baseline than the reference's numpy / torch code).
+Multi-GPU: frames are sharded over ranks (independent units, no data-path collective) -> weak scaling; the train step adds the
+gradient all-reduce.
 """
 import argparse
 import json
@@ -37,44 +39,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-C, H, W = 5, 480, 640
-N_EVENTS = 100_000
-WINDOW_US = 50_000
+from openess_b200.utils.synth import (C, H, W, N_EVENTS, WINDOW_US, synth_raw_frames,  # noqa: E402,F401
+                                      synth_rectify_map)
+
 METRIC = "event-frames/sec at DSEC 640x480 50 ms window"
 UNIT = "frames/s"
+HC = 440                      # sequence_ov.py:307 bottom crop
 
 
-def synth_rectify_map(rng):
-    """identity + U(-0.75, 0.75) px jitter: ~0.2 % of corners leave the sensor, some x' < 0."""
-    yy, xx = np.meshgrid(np.arange(H), np.arange(W), indexing="ij")
-    return (np.stack([xx, yy], -1) + rng.uniform(-0.75, 0.75, (H, W, 2))).astype(np.float32)
-
-
-def synth_raw_frames(rng, F, n=N_EVENTS, clustered_every=2):
-    """Raw DSEC records for F frames of n events over 50 ms; every `clustered_every`-th frame has 80 % of its events
-    on 16 line segments (edge-like, stresses same-voxel accumulation)."""
-    xs, ys, ts, ps = [], [], [], []
-    for f in range(F):
-        if clustered_every and f % clustered_every == clustered_every - 1:
-            k = int(0.8 * n)
-            seg = rng.integers(0, 16, k)
-            a = rng.random(k)
-            x0, y0, x1, y1 = (rng.uniform(0, s, 16) for s in (W, H, W, H))
-            x = np.concatenate([x0[seg] + a * (x1[seg] - x0[seg]) + rng.normal(0, 0.7, k), rng.uniform(0, W, n - k)])
-            y = np.concatenate([y0[seg] + a * (y1[seg] - y0[seg]) + rng.normal(0, 0.7, k), rng.uniform(0, H, n - k)])
-            perm = rng.permutation(n)
-            x, y = x[perm], y[perm]
-        else:
-            x, y = rng.uniform(0, W, n), rng.uniform(0, H, n)
-        xs.append(np.clip(x, 0, W - 1).astype(np.uint16))
-        ys.append(np.clip(y, 0, H - 1).astype(np.uint16))
-        ts.append((np.sort(rng.integers(0, WINDOW_US, n)) + 1_000_000 + f * WINDOW_US).astype(np.uint32))
-        ps.append(rng.integers(0, 2, n).astype(np.uint8))
-    return [np.concatenate(a) for a in (xs, ys, ts, ps)]
+def workload_config(args):
+    """The `config` object: identical in the GPU arm and in `--impl reference`."""
+    return {"workload": f"DSEC 640x480 raw records (u16 x, u16 y, u32 t, u8 p), {N_EVENTS} events per 50 ms frame -> rectify "
+                        f"(sequence_ov.py:204-210) + t-normalise (:154-159) + VoxelGrid.convert trilinear splat C={C} "
+                        f"(representations.py:15-55); batches of F={args.frames} frames (8 samples x 20 frames) per GPU, every "
+                        f"{args.clustered_every} frame(s) edge-clustered",
+            "frames_per_batch": args.frames, "events_per_frame": N_EVENTS, "clustered_every": args.clustered_every,
+            "mode": args.mode, "bit_exact_vs_reference": args.mode == "ordered"}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_throughput(frames_total, budget_s, threads=None, seed=1205):
+def cpu_port_throughput(frames_total, budget_s, threads=None, seed=1205, clustered_every=2):
     """Oracle C port (rectify + t-normalise + VoxelGrid.convert) on `threads` host threads, one frame per call
     (ctypes releases the GIL)."""
     from concurrent.futures import ThreadPoolExecutor
@@ -84,7 +68,7 @@ def cpu_port_throughput(frames_total, budget_s, threads=None, seed=1205):
     rng = np.random.default_rng(seed)
     rmap = synth_rectify_map(rng)
     nb = min(frames_total, 8)
-    x, y, t, p = synth_raw_frames(rng, nb)
+    x, y, t, p = synth_raw_frames(rng, nb, clustered_every=clustered_every)
     t = t.astype(np.int64)
     frames = [tuple(a[i * N_EVENTS:(i + 1) * N_EVENTS] for a in (x, y, t, p)) for i in range(nb)]
     tls = threading.local()
@@ -115,13 +99,13 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    per_step = max(threads * 4, 16)
+    per_step = max(threads * 4, 16)                   # bounded sample of the workload per step
     for _ in range(args.warmup):
-        cpu_port_throughput(threads, 5.0, threads)
+        cpu_port_throughput(threads, 5.0, threads, clustered_every=args.clustered_every)
     frames, busy = 0, 0.0
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, done, dt, _ = cpu_port_throughput(per_step, 20.0, threads)
+        _, done, dt, _ = cpu_port_throughput(per_step, 20.0, threads, clustered_every=args.clustered_every)
         frames += done
         busy += dt
     wall = time.perf_counter() - t0
@@ -130,9 +114,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * busy / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DSEC 640x480, {N_EVENTS} events per 50 ms frame: rectify + t-normalise + VoxelGrid.convert "
-                               f"trilinear splat, C={C}; reference arm = C oracle port on {threads} host threads, "
-                               f"{per_step} frames per step", "wall_s": wall},
+        "config": workload_config(args),
+        "arm": {"what": f"C oracle port of the reference's CPU path on {threads} host threads (one frame per thread), "
+                        f"{per_step} frames per step (bounded sample of the workload)", "wall_s": wall},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{frames} frames of {N_EVENTS} events over {args.steps} steps"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -187,6 +171,22 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def pin_rank_to_cpus(local, n_local):
+    """Give every local rank its own slice of the host cores BEFORE it allocates pinned memory (first touch = local), so
+    the ranks' staging copies do not fight over the same cores (e2e per-GPU H2D fell from 54 to 23 GB/s at
+    N = 8 with every rank on the default affinity mask)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = len(cpus) // max(n_local, 1)
+        if n_local > 1 and per >= 1:
+            mine = cpus[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, mine)
+            return {"cpus": [mine[0], mine[-1]], "n": len(mine)}
+        return {"cpus": [cpus[0], cpus[-1]], "n": len(cpus)}
+    except Exception as e:          # pragma: no cover
+        return {"error": str(e)}
+
+
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
@@ -196,49 +196,53 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_local = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (openess_b200 has no CPU fallback)")
+    affinity = pin_rank_to_cpus(local, n_local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.lib()
 
-    F, K, Wm = args.frames, args.steps, args.warmup
+    F, K, Wm, INNER = args.frames, args.steps, args.warmup, args.inner
     mode = args.mode
     rng = np.random.default_rng(1205 + rank)
     rmap = torch.from_numpy(synth_rectify_map(rng)).to(dev)
     fo = (torch.arange(F + 1, dtype=torch.int64) * N_EVENTS).to(dev)
-    # two input sets, alternated between steps.  Raw records live in pinned host memory (e2e); the four float32
-    # arrays VoxelGrid.convert takes are derived from them once and stay in HBM (16 B x F x N = 256 MB per set
-    # at F=160 > 126 MB L2).
+    # two input sets, alternated between batches.  The raw records live in pinned host memory (e2e) and as a resident copy
+    # in HBM (`value`): 9 B x F x N = 144 MB per set + 983 MB of output per batch > 126 MB L2.
     host_sets = [[torch.from_numpy(a).pin_memory() for a in synth_raw_frames(rng, F, clustered_every=args.clustered_every)]
                  for _ in range(2)]
-    dev_sets = [list(voxel.dsec_rectify_tnorm(*(a.to(dev) for a in hs), rmap, fo)) for hs in host_sets]
-    out = torch.empty((F, C, H, W), dtype=torch.float32, device=dev)
-    # Steps are independent batches: they alternate over `--streams` CUDA streams (own output buffer and workspace each), so
-    # the latency-bound sort kernels of step i + 1 run under the issue-bound strip splat of step i.
-    NSV = max(1, args.streams)
+    dev_raw = [[a.to(dev) for a in hs] for hs in host_sets]
+    NSV = 3
     vstreams = [torch.cuda.Stream(dev) for _ in range(NSV)]
-    vouts = [out] + [torch.empty_like(out) for _ in range(NSV - 1)]
+    outs = [torch.empty((F, C, H, W), dtype=torch.float32, device=dev) for _ in range(NSV)]
+    scratches = [tuple(torch.empty(F * N_EVENTS, dtype=torch.float32, device=dev) for _ in range(4)) for _ in range(NSV)]
+    out = outs[0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def batch(j, m=mode, k=0):
+        x, y, t, p = dev_raw[j & 1]
+        voxel.dsec_events_to_voxel_grid(x, y, t, p, rmap, C, frame_offsets=fo, mode=m, out=outs[k], scratch=scratches[k])
+
     def step(i, m=mode):
-        x, y, p, t = dev_sets[i & 1]
-        voxel.voxel_trilinear(x, y, p, t, C, H, W, frame_offsets=fo, mode=m, out=out)
+        for j in range(INNER):
+            batch(i * INNER + j, m)
 
     def step_streams(i, m=mode):
-        x, y, p, t = dev_sets[i & 1]
-        k = i % NSV
-        with torch.cuda.stream(vstreams[k]):
-            voxel.voxel_trilinear(x, y, p, t, C, H, W, frame_offsets=fo, mode=m, out=vouts[k])
+        for j in range(INNER):
+            k = (i * INNER + j) % NSV
+            with torch.cuda.stream(vstreams[k]):
+                batch(i * INNER + j, m, k)
 
-    def timed(fn, steps, profile=False):
-        for i in range(max(Wm, NSV)):                          # at least one untimed step per stream (workspace allocation)
+    def timed(fn, steps, profile=False, warm=None):
+        for i in range(Wm if warm is None else warm):
             fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -262,30 +266,37 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), _lib.launch_count() - launches0, (prof.kernels if prof else {})
 
-    # ---- device-resident throughput (the `value`), clocks sampled during the timed region
+    # ---- device-resident throughput on ONE stream (the `value`), clocks sampled during the timed region
     sampler = ClockSampler(local)
     sampler.start()
-    ms, launches, _ = timed(step_streams, K)
+    ms, launches, _ = timed(step, K)
     clocks = sampler.stop()
-    value = world * F * K / (ms * 1e-3)
-    # ---- per-kernel CUDA-event times: the same K steps on ONE stream under the library's launch recorder (kernels of
-    #      different steps must not overlap for a per-launch duration to mean anything)
-    ms_1, _, kernels = timed(step, K, profile=True)
-    value_1 = world * F * K / (ms_1 * 1e-3)
-
-    # ---- the other mode, for the record
+    frames_per_step = F * INNER
+    value = world * frames_per_step * K / (ms * 1e-3)
+    # ---- per-kernel CUDA-event times: a few batches under the library's launch recorder
+    KP = max(2, min(K, 4))
+    ms_p, _, kernels = timed(lambda i: batch(i), KP * 4, profile=True, warm=2)
+    # ---- the same steps alternating over three streams, and the other mode, for the record
+    ms_s, _, _ = timed(step_streams, max(K // 2, 2))
+    value_streams = world * frames_per_step * max(K // 2, 2) / (ms_s * 1e-3)
     other = "atomic" if mode == "ordered" else "ordered"
-    ms_o, _, _ = timed(lambda i: step_streams(i, other), K)
-    value_other = world * F * K / (ms_o * 1e-3)
+    ms_o, _, _ = timed(lambda i: step(i, other), max(K // 4, 2), warm=1)
+    value_other = world * frames_per_step * max(K // 4, 2) / (ms_o * 1e-3)
 
-    # ---- end to end from pinned host buffers: H2D of the raw records + rectify/normalise + voxelise + D2H of one
-    #      grid row per frame, pipelined over sub-batches on two streams
+    # ---- end to end from pinned host buffers, through the grids' first consumer
+    from types import SimpleNamespace
+    from openess_b200.e2vid.image_reconstructor import ImageReconstructor
+    from openess_b200.training import bench_step
+    e2vid, back, teacher = bench_step.build_modules(dev)
+    del back, teacher
+    opts = SimpleNamespace(no_normalize=False, hot_pixels_file=None, flip=False, no_recurrent=False)
     sub = args.e2e_sub
-    assert F % sub == 0
-    NS_ = max(2, args.e2e_streams)      # pipeline depth: staging buffers / streams (H2D of later sub-batches runs ahead)
+    assert F % sub == 0 and sub % 20 == 0
+    NS_ = 2                              # pipeline depth: staging buffers / streams (H2D of the next sub-batch runs ahead)
     streams = [torch.cuda.Stream(dev) for _ in range(NS_)]
+    recs = [ImageReconstructor(e2vid, HC, W, C, dev, opts) for _ in range(NS_)]
     # The loader stages the raw records of one sub-batch CONTIGUOUSLY in pinned memory ([x u16 | y u16 | t u32 | p u8],
-    # 9 bytes / event), so a sub-batch is ONE host->device copy (fewer, larger DMA transfers: 52 vs 49.7 GB/s measured).
+    # 9 bytes / event), so a sub-batch is ONE host->device copy.
     ns = sub * N_EVENTS
     offs = (0, 2 * ns, 4 * ns, 8 * ns, 9 * ns)
     dts = (torch.uint16, torch.uint16, torch.uint32, torch.uint8)
@@ -302,36 +313,64 @@ def run_ours(args):
     raw_views = [[raw_stage[b][offs[k]:offs[k + 1]].view(dts[k]) for k in range(4)] for b in range(NS_)]
     f32_stage = [tuple(torch.empty(sub * N_EVENTS, dtype=torch.float32, device=dev) for _ in range(4)) for _ in range(NS_)]
     fo_sub = (torch.arange(sub + 1, dtype=torch.int64) * N_EVENTS).to(dev)
-    rows_host = torch.empty((F, C, W), dtype=torch.float32).pin_memory()
+    n_sub = F // sub
+    check_host = torch.zeros((n_sub, 2), dtype=torch.float32).pin_memory()
     full_host = torch.empty((F, C, H, W), dtype=torch.float32).pin_memory() if args.host_output else None
+    E2E_INNER = max(1, INNER // 4)
 
-    def e2e_step(i, full=False):
-        ph = packed_host[i & 1]
+    def e2e_batch(j, consumer="encoder"):
+        ph = packed_host[j & 1]
         for s, f0 in enumerate(range(0, F, sub)):
             b = s % NS_
             with torch.cuda.stream(streams[b]):
                 raw_stage[b].copy_(ph[s], non_blocking=True)
-                voxel.dsec_events_to_voxel_grid(*raw_views[b], rmap, C, frame_offsets=fo_sub, mode=mode,
-                                                out=out[f0:f0 + sub], scratch=f32_stage[b])
-                if full:
-                    full_host[f0:f0 + sub].copy_(out[f0:f0 + sub], non_blocking=True)
+                grids = voxel.dsec_events_to_voxel_grid(*raw_views[b], rmap, C, frame_offsets=fo_sub, mode=mode,
+                                                        out=out[f0:f0 + sub], scratch=f32_stage[b])
+                if consumer == "host":
+                    full_host[f0:f0 + sub].copy_(grids, non_blocking=True)
+                elif consumer == "encoder":
+                    dense = grids.view(sub // 20, 20 * C, H, W)[:, :, :HC, :]        # sequence_ov.py:223, 307
+                    rec = recs[b]
+                    rec.last_states_for_each_channel = {'grayscale': None}
+                    _, _, latent = rec.update_reconstruction(dense[:, :C])            # EventPreprocessor + E2VID step 1
+                    check_host[s, 0].copy_(latent[8].sum(), non_blocking=True)
                 else:
-                    rows_host[f0:f0 + sub].copy_(out[f0:f0 + sub, :, 0, :], non_blocking=True)
+                    check_host[s, 1].copy_(grids[0, 0, 0, 0], non_blocking=True)
         for st in streams:
             torch.cuda.current_stream().wait_stream(st)
 
-    ms_e, launches_e, _ = timed(e2e_step, K)
-    e2e_value = world * F * K / (ms_e * 1e-3)
-    h2d = 9 * F * N_EVENTS
-    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 * F * C * W,
-           "ms_per_step": ms_e / K, "input": "raw DSEC records (u16 x, u16 y, u32 t, u8 p) in pinned host memory",
-           "h2d_gbs": h2d / (ms_e / K * 1e-3) / 1e9}
+    def e2e_step(i, consumer="encoder"):
+        for j in range(E2E_INNER):
+            e2e_batch(i * E2E_INNER + j, consumer)
+
+    KE = max(K // 2, 3)
+    ms_e, launches_e, _ = timed(e2e_step, KE, warm=2)
+    e2e_frames = F * E2E_INNER
+    h2d = 9 * F * N_EVENTS * E2E_INNER
+    e2e = {"value": world * e2e_frames * KE / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 4 * n_sub * E2E_INNER, "ms_per_step": ms_e / KE, "frames_per_step": e2e_frames,
+           "input": "raw DSEC records (u16 x, u16 y, u32 t, u8 p) in pinned host memory",
+           "ends_in": "EventPreprocessor + first E2VID recurrent step (tcgen05 kernels) on the first 5-bin slice of every sample; "
+                      "D2H of the latent checksum",
+           "h2d_gbs_per_gpu": h2d / (ms_e / KE * 1e-3) / 1e9, "checksum": float(check_host[:, 0].sum())}
+    ms_v, _, _ = timed(lambda i: e2e_step(i, "voxel"), KE, warm=1)
+    e2e_voxel = {"value": world * e2e_frames * KE / (ms_v * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                 "d2h_bytes_per_step": 4 * n_sub * E2E_INNER, "h2d_gbs_per_gpu": h2d / (ms_v / KE * 1e-3) / 1e9,
+                 "ends_in": "voxel grids in HBM (no consumer); D2H of one grid element per sub-batch"}
     e2e_host = None
     if args.host_output:
-        kh = max(2, K // 4)
-        ms_h, _, _ = timed(lambda i: e2e_step(i, True), kh)
-        e2e_host = {"value": world * F * kh / (ms_h * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4 * F * C * H * W}
+        kh = 2
+        ms_h, _, _ = timed(lambda i: e2e_step(i, "host"), kh, warm=1)
+        e2e_host = {"value": world * e2e_frames * kh / (ms_h * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4 * F * C * H * W * E2E_INNER,
+                    "ends_in": "every voxel grid copied back to pinned host memory"}
+    del recs, e2vid, full_host, outs, scratches, raw_stage, f32_stage
+    torch.cuda.empty_cache()
+
+    # ---- end-to-end training step with the NCCL gradient all-reduce
+    train = None
+    if args.train_steps > 0:
+        train = bench_step.run(args.train_batch, args.train_steps, 2, N_EVENTS, args.train_baseline_steps, rank, local, world)
 
     if rank != 0:
         if world > 1:
@@ -348,42 +387,43 @@ def run_ours(args):
     dom = max(kernels.items(), key=lambda kv: kv[1][1]) if kernels else (None, (0, 0.0))
     dom_name, (dom_cnt, dom_ms) = dom
     per_launch_ms = dom_ms / max(dom_cnt, 1)
-    launches_per_step = max(dom_cnt // max(K, 1), 1)
-    achieved = alg_bytes_frame * F / launches_per_step / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0.0
-    path_gbs = alg_bytes_frame * F / (ms / K * 1e-3) / 1e9
+    achieved = alg_bytes_frame * F / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0.0
+    ms_batch = ms / (K * INNER)
+    path_gbs = alg_bytes_frame * F / (ms_batch * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")   # per-launch dram bytes from the committed ncu capture
     if os.path.exists(tpath):
         tj = json.load(open(tpath))      # keyed by __global__ name; the launch recorder names kernels "tri_<x>" for "k_<x>"
         traffic = tj.get(dom_name, tj.get("k_" + str(dom_name).split("_", 1)[-1]))
+    ksum = sum(v[1] for v in kernels.values()) or 1.0
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel_ms_per_launch": per_launch_ms,
-                "algorithmic_bytes_per_launch": alg_bytes_frame * F // launches_per_step,
+                "kernel_ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes_frame * F,
                 "path_achieved": path_gbs, "path_frac": path_gbs / peak,
-                "kernel_share_of_step": {k: round(v[1] / (ms_1 if ms_1 else 1), 4) for k, v in kernels.items()},
-                "kernel_timing": "single-stream pass of the same K steps under the launch recorder "
-                                 f"({ms_1 / K:.4f} ms / step); `value` is the {NSV}-stream pass"}
+                "path_note": "whole single-stream path (rectify + normalise + sort + splat) against the convert-only algorithmic bytes",
+                "kernel_share_of_step": {k: round(v[1] / ksum, 4) for k, v in kernels.items()},
+                "kernel_ms_per_batch": {k: round(v[1] / (KP * 4), 4) for k, v in kernels.items()}}
 
     # ---- CPU baseline (oracle port, all host threads, bounded sample)
-    cpu_val, cpu_frames, cpu_dt, cpu_threads = cpu_port_throughput(args.cpu_frames, args.cpu_budget)
-    cpu1_val, _, _, _ = cpu_port_throughput(8, 10.0, threads=1)
+    cpu_val, cpu_frames, cpu_dt, cpu_threads = cpu_port_throughput(args.cpu_frames, args.cpu_budget,
+                                                                   clustered_every=args.clustered_every)
+    cpu1_val, _, _, _ = cpu_port_throughput(8, 10.0, threads=1, clustered_every=args.clustered_every)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"DSEC 640x480, {N_EVENTS} events per 50 ms frame, VoxelGrid.convert trilinear splat C={C}, "
-                               f"F={F} frames per step per GPU (8 samples x 20 frames); every "
-                               f"{args.clustered_every} frame(s) edge-clustered",
-                   "mode": mode, "bit_exact_vs_reference": mode == "ordered",
-                   "l2": f"inputs {16 * F * N_EVENTS / 1e6:.0f} MB + outputs {4 * F * C * H * W / 1e6:.0f} MB per step > 126 MB L2; "
-                         "two input sets alternated",
-                   "streams": f"steps alternate over {NSV} CUDA stream(s): sort kernels of step i+1 overlap the splat of step i",
-                   "parallelism": f"frames sharded over {world} GPU(s), no collective"},
-        "value_single_stream": {"value": value_1, "unit": UNIT, "ms_per_step": ms_1 / K},
+        "config": workload_config(args),
+        "arm": {"step": f"one step = {INNER} consecutive batches of F={F} frames = {frames_per_step} frames per GPU; ONE CUDA stream",
+                "timed_region_s": ms * 1e-3,
+                "l2": f"raw inputs {9 * F * N_EVENTS / 1e6:.0f} MB + float32 event arrays {16 * F * N_EVENTS / 1e6:.0f} MB + outputs "
+                      f"{4 * F * C * H * W / 1e6:.0f} MB per batch > 126 MB L2; two input sets alternated",
+                "parallelism": f"frames sharded over {world} GPU(s), no data-path collective", "cpu_affinity": affinity},
+        "value_streams3": {"value": value_streams, "unit": UNIT,
+                           "note": "same steps, batches alternating over 3 CUDA streams (independent batches overlap)"},
         "value_other_mode": {"mode": other, "value": value_other, "unit": UNIT},
-        "e2e": e2e, "e2e_host_output": e2e_host,
+        "e2e": e2e, "e2e_voxel_only": e2e_voxel, "e2e_host_output": e2e_host,
         "gpu_launches": launches, "gpu_launches_e2e": launches_e, "clocks": clocks, "roofline": roofline,
+        "train_step": train,
         "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cpu_threads, "kind": "port",
                          "sample": f"{cpu_frames} frames of {N_EVENTS} events in {cpu_dt:.1f} s (C oracle port: rectify + "
                                    "t-normalise + VoxelGrid.convert, one frame per thread)",
@@ -402,12 +442,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="ordered", choices=["ordered", "atomic"])
-    ap.add_argument("--frames", type=int, default=160, help="event-frames per step per GPU")
-    ap.add_argument("--streams", type=int, default=3, help="CUDA streams the device-resident steps alternate over")
-    ap.add_argument("--e2e-streams", type=int, default=2, help="pipeline depth (streams / staging buffers) of the e2e leg")
+    ap.add_argument("--frames", type=int, default=160, help="event-frames per batch per GPU")
+    ap.add_argument("--inner", type=int, default=32, help="batches per bench step (so that K steps last about a second)")
     ap.add_argument("--e2e-sub", type=int, default=80, help="frames per pipelined H2D/compute sub-batch")
     ap.add_argument("--host-output", type=int, default=1, help="also measure e2e with full D2H of the grids")
     ap.add_argument("--clustered-every", type=int, default=2, help="every k-th frame is edge-clustered (0: none, 1: all)")
+    ap.add_argument("--train-steps", type=int, default=5, help="timed steps of the end-to-end pretraining step (0: skip)")
+    ap.add_argument("--train-batch", type=int, default=4, help="samples per GPU of the pretraining step (BASELINE config 3: 32 / 8)")
+    ap.add_argument("--train-baseline-steps", type=int, default=2, help="timed steps of the literal torch / cuDNN formulation on rank 0")
     ap.add_argument("--cpu-frames", type=int, default=2000)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     args = ap.parse_args()

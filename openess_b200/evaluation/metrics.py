@@ -56,7 +56,7 @@ class MetricsSemseg:
             if self.metrics_acc is None:
                 self.metrics_acc = metrics_batch
             else:
-                self.metrics_acc += metrics_batch
+                self.metrics_acc += metrics_batch.to(self.metrics_acc.device)     # the accumulator may live on the device
 
     def update_batch_logits(self, logits, y_lbl):
         """Fused validation step: `update_batch(logits.argmax(dim=1), y_lbl)` of base_trainer_ov.py:463-471

@@ -143,6 +143,12 @@ class _DiceCE(torch.autograd.Function):
         losses = dice_ce_finish(partials, K, w_dice, w_ce)
         ctx.save_for_backward(logits, target, partials)
         ctx.cfg = (ignore_index, w_dice, w_ce)
+        # With all-reduced partial sums every rank differentiates the GLOBAL loss w.r.t. its LOCAL logits, so the true
+        # parameter gradient is the SUM over ranks; the data-parallel step AVERAGES gradients (parallel.GradientReducer /
+        # allreduce_gradients, average=True), hence the factor world_size here (without it the Dice/CE term
+        # is down-weighted by 1 / world_size against the locally computed contrastive loss).
+        from . import parallel as _parallel
+        ctx.grad_scale = float(_parallel.world_size()) if reduce_partials is not None else 1.0
         return losses[2]
 
     @staticmethod
@@ -152,6 +158,8 @@ class _DiceCE(torch.autograd.Function):
         B, K, H, W = logits.shape
         d = torch.empty_like(logits)
         gs = g.reshape(1).to(torch.float32).contiguous()
+        if ctx.grad_scale != 1.0:
+            gs = gs * ctx.grad_scale
         ig = -(1 << 62) if ignore_index is None else int(ignore_index)
         with torch.cuda.device(logits.device):
             check(lib().oess_dice_ce_bwd(ptr(logits), ptr(target), B, K, H, W, ig, ptr(partials), float(w_dice),

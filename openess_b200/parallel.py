@@ -93,6 +93,105 @@ def allreduce_gradients(params, bucket_bytes=32 << 20, average=True):
     return n_calls
 
 
+class GradientReducer:
+    """Bucketed gradient all-reduce OVERLAPPED with backward ("bucketed and overlapped with backward").
+
+    Parameters are cut into buckets of `bucket_bytes` in REVERSE registration order (the order backward produces
+    gradients in); a post-accumulate-grad hook copies each finished gradient into its bucket's flat buffer, and a bucket
+    whose gradients are all in is all-reduced asynchronously (buckets are always launched in index order, so every rank
+    issues the same collective sequence) while backward keeps running.  `finish()` waits, averages and scatters the reduced
+    values back into the `.grad` tensors.  Parameters that never receive a gradient (SemSegE2VID.decoder_scale_5,
+    DeepLabHead.pixel_feature: unused in the reference's forward) are detected on the first step, which runs the plain
+    post-backward `allreduce_gradients`, and are left out of the buckets -- their `.grad` stays None, so AdamW skips them
+    exactly as in the single-GPU reference."""
+
+    def __init__(self, params, bucket_bytes=8 << 20, average=True):
+        self.params = [p for p in params if p.requires_grad]
+        self.bucket_bytes, self.average = int(bucket_bytes), average
+        self.buckets = None           # list of dicts: params, flat, offsets, pending, launched, work
+        self._hooks = []
+        self._index = {}
+        self.stats = {"buckets": 0, "bytes": 0, "overlapped_calls": 0}
+
+    def _build(self):
+        live = [p for p in self.params if p.grad is not None]
+        self.buckets, cur, size = [], [], 0
+        for p in reversed(live):
+            nb = p.numel() * p.element_size()
+            if cur and (size + nb > self.bucket_bytes or p.dtype != cur[0].dtype):
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += nb
+        if cur:
+            self.buckets.append(cur)
+        built = []
+        for bi, ps in enumerate(self.buckets):
+            n = sum(p.numel() for p in ps)
+            flat = torch.empty(n, dtype=ps[0].dtype, device=ps[0].device)
+            offs, o = [], 0
+            for p in ps:
+                offs.append(o)
+                o += p.numel()
+            built.append({"params": ps, "flat": flat, "offsets": offs, "pending": len(ps), "work": None})
+            for j, p in enumerate(ps):
+                self._index[p] = (bi, j)
+        self.buckets = built
+        self.stats["buckets"] = len(built)
+        self.stats["bytes"] = sum(b["flat"].numel() * b["flat"].element_size() for b in built)
+        for p in live:
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _on_grad(self, p):
+        bi, j = self._index[p]
+        b = self.buckets[bi]
+        o = b["offsets"][j]
+        b["flat"][o:o + p.numel()].copy_(p.grad.reshape(-1))
+        b["pending"] -= 1
+        self._launch_ready()
+
+    def _launch_ready(self):
+        while self._next < len(self.buckets) and self.buckets[self._next]["pending"] <= 0:
+            b = self.buckets[self._next]
+            b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, async_op=True)
+            self.stats["overlapped_calls"] += 1
+            self._next += 1
+
+    def prepare(self):
+        """Call before backward()."""
+        if self.buckets is None:
+            return
+        self._next = 0
+        for b in self.buckets:
+            b["pending"], b["work"] = len(b["params"]), None
+
+    def finish(self):
+        """Call after backward(): returns the number of all-reduce calls of this step."""
+        w = world_size()
+        if w == 1:
+            return 0
+        if self.buckets is None:                 # first step: learn which parameters receive gradients
+            n = allreduce_gradients(self.params, self.bucket_bytes, self.average)
+            self._build()
+            return n
+        for b in self.buckets:                   # a gradient that did not arrive this step counts as zero
+            if b["pending"] > 0:
+                for p, o in zip(b["params"], b["offsets"]):
+                    if p.grad is None:
+                        b["flat"][o:o + p.numel()].zero_()
+                b["pending"] = 0
+        self._launch_ready()
+        for b in self.buckets:
+            b["work"].wait()
+            if self.average:
+                b["flat"].div_(w)
+            grads = [p.grad for p in b["params"] if p.grad is not None]
+            views = [b["flat"][o:o + p.numel()].view_as(p) for p, o in zip(b["params"], b["offsets"]) if p.grad is not None]
+            if grads:
+                torch._foreach_copy_(grads, views)
+        return len(self.buckets)
+
+
 def allreduce_confusion_(conf):
     """Integer confusion matrices add exactly across ranks (validation, metrics.py)."""
     return allreduce_sum_(conf)

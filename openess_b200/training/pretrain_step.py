@@ -13,8 +13,9 @@ What changes on the B200:
   * E2VID (20 recurrent steps) and the frozen teacher run on the tcgen05 kernels, sync-free;
   * `SemSegE2VID.forward_pooled` + `superpixel_pool` replace the sparse one-hot matmuls on permuted 2.3 GB copies
     (:446-465) -- k and q are produced by fused segment reductions, the 256 / 512-channel event-branch maps never exist;
-  * `NCELoss` / `TaskLoss` are the fused kernels; under data parallelism `allreduce_gradients` averages the gradients
-    of the two trainable modules over NCCL after backward (the reference is single-GPU, README.md:303).
+  * `NCELoss` / `TaskLoss` are the fused kernels; under data parallelism `parallel.GradientReducer` averages the gradients
+    of the two trainable modules over NCCL in buckets that are all-reduced WHILE backward is still running (the
+    reference is single-GPU, README.md:303).
 """
 from collections import namedtuple
 
@@ -25,14 +26,36 @@ from .. import voxel as _voxel
 from ..losses import superpixel_pool
 
 # raw DSEC records of B samples x nr_events_data windows: x, y uint16; t uint32 or int64 (us); p uint8; frame_offsets
-# int64 [B * nr_events_data + 1]; rectify_map float32 [Hs, Ws, 2] (sequence_ov.py:204-210); sensor (Hs, Ws); crop rows
-RawEvents = namedtuple("RawEvents", "x y t p frame_offsets rectify_map sensor_hw crop_h")
+# int64 [B * nr_events_data + 1]; rectify_map float32 [Hs, Ws, 2] (sequence_ov.py:204-210); sensor (Hs, Ws); crop rows;
+# flip: None or uint8 / bool [B], samples whose event tensor the loader's augmentation flipped horizontally (:387-389)
+RawEvents = namedtuple("RawEvents", "x y t p frame_offsets rectify_map sensor_hw crop_h flip", defaults=(None,))
+
+
+def assemble_event_tensor(ev, device, nr_events_data=20, C=5):
+    """batch[0] of a trainer step -> dense [B, nr_events_data * C, crop_h, W] on `device`: a `RawEvents` slab is rectified,
+    time-normalised and voxelised there in one batched call (F = B * nr_events_data frames; sequence_ov.py:282-307); the
+    reference's dense tensor is just moved."""
+    if not isinstance(ev, RawEvents):
+        return ev.to(device)                                   # reference format: dense [B, 20*5, H, W]
+    Hs, Ws = ev.sensor_hw
+    x, y, t, p = (a.to(device, non_blocking=True) for a in (ev.x, ev.y, ev.t, ev.p))
+    fo = ev.frame_offsets.to(device, non_blocking=True)
+    grids = _voxel.dsec_events_to_voxel_grid(x, y, t, p, ev.rectify_map.to(device), C, frame_offsets=fo,
+                                             mode="ordered")                        # [F, C, Hs, Ws]
+    F = fo.numel() - 1
+    B = F // nr_events_data
+    dense = grids.view(B, nr_events_data * C, Hs, Ws)
+    if ev.flip is not None:                                    # sequence_ov.py:387-389 torch.flip(event_tensor, [2]) per sample
+        from ..DSEC.dataset.augment import hflip_rows_
+        hflip_rows_(dense, torch.as_tensor(ev.flip).to(device).to(torch.uint8))
+    return dense[:, :, :ev.crop_h, :]                          # sequence_ov.py:307 bottom crop, a view
 
 
 class OpenESSPretrainStep:
     def __init__(self, reconstructor, back_end, model_frame, task_loss, nce_loss, *, nr_events_data_b=20,
                  input_channels_b=5, superpixel_size=100, weight_task_loss=1.0, if_spatial_contrastive=True,
-                 if_dense_clip_supervision=True, lr_voxel=5e-4, lr_frame=5e-4, device=None, data_parallel=False):
+                 if_dense_clip_supervision=True, lr_voxel=5e-4, lr_frame=5e-4, device=None, data_parallel=False,
+                 optimizers_dict=None):
         self.reconstructor = reconstructor
         self.models_dict = {"front_sensor_b": reconstructor.model, "back_end": back_end, "model_frame": model_frame}
         self.task_loss, self.nce_loss = task_loss, nce_loss
@@ -47,25 +70,17 @@ class OpenESSPretrainStep:
         params_voxel = [p for p in back_end.parameters() if p.requires_grad]
         params_frame = [p for p in model_frame.parameters() if p.requires_grad]
         fused = self.device.type == "cuda"
-        self.optimizers_dict = {"optimizer_voxel": torch.optim.AdamW(params_voxel, lr=lr_voxel, fused=fused),
-                                "optimizer_frame": torch.optim.AdamW(params_frame, lr=lr_frame, fused=fused)}
+        if optimizers_dict is not None:                        # a reference trainer's own optimisers (drop_in.py)
+            self.optimizers_dict = optimizers_dict
+        else:
+            self.optimizers_dict = {"optimizer_voxel": torch.optim.AdamW(params_voxel, lr=lr_voxel, fused=fused),
+                                    "optimizer_frame": torch.optim.AdamW(params_frame, lr=lr_frame, fused=fused)}
         self._trainable = params_voxel + params_frame
+        self._reducer = _parallel.GradientReducer(self._trainable) if data_parallel else None
 
     # ---- sample assembly on the device (replaces Sequence.__getitem__'s voxel branch, sequence_ov.py:282-307) ----
     def event_tensor(self, ev):
-        if not isinstance(ev, RawEvents):
-            return ev.to(self.device)                          # reference format: dense [B, 20*5, H, W]
-        C = self.input_channels_b
-        Hs, Ws = ev.sensor_hw
-        dev = self.device
-        x, y, t, p = (a.to(dev, non_blocking=True) for a in (ev.x, ev.y, ev.t, ev.p))
-        fo = ev.frame_offsets.to(dev, non_blocking=True)
-        grids = _voxel.dsec_events_to_voxel_grid(x, y, t, p, ev.rectify_map.to(dev), C, frame_offsets=fo,
-                                                 mode="ordered")                        # [F, C, Hs, Ws]
-        F = fo.numel() - 1
-        B = F // self.nr_events_data_b
-        dense = grids.view(B, self.nr_events_data_b * C, Hs, Ws)
-        return dense[:, :, :ev.crop_h, :]                      # sequence_ov.py:307 bottom crop, a view
+        return assemble_event_tensor(ev, self.device, self.nr_events_data_b, self.input_channels_b)
 
     # ---- pretrain_trainer.py:550-562 ----
     def trainTaskStepPretrain(self, content_features, pl, superpixels, losses):
@@ -84,8 +99,8 @@ class OpenESSPretrainStep:
         losses, outputs, t_loss = {}, {}, 0.0
         for name, m in self.models_dict.items():
             m.train()                                          # :370-371 (the "frozen" teacher's BN uses batch statistics)
-            if name == "front_sensor_b":
-                m.eval()                                       # :372-374
+            if name in ("front_sensor_b", "model_clip"):
+                m.eval()                                       # :372-377
         event = self.event_tensor(batch[0])
         frame = batch[2].to(self.device)
         pl = batch[3].to(self.device)
@@ -117,9 +132,11 @@ class OpenESSPretrainStep:
         for opt in self.optimizers_dict.values():
             opt.zero_grad(set_to_none=True)
         final_loss, losses, outputs = self.task_train_step(input_batch)
+        if self._reducer is not None:
+            self._reducer.prepare()
         final_loss.backward()
-        if self.data_parallel:
-            _parallel.allreduce_gradients(self._trainable)
+        if self._reducer is not None:
+            self._reducer.finish()                         # bucketed all-reduce, overlapped with backward from step 2 on
         for opt in self.optimizers_dict.values():
             opt.step()
         return losses, outputs, final_loss

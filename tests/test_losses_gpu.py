@@ -210,3 +210,35 @@ def test_argmax_confusion_fused_vs_oracle_and_metrics(dev, oracle):
     s1, s2 = m1.get_metrics_summary(), m2.get_metrics_summary()
     assert np.array_equal(s1['cm'].cpu().numpy(), s2['cm'].cpu().numpy()) and np.array_equal(s2['cm'].cpu().numpy(), 2 * ref)
     assert float(s1['miou']) == float(s2['miou']) and float(s1['acc']) == float(s2['acc'])
+
+
+def test_task_loss_global_partials_gradient_scaling(dev, monkeypatch):
+    """`TaskLoss.reduce_partials` (all-reduced Dice / CE partial sums) combined with the AVERAGED gradient
+    all-reduce.  Two ranks are emulated on one device: each shard's partial sums are completed with the other shard's, each
+    shard back-propagates, and the averaged input gradients must equal the gradient of the single-process loss on the
+    concatenated batch (exact global-batch semantics, SURVEY.md 8e option B)."""
+    from openess_b200 import losses, parallel
+    from openess_b200.utils.loss_functions import TaskLoss
+    g = torch.Generator().manual_seed(5)
+    K, H, W = 7, 24, 40
+    logits = [torch.randn(2, K, H, W, generator=g).to(dev).requires_grad_(True) for _ in range(2)]
+    target = [torch.randint(0, K, (2, H, W), generator=g).to(dev) for _ in range(2)]
+    for t in target:
+        t[torch.rand(t.shape, device=dev) < 0.05] = 255
+    full_logits = torch.cat([l.detach() for l in logits]).requires_grad_(True)
+    tl = TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
+    full = tl(full_logits, torch.cat(target))
+    full.backward()
+    world = 2
+    monkeypatch.setattr(parallel, "world_size", lambda: world)
+    parts = [losses.dice_ce_partials(l.detach().contiguous(), t.contiguous(), 255) for l, t in zip(logits, target)]
+    for r in range(world):
+        other = parts[1 - r]
+        tl_r = TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255)
+        tl_r.reduce_partials = lambda p, other=other: p.add_(other)          # what parallel.allreduce_sum_ does across ranks
+        loss_r = tl_r(logits[r], target[r])
+        assert float(loss_r) == pytest.approx(float(full), rel=1e-5)         # every rank sees the global loss
+        loss_r.backward()
+    # the data-parallel step AVERAGES gradients over ranks; the parameter gradient is linear in d(loss)/d(logits)
+    got = torch.cat([l.grad for l in logits]) / world
+    torch.testing.assert_close(got, full_logits.grad, rtol=2e-4, atol=1e-9)

@@ -203,3 +203,71 @@ def test_consistency_losses_golden():
     cs.backward()
     np.testing.assert_allclose(la.grad.cpu().numpy(), z["dla"], rtol=2e-4, atol=2e-9)
     np.testing.assert_allclose(lb.grad.cpu().numpy(), z["dlb"], rtol=2e-4, atol=2e-9)
+
+
+@pytest.mark.gpu
+def test_image_reconstructor_matches_reference_class_golden():
+    """a9 against the REFERENCE's own ImageReconstructor (e2vid/image_reconstructor.py:80-123, run on CPU with CudaTimer -> Timer
+    by oracle/make_golden_trainer.py): three recurrent steps at 30 x 44 (reflection-padded to 32 x 48), image, latents, states,
+    the all-zero input branch of the EventPreprocessor and `standardization=True`."""
+    from types import SimpleNamespace
+    from openess_b200.e2vid.image_reconstructor import ImageReconstructor
+    z = load_golden("reconstructor")
+    ze = load_golden("e2vid_tiny")
+    dev = torch.device("cuda:0")
+    H, W = int(z["H"]), int(z["W"])
+    opts = SimpleNamespace(no_normalize=False, hot_pixels_file=None, flip=False, no_recurrent=False)
+    m = _build(ze, latent_only=False).to(dev)
+    rec = ImageReconstructor(m, H, W, 5, dev, opts)
+    assert not rec.crop.is_noop
+    for i in range(3):
+        img, states, latent = rec.update_reconstruction(torch.from_numpy(z[f"in{i}"]))
+        np.testing.assert_allclose(img.cpu().numpy(), z[f"img{i}"], atol=3e-4)
+        for k in latent:
+            np.testing.assert_allclose(latent[k].cpu().numpy(), z[f"latent{i}__{k}"], atol=3e-4)
+        for li, (h, c) in enumerate(states):
+            np.testing.assert_allclose(h.cpu().numpy(), z[f"state{i}__{li}__h"], atol=3e-4)
+            np.testing.assert_allclose(c.cpu().numpy(), z[f"state{i}__{li}__c"], atol=3e-4)
+    assert rec.last_states_for_each_channel['grayscale'] is states
+    rec.last_states_for_each_channel = {'grayscale': None}
+    img, _, latent = rec.update_reconstruction(torch.zeros(1, 5, H, W))
+    np.testing.assert_allclose(img.cpu().numpy(), z["zero_img"], atol=3e-4)
+    np.testing.assert_allclose(latent[8].cpu().numpy(), z["zero_latent8"], atol=3e-4)
+    rec_s = ImageReconstructor(m, H, W, 5, dev, opts, standardization=True)      # keyword as in the reference signature
+    img_s, _, _ = rec_s.update_reconstruction(torch.from_numpy(z["in0"]))
+    np.testing.assert_allclose(img_s.cpu().numpy(), z["std_img0"], atol=2e-3)
+    # latent-only encoder (what the trainers run): same latents, no image
+    m2 = _build(ze, latent_only=True).to(dev).fold_bn()
+    rec2 = ImageReconstructor(m2, H, W, 5, dev, opts)
+    for i in range(3):
+        img, _, latent = rec2.update_reconstruction(torch.from_numpy(z[f"in{i}"]))
+        assert img is None
+        for k in latent:
+            np.testing.assert_allclose(latent[k].cpu().numpy(), z[f"latent{i}__{k}"], atol=3e-4)
+
+
+@pytest.mark.gpu
+def test_post_processor_matches_reference_golden():
+    """8f row 3 leftovers: PostProcessor = UnsharpMaskFilter + IntensityRescaler (e2vid/image_reconstructor.py:126-140,
+    e2vid/utils/inference_utils.py:90-129, 234-252) as one kernel, against the reference classes' output on the reference's
+    own reconstructions; 8-bit quantisation: a pixel may land on the neighbouring level when the float chain differs in the
+    last bit, so at most 0.5 % of the pixels may differ, by exactly one level."""
+    from types import SimpleNamespace
+    from openess_b200.e2vid.image_reconstructor import PostProcessor, gaussian_kernel_5x5
+    z = load_golden("reconstructor")
+    dev = torch.device("cuda:0")
+    opts = SimpleNamespace(unsharp_mask_amount=float(z["unsharp_amount"]), unsharp_mask_sigma=float(z["unsharp_sigma"]),
+                           auto_hdr=False, auto_hdr_median_filter_size=10, Imin=0.0, Imax=1.0, bilateral_filter_sigma=0.0)
+    k = gaussian_kernel_5x5(1.0)
+    assert abs(float(k.sum()) - 1.0) < 1e-6 and tuple(k.shape) == (5, 5)
+
+    def check(got, want):
+        d = np.abs(got.cpu().numpy() - want)
+        assert float(d.max()) <= 1.0 / 255 + 1e-6
+        assert float((d > 1e-6).mean()) < 5e-3
+
+    check(PostProcessor(dev, opts).process(torch.from_numpy(z["img0"])), z["post_img0"])
+    opts.auto_hdr = True
+    post = PostProcessor(dev, opts)                      # running median of the clipped per-image bounds over three images
+    for i in range(3):
+        check(post.process(torch.from_numpy(z[f"img{i}"])), z[f"post_hdr_img{i}"])

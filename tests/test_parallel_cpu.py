@@ -93,6 +93,63 @@ def test_gloo_world2_gradient_allreduce_matches_full_batch():
     assert [r[5] for r in res] == [(0, 4), (4, 7)]
 
 
+def _make_model():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3), torch.nn.Linear(3, 3))
+
+
+def _reducer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    parallel.init(backend="gloo")
+    model = _make_model()                                          # model[3] unused -> its gradients stay None
+    red = parallel.GradientReducer(list(model.parameters()), bucket_bytes=64)
+    opt = torch.optim.SGD([p for p in model.parameters()], lr=0.1)
+    calls = []
+    for step in range(3):
+        opt.zero_grad(set_to_none=True)
+        x = torch.arange(24, dtype=torch.float32).reshape(4, 6) / 10 + rank + step
+        loss = model[2](model[1](model[0](x))).square().sum()
+        red.prepare()
+        loss.backward()
+        calls.append(red.finish())
+        opt.step()
+    q.put((rank, torch.cat([p.detach().reshape(-1) for p in model.parameters()]).tolist(), calls, dict(red.stats),
+           [p.grad is None for p in model[3].parameters()]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_overlapped_gradient_reducer_matches_full_batch_training():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_reducer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference: three SGD steps on the average of the two ranks' gradients
+    model = _make_model()
+    opt = torch.optim.SGD([p for p in model.parameters()], lr=0.1)
+    for step in range(3):
+        opt.zero_grad(set_to_none=True)
+        total = 0
+        for rank in range(world):
+            x = torch.arange(24, dtype=torch.float32).reshape(4, 6) / 10 + rank + step
+            total = total + model[2](model[1](model[0](x))).square().sum() / world
+        total.backward()
+        opt.step()
+    want = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    for rank, flat, calls, stats, unused_none in res:
+        torch.testing.assert_close(torch.tensor(flat), want, rtol=1e-5, atol=1e-6)
+        assert calls[0] >= 2 and calls[1] == calls[2] == stats["buckets"] >= 2     # 64-byte buckets
+        assert stats["overlapped_calls"] == 2 * stats["buckets"]                 # steps 2 and 3 went through the hooks
+        assert all(unused_none)                                                   # the unused layer never got a gradient
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree only exists in the build container")
 def test_patch_reference_rebinds_boundary_callables():
     import subprocess

@@ -170,3 +170,77 @@ def test_pretrain_step_raw_event_slab_equals_dense_event_tensor():
         g = voxel.dsec_events_to_voxel_grid(x[sl].to(dev), y[sl].to(dev), t[sl].to(dev), p[sl].to(dev), rmap.to(dev), C)
         b, i = divmod(f, steps)
         assert torch.equal(dense[b, i * C:(i + 1) * C], g[0, :, :crop])
+
+
+def test_pretrain_step_matches_reference_trainer_golden():
+    """a19 against the REFERENCE's own trainer: tests/golden/pretrain_step.npz holds losses, every gradient and the parameters
+    after one optimiser step of `OpenESSPretrainModel.task_train_step` / `train_step` (training/pretrain_trainer.py:324-361,
+    364-372, 427-472, 550-562), executed unmodified on CPU by oracle/make_golden_trainer.py with the reference's module
+    classes and the same seeded weights."""
+    from openess_b200.e2vid.image_reconstructor import ImageReconstructor
+    from openess_b200.models import image_model as im
+    from openess_b200.models import style_networks as sn
+    from openess_b200.training.pretrain_step import OpenESSPretrainStep
+    from openess_b200.utils.loss_functions import NCELoss, TaskLoss
+    z = load_golden("pretrain_step")
+    dev = torch.device("cuda:0")
+    e2vid, back, teacher, opts, K = _models(dev)
+    assert K == int(z["K"])
+    S, steps, stride = int(z["S"]), int(z["steps"]), int(z["stride"])
+    event, frame, pl, sp = (torch.from_numpy(z[k]).to(dev) for k in ("event", "frame", "pl", "sp"))
+    H, W = event.shape[-2:]
+    sd_back = {k: v.clone() for k, v in back.state_dict().items()}
+    sd_teacher = {k: v.clone() for k, v in teacher.state_dict().items()}
+    im.USE_TENSOR_CORES = False                       # fp32 modules: the golden is the reference's fp32 CPU run
+    sn.TRAIN_ON_TENSOR_CORES = False
+    try:
+        rec = ImageReconstructor(e2vid, H, W, 5, dev, opts)
+        step = OpenESSPretrainStep(rec, back, teacher, TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255),
+                                   NCELoss(temperature=0.07), nr_events_data_b=steps, superpixel_size=S, lr_voxel=1e-3, lr_frame=1e-3)
+        total, losses, outputs = step.task_train_step((event, None, frame, pl, sp))
+        assert float(losses["contrastive_nce_loss"]) == pytest.approx(float(z["nce"]), rel=3e-4)
+        assert float(losses["dense_clip_loss"]) == pytest.approx(float(z["dense"]), rel=3e-4)
+        assert float(total) == pytest.approx(float(z["total"]), rel=3e-4)
+        if z["logits"].size:                          # the reference's frame2voxel branch leaves `outputs` empty
+            np.testing.assert_allclose(outputs["pred"][1].detach().cpu().numpy(), z["logits"], atol=2e-3 * float(np.abs(z["logits"]).max()))
+        total.backward()
+        named = {"back_end." + n: p for n, p in back.named_parameters()}
+        named.update({"model_frame." + n: p for n, p in teacher.named_parameters()})
+        nograd = set(str(n) for n in z["nograd"])
+        checked = 0
+        for n, p in named.items():
+            if n in nograd:
+                assert p.grad is None, n              # decoder_scale_5, frozen ResNet-50 encoder
+                continue
+            ref = z["grad__" + n]
+            got = p.grad.cpu().numpy()
+            if got.size != ref.size:
+                got = got.reshape(-1)[::stride]
+            if n.endswith(".model.0.bias") or n.endswith(".model.3.bias"):
+                continue                              # bias in front of an affine-free InstanceNorm: gradient is round-off noise
+            np.testing.assert_allclose(got.reshape(ref.shape), ref, atol=3e-3 * float(np.abs(ref).max()) + 1e-7, err_msg=n)
+            checked += 1
+        assert checked >= 20
+        # one full train_step from the same starting point: zero_grad + forward + backward + 2 x AdamW
+        back.load_state_dict(sd_back); teacher.load_state_dict(sd_teacher)
+        for p in named.values():
+            p.grad = None
+        step = OpenESSPretrainStep(rec, back, teacher, step.task_loss, step.nce_loss, nr_events_data_b=steps, superpixel_size=S,
+                                   lr_voxel=1e-3, lr_frame=1e-3)
+        _, _, final = step.train_step((event, None, frame, pl, sp))
+        assert float(final) == pytest.approx(float(z["step_total"]), rel=3e-4)
+        after = [k for k in z.files if k.startswith("after__")]
+        assert len(after) >= 4
+        for key in after:
+            n = key[len("after__"):]
+            ref = z[key]
+            got = named[n].detach().cpu().numpy()
+            if got.size != ref.size:
+                got = got.reshape(-1)[::stride]
+            d = np.abs(got.reshape(ref.shape) - ref)
+            # AdamW's first step moves every weight by ~lr * sign(g): entries whose gradient is round-off noise may flip sign
+            assert float(d.max()) <= 2.1e-3, n
+            assert float((d < 2e-5).mean()) > 0.98, (n, float((d < 2e-5).mean()))
+    finally:
+        im.USE_TENSOR_CORES = True
+        sn.TRAIN_ON_TENSOR_CORES = True
