@@ -110,5 +110,28 @@ def patch_reference(ref_root, voxel_mode=None):
                "openess_b200.datasets.extract_data_tools.example_loader_ddd17", stand_in=True)
     try_rebind("DSEC.utils.eventslicer", "DSEC/utils/eventslicer.py", ["EventSlicer"], "openess_b200.DSEC.utils.eventslicer",
                stand_in=True)
+    # what `models/__init__.py` exports (`from models.image_model import *`, `from models.maskclip_model import *`), without
+    # executing it: the trainers do `from models import Preprocessing, maskClipFeatureExtractor`
+    models_pkg = sys.modules.get("models")
+    if models_pkg is not None:
+        for sub in ("models.image_model", "models.maskclip_model"):
+            m = sys.modules.get(sub)
+            if m is not None:
+                for n in getattr(m, "__all__", [k for k in vars(m) if not k.startswith("_")]):
+                    if not hasattr(models_pkg, n):
+                        setattr(models_pkg, n, getattr(m, n))
+    # zero-edit drop-in of the fused pretraining step and of device-side sample assembly (training/drop_in.py): best effort,
+    # the trainer / dataset modules import their environment's optional packages (matplotlib, h5py, hdf5plugin, numba, ...)
+    from .training import drop_in
+    try:
+        pt = _load(ref_root, "training.pretrain_trainer", "training/pretrain_trainer.py")
+        done.update(drop_in.install(pretrain_trainer_module=pt))
+    except Exception as e:  # pragma: no cover - depends on the reference's optional imports
+        done["training.pretrain_trainer.OpenESSPretrainModel.task_train_step"] = e
+    try:
+        seq = _load(ref_root, "DSEC.dataset.sequence_ov", "DSEC/dataset/sequence_ov.py")
+        done.update(drop_in.install(sequence_module=seq))
+    except Exception as e:  # pragma: no cover
+        done["DSEC.dataset.sequence_ov.Sequence.__getitem__"] = e
     _PATCHED.update(done)
     return done
