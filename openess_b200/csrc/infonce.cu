@@ -8,6 +8,8 @@
 // Parallelism: grid = (row tiles) x (column splits); a CTA handles column tiles s, s+nsplit, ... and writes
 // PARTIAL results that small combine kernels reduce in a fixed order (deterministic, no float atomics).
 // M = 800 (batch 8 x 100 superpixels) would otherwise run on 13 of 148 SMs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace oess {
@@ -230,13 +232,199 @@ static int run_infonce(const float* k, const float* q, int64_t M, int Dr, float 
     return OESS_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core formulation for large M (BASELINE config 3: M = 3 200 superpixels of an exact-global batch of 32): the three
+// contractions  S = k q^T,  dk = G q,  dq = G^T k  (2 M^2 D flops each) run on the tcgen05 GEMM (oess_gemm_tf32) instead of
+// fp32 FMA tiles.  The reference computes in fp32, and the logits are divided by T = 0.07, so plain TF32 (10-bit
+// mantissa) would cost ~3 digits of the loss: every operand is split into TF32-exact parts  a = hi + lo
+// (hi = rna_tf32(a), lo = rna_tf32(a - hi))  and the product is  hi_a hi_b + hi_a lo_b + lo_a hi_b  -- ONE GEMM over a
+// 3x longer K with the parts concatenated ("3xTF32": the dropped lo_a lo_b term is 2^-22 relative, accumulation is fp32).
+//   1. k3 = [hi hi lo](k), q3 = [hi lo hi](q)            [Mp, 3 D]  (Mp = M rounded up to 4, padded rows are zero)
+//   2. S  = k3 q3^T                                        [M, Mp]     tcgen05
+//   3. lse_i, loss (one CTA per row, row in registers, deterministic final reduction in double)
+//   4. G3 = [hi hi lo](G),  G_ij = (exp(S_ij / T - lse_i) - [i == j]) / (M T)      [M, 3 Mp]
+//   5. dk = G3 qT3^T   with qT3 = [hi lo hi](q^T)  [D, 3 Mp]                           tcgen05
+//   6. S' = q3' k3'^T = S^T  (second small GEMM: cheaper and simpler than transposing G), G3 <- [hi hi lo](G^T) from S' with
+//      lse indexed by column,  dq = G3 kT3^T                                             tcgen05
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float rna_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// out[i][0:D | D:2D | 2D:3D] = pattern 0: (hi, hi, lo), pattern 1: (hi, lo, hi) of a[i][:], rows >= M zero.  a: [M, D]
+__global__ void k_nce_split3(const float* __restrict__ a, int64_t M, int D, int64_t Mp, int pattern, float* __restrict__ out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Mp * D) return;
+    const int64_t i = idx / D;
+    const int d = (int)(idx - i * D);
+    const float v = i < M ? a[idx] : 0.0f;
+    const float hi = rna_tf32(v), lo = rna_tf32(v - hi);
+    float* o = out + i * 3 * D;
+    o[d] = hi;
+    o[D + d] = pattern ? lo : hi;
+    o[2 * D + d] = pattern ? hi : lo;
+}
+
+// out[d][0:Mp | Mp:2Mp | 2Mp:3Mp] = (hi, lo, hi) of a[:, d] (a: [M, D]; columns >= M zero).  32 x 32 shared-memory transpose.
+__global__ void __launch_bounds__(256)
+k_nce_split3_t(const float* __restrict__ a, int64_t M, int D, int64_t Mp, float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int64_t i0 = (int64_t)blockIdx.x * 32;
+    const int d0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t i = i0 + r;
+        const int d = d0 + tx;
+        tile[r][tx] = (i < M && d < D) ? a[i * D + d] : 0.0f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int d = d0 + r;
+        const int64_t i = i0 + tx;
+        if (d < D && i < Mp) {
+            const float v = tile[tx][r];
+            const float hi = rna_tf32(v), lo = rna_tf32(v - hi);
+            float* o = out + (int64_t)d * 3 * Mp;
+            o[i] = hi;
+            o[Mp + i] = lo;
+            o[2 * Mp + i] = hi;
+        }
+    }
+}
+
+// one CTA per row i of S [M, ld]: lse_i = logsumexp_j<M (S_ij * inv_T), rowloss_i = lse_i - S_ii * inv_T
+__global__ void __launch_bounds__(256)
+k_nce_rows(const float* __restrict__ S, int64_t M, int64_t ld, float inv_T, float* __restrict__ lse, float* __restrict__ rowloss) {
+    __shared__ float s_red[8];
+    const int64_t i = blockIdx.x;
+    const float* row = S + i * ld;
+    float m = -INFINITY;
+    for (int64_t j = threadIdx.x; j < M; j += 256) m = fmaxf(m, row[j] * inv_T);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = s_red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
+    __syncthreads();
+    float l = 0.0f;
+    for (int64_t j = threadIdx.x; j < M; j += 256) l += expf(row[j] * inv_T - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = l;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.0f;
+        for (int w = 0; w < 8; ++w) t += s_red[w];
+        const float lg = logf(t);
+        lse[i] = m + lg;
+        rowloss[i] = (m - row[i] * inv_T) + lg;      // lse - s_ii without cancelling two numbers of magnitude 1 / T
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+k_nce_loss(const float* __restrict__ rowloss, int64_t M, float* __restrict__ loss) {
+    __shared__ double s_red[32];
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < M; i += 1024) a += (double)rowloss[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 32; ++k) t += s_red[k];
+        loss[0] = (float)(t / (double)M);                    // CrossEntropyLoss mean reduction
+    }
+}
+
+// G3[r][0:Mp | Mp:2Mp | 2Mp:3Mp] = (hi, hi, lo) of G[r][c] = (exp(X[r][c] * inv_T - lse[by_col ? c : r]) - [r == c]) * inv_MT,
+// columns >= M zero.  X: [M, ld]
+__global__ void __launch_bounds__(256)
+k_nce_grad_split(const float* __restrict__ X, int64_t M, int64_t Mp, int64_t ld, float inv_T, float inv_MT,
+                 const float* __restrict__ lse, int by_col, float* __restrict__ G3) {
+    const int64_t r = blockIdx.y;
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= Mp) return;
+    float g = 0.0f;
+    if (c < M) g = (expf(X[r * ld + c] * inv_T - lse[by_col ? c : r]) - (r == c ? 1.0f : 0.0f)) * inv_MT;
+    const float hi = rna_tf32(g), lo = rna_tf32(g - hi);
+    float* o = G3 + r * 3 * Mp;
+    o[c] = hi;
+    o[Mp + c] = hi;
+    o[2 * Mp + c] = lo;
+}
+
+struct NceTcWs {
+    float *k3, *q3, *qa3, *kb3, *qT3, *kT3, *S, *G3, *lse, *rowloss;
+    size_t bytes;
+};
+static NceTcWs nce_tc_carve(void* ws, int64_t M, int D) {
+    NceTcWs r{};
+    WsCarver c(ws);
+    const int64_t Mp = (M + 3) & ~(int64_t)3;
+    r.k3 = c.take<float>((size_t)Mp * 3 * D);     // (hi hi lo)(k): A operand of S
+    r.q3 = c.take<float>((size_t)Mp * 3 * D);     // (hi lo hi)(q): B operand of S
+    r.qa3 = c.take<float>((size_t)Mp * 3 * D);    // (hi hi lo)(q): A operand of S^T
+    r.kb3 = c.take<float>((size_t)Mp * 3 * D);    // (hi lo hi)(k): B operand of S^T
+    r.qT3 = c.take<float>((size_t)D * 3 * Mp);
+    r.kT3 = c.take<float>((size_t)D * 3 * Mp);
+    r.S = c.take<float>((size_t)M * Mp);
+    r.G3 = c.take<float>((size_t)M * 3 * Mp);
+    r.lse = c.take<float>((size_t)M);
+    r.rowloss = c.take<float>((size_t)M);
+    r.bytes = c.total();
+    return r;
+}
+
+static bool nce_use_tc(int64_t M, int D) {
+    static const int mode = [] { const char* e = getenv("OESS_INFONCE"); return e ? (e[0] == 's' ? 0 : e[0] == 't' ? 2 : 1) : 1; }();
+    if (mode == 0 || (D & 3) || M >= (1ll << 30)) return false;
+    return mode == 2 ? true : M >= 1024;      // below ~1 k rows the fp32 tiles win (launch count, operand splitting)
+}
+
+static int run_infonce_tc(const float* k, const float* q, int64_t M, int D, float T, float* loss, float* dk, float* dq,
+                          const NceTcWs& w, cudaStream_t st) {
+    const int64_t Mp = (M + 3) & ~(int64_t)3;
+    const float inv_T = 1.0f / T, inv_MT = inv_T / (float)M;
+    const unsigned sb = (unsigned)((Mp * D + 255) / 256);
+    OESS_KERNEL("nce_split3", st, k_nce_split3<<<sb, 256, 0, st>>>(k, M, D, Mp, 0, w.k3));
+    OESS_KERNEL("nce_split3", st, k_nce_split3<<<sb, 256, 0, st>>>(q, M, D, Mp, 1, w.q3));
+    int rc = oess_gemm_tf32(w.k3, w.q3, nullptr, w.S, M, (int)Mp, 3 * D, (oess_stream_t)st);      // S = k q^T
+    if (rc) return rc;
+    OESS_KERNEL("nce_rows", st, k_nce_rows<<<(unsigned)M, 256, 0, st>>>(w.S, M, Mp, inv_T, w.lse, w.rowloss));
+    OESS_KERNEL("nce_loss", st, k_nce_loss<<<1, 1024, 0, st>>>(w.rowloss, M, loss));
+    const dim3 gg((unsigned)((Mp + 255) / 256), (unsigned)M), tg((unsigned)((Mp + 31) / 32), (unsigned)((D + 31) / 32));
+    if (dk) {
+        OESS_KERNEL("nce_grad_split", st, k_nce_grad_split<<<gg, 256, 0, st>>>(w.S, M, Mp, Mp, inv_T, inv_MT, w.lse, 0, w.G3));
+        OESS_KERNEL("nce_split3_t", st, k_nce_split3_t<<<tg, 256, 0, st>>>(q, M, D, Mp, w.qT3));
+        rc = oess_gemm_tf32(w.G3, w.qT3, nullptr, dk, M, D, (int)(3 * Mp), (oess_stream_t)st);                 // dk = G q
+        if (rc) return rc;
+    }
+    if (dq) {
+        OESS_KERNEL("nce_split3", st, k_nce_split3<<<sb, 256, 0, st>>>(q, M, D, Mp, 0, w.qa3));
+        OESS_KERNEL("nce_split3", st, k_nce_split3<<<sb, 256, 0, st>>>(k, M, D, Mp, 1, w.kb3));
+        rc = oess_gemm_tf32(w.qa3, w.kb3, nullptr, w.S, M, (int)Mp, 3 * D, (oess_stream_t)st);   // S^T = q k^T
+        if (rc) return rc;
+        OESS_KERNEL("nce_grad_split", st, k_nce_grad_split<<<gg, 256, 0, st>>>(w.S, M, Mp, Mp, inv_T, inv_MT, w.lse, 1, w.G3));
+        OESS_KERNEL("nce_split3_t", st, k_nce_split3_t<<<tg, 256, 0, st>>>(k, M, D, Mp, w.kT3));
+        rc = oess_gemm_tf32(w.G3, w.kT3, nullptr, dq, M, D, (int)(3 * Mp), (oess_stream_t)st);                 // dq = G^T k
+        if (rc) return rc;
+    }
+    return OESS_OK;
+}
+
 }  // namespace oess
 
 using namespace oess;
 
 OESS_API int oess_infonce_ws_bytes(int64_t M, int D, size_t* ws_bytes) {
     if (!ws_bytes || M <= 0 || D <= 0) return OESS_E_ARG;
-    *ws_bytes = nce_carve(nullptr, M, D).bytes;
+    *ws_bytes = nce_use_tc(M, D) ? nce_tc_carve(nullptr, M, D).bytes : nce_carve(nullptr, M, D).bytes;
     return OESS_OK;
 }
 
@@ -247,8 +435,9 @@ OESS_API int oess_infonce(const float* k, const float* q, int64_t M, int D, floa
     if (rc) return rc;
     if (!k || !q || !loss) return OESS_E_ARG;
     if (!ws || ws_bytes < need) return OESS_E_WORKSPACE;
-    const NceWs w = nce_carve(ws, M, D);
     cudaStream_t st = (cudaStream_t)stream;
+    if (nce_use_tc(M, D)) return run_infonce_tc(k, q, M, D, temperature, loss, dk, dq, nce_tc_carve(ws, M, D), st);
+    const NceWs w = nce_carve(ws, M, D);
     // feature width D is zero-padded to 16 * DC columns (OpenESS uses D = 256)
     if (D <= 16) return run_infonce<1>(k, q, M, D, temperature, loss, dk, dq, w, st);
     if (D <= 32) return run_infonce<2>(k, q, M, D, temperature, loss, dk, dq, w, st);

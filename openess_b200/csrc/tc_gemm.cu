@@ -252,8 +252,14 @@ OESS_API int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias
     // fewer tiles than SMs: a second resident CTA has nothing to overlap with, the deeper ring hides the load latency instead
     const int64_t tiles = ((M + 127) / 128) * (int64_t)((N + (N > 128 ? 255 : (N > 64 ? 127 : 63))) / (N > 128 ? 256 : (N > 64 ? 128 : 64)));
     if (variant == 0 || (variant == 1 && tiles <= kNumSMs)) {
-        if (N > 128) return tc::launch_gemm<256, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
-        if (N > 64) return tc::launch_gemm<128, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
+        // tall-skinny products (e.g. the InfoNCE gradient G q: M = 3 200, N = 256, K = 9 600 -> 25 tiles of 128 x 256): narrower
+        // N tiles put more SMs to work; the extra A-tile reads hit L2
+        const int64_t mt = (M + 127) / 128;
+        const bool few = variant == 1 && tiles * 5 < kNumSMs * 3;
+        const int bn = !few ? (N > 128 ? 256 : (N > 64 ? 128 : 64))
+                            : ((N > 128 && mt * ((N + 127) / 128) * 5 >= kNumSMs * 3) ? 128 : 64);
+        if (bn == 256) return tc::launch_gemm<256, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
+        if (bn == 128) return tc::launch_gemm<128, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
         return tc::launch_gemm<64, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
     }
     if (variant == 1) {

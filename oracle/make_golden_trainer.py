@@ -216,11 +216,83 @@ def golden_reconstructor(R):
     print("reconstructor.npz", os.path.getsize(os.path.join(OUT, "reconstructor.npz")) // 1024, "KiB")
 
 
+def golden_openess_step(R):
+    """training/openess_trainer.py:OpenESSModel, `frame2recon` branch (the only coherent one):
+    task_train_step (:360-372, 476-529) and train_step (:339-358) of the unmodified class with two reference
+    deeplabv3_resnet50 networks (seeded weights, Dropout p = 0 for determinism)."""
+    from seeded_weights import seeded_state_dict
+    import training.openess_trainer as ot
+    from models.deeplabv3 import deeplabv3_resnet50
+    torch.manual_seed(1205)
+    K = 11
+    nets = []
+    for seed in (4, 5):
+        m = deeplabv3_resnet50(num_classes=K, text_embeddings_path=None, output_stride=32, pretrained_backbone='')
+        m.load_state_dict(seeded_state_dict(m, seed), strict=True)
+        m.classifier.ASPP.project[3].p = 0.0
+        nets.append(m)
+    model_frame, model_recon = nets
+    rng = np.random.default_rng(21)
+    B, H, W = 2, 64, 96
+    frame = torch.from_numpy(rng.random((B, 3, H, W)).astype(np.float32))
+    recon = torch.from_numpy(rng.random((B, 3, H, W)).astype(np.float32))
+    pl = rng.integers(0, K, (B, H, W))
+    pl[rng.random(pl.shape) < 0.03] = 255
+    pl = torch.from_numpy(pl.astype(np.int64))
+    sp = torch.from_numpy(rng.integers(0, 30, (B, H, W)).astype(np.int64))
+    settings = SimpleNamespace(config_option='frame2recon', if_spatial_contrastive=True, weight_task_loss=1.0,
+                               lr_recon=1e-3, lr_frame=1e-3, task_loss=['dice', 'cross_entropy'], semseg_num_classes=K,
+                               semseg_ignore_label=255, logger=logging.getLogger("golden"))
+    T = ot.OpenESSModel
+    tr = object.__new__(T)
+    tr.is_training, tr.settings, tr.device, tr.epoch_count = True, settings, torch.device("cpu"), 0
+    tr.model_frame, tr.model_recon = model_frame, model_recon
+    tr.models_dict = {"model_recon": model_recon, "model_frame": model_frame}
+    tr.task_loss = R.TaskLoss(losses=settings.task_loss, gamma=2.0, num_classes=K, ignore_index=255, reduction='mean')
+    tr.l1_loss = torch.nn.L1Loss()
+    tr.nce_loss = R.NCELoss(temperature=0.07)
+    T.createOptimizerDict(tr)
+    sd = [{k: v.clone() for k, v in m.state_dict().items()} for m in nets]
+    batch = (frame, None, recon, pl, sp)
+    t_loss, losses, _ = T.task_train_step(tr, batch)
+    t_loss.backward()
+    d = {"frame": frame.numpy(), "recon": recon.numpy(), "pl": pl.numpy(), "sp": sp.numpy(), "K": np.array(K),
+         "total": np.array(t_loss.item())}
+    for k, v in losses.items():
+        d["loss__" + k] = np.array(v.item())
+    picks = ("classifier.text_embeddings", "classifier.ASPP.project.0.weight", "backbone.conv1.weight",
+             "backbone.layer4.2.conv3.weight", "classifier.classifier.0.weight")
+    for prefix, m in (("model_frame.", model_frame), ("model_recon.", model_recon)):
+        named = dict(m.named_parameters())
+        for n in picks:
+            g = named[n].grad.numpy()
+            d["grad__" + prefix + n] = g if g.size < 50_000 else g.reshape(-1)[::STRIDE * 7].copy()
+        d["nograd__" + prefix] = np.array([n for n, p in named.items() if p.grad is None])
+    for m, s0 in zip(nets, sd):
+        m.load_state_dict(s0)
+        for p in m.parameters():
+            p.grad = None
+    T.createOptimizerDict(tr)
+    _, _, final = T.train_step(tr, batch)
+    d["step_total"] = np.array(final.item())
+    for prefix, m in (("model_frame.", model_frame), ("model_recon.", model_recon)):
+        named = dict(m.named_parameters())
+        for n in ("classifier.text_embeddings", "backbone.conv1.weight"):
+            v = named[n].detach().numpy()
+            d["after__" + prefix + n] = v.copy() if v.size < 50_000 else v.reshape(-1)[::STRIDE * 7].copy()
+    d["stride"] = np.array(STRIDE * 7)
+    np.savez_compressed(os.path.join(OUT, "openess_step.npz"), **d)
+    print("openess_step.npz", os.path.getsize(os.path.join(OUT, "openess_step.npz")) // 1024, "KiB",
+          {k: float(v) for k, v in d.items() if k.startswith("loss__") or k in ("total", "step_total")})
+
+
 def main():
     torch.set_num_threads(1)
     R = import_reference()
-    golden_reconstructor(R)
-    golden_pretrain_step(R)
+    if "--openess-only" not in sys.argv:
+        golden_reconstructor(R)
+        golden_pretrain_step(R)
+    golden_openess_step(R)
 
 
 if __name__ == "__main__":

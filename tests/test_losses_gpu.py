@@ -101,7 +101,7 @@ def test_segpool_vs_oracle(dev, oracle, B, Cf, H, W, S):
     assert int(st.item()) == 1
 
 
-@pytest.mark.parametrize("M,D", [(50, 32), (200, 256), (801, 256), (130, 64), (3200, 256)])
+@pytest.mark.parametrize("M,D", [(50, 32), (200, 256), (801, 256), (130, 64), (3200, 256), (1027, 256), (2050, 64)])
 def test_infonce_vs_oracle(dev, oracle, M, D):
     from openess_b200 import losses
     rng = np.random.default_rng(M)
@@ -122,7 +122,9 @@ def test_infonce_vs_oracle(dev, oracle, M, D):
     kd = torch.from_numpy(k).to(dev).requires_grad_(True)
     qd = torch.from_numpy(q).to(dev).requires_grad_(True)
     loss = losses.infonce(kd, qd, 0.07)
-    assert float(loss) == pytest.approx(ref_loss, rel=2e-5)
+    # M >= 1024: tensor-core path ("3xTF32" operand splitting, fp32 accumulate); the loss is the mean of lse_i - s_ii with both
+    # terms of magnitude 1 / T = 14.3, i.e. one fp32 ulp there (9.5e-7) is 2e-5 of a loss of 0.05
+    assert float(loss) == pytest.approx(ref_loss, rel=4e-5 if M >= 1024 else 2e-5)
     loss.backward()
     np.testing.assert_allclose(kd.grad.cpu().numpy(), rdk, rtol=2e-4, atol=2e-7)
     np.testing.assert_allclose(qd.grad.cpu().numpy(), rdq, rtol=2e-4, atol=2e-7)

@@ -193,7 +193,9 @@ def test_pretrain_step_matches_reference_trainer_golden():
     sd_teacher = {k: v.clone() for k, v in teacher.state_dict().items()}
     im.USE_TENSOR_CORES = False                       # fp32 modules: the golden is the reference's fp32 CPU run
     sn.TRAIN_ON_TENSOR_CORES = False
-    try:
+    tf32_was = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False           # torch's default TF32 convolutions drift by percents through the 16 conv +
+    try:                                              # InstanceNorm layers of the (x8-weight-scaled) tiny SemSegE2VID trunk
         rec = ImageReconstructor(e2vid, H, W, 5, dev, opts)
         step = OpenESSPretrainStep(rec, back, teacher, TaskLoss(losses=['dice', 'cross_entropy'], num_classes=K, ignore_index=255),
                                    NCELoss(temperature=0.07), nr_events_data_b=steps, superpixel_size=S, lr_voxel=1e-3, lr_frame=1e-3)
@@ -242,5 +244,6 @@ def test_pretrain_step_matches_reference_trainer_golden():
             assert float(d.max()) <= 2.1e-3, n
             assert float((d < 2e-5).mean()) > 0.98, (n, float((d < 2e-5).mean()))
     finally:
+        torch.backends.cudnn.allow_tf32 = tf32_was
         im.USE_TENSOR_CORES = True
         sn.TRAIN_ON_TENSOR_CORES = True
