@@ -241,6 +241,8 @@ def run_ours(args):
             with torch.cuda.stream(vstreams[k]):
                 batch(i * INNER + j, m, k)
 
+    last_per_rank = []
+
     def timed(fn, steps, profile=False, warm=None):
         for i in range(Wm if warm is None else warm):
             fn(i)
@@ -263,13 +265,19 @@ def run_ours(args):
             prof.__exit__(None, None, None)
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
+            per_rank = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(per_rank, ms)
+            last_per_rank[:] = [float(t.item()) for t in per_rank]
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        else:
+            last_per_rank[:] = [float(ms.item())]
         return float(ms.item()), _lib.launch_count() - launches0, (prof.kernels if prof else {})
 
     # ---- device-resident throughput on ONE stream (the `value`), clocks sampled during the timed region
     sampler = ClockSampler(local)
     sampler.start()
     ms, launches, _ = timed(step, K)
+    ms_per_rank = list(last_per_rank)
     clocks = sampler.stop()
     frames_per_step = F * INNER
     value = world * frames_per_step * K / (ms * 1e-3)
@@ -414,7 +422,7 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args),
         "arm": {"step": f"one step = {INNER} consecutive batches of F={F} frames = {frames_per_step} frames per GPU; ONE CUDA stream",
-                "timed_region_s": ms * 1e-3,
+                "timed_region_s": ms * 1e-3, "timed_region_ms_per_rank": ms_per_rank,
                 "l2": f"raw inputs {9 * F * N_EVENTS / 1e6:.0f} MB + float32 event arrays {16 * F * N_EVENTS / 1e6:.0f} MB + outputs "
                       f"{4 * F * C * H * W / 1e6:.0f} MB per batch > 126 MB L2; two input sets alternated",
                 "parallelism": f"frames sharded over {world} GPU(s), no data-path collective", "cpu_affinity": affinity},

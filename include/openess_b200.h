@@ -392,6 +392,16 @@ int oess_upnorm_pool_bwd(const float* d, const int64_t* seg, const float* g_sum,
  * tensor-core head convolution of E2VID (e2vid/model/unet.py:126-127: 5 event channels). */
 int oess_planes_to_nhwc_padded(const float* x, int B, int C, int64_t HW, const double* stats, int Cp, float* y,
                                oess_stream_t stream);
+/* Same with every row zero-padded by pad_w pixels at both ends: y [B, H, W + 2 pad_w, Cp]. */
+int oess_planes_to_nhwc_padded_w(const float* x, int B, int C, int H, int W, const double* stats, int Cp, int pad_w,
+                                 float* y, oess_stream_t stream);
+/* Thin-input stride-1 convolution (E2VID head conv, e2vid/model/unet.py:126-127: 5 -> 32 channels, 5 x 5): the KW taps of a
+ * kernel row are folded into the channel dimension through an overlapping-window tensor map, K = KH * roundup(KW * Cin, 32)
+ * instead of KH * KW * 32.  x: [B, H, W + KW - 1, Cin] channels-last, rows zero-padded by (KW - 1) / 2 pixels at both ends
+ * (oess_planes_to_nhwc_padded_w), Cin % 4 == 0, KW * Cin <= 256; w_packed: [Cout, KH * roundup(KW * Cin, 32)] with column
+ * (ky, kx * Cin + c); y: [B, H, W, Cout]; relu bit 0: ReLU, bit 1: store rounded to TF32.  TF32 operands, fp32 accumulate. */
+int oess_conv2d_nhwc_tf32_rowunfold(const float* x, const float* w_packed, const float* bias, float* y, int B, int H, int W,
+                                    int Cin, int Cout, int KH, int KW, int relu, oess_stream_t stream);
 
 /* Weight gradient of a stride-1 convolution as a tcgen05 split-K GEMM over pixels (TF32 operands, fp32 accumulate):
  *   dW[co, ci, ky, kx] = sum_{b,y,x} dy[b, co, y, x] * x[b, ci, y + ky dil - pad, x + kx dil - pad]

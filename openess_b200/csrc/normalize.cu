@@ -91,7 +91,7 @@ k_apply(float* __restrict__ x, int64_t group_numel, const double* __restrict__ s
 // a 16-byte-aligned TMA row).
 __global__ void __launch_bounds__(kThreads)
 k_to_nhwc_padded(const float* __restrict__ x, int C, int64_t HW, int64_t total, const double* __restrict__ stats, int Cp,
-                 float* __restrict__ y) {
+                 float* __restrict__ y, int W, int pad_w) {
     bool norm = false;
     float mean = 0.f, sd = 1.f;
     if (stats) {
@@ -107,7 +107,9 @@ k_to_nhwc_padded(const float* __restrict__ x, int C, int64_t HW, int64_t total, 
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
         const int64_t b = i / HW, px = i - b * HW;
         const float* xp = x + b * C * HW + px;
-        float* yp = y + i * Cp;
+        // pad_w > 0: the output rows are W + 2 pad_w pixels wide with zero borders (written by k_zero_borders)
+        const int64_t row = (b * HW + px) / W;
+        float* yp = y + (pad_w ? (i + (2 * row + 1) * (int64_t)pad_w) : i) * Cp;
         for (int c0 = 0; c0 < Cp; c0 += 4) {
             float v[4];
 #pragma unroll
@@ -122,10 +124,37 @@ k_to_nhwc_padded(const float* __restrict__ x, int C, int64_t HW, int64_t total, 
     }
 }
 
+// zero the pad_w border pixels at both ends of every row of y [rows, W + 2 pad_w, Cp]
+__global__ void k_zero_borders(float* __restrict__ y, int64_t rows, int W, int pad_w, int Cp) {
+    const int64_t n = rows * 2 * pad_w * Cp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / (2 * pad_w * Cp);
+        const int j = (int)(i - r * 2 * pad_w * Cp);
+        const int px = j / Cp, c = j - px * Cp;
+        const int col = px < pad_w ? px : W + px;          // left border, then right border
+        y[(r * (W + 2 * pad_w) + col) * Cp + c] = 0.0f;
+    }
+}
+
 }  // namespace norm
 }  // namespace oess
 
 using namespace oess;
+
+// Same as oess_planes_to_nhwc_padded with the rows additionally zero-padded by pad_w pixels at both ends:
+// y [B, H, W + 2 pad_w, Cp] (the input layout of oess_conv2d_nhwc_tf32_rowunfold).
+OESS_API int oess_planes_to_nhwc_padded_w(const float* x, int B, int C, int H, int W, const double* stats, int Cp, int pad_w,
+                                          float* y, oess_stream_t stream) {
+    if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0 || Cp < C || (Cp & 3) || pad_w <= 0 || ((uintptr_t)y & 15)) return OESS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t HW = (int64_t)H * W, total = (int64_t)B * HW;
+    int64_t blocks = (total + norm::kThreads - 1) / norm::kThreads;
+    if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+    OESS_KERNEL("k_zero_borders", st, norm::k_zero_borders<<<kNumSMs, 256, 0, st>>>(y, (int64_t)B * H, W, pad_w, Cp));
+    OESS_KERNEL("k_to_nhwc_padded", st, norm::k_to_nhwc_padded<<<(unsigned)blocks, norm::kThreads, 0, st>>>(
+        x, C, HW, total, stats, Cp, y, W, pad_w));
+    return OESS_OK;
+}
 
 OESS_API int oess_planes_to_nhwc_padded(const float* x, int B, int C, int64_t HW, const double* stats, int Cp, float* y,
                                         oess_stream_t stream) {
@@ -135,7 +164,7 @@ OESS_API int oess_planes_to_nhwc_padded(const float* x, int B, int C, int64_t HW
     int64_t blocks = (total + norm::kThreads - 1) / norm::kThreads;
     if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
     OESS_KERNEL("k_to_nhwc_padded", st, norm::k_to_nhwc_padded<<<(unsigned)blocks, norm::kThreads, 0, st>>>(
-        x, C, HW, total, stats, Cp, y));
+        x, C, HW, total, stats, Cp, y, 1, 0));
     return OESS_OK;
 }
 

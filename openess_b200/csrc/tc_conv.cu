@@ -27,7 +27,7 @@ struct ConvSmem {
 };
 
 struct ConvArgs {
-    int Ho, Wo, Cout, KW, taps, chunks, stride, pad, dil, relu, tiles_w;
+    int Ho, Wo, Cout, KW, taps, chunks, stride, pad, pad_x, dil, relu, tiles_w;   // pad: rows, pad_x: columns
     int stats_stride;   // doubles between the statistics of consecutive samples (0: one set for the whole batch)
 };
 
@@ -77,7 +77,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                 mbar_wait(&empty[s], ((kb / kVStages) & 1) ^ 1);
                 mbar_expect_tx(&full[s], kVABytes + S::kBBytes);
                 const int ky = tap / a.KW, kx = tap - ky * a.KW;
-                tma_load_4d(sA + s * kVABytes, &tmX, &full[s], chunk * kBlockK, w0 * a.stride - a.pad + kx * a.dil,
+                tma_load_4d(sA + s * kVABytes, &tmX, &full[s], chunk * kBlockK, w0 * a.stride - a.pad_x + kx * a.dil,
                             h0 * a.stride - a.pad + ky * a.dil, b);
                 tma_load_2d(sB + s * S::kBBytes, &tmW, &full[s], kb * kBlockK, n0);
                 if (++chunk == a.chunks) { chunk = 0; ++tap; }
@@ -257,13 +257,44 @@ static int conv2d_impl(const float* x, const float* w_packed, const float* bias,
     const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
     int rc = tc::make_tmap_f32_strided(&tmX, x, 4, dims, strides, box, estr);
     if (rc) return rc;
-    tc::ConvArgs a{Ho, Wo, Cout, KW, KH * KW, chunks, stride, pad, dil, relu & 3, (Wo + tc::kVW - 1) / tc::kVW,
+    tc::ConvArgs a{Ho, Wo, Cout, KW, KH * KW, chunks, stride, pad, pad, dil, relu & 3, (Wo + tc::kVW - 1) / tc::kVW,
                    per_sample ? 2 * Cout : 0};
     if (bn_sums) OESS_CUDA(cudaMemsetAsync(bn_sums, 0, sizeof(double) * 2 * (size_t)Cout * (per_sample ? B : 1), st));
     if (Cout > 128) return tc::launch_conv<256>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
     if (Cout > 64) return tc::launch_conv<128>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
     if (Cout > 32) return tc::launch_conv<64>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
     return tc::launch_conv<32>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
+}
+
+// Thin-input convolution (E2VID head: 5 event channels padded to 8, 5 x 5 kernel, unet.py:126-127).  With one K block of 32
+// channels per tap, 25 taps x 32 = 800 K columns carry 25 x 5 useful ones.  Here the KW taps of a kernel row are folded into the
+// channel dimension instead: the A operand of tap ky is the OVERLAPPING window x[b, oy + ky - pad, ox .. ox + KW), all Cin
+// channels = KW * Cin contiguous floats of the channels-last row -- a tensor map whose pixel stride (Cin floats) is smaller than
+// its innermost extent (KW * Cin floats).  K = KH * roundup(KW * Cin, 32) (5 x 64 = 320 for the head).  x must be zero-padded
+// by (KW - 1) / 2 pixels at both row ends: x [B, H, W + KW - 1, Cin] (oess_planes_to_nhwc_padded_w); rows are padded by the
+// TMA out-of-bounds fill as usual.  w_packed: [Cout, KH * chunks * 32], column (ky, kx * Cin + c).  Stride 1, dilation 1.
+OESS_API int oess_conv2d_nhwc_tf32_rowunfold(const float* x, const float* w_packed, const float* bias, float* y, int B, int H,
+                                             int W, int Cin, int Cout, int KH, int KW, int relu, oess_stream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || !(KH & 1) || !(KW & 1)) return OESS_E_ARG;
+    if (!x || !w_packed || !y || (Cin & 3) || KW * Cin > 256 || KH > 64) return OESS_E_ARG;
+    if (((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)bias | (uintptr_t)y) & 15) return OESS_E_ARG;
+    if (B > 65535) return OESS_E_RANGE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Wp = W + KW - 1, Cv = KW * Cin;
+    const int chunks = (Cv + tc::kBlockK - 1) / tc::kBlockK;
+    const int Ktot = KH * chunks * tc::kBlockK;
+    CUtensorMap tmX;
+    const uint64_t dims[4] = {(uint64_t)Cv, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cin * 4, (uint64_t)Wp * Cin * 4, (uint64_t)H * Wp * Cin * 4};
+    const uint32_t box[4] = {tc::kBlockK, (uint32_t)tc::kVW, (uint32_t)tc::kVH, 1};
+    const uint32_t estr[4] = {1, 1, 1, 1};
+    int rc = tc::make_tmap_f32_strided(&tmX, x, 4, dims, strides, box, estr);
+    if (rc) return rc;
+    tc::ConvArgs a{H, W, Cout, 1, KH, chunks, 1, (KH - 1) / 2, 0, 1, relu & 3, (W + tc::kVW - 1) / tc::kVW, 0};
+    if (Cout > 128) return tc::launch_conv<256>(tmX, w_packed, Cout, Ktot, bias, nullptr, y, nullptr, a, B, st);
+    if (Cout > 64) return tc::launch_conv<128>(tmX, w_packed, Cout, Ktot, bias, nullptr, y, nullptr, a, B, st);
+    if (Cout > 32) return tc::launch_conv<64>(tmX, w_packed, Cout, Ktot, bias, nullptr, y, nullptr, a, B, st);
+    return tc::launch_conv<32>(tmX, w_packed, Cout, Ktot, bias, nullptr, y, nullptr, a, B, st);
 }
 
 OESS_API int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,

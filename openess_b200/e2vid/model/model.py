@@ -241,10 +241,20 @@ class UNetRecurrent(nn.Module):
         conv = self.head.conv2d
         w, b = conv.weight, conv.bias
         key = (w.data_ptr(), w._version, w.device)
+        k = conv.kernel_size[0]
+        # odd 'same' kernels: the taps of a kernel row are folded into the channel dimension (oess_conv2d_nhwc_tf32_rowunfold:
+        # K = 5 x 64 instead of 25 x 32 for the 5 x 5 head of E2VID)
+        unfold = (conv.kernel_size[0] == conv.kernel_size[1] and k % 2 == 1 and conv.stride[0] == 1 and conv.dilation[0] == 1
+                  and conv.padding[0] == k // 2 and k * 8 <= 256)
         if getattr(self, "_head_packed", None) is None or self._head_packed[0] != key:
             wpad = torch.zeros(w.shape[0], 8, w.shape[2], w.shape[3], dtype=torch.float32, device=w.device)
             wpad[:, :w.shape[1]] = w.detach()
-            self._head_packed = (key, _tc.conv2d_pack(wpad), None if b is None else b.detach().float().contiguous())
+            self._head_packed = (key, _tc.conv2d_pack_rowunfold(wpad) if unfold else _tc.conv2d_pack(wpad),
+                                 None if b is None else b.detach().float().contiguous())
+        if unfold:
+            x8 = _tc.planes_to_nhwc_padded_w(x, 8, k // 2)
+            return _tc.conv2d_rowunfold(x8, self._head_packed[1], self._head_packed[2], k, k, x.shape[3],
+                                        relu=self.head.activation is not None)
         x8 = _tc.planes_to_nhwc_padded(x, 8)
         return _tc.conv2d_tc(x8, self._head_packed[1], self._head_packed[2], conv.kernel_size[0], conv.stride[0],
                              conv.padding[0], conv.dilation[0], relu=self.head.activation is not None)

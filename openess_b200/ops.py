@@ -437,6 +437,47 @@ def planes_to_nhwc_padded(x, cp, stats=None):
     return y
 
 
+def planes_to_nhwc_padded_w(x, cp, pad_w, stats=None):
+    """planes_to_nhwc_padded with the rows zero-padded by pad_w pixels at both ends: returns the raw [B, H, W + 2 pad_w, cp]
+    channels-last buffer (input of conv2d_rowunfold)."""
+    _lib.require_cuda(x)
+    x = _f32c(x)
+    B, C, H, W = x.shape
+    y = torch.empty((B, H, W + 2 * pad_w, cp), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().oess_planes_to_nhwc_padded_w(ptr(x), B, C, H, W, ptr(stats), cp, pad_w, ptr(y), stream_ptr(x.device)),
+              "oess_planes_to_nhwc_padded_w")
+    return y
+
+
+def conv2d_pack_rowunfold(weight):
+    """[Cout, Cin, KH, KW] -> [Cout, KH * roundup(KW * Cin, 32)], column (ky, kx * Cin + c): the K order of
+    oess_conv2d_nhwc_tf32_rowunfold (thin-input convolution: the taps of a kernel row folded into the channel dimension)."""
+    Cout, Cin, KH, KW = weight.shape
+    cv = KW * Cin
+    cvp = (cv + 31) // 32 * 32
+    w = torch.zeros(Cout, KH, cvp, dtype=torch.float32, device=weight.device)
+    w[:, :, :cv] = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, KH, cv)
+    return round_tf32(w.reshape(Cout, KH * cvp).contiguous())
+
+
+def conv2d_rowunfold(x_padded, w_packed, bias, KH, KW, W, relu=False, round_out=False):
+    """Stride-1 'same' convolution of a thin channels-last input on the tensor cores.  x_padded: [B, H, W + KW - 1, Cin] from
+    planes_to_nhwc_padded_w; returns [B, Cout, H, W] channels-last."""
+    _lib.require_cuda(x_padded, w_packed, bias)
+    B, H, Wp, Cin = x_padded.shape
+    if Wp != W + KW - 1 or not x_padded.is_contiguous():
+        raise ValueError("conv2d_rowunfold: x_padded must be a contiguous [B, H, W + KW - 1, Cin] tensor")
+    Cout = w_packed.shape[0]
+    y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x_padded.device, memory_format=torch.channels_last)
+    bc = None if bias is None else _f32c(bias)
+    with torch.cuda.device(x_padded.device):
+        check(lib().oess_conv2d_nhwc_tf32_rowunfold(ptr(x_padded), ptr(w_packed), ptr(bc), ptr(y), B, H, W, Cin, Cout, KH, KW,
+                                                    (1 if relu else 0) | (2 if round_out else 0), stream_ptr(x_padded.device)),
+              "oess_conv2d_nhwc_tf32_rowunfold")
+    return y
+
+
 def conv_in(x, w_packed, bias, kernel_size, stride=1, padding=0, dilation=1, eps=1e-5, residual=None, relu=False):
     """act(InstanceNorm2d(conv(x) + bias) + residual) on the tensor cores, forward only (no autograd): per-sample
     statistics are accumulated in the conv's TMEM epilogue, one in-place pass normalises."""
