@@ -284,6 +284,27 @@ def run_ours(args):
     # ---- per-kernel CUDA-event times: a few batches under the library's launch recorder
     KP = max(2, min(K, 4))
     ms_p, _, kernels = timed(lambda i: batch(i), KP * 4, profile=True, warm=2)
+    # ---- the two halves of the workload separately (uniform frames and the edge-clustered variant)
+    variants = {}
+    alg_frame = 16 * N_EVENTS + 4 * C * H * W
+    peak_v = 6545.0
+    try:
+        peak_v = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    for vname, ce in (("uniform_frames_only", 0), ("edge_clustered_frames_only", 1)):
+        vraw = [torch.from_numpy(a).to(dev) for a in synth_raw_frames(rng, F, clustered_every=ce)]
+
+        def vbatch(j, vraw=vraw):
+            voxel.dsec_events_to_voxel_grid(*vraw, rmap, C, frame_offsets=fo, mode=mode, out=outs[0], scratch=scratches[0])
+        ms_v1, _, kv = timed(vbatch, 8, profile=True, warm=2)
+        conv_ms = sum(v[1] for k, v in kv.items() if k != "dsec_rectify_tnorm") / 8
+        dk = max(kv.items(), key=lambda kv_: kv_[1][1])
+        variants[vname] = {"value": world * F * 8 / (ms_v1 * 1e-3), "unit": UNIT, "ms_per_batch": ms_v1 / 8,
+                           "dominant_kernel": dk[0], "dominant_kernel_ms": dk[1][1] / max(dk[1][0], 1),
+                           "roofline_frac_dominant_kernel": alg_frame * F / (dk[1][1] / max(dk[1][0], 1) * 1e-3) / 1e9 / peak_v,
+                           "path_frac_convert_only": alg_frame * F / (conv_ms * 1e-3) / 1e9 / peak_v}
+        del vraw
     # ---- the same steps alternating over three streams, and the other mode, for the record
     ms_s, _, _ = timed(step_streams, max(K // 2, 2))
     value_streams = world * frames_per_step * max(K // 2, 2) / (ms_s * 1e-3)
@@ -409,6 +430,8 @@ def run_ours(args):
                 "kernel_ms_per_launch": per_launch_ms, "algorithmic_bytes_per_launch": alg_bytes_frame * F,
                 "path_achieved": path_gbs, "path_frac": path_gbs / peak,
                 "path_note": "whole single-stream path (rectify + normalise + sort + splat) against the convert-only algorithmic bytes",
+                "path_frac_convert_only": alg_bytes_frame * F / (sum(v[1] for k, v in kernels.items() if k != "dsec_rectify_tnorm")
+                                                                 / (KP * 4) * 1e-3) / 1e9 / peak,
                 "kernel_share_of_step": {k: round(v[1] / ksum, 4) for k, v in kernels.items()},
                 "kernel_ms_per_batch": {k: round(v[1] / (KP * 4), 4) for k, v in kernels.items()}}
 
@@ -429,6 +452,7 @@ def run_ours(args):
         "value_streams3": {"value": value_streams, "unit": UNIT,
                            "note": "same steps, batches alternating over 3 CUDA streams (independent batches overlap)"},
         "value_other_mode": {"mode": other, "value": value_other, "unit": UNIT},
+        "variants": variants,
         "e2e": e2e, "e2e_voxel_only": e2e_voxel, "e2e_host_output": e2e_host,
         "gpu_launches": launches, "gpu_launches_e2e": launches_e, "clocks": clocks, "roofline": roofline,
         "train_step": train,

@@ -41,9 +41,11 @@ typedef struct CUstream_st* oess_stream_t; /* == cudaStream_t */
  *  ORDERED: replays the reference's sequential accumulation order per voxel (stable radix sort by
  *           pixel + per-pixel gather) -> bit-exact with the reference's single-thread CPU result,
  *           deterministic.
- *  ATOMIC : float atomics (red.global.add.f32) in event order of arrival -> fastest path for dense
- *           reuse of one grid, result within 2e-5 + 1e-5 |v| of ORDERED (same noise class as the reference's
- *           own multi-threaded put_), not run-to-run deterministic.            */
+ *  ATOMIC : throughput mode, any accumulation order: result within 2e-5 + 1e-5 |v| of ORDERED (same noise class as the
+ *           reference's own multi-threaded put_), not necessarily run-to-run deterministic.  Dense frames
+ *           (> 200 000 events per frame on average) use float atomics (red.global.add.f32); on sparser frames the
+ *           trilinear voxeliser runs the ORDERED pipeline, which is faster there than the L2 reduction rate allows the
+ *           atomics kernel to be (OESS_ATOMIC_DISPATCH=0 forces the atomics kernel).            */
 #define OESS_MODE_ORDERED 0
 #define OESS_MODE_ATOMIC 1
 

@@ -106,5 +106,17 @@ fod = torch.tensor([0, 1200, 1200, nd], dtype=torch.int64)
 voxel.voxel_tbilinear_ddd17(td, xypd, 5, 260, 346, frame_offsets=fod, separate_pol=False)
 voxel.voxel_tbilinear_ddd17(td, xypd, 5, 260, 346, frame_offsets=fod, separate_pol=True, mode="atomic")
 voxel.voxel_histogram_ddd17(td, xypd, 260, 346, frame_offsets=fod)
+# rows added in round 2: thin-input head conv through the overlapping-window tensor map, reconstruction post-processing,
+# InfoNCE on the tensor cores (3xTF32 operand splitting; OESS_INFONCE=tc forces it for a small, ragged M)
+w5 = torch.zeros(32, 8, 5, 5, device=dev)
+w5[:, :5] = torch.randn(32, 5, 5, 5, device=dev) * 0.05
+x5 = ops.planes_to_nhwc_padded_w(torch.randn(2, 5, 19, 37, device=dev), 8, 2)
+ops.conv2d_rowunfold(x5, ops.conv2d_pack_rowunfold(w5), torch.randn(32, device=dev), 5, 5, 37, relu=True)
+from openess_b200.e2vid.image_reconstructor import gaussian_kernel_5x5  # noqa: E402
+ops.unsharp_rescale(torch.rand(2, 1, 21, 33, device=dev), gaussian_kernel_5x5(1.0).to(dev), 0.3, 0.0, 1.0)
+if os.environ.get("OESS_INFONCE", "")[:1] == "t":
+    kk = torch.nn.functional.normalize(torch.randn(133, 64, device=dev), dim=1).requires_grad_(True)
+    qq = torch.nn.functional.normalize(torch.randn(133, 64, device=dev), dim=1).requires_grad_(True)
+    losses.infonce(kk, qq, 0.07).backward()
 torch.cuda.synchronize()
 print("sanitize smoke done")
