@@ -310,6 +310,17 @@ int oess_bilinear_tokens_to_nchw(const float* tok, int B, int h, int w, int K, i
 int oess_convlstm_step_nhwc(const float* x, const float* h_prev, const float* c_prev, const float* w_packed,
                             const float* bias_packed, float* h_out, float* c_out, int B, int H, int W, int C,
                             oess_stream_t stream);
+/* bf16-operand variant for the FROZEN E2VID encoder (tcgen05.mma.kind::f16, fp32 accumulate): x, h_prev and w_packed are
+ * bfloat16 with the layouts above; bias, cell state and the LSTM pointwise math stay fp32.  h_bf16_out (required): the hidden
+ * state as the next step's operand; h_out (fp32, may be NULL): the same state for fp32 consumers (next encoder level, the
+ * latent dictionary of e2vid/model/unet.py:163).  Stated tolerance vs the fp32 reference: see tests/test_tc_convlstm.py. */
+int oess_convlstm_step_nhwc_bf16(const void* x, const void* h_prev, const float* c_prev, const void* w_packed,
+                                 const float* bias_packed, float* h_out, void* h_bf16_out, float* c_out, int B, int H, int W,
+                                 int C, oess_stream_t stream);
+/* oess_conv2d_nhwc_tf32 (no residual) whose output is also (y != NULL) or only (y == NULL) stored as bfloat16. */
+int oess_conv2d_nhwc_tf32_bf16out(const float* x, const float* w_packed, const float* bias, float* y, void* y_bf16, int B,
+                                  int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil, int relu,
+                                  oess_stream_t stream);
 
 /* 2-D convolution over channels-last activations as a tcgen05 implicit GEMM (TF32 operands, fp32 accumulate), with
  * bias, optional residual add and optional ReLU fused into the TMEM epilogue.  Serves the frozen / inference

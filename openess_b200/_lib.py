@@ -75,6 +75,8 @@ SIGNATURES = {
     "oess_l2norm_rows": [_vp, _i64, _int, _vp],
     "oess_bilinear_tokens_to_nchw": [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp],
     "oess_convlstm_step_nhwc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp],
+    "oess_convlstm_step_nhwc_bf16": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _vp],
+    "oess_conv2d_nhwc_tf32_bf16out": [_vp, _vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _vp],
     "oess_upnorm_pool_fwd": [_vp, _vp, _int, _int, _int, _int, _int, _int, _int, _i64, _vp, _vp, _vp, _vp],
     "oess_upnorm_pool_bwd": [_vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _i64, _vp, _vp],
     "oess_conv2d_nhwc_tf32_stats": [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _vp],

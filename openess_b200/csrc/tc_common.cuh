@@ -157,6 +157,20 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) {
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 with BF16 operands (a / b format 1), fp32 accumulate, A and B K-major.  One instruction consumes K = 16 elements
+// = 32 bytes, so a 128-byte swizzle line holds 64 elements and the descriptor advance per instruction (32 bytes) is the
+// same as for kind::tf32.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues on behalf of the CTA
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -186,6 +200,9 @@ EncodeTiledFn encode_tiled_fn();   // resolved once through cudaGetDriverEntryPo
 // fp32 tensor of `rank` dims (dims[0] innermost, strides in bytes for dims 1..), box[0] = 32 floats = 128 B, 128B swizzle
 int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
+// bf16 tensor (2-byte elements): box[0] = 64 elements = 128 B, 128B swizzle
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
 // same with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B (MN-major tf32 operands)
 int make_tmap_f32_atom32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                          const uint32_t* box);

@@ -9,6 +9,8 @@
 // The A tile of one (tap, 32-channel chunk) is ONE 4-D TMA box {32 ch, 16 s, 8 s, 1} with element strides {1, s, s, 1}
 // (stride-s convolution = strided box traversal) at coordinates shifted by the tap (dilation d): the TMA unit's
 // out-of-bounds zero fill is the convolution's zero padding.
+#include <cuda_bf16.h>
+
 #include "tc_common.cuh"
 
 namespace oess {
@@ -34,7 +36,8 @@ struct ConvArgs {
 template <int BN>
 __global__ void __launch_bounds__(192, 2)
 k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
-          const float* __restrict__ residual, float* __restrict__ y, double* __restrict__ bn_sums, const ConvArgs a) {
+          const float* __restrict__ residual, float* __restrict__ y, __nv_bfloat16* __restrict__ ybf,
+          double* __restrict__ bn_sums, const ConvArgs a) {
     extern __shared__ uint8_t smem_raw[];
     using S = ConvSmem<BN>;
     constexpr int kVStages = S::kStages;
@@ -162,7 +165,14 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                     }
                     if (a.relu & 1) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                     if (a.relu & 2) { o.x = rna_tf32(o.x); o.y = rna_tf32(o.y); o.z = rna_tf32(o.z); o.w = rna_tf32(o.w); }
-                    *reinterpret_cast<float4*>(y + pix + col + j) = o;
+                    if (y) *reinterpret_cast<float4*>(y + pix + col + j) = o;
+                    if (ybf) {                                        // bf16 copy: operand of a kind::f16 consumer
+                        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                        *reinterpret_cast<uint2*>(ybf + pix + col + j) = pk;
+                    }
                 }
             } else {
 #pragma unroll
@@ -170,7 +180,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                     if (col + j < a.Cout) {
                         float o = v[j] + (bias ? bias[col + j] : 0.f) + (residual ? residual[pix + col + j] : 0.f);
                         if (a.relu & 1) o = fmaxf(o, 0.f);
-                        y[pix + col + j] = (a.relu & 2) ? rna_tf32(o) : o;
+                        if (y) y[pix + col + j] = (a.relu & 2) ? rna_tf32(o) : o;
+                        if (ybf) ybf[pix + col + j] = __float2bfloat16_rn(o);
                     }
                 }
             }
@@ -195,7 +206,8 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
 
 template <int BN>
 static int launch_conv(const CUtensorMap& tmX, const float* w_packed, int Cout, int Ktot, const float* bias,
-                       const float* residual, float* y, double* bn_sums, const ConvArgs& a, int B, cudaStream_t st) {
+                       const float* residual, float* y, double* bn_sums, const ConvArgs& a, int B, cudaStream_t st,
+                       __nv_bfloat16* ybf = nullptr) {
     CUtensorMap tmW;
     const uint64_t dW[2] = {(uint64_t)Ktot, (uint64_t)Cout}, sW[1] = {(uint64_t)Ktot * 4};
     const uint32_t bW[2] = {kBlockK, (uint32_t)BN};
@@ -205,7 +217,7 @@ static int launch_conv(const CUtensorMap& tmX, const float* w_packed, int Cout, 
     OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN>::kBytes));
     const int tiles_h = (a.Ho + kVH - 1) / kVH;
     const dim3 grid((unsigned)(a.tiles_w * tiles_h), (unsigned)((Cout + BN - 1) / BN), (unsigned)B);
-    OESS_KERNEL("tc_conv2d", st, kern<<<grid, 192, ConvSmem<BN>::kBytes, st>>>(tmX, tmW, bias, residual, y, bn_sums, a));
+    OESS_KERNEL("tc_conv2d", st, kern<<<grid, 192, ConvSmem<BN>::kBytes, st>>>(tmX, tmW, bias, residual, y, ybf, bn_sums, a));
     return 0;
 }
 
@@ -237,12 +249,12 @@ using namespace oess;
 // (tap = ky * KW + kx, channel)); bias [Cout] or NULL; residual [B, Ho, Wo, Cout] or NULL; y: [B, Ho, Wo, Cout].
 static int conv2d_impl(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
                        int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
-                       int relu, double* bn_sums, int per_sample, oess_stream_t stream) {
+                       int relu, double* bn_sums, int per_sample, oess_stream_t stream, __nv_bfloat16* ybf = nullptr) {
     if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || dil <= 0 || pad < 0)
         return OESS_E_ARG;
-    if (!x || !w_packed || !y) return OESS_E_ARG;
+    if (!x || !w_packed || (!y && !ybf)) return OESS_E_ARG;
     if ((Cin & 3) || stride > 8 || KH * KW > 64) return OESS_E_ARG;      // TMA: 16-byte pixel stride; box <= 256 per dim
-    if (((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)y) & 15) return OESS_E_ARG;
+    if (((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)y | (uintptr_t)ybf) & 15) return OESS_E_ARG;
     if (B > 65535) return OESS_E_RANGE;
     const int Ho = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
     const int Wo = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
@@ -260,10 +272,20 @@ static int conv2d_impl(const float* x, const float* w_packed, const float* bias,
     tc::ConvArgs a{Ho, Wo, Cout, KW, KH * KW, chunks, stride, pad, pad, dil, relu & 3, (Wo + tc::kVW - 1) / tc::kVW,
                    per_sample ? 2 * Cout : 0};
     if (bn_sums) OESS_CUDA(cudaMemsetAsync(bn_sums, 0, sizeof(double) * 2 * (size_t)Cout * (per_sample ? B : 1), st));
-    if (Cout > 128) return tc::launch_conv<256>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
-    if (Cout > 64) return tc::launch_conv<128>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
-    if (Cout > 32) return tc::launch_conv<64>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
-    return tc::launch_conv<32>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st);
+    if (Cout > 128) return tc::launch_conv<256>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st, ybf);
+    if (Cout > 64) return tc::launch_conv<128>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st, ybf);
+    if (Cout > 32) return tc::launch_conv<64>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st, ybf);
+    return tc::launch_conv<32>(tmX, w_packed, Cout, Ktot, bias, residual, y, bn_sums, a, B, st, ybf);
+}
+
+// Same convolution (TF32 operands) whose output is ALSO / ONLY stored as bfloat16 (y may be NULL): the operand of a bf16
+// tensor-core consumer (oess_convlstm_step_nhwc_bf16).  Cout % 4 == 0 for the vector stores.
+OESS_API int oess_conv2d_nhwc_tf32_bf16out(const float* x, const float* w_packed, const float* bias, float* y, void* y_bf16,
+                                           int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                                           int relu, oess_stream_t stream) {
+    if (!y_bf16 || (Cout & 3)) return OESS_E_ARG;
+    return conv2d_impl(x, w_packed, bias, nullptr, y, B, H, W, Cin, Cout, KH, KW, stride, pad, dil, relu, nullptr, 0, stream,
+                       (__nv_bfloat16*)y_bf16);
 }
 
 // Thin-input convolution (E2VID head: 5 event channels padded to 8, 5 x 5 kernel, unet.py:126-127).  With one K block of 32

@@ -12,6 +12,8 @@
 //   warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma.kind::tf32, fp32 accumulator in 256 TMEM columns),
 //   warps 2..5 = epilogue: tcgen05.ld the four gates of 16 channels of one pixel, LSTM pointwise math, write h and c.
 // fp32 operands are read as TF32 (torch's default cuDNN conv arithmetic on the reference's GPU run), fp32 accumulate.
+#include <cuda_bf16.h>
+
 #include "tc_common.cuh"
 
 namespace oess {
@@ -26,10 +28,16 @@ constexpr int kCSmem = 1024 + kCStages * (kCABytes + kCBBytes) + 256;
 
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
+// BF16 = false: fp32 operands read as TF32 (32 channels per 128-byte K block).  BF16 = true: bf16 operands
+// (tcgen05.mma.kind::f16, 64 channels per K block: half the operand bytes per flop, twice the MMA rate), fp32 accumulate,
+// fp32 cell state; the hidden state is written as fp32 (h_out, may be NULL) and as bf16 (h_bf, the next step's operand).
+template <bool BF16>
 __global__ void __launch_bounds__(192, 2)
 k_convlstm_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
               const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias, const float* __restrict__ c_prev,
-              float* __restrict__ h_out, float* __restrict__ c_out, int H, int W, int C, int has_h, int tiles_w) {
+              float* __restrict__ h_out, __nv_bfloat16* __restrict__ h_bf, float* __restrict__ c_out, int H, int W, int C,
+              int has_h, int tiles_w) {
+    constexpr int kKE = BF16 ? 64 : kBlockK;           // elements (channels) per K block
     extern __shared__ uint8_t smem_raw[];
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = base;
@@ -43,7 +51,7 @@ k_convlstm_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int th = blockIdx.x / tiles_w, tw = blockIdx.x - th * tiles_w;
     const int h0 = th * kTH, w0 = tw * kTW;
     const int nchunk = blockIdx.y, b = blockIdx.z;
-    const int chunks = C / kBlockK;
+    const int chunks = C / kKE;
     const int kblocks = (has_h ? 2 : 1) * 9 * chunks;
 
     if (warp == 0 && lane == 0) {
@@ -71,14 +79,14 @@ k_convlstm_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 mbar_wait(&empty[s], ((kb / kCStages) & 1) ^ 1);
                 mbar_expect_tx(&full[s], kCABytes + kCBBytes);
                 const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
-                tma_load_4d(sA + s * kCABytes, src ? &tmH : &tmX, &full[s], chunk * kBlockK, w0 + dx, h0 + dy, b);
-                tma_load_2d(sB + s * kCBBytes, &tmW, &full[s], kb * kBlockK, nchunk * kCN);
+                tma_load_4d(sA + s * kCABytes, src ? &tmH : &tmX, &full[s], chunk * kKE, w0 + dx, h0 + dy, b);
+                tma_load_2d(sB + s * kCBBytes, &tmW, &full[s], kb * kKE, nchunk * kCN);
                 if (++chunk == chunks) { chunk = 0; if (++tap == 9) { tap = 0; ++src; } }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                  // ===== MMA issuer =====
-            constexpr uint32_t idesc = umma_idesc_tf32(128, kCN);
+            constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(128, kCN) : umma_idesc_tf32(128, kCN);
             for (int kb = 0; kb < kblocks; ++kb) {
                 const int s = kb % kCStages;
                 mbar_wait(&full[s], (kb / kCStages) & 1);
@@ -86,8 +94,10 @@ k_convlstm_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                 const uint64_t da = umma_desc_k128(smem_u32(sA + s * kCABytes));
                 const uint64_t db = umma_desc_k128(smem_u32(sB + s * kCBBytes));
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                    umma_tf32(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {       // 4 instructions of 32 operand bytes per 128-byte line
+                    if (BF16) umma_bf16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    else umma_tf32(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                }
                 umma_commit(&empty[s]);
             }
             umma_commit(acc_full);
@@ -130,7 +140,14 @@ k_convlstm_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                     h.z = sigm(go[j + 2] + bo.z) * tanhf(c.z);
                     h.w = sigm(go[j + 3] + bo.w) * tanhf(c.w);
                     *reinterpret_cast<float4*>(c_out + e + j) = c;
-                    *reinterpret_cast<float4*>(h_out + e + j) = h;
+                    if (h_out) *reinterpret_cast<float4*>(h_out + e + j) = h;
+                    if (BF16) {
+                        __nv_bfloat162 lo = __floats2bfloat162_rn(h.x, h.y), hi = __floats2bfloat162_rn(h.z, h.w);
+                        uint2 pk;
+                        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                        *reinterpret_cast<uint2*>(h_bf + e + j) = pk;
+                    }
                 }
             }
         }
@@ -148,13 +165,15 @@ using namespace oess;
 // x, h_prev, c_prev, h_out, c_out: [B, H, W, C] channels-last float32 (h_prev / c_prev NULL = zero state).
 // w_packed: [4C, 2 * 9 * C] with row n' = chunk * 256 + gate * 64 + c  (hidden channel chunk * 64 + c) and column
 // (source, tap = ky * 3 + kx, channel); bias_packed: [4C] in the same row order.  C % 64 == 0.
-OESS_API int oess_convlstm_step_nhwc(const float* x, const float* h_prev, const float* c_prev, const float* w_packed,
-                                     const float* bias_packed, float* h_out, float* c_out, int B, int H, int W, int C,
-                                     oess_stream_t stream) {
+template <bool BF16>
+static int convlstm_impl(const void* x, const void* h_prev, const float* c_prev, const void* w_packed, const float* bias_packed,
+                         float* h_out, __nv_bfloat16* h_bf, float* c_out, int B, int H, int W, int C, oess_stream_t stream) {
+    constexpr int ES = BF16 ? 2 : 4;                      // operand element size
+    constexpr uint32_t KE = BF16 ? 64 : tc::kBlockK;
     if (B <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 64) != 0) return OESS_E_ARG;
-    if (!x || !w_packed || !bias_packed || !h_out || !c_out) return OESS_E_ARG;
+    if (!x || !w_packed || !bias_packed || !c_out || (BF16 ? !h_bf : !h_out)) return OESS_E_ARG;
     if (((uintptr_t)x | (uintptr_t)h_prev | (uintptr_t)c_prev | (uintptr_t)w_packed | (uintptr_t)bias_packed |
-         (uintptr_t)h_out | (uintptr_t)c_out) & 15)
+         (uintptr_t)h_out | (uintptr_t)h_bf | (uintptr_t)c_out) & 15)
         return OESS_E_ARG;
     if (B > 65535 || C / 64 > 65535) return OESS_E_RANGE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -163,20 +182,37 @@ OESS_API int oess_convlstm_step_nhwc(const float* x, const float* h_prev, const 
     const uint64_t Kfull = (uint64_t)2 * 9 * C;
     CUtensorMap tmX, tmH, tmW;
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
-    const uint32_t box[4] = {tc::kBlockK, tc::kTW, tc::kTH, 1};
-    int rc = tc::make_tmap_f32(&tmX, x, 4, dims, strides, box);
+    const uint64_t strides[3] = {(uint64_t)C * ES, (uint64_t)W * C * ES, (uint64_t)H * W * C * ES};
+    const uint32_t box[4] = {KE, tc::kTW, tc::kTH, 1};
+    auto mk = BF16 ? tc::make_tmap_bf16 : tc::make_tmap_f32;
+    int rc = mk(&tmX, x, 4, dims, strides, box);
     if (rc) return rc;
-    rc = tc::make_tmap_f32(&tmH, h_prev ? h_prev : x, 4, dims, strides, box);
+    rc = mk(&tmH, h_prev ? h_prev : x, 4, dims, strides, box);
     if (rc) return rc;
-    const uint64_t dW[2] = {Kfull, (uint64_t)4 * C}, sW[1] = {Kfull * 4};
-    const uint32_t bW[2] = {tc::kBlockK, tc::kCN};
-    rc = tc::make_tmap_f32(&tmW, w_packed, 2, dW, sW, bW);
+    const uint64_t dW[2] = {Kfull, (uint64_t)4 * C}, sW[1] = {Kfull * ES};
+    const uint32_t bW[2] = {KE, tc::kCN};
+    rc = mk(&tmW, w_packed, 2, dW, sW, bW);
     if (rc) return rc;
-    OESS_CUDA(cudaFuncSetAttribute(tc::k_convlstm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kCSmem));
+    OESS_CUDA(cudaFuncSetAttribute(tc::k_convlstm_tc<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kCSmem));
     const int tiles_w = (W + tc::kTW - 1) / tc::kTW, tiles_h = (H + tc::kTH - 1) / tc::kTH;
     const dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(C / 64), (unsigned)B);
-    OESS_KERNEL("tc_convlstm_step", st, tc::k_convlstm_tc<<<grid, 192, tc::kCSmem, st>>>(
-        tmX, tmH, tmW, bias_packed, c_prev, h_out, c_out, H, W, C, h_prev ? 1 : 0, tiles_w));
+    OESS_KERNEL(BF16 ? "tc_convlstm_step_bf16" : "tc_convlstm_step", st, tc::k_convlstm_tc<BF16><<<grid, 192, tc::kCSmem, st>>>(
+        tmX, tmH, tmW, bias_packed, c_prev, h_out, h_bf, c_out, H, W, C, h_prev ? 1 : 0, tiles_w));
     return 0;
+}
+
+OESS_API int oess_convlstm_step_nhwc(const float* x, const float* h_prev, const float* c_prev, const float* w_packed,
+                                     const float* bias_packed, float* h_out, float* c_out, int B, int H, int W, int C,
+                                     oess_stream_t stream) {
+    return convlstm_impl<false>(x, h_prev, c_prev, w_packed, bias_packed, h_out, nullptr, c_out, B, H, W, C, stream);
+}
+
+// bf16-operand variant for the FROZEN E2VID encoder: x, h_prev, w_packed are bfloat16 (same layouts), the cell state and the
+// bias stay fp32, accumulation is fp32.  h_bf16_out (required) is the hidden state as the next step's operand; h_out
+// (fp32, may be NULL) is the same state for fp32 consumers (the next encoder level, the latent dictionary).
+OESS_API int oess_convlstm_step_nhwc_bf16(const void* x, const void* h_prev, const float* c_prev, const void* w_packed,
+                                          const float* bias_packed, float* h_out, void* h_bf16_out, float* c_out, int B, int H,
+                                          int W, int C, oess_stream_t stream) {
+    return convlstm_impl<true>(x, h_prev, c_prev, w_packed, bias_packed, h_out, (__nv_bfloat16*)h_bf16_out, c_out, B, H, W, C,
+                               stream);
 }

@@ -29,7 +29,12 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 static int make_tmap_f32_sw(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                            const uint32_t* box, CUtensorMapSwizzle sw);
+                            const uint32_t* box, CUtensorMapSwizzle sw, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+    return make_tmap_f32_sw(m, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
 
 int make_tmap_f32(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box) {
@@ -41,7 +46,7 @@ int make_tmap_f32_atom32(CUtensorMap* m, const void* base, int rank, const uint6
 }
 
 static int make_tmap_f32_sw(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                            const uint32_t* box, CUtensorMapSwizzle sw) {
+                            const uint32_t* box, CUtensorMapSwizzle sw, CUtensorMapDataType dt) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return (int)cudaErrorNotSupported;
     cuuint64_t gdim[5], gstr[5];
@@ -52,7 +57,7 @@ static int make_tmap_f32_sw(CUtensorMap* m, const void* base, int rank, const ui
         es[i] = 1;
         if (i + 1 < rank) gstr[i] = strides_bytes[i];
     }
-    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+    const CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;

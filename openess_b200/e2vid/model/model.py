@@ -31,6 +31,10 @@ from ... import losses as _ops
 from ... import ops as _tc
 
 USE_TENSOR_CORES = os.environ.get("OESS_E2VID_TC", "1") != "0"
+# bf16 operands (tcgen05.mma.kind::f16, fp32 accumulate / cell state) for the ConvLSTM steps of the FROZEN encoder: the strided
+# encoder convolution writes its output as bf16, the ConvLSTM keeps a bf16 copy of its hidden state for the next step.
+# OESS_E2VID_DTYPE=tf32 keeps fp32 operands read as TF32.
+CONVLSTM_BF16 = os.environ.get("OESS_E2VID_DTYPE", "bf16") == "bf16"
 
 
 class ConvLayer(nn.Module):
@@ -135,6 +139,10 @@ class ConvLSTM(nn.Module):
         if (USE_TENSOR_CORES and input_.is_cuda and not torch.is_grad_enabled() and self.hidden_size % 64 == 0
                 and self.input_size == self.hidden_size and tuple(self.Gates.kernel_size) == (3, 3)):
             wp, bp = self._tc_weights()
+            if CONVLSTM_BF16:
+                if getattr(self, "_packed_bf", None) is None or self._packed_bf[0] is not wp:
+                    self._packed_bf = (wp, wp.to(torch.bfloat16))
+                return _tc.convlstm_step_bf16(input_, prev_state, self._packed_bf[1], bp)
             return _tc.convlstm_step(input_, prev_state, wp, bp)
         if prev_state is None:
             # zero state: the hidden half of the stacked input contributes nothing -> convolve the input half only
@@ -165,7 +173,15 @@ class RecurrentConvLayer(nn.Module):
         self.recurrent_block = ConvLSTM(input_size=out_channels, hidden_size=out_channels, kernel_size=3)
 
     def forward(self, x, prev_state):
-        x = self.conv(x)
+        rb = self.recurrent_block
+        if (CONVLSTM_BF16 and USE_TENSOR_CORES and self.conv._tc_ok(x) and rb.hidden_size % 64 == 0
+                and rb.input_size == rb.hidden_size and tuple(rb.Gates.kernel_size) == (3, 3)):
+            wp, b = self.conv._tc_weights()                     # the conv output goes straight to bf16: ConvLSTM operand
+            c = self.conv.conv2d
+            x = _tc.conv2d_tc_bf16out(x, wp, b, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0],
+                                      relu=self.conv.activation is not None)
+        else:
+            x = self.conv(x)
         state = self.recurrent_block(x, prev_state)
         return state[0], state
 

@@ -226,6 +226,51 @@ def convlstm_step(x, prev_state, w_packed, b_packed):
     return h, c
 
 
+def convlstm_step_bf16(x_bf, prev_state, w_packed_bf, b_packed):
+    """One ConvLSTM step with bf16 tensor-core operands (oess_convlstm_step_nhwc_bf16; frozen E2VID only).
+    x_bf: [B, C, H, W] bfloat16 channels-last; prev_state None or (h_fp32, c_fp32) where h carries its bf16 copy as the
+    attribute `_oess_bf16` (set by this function; converted on the fly otherwise); w_packed_bf: convlstm_pack(...)[0] in
+    bfloat16.  Returns (h, c) fp32 channels-last, h with `_oess_bf16` attached."""
+    _lib.require_cuda(x_bf, w_packed_bf, b_packed)
+    B, C, H, W = x_bf.shape
+    cl = torch.channels_last
+    if x_bf.dtype != torch.bfloat16 or not x_bf.is_contiguous(memory_format=cl):
+        x_bf = x_bf.to(torch.bfloat16).contiguous(memory_format=cl)
+    hp = cp = None
+    if prev_state is not None:
+        hp = getattr(prev_state[0], "_oess_bf16", None)
+        if hp is None:
+            hp = prev_state[0].to(torch.bfloat16).contiguous(memory_format=cl)
+        cp = prev_state[1].float().contiguous(memory_format=cl)
+    h = torch.empty((B, C, H, W), dtype=torch.float32, device=x_bf.device, memory_format=cl)
+    hb = torch.empty((B, C, H, W), dtype=torch.bfloat16, device=x_bf.device, memory_format=cl)
+    c = torch.empty((B, C, H, W), dtype=torch.float32, device=x_bf.device, memory_format=cl)
+    with torch.cuda.device(x_bf.device):
+        check(lib().oess_convlstm_step_nhwc_bf16(ptr(x_bf), ptr(hp), ptr(cp), ptr(w_packed_bf), ptr(b_packed), ptr(h), ptr(hb),
+                                                 ptr(c), B, H, W, C, stream_ptr(x_bf.device)), "oess_convlstm_step_nhwc_bf16")
+    h._oess_bf16 = hb
+    return h, c
+
+
+def conv2d_tc_bf16out(x, w_packed, bias, kernel_size, stride=1, padding=0, dilation=1, relu=False):
+    """conv2d_tc whose output is stored ONLY as bfloat16 (channels-last): the x operand of convlstm_step_bf16."""
+    _lib.require_cuda(x, w_packed, bias)
+    B, Cin, H, W = x.shape
+    KH, KW = (kernel_size, kernel_size) if isinstance(kernel_size, int) else tuple(kernel_size)
+    Cout = w_packed.shape[0]
+    cl = torch.channels_last
+    xc = x.float().contiguous(memory_format=cl)
+    Ho = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
+    Wo = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+    yb = torch.empty((B, Cout, Ho, Wo), dtype=torch.bfloat16, device=x.device, memory_format=cl)
+    bc = None if bias is None else _f32c(bias)
+    with torch.cuda.device(x.device):
+        check(lib().oess_conv2d_nhwc_tf32_bf16out(ptr(xc), ptr(w_packed), ptr(bc), None, ptr(yb), B, H, W, Cin, Cout, KH, KW,
+                                                  stride, padding, dilation, 1 if relu else 0, stream_ptr(x.device)),
+              "oess_conv2d_nhwc_tf32_bf16out")
+    return yb
+
+
 def conv2d_pack(weight):
     """[Cout, Cin, KH, KW] -> [Cout, KH * KW * Cin_p] (Cin_p = Cin rounded up to 32, zero padded), column (tap, channel):
     the K order of oess_conv2d_nhwc_tf32."""

@@ -44,9 +44,11 @@ def test_abi_version_and_errors(lib):
 
 def test_ws_query_is_host_only(lib):
     from openess_b200 import _lib
-    small = _lib.voxel_ws_bytes(_lib.KIND_TRILINEAR, _lib.MODE_ATOMIC, 100000, 1, 5, 480, 640)
     big = _lib.voxel_ws_bytes(_lib.KIND_TRILINEAR, _lib.MODE_ORDERED, 100000, 1, 5, 480, 640)
-    assert 0 < small < big
+    # ATOMIC on sparse frames runs the sort-based pipeline (density dispatch): same workspace; dense frames: atomics kernel
+    assert _lib.voxel_ws_bytes(_lib.KIND_TRILINEAR, _lib.MODE_ATOMIC, 100000, 1, 5, 480, 640) == big
+    small = _lib.voxel_ws_bytes(_lib.KIND_TRILINEAR, _lib.MODE_ATOMIC, 1000000, 1, 5, 480, 640)
+    assert 0 < small < _lib.voxel_ws_bytes(_lib.KIND_TRILINEAR, _lib.MODE_ORDERED, 1000000, 1, 5, 480, 640)
     # ordered: two float4 record buffers + radix histograms (+ per-cell CSR on the generic tall-sensor path)
     assert big >= 2 * 16 * 100000
     tall = _lib.voxel_ws_bytes(_lib.KIND_TRILINEAR, _lib.MODE_ORDERED, 100000, 1, 5, 2000, 640)

@@ -70,28 +70,35 @@ def test_e2vid_full_width_tensor_core_convlstm_vs_reference_golden():
     m.load_state_dict(seeded_state_dict(m, int(z["seed"])), strict=True)
     m = m.eval().to(dev).fold_bn()
     errs = {}
-    for use_tc in (False, True):
+    bf16_was = mm.CONVLSTM_BF16
+    for mode in ("fp32", "tf32", "bf16"):
+        use_tc = mode != "fp32"
         mm.USE_TENSOR_CORES = use_tc
+        mm.CONVLSTM_BF16 = mode == "bf16"
         try:
             states = None
             with _lib.profile() as prof:
                 with torch.no_grad():
                     for i in range(3):
                         _, states, latent = m(torch.from_numpy(z[f"in{i}"]).to(dev), states)
-            tol = 1e-2 if use_tc else 3e-4
+            # stated tolerances on O(1) activations after three recurrent steps through three levels: strict fp32 3e-4, TF32
+            # operands 1e-2, bf16 ConvLSTM operands (default for the frozen encoder) 3e-2
+            tol = {"fp32": 3e-4, "tf32": 1e-2, "bf16": 3e-2}[mode]
             worst = 0.0
             for k in latent:
                 worst = max(worst, float(np.abs(latent[k].cpu().numpy() - z[f"latent__{k}"]).max()))
                 np.testing.assert_allclose(latent[k].cpu().numpy(), z[f"latent__{k}"], atol=tol)
             for li, (h, c) in enumerate(states):
                 np.testing.assert_allclose(c.cpu().numpy(), z[f"state__{li}__c"], atol=tol)
-            errs[use_tc] = worst
+            errs[mode] = worst
             # 3 levels x 3 steps of ConvLSTM and encoder convs + 3 head convs on the tensor cores, none otherwise
-            assert prof.kernels.get("tc_convlstm_step", (0, 0.0))[0] == (9 if use_tc else 0)
+            assert prof.kernels.get("tc_convlstm_step", (0, 0.0))[0] == (9 if mode == "tf32" else 0)
+            assert prof.kernels.get("tc_convlstm_step_bf16", (0, 0.0))[0] == (9 if mode == "bf16" else 0)
             assert prof.kernels.get("tc_conv2d", (0, 0.0))[0] == (12 if use_tc else 0)
         finally:
             mm.USE_TENSOR_CORES = True
-    print("max |latent error| fp32 path %.2e, tensor-core path %.2e" % (errs[False], errs[True]))
+            mm.CONVLSTM_BF16 = bf16_was
+    print("max |latent error| fp32 path %.2e, TF32 tensor-core path %.2e, bf16 ConvLSTM path %.2e" % (errs["fp32"], errs["tf32"], errs["bf16"]))
 
 
 @pytest.mark.gpu

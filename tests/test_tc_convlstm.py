@@ -80,3 +80,38 @@ def test_convlstm_step_exact_on_tf32_representable_inputs():
     hr, cr = _ref(x, (hp, cp), weight, bias)
     assert float((c.double() - cr).abs().max()) < 2e-6 * float(cr.abs().max() + 1)
     assert float((h.double() - hr).abs().max()) < 2e-6
+
+
+@pytest.mark.parametrize("B,C,H,W,with_state", [(1, 64, 8, 16, False), (2, 64, 20, 40, True), (1, 128, 13, 22, True), (1, 256, 7, 10, True)])
+def test_convlstm_step_bf16_operands(B, C, H, W, with_state):
+    """bf16-operand variant (oess_convlstm_step_nhwc_bf16, tcgen05.mma.kind::f16) for the frozen encoder.  (i) With operands
+    that are exactly representable in bf16 the gate pre-activations are exact fp32 sums of exact products, so the result
+    must agree with the float64 reference to fp32 round-off (this pins descriptors, K-block order and the packing);
+    (ii) with generic fp32 inputs the operands are rounded to bf16 (2^-9 relative each): stated tolerance 2e-2 on h and c
+    of O(1) values (measured ~5e-3)."""
+    from openess_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(C + H + 1)
+    for exact in (True, False):
+        x = torch.randn(B, C, H, W, device="cuda", generator=g)
+        weight = torch.randn(4 * C, 2 * C, 3, 3, device="cuda", generator=g) / (18 * C) ** 0.5
+        bias = torch.randn(4 * C, device="cuda", generator=g) * 0.1
+        state = None
+        if with_state:
+            state = (torch.tanh(torch.randn(B, C, H, W, device="cuda", generator=g)),
+                     torch.randn(B, C, H, W, device="cuda", generator=g))
+        if exact:
+            x, weight = x.bfloat16().float(), weight.bfloat16().float()
+            if state is not None:
+                state = (state[0].bfloat16().float(), state[1])
+        wp, bp = ops.convlstm_pack(weight, bias, C)
+        h, c = ops.convlstm_step_bf16(x.bfloat16().contiguous(memory_format=torch.channels_last), state, wp.bfloat16(), bp)
+        hr, cr = _ref(x, state, weight, bias)
+        tol = 2e-5 if exact else 2e-2
+        assert float((c.double() - cr).abs().max()) < tol, (exact, float((c.double() - cr).abs().max()))
+        assert float((h.double() - hr).abs().max()) < tol
+        hb = h._oess_bf16
+        assert hb.dtype == torch.bfloat16 and torch.equal(hb.float(), h.bfloat16().float())       # the next step's operand
+        if with_state and not exact:                                                              # second step from the bf16 state
+            h2, c2 = ops.convlstm_step_bf16(x.bfloat16().contiguous(memory_format=torch.channels_last), (h, c), wp.bfloat16(), bp)
+            hr2, cr2 = _ref(x, (hr.float(), cr.float()), weight, bias)
+            assert float((h2.double() - hr2).abs().max()) < 3e-2

@@ -64,10 +64,15 @@ def convlstm():
             return losses.convlstm_gates(gates, c.contiguous())
 
         t_ours = timeit(lambda: ops.convlstm_step(x, (h, c), wp, bp))
+        xb, wpb = x.bfloat16(), wp.bfloat16()
+        hs = h.clone()
+        hs._oess_bf16 = h.bfloat16()
+        t_bf16 = timeit(lambda: ops.convlstm_step_bf16(xb, (hs, c), wpb, bp))
         t_lib = timeit(lib_path)
         t_lib2 = timeit(lib_path_nchw)
         fl = 2.0 * B * H * W * 4 * C * 18 * C
         print(json.dumps({"op": "convlstm_step", "B": B, "C": C, "H": H, "W": W, "ms": t_ours, "tflops": fl / t_ours / 1e9,
+                          "ms_bf16_operands": t_bf16, "tflops_bf16_operands": fl / t_bf16 / 1e9,
                           "torch_cudnn_tf32_channels_last_plus_fused_gates_ms": t_lib, "torch_tflops": fl / t_lib / 1e9,
                           "torch_cudnn_tf32_nchw_plus_fused_gates_ms": t_lib2}))
 
