@@ -348,6 +348,19 @@ int oess_batchnorm_nhwc_sums(float* x, int64_t R, int C, const float* gamma, con
                              float* running_var, float eps, float momentum, const float* residual, int relu, void* ws,
                              size_t ws_bytes, oess_stream_t stream);
 
+/* bfloat16-operand variants for the FROZEN networks of the path (teacher ResNet-50 models/image_model.py:32-62, E2VID encoder
+ * convs e2vid/model/submodules.py:7-31): tcgen05.mma.kind::f16, fp32 accumulation, fp32 bias / residual / BatchNorm statistics.
+ * x_bf16 [B, H, W, Cin] bf16 channels-last (Cin % 8 == 0); w_packed_bf16 [Cout, KH * KW * Cin_p] bf16, Cin_p = Cin rounded up to
+ * 64; the result goes to y (fp32, may be NULL) and / or y_bf16 (may be NULL; Cout % 4 == 0).  bn_sums != NULL: batch statistics of
+ * the raw output as oess_conv2d_nhwc_tf32_stats (then residual = NULL, relu = 0).  oess_batchnorm_nhwc_sums_bf16 is
+ * oess_batchnorm_nhwc_sums whose result is also (write_f32 != 0) or only (write_f32 == 0) stored as bf16 in y_bf16. */
+int oess_conv2d_nhwc_bf16(const void* x_bf16, const void* w_packed_bf16, const float* bias, const float* residual, float* y,
+                          void* y_bf16, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
+                          int relu, double* bn_sums, oess_stream_t stream);
+int oess_batchnorm_nhwc_sums_bf16(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
+                                  float* running_var, float eps, float momentum, const float* residual, int relu, void* y_bf16,
+                                  int write_f32, void* ws, size_t ws_bytes, oess_stream_t stream);
+
 /* Conv + InstanceNorm2d(affine=False) (+ residual) (+ ReLU) of the SemSegE2VID task decoder (models/style_networks.py:
  * 252-289 ReLUINSConv2d / INSResBlock) for its forward-only uses (validation, linear probing, test.py): the conv
  * accumulates PER-SAMPLE statistics in its epilogue (in_sums [B][2 Cout] doubles, zeroed inside), the second call

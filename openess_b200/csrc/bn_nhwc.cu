@@ -8,6 +8,8 @@
 //   k_bn_finalize: scale / shift per channel (+ running-statistics update) on the device: no host synchronisation
 //   k_bn_apply   : y = act(x * scale[c] + shift[c] (+ residual)), in place, 128-bit accesses
 // All three are HBM-bound: 4 B / element read (stats), 8-12 B / element (apply).
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace oess {
@@ -84,9 +86,12 @@ __global__ void k_bn_finalize(const double* __restrict__ sums, const float* __re
     shift[c] = (float)((beta ? (double)beta[c] : 0.0) - mean * g * inv);
 }
 
+// y_bf (optional): bfloat16 copy of the result, the operand of a kind::f16 consumer (oess_conv2d_nhwc_bf16); with
+// write_f32 == 0 only that copy is written (x keeps the raw conv output).
 __global__ void __launch_bounds__(256)
 k_bn_apply(float* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
-           const float* __restrict__ residual, int64_t total4, int C4, int relu, float* __restrict__ y_out) {
+           const float* __restrict__ residual, int64_t total4, int C4, int relu, float* __restrict__ y_out,
+           __nv_bfloat16* __restrict__ y_bf, int write_f32) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += stride) {
         const int q = (int)(i % C4);
@@ -99,7 +104,14 @@ k_bn_apply(float* __restrict__ x, const float* __restrict__ scale, const float* 
             v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
         }
         if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-        reinterpret_cast<float4*>(y_out ? y_out : x)[i] = v;
+        if (write_f32) reinterpret_cast<float4*>(y_out ? y_out : x)[i] = v;
+        if (y_bf) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            reinterpret_cast<uint2*>(y_bf)[i] = pk;
+        }
     }
 }
 
@@ -293,7 +305,8 @@ OESS_API int oess_bn_ws_bytes(int C, size_t* ws_bytes) {
 
 static int batchnorm_impl(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
                           float* running_var, float eps, float momentum, int training, const float* residual,
-                          int relu, void* ws, size_t ws_bytes, int have_sums, oess_stream_t stream, float* y_out = nullptr) {
+                          int relu, void* ws, size_t ws_bytes, int have_sums, oess_stream_t stream, float* y_out = nullptr,
+                          __nv_bfloat16* y_bf = nullptr, int write_f32 = 1) {
     size_t need = 0;
     if (oess_bn_ws_bytes(C, &need)) return OESS_E_ARG;
     if (!x || R < 0 || (C & 3)) return OESS_E_ARG;
@@ -321,7 +334,8 @@ static int batchnorm_impl(float* x, int64_t R, int C, const float* gamma, const 
         sums, gamma, beta, running_mean, running_var, C, (double)R, eps, momentum, training ? 1 : 0, scale, shift));
     const int64_t total4 = R * C4;
     const unsigned blocks = (unsigned)((total4 + 255) / 256 < (int64_t)kNumSMs * 16 ? (total4 + 255) / 256 : (int64_t)kNumSMs * 16);
-    OESS_KERNEL("bn_apply", st, k_bn_apply<<<blocks, 256, 0, st>>>(x, scale, shift, residual, total4, C4, relu ? 1 : 0, y_out));
+    OESS_KERNEL("bn_apply", st, k_bn_apply<<<blocks, 256, 0, st>>>(x, scale, shift, residual, total4, C4, relu ? 1 : 0, y_out,
+                                                                y_bf, write_f32));
     return OESS_OK;
 }
 
@@ -339,6 +353,17 @@ OESS_API int oess_batchnorm_nhwc_sums(float* x, int64_t R, int C, const float* g
                                       void* ws, size_t ws_bytes, oess_stream_t stream) {
     return batchnorm_impl(x, R, C, gamma, beta, running_mean, running_var, eps, momentum, 1, residual, relu, ws, ws_bytes,
                           1, stream);
+}
+
+// oess_batchnorm_nhwc_sums for a frozen network run with bfloat16 operands: the result is ALSO (write_f32 != 0, in place) or ONLY
+// (write_f32 == 0: x keeps the raw conv output) stored as bfloat16 in y_bf16, the input of the next oess_conv2d_nhwc_bf16.
+OESS_API int oess_batchnorm_nhwc_sums_bf16(float* x, int64_t R, int C, const float* gamma, const float* beta,
+                                           float* running_mean, float* running_var, float eps, float momentum,
+                                           const float* residual, int relu, void* y_bf16, int write_f32, void* ws,
+                                           size_t ws_bytes, oess_stream_t stream) {
+    if (!y_bf16 || ((uintptr_t)y_bf16 & 7)) return OESS_E_ARG;
+    return batchnorm_impl(x, R, C, gamma, beta, running_mean, running_var, eps, momentum, 1, residual, relu, ws, ws_bytes,
+                          1, stream, nullptr, (__nv_bfloat16*)y_bf16, write_f32 ? 1 : 0);
 }
 
 // Training forward of conv -> BatchNorm (batch statistics already in the first 2 C doubles of `ws`): z (the conv output) is

@@ -33,7 +33,9 @@ struct ConvArgs {
     int stats_stride;   // doubles between the statistics of consecutive samples (0: one set for the whole batch)
 };
 
-template <int BN>
+// BF16: bfloat16 activations and packed weights (tcgen05.mma.kind::f16, 64 elements per 128-byte K block, fp32 accumulate) for
+// the FROZEN networks (teacher ResNet-50, E2VID encoder convs): half the operand bytes and twice the MMA rate of TF32.
+template <int BN, bool BF16>
 __global__ void __launch_bounds__(192, 2)
 k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
           const float* __restrict__ residual, float* __restrict__ y, __nv_bfloat16* __restrict__ ybf,
@@ -55,6 +57,7 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
     const int h0 = th * kVH, w0 = tw * kVW;
     const int n0 = blockIdx.y * BN, b = blockIdx.z;
     const int kblocks = a.taps * a.chunks;
+    constexpr int kKE = BF16 ? 64 : kBlockK;              // operand elements per 128-byte K block
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
@@ -80,15 +83,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                 mbar_wait(&empty[s], ((kb / kVStages) & 1) ^ 1);
                 mbar_expect_tx(&full[s], kVABytes + S::kBBytes);
                 const int ky = tap / a.KW, kx = tap - ky * a.KW;
-                tma_load_4d(sA + s * kVABytes, &tmX, &full[s], chunk * kBlockK, w0 * a.stride - a.pad_x + kx * a.dil,
+                tma_load_4d(sA + s * kVABytes, &tmX, &full[s], chunk * kKE, w0 * a.stride - a.pad_x + kx * a.dil,
                             h0 * a.stride - a.pad + ky * a.dil, b);
-                tma_load_2d(sB + s * S::kBBytes, &tmW, &full[s], kb * kBlockK, n0);
+                tma_load_2d(sB + s * S::kBBytes, &tmW, &full[s], kb * kKE, n0);
                 if (++chunk == a.chunks) { chunk = 0; ++tap; }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {                                  // ===== MMA issuer =====
-            constexpr uint32_t idesc = umma_idesc_tf32(128, BN);
+            constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(128, BN) : umma_idesc_tf32(128, BN);
             for (int kb = 0; kb < kblocks; ++kb) {
                 const int s = kb % kVStages;
                 mbar_wait(&full[s], (kb / kVStages) & 1);
@@ -96,8 +99,10 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
                 const uint64_t da = umma_desc_k128(smem_u32(sA + s * kVABytes));
                 const uint64_t db = umma_desc_k128(smem_u32(sB + s * S::kBBytes));
 #pragma unroll
-                for (int k = 0; k < kBlockK / kUmmaK; ++k)
-                    umma_tf32(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                for (int k = 0; k < kBlockK / kUmmaK; ++k) {   // four 32-byte K steps per block: K = 8 (tf32) / 16 (bf16) each
+                    if (BF16) umma_bf16(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    else umma_tf32(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                }
                 umma_commit(&empty[s]);
             }
             umma_commit(acc_full);
@@ -204,26 +209,27 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
     if (warp == 1) tmem_dealloc(tmem_acc, BN);
 }
 
-template <int BN>
-static int launch_conv(const CUtensorMap& tmX, const float* w_packed, int Cout, int Ktot, const float* bias,
+template <int BN, bool BF16 = false>
+static int launch_conv(const CUtensorMap& tmX, const void* w_packed, int Cout, int Ktot, const float* bias,
                        const float* residual, float* y, double* bn_sums, const ConvArgs& a, int B, cudaStream_t st,
                        __nv_bfloat16* ybf = nullptr) {
     CUtensorMap tmW;
-    const uint64_t dW[2] = {(uint64_t)Ktot, (uint64_t)Cout}, sW[1] = {(uint64_t)Ktot * 4};
-    const uint32_t bW[2] = {kBlockK, (uint32_t)BN};
-    int rc = make_tmap_f32(&tmW, w_packed, 2, dW, sW, bW);
+    const uint64_t dW[2] = {(uint64_t)Ktot, (uint64_t)Cout}, sW[1] = {(uint64_t)Ktot * (BF16 ? 2 : 4)};
+    const uint32_t bW[2] = {BF16 ? 64u : (uint32_t)kBlockK, (uint32_t)BN};
+    int rc = BF16 ? make_tmap_bf16(&tmW, w_packed, 2, dW, sW, bW) : make_tmap_f32(&tmW, w_packed, 2, dW, sW, bW);
     if (rc) return rc;
-    auto kern = k_conv_tc<BN>;
+    auto kern = k_conv_tc<BN, BF16>;
     OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN>::kBytes));
     const int tiles_h = (a.Ho + kVH - 1) / kVH;
     const dim3 grid((unsigned)(a.tiles_w * tiles_h), (unsigned)((Cout + BN - 1) / BN), (unsigned)B);
-    OESS_KERNEL("tc_conv2d", st, kern<<<grid, 192, ConvSmem<BN>::kBytes, st>>>(tmX, tmW, bias, residual, y, ybf, bn_sums, a));
+    OESS_KERNEL(BF16 ? "tc_conv2d_bf16" : "tc_conv2d", st,
+                kern<<<grid, 192, ConvSmem<BN>::kBytes, st>>>(tmX, tmW, bias, residual, y, ybf, bn_sums, a));
     return 0;
 }
 
 // strided variant of make_tmap_f32 (element strides per dimension)
 static int make_tmap_f32_strided(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                 const uint32_t* box, const uint32_t* estr) {
+                                 const uint32_t* box, const uint32_t* estr, bool bf16 = false) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return (int)cudaErrorNotSupported;
     cuuint64_t gdim[5], gstr[5];
@@ -234,7 +240,8 @@ static int make_tmap_f32_strided(CUtensorMap* m, const void* base, int rank, con
         es[i] = estr[i];
         if (i + 1 < rank) gstr[i] = strides_bytes[i];
     }
-    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+    const CUresult r = enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                           const_cast<void*>(base), gdim, gstr, bx, es,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)cudaErrorInvalidValue;
@@ -342,4 +349,41 @@ OESS_API int oess_conv2d_nhwc_tf32_instats(const float* x, const float* w_packed
                                            double* in_sums, oess_stream_t stream) {
     if (!in_sums) return OESS_E_ARG;
     return conv2d_impl(x, w_packed, bias, nullptr, y, B, H, W, Cin, Cout, KH, KW, stride, pad, dil, 0, in_sums, 1, stream);
+}
+
+// bfloat16-operand convolution for the frozen networks: x [B, H, W, Cin] bf16 channels-last (Cin % 8 == 0), w_packed
+// [Cout, KH * KW * Cin_p] bf16 (Cin_p = Cin rounded up to 64, zero padded), fp32 accumulate / bias / residual; the result goes
+// to y (fp32, may be NULL) and / or y_bf16 (may be NULL; Cout % 4 == 0), optionally with the BatchNorm batch statistics of the
+// raw output in bn_sums (then residual = NULL, relu = 0, as oess_conv2d_nhwc_tf32_stats).
+OESS_API int oess_conv2d_nhwc_bf16(const void* x_bf16, const void* w_packed_bf16, const float* bias, const float* residual,
+                                   float* y, void* y_bf16, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
+                                   int pad, int dil, int relu, double* bn_sums, oess_stream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || stride <= 0 || dil <= 0 || pad < 0)
+        return OESS_E_ARG;
+    if (!x_bf16 || !w_packed_bf16 || (!y && !y_bf16)) return OESS_E_ARG;
+    if ((Cin & 7) || stride > 8 || KH * KW > 64 || (y_bf16 && (Cout & 3))) return OESS_E_ARG;
+    if (bn_sums && (residual || relu)) return OESS_E_ARG;
+    if (((uintptr_t)x_bf16 | (uintptr_t)w_packed_bf16 | (uintptr_t)bias | (uintptr_t)residual | (uintptr_t)y | (uintptr_t)y_bf16) & 15)
+        return OESS_E_ARG;
+    if (B > 65535) return OESS_E_RANGE;
+    const int Ho = (H + 2 * pad - dil * (KH - 1) - 1) / stride + 1;
+    const int Wo = (W + 2 * pad - dil * (KW - 1) - 1) / stride + 1;
+    if (Ho <= 0 || Wo <= 0) return OESS_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int chunks = (Cin + 63) / 64;
+    const int Ktot = KH * KW * chunks * 64;
+    CUtensorMap tmX;
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    const uint32_t box[4] = {64, (uint32_t)(tc::kVW * stride), (uint32_t)(tc::kVH * stride), 1};
+    const uint32_t estr[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    int rc = tc::make_tmap_f32_strided(&tmX, x_bf16, 4, dims, strides, box, estr, true);
+    if (rc) return rc;
+    tc::ConvArgs a{Ho, Wo, Cout, KW, KH * KW, chunks, stride, pad, pad, dil, relu & 1, (Wo + tc::kVW - 1) / tc::kVW, 0};
+    if (bn_sums) OESS_CUDA(cudaMemsetAsync(bn_sums, 0, sizeof(double) * 2 * (size_t)Cout, st));
+    __nv_bfloat16* ybf = (__nv_bfloat16*)y_bf16;
+    if (Cout > 128) return tc::launch_conv<256, true>(tmX, w_packed_bf16, Cout, Ktot, bias, residual, y, bn_sums, a, B, st, ybf);
+    if (Cout > 64) return tc::launch_conv<128, true>(tmX, w_packed_bf16, Cout, Ktot, bias, residual, y, bn_sums, a, B, st, ybf);
+    if (Cout > 32) return tc::launch_conv<64, true>(tmX, w_packed_bf16, Cout, Ktot, bias, residual, y, bn_sums, a, B, st, ybf);
+    return tc::launch_conv<32, true>(tmX, w_packed_bf16, Cout, Ktot, bias, residual, y, bn_sums, a, B, st, ybf);
 }

@@ -197,6 +197,199 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 1) tmem_dealloc(tmem_acc, BN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant (default when N % 4 == 0): one CTA per SM walks tiles blockIdx.x, + gridDim.x, ...; a 4 / 6 / 8-stage
+// operand ring that keeps running across tile boundaries; TWO TMEM accumulators (2 x BN columns), so the MMA warp starts the
+// next tile while the eight epilogue warps drain the previous one; each epilogue warp stages 32 x 32 blocks of its TMEM lane
+// quarter in shared memory (the 128-byte swizzle pattern, conflict-free float4 stores) and writes them with its own TMA stores
+// (cp.async.bulk.tensor ... .global.shared::cta), which also clip the ragged M / N edges.
+template <int BN>
+struct PGemmSmem {
+    static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+    static constexpr int kABytes = kBM * kBlockK * 4;      // 16 KB
+    static constexpr int kBBytes = BN * kBlockK * 4;
+    static constexpr int kCBytes = kBM * 32 * 4;           // one staged 128 x 32 output block
+    static constexpr int kBytes = 1024 + kStages * (kABytes + kBBytes) + 2 * kCBytes + 256;
+};
+
+constexpr int kPGemmThreads = 320;          // TMA producer warp, MMA warp, eight epilogue warps
+
+template <int BN>
+__global__ void __launch_bounds__(kPGemmThreads, 1)
+k_gemm_tf32_persist(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual,
+                    int64_t M, int N, int K, int act, int tiles_m, int tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = PGemmSmem<BN>;
+    constexpr int kStages = S::kStages;
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;
+    uint8_t* sB = sA + kStages * S::kABytes;
+    uint8_t* sC = sB + kStages * S::kBBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sC + 2 * S::kCBytes);
+    uint64_t* empty = full + kStages;
+    uint64_t* acc_full = empty + kStages;                  // [2]
+    uint64_t* acc_empty = acc_full + 2;                    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = (K + kBlockK - 1) / kBlockK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 8);                   // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                  // ===== TMA producer =====
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (tile % tiles_m) * kBM, n0 = (tile / tiles_m) * BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kStages;
+                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], S::kABytes + S::kBBytes);
+                    tma_load_2d(sA + s * S::kABytes, &tmA, &full[s], kb * kBlockK, m0);
+                    tma_load_2d(sB + s * S::kBBytes, &tmB, &full[s], kb * kBlockK, n0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                  // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
+                const uint32_t buf = lt & 1;
+                mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d = tmem_acc + buf * BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kStages;
+                    mbar_wait(&full[s], (it / kStages) & 1);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k128(smem_u32(sA + s * S::kABytes));
+                    const uint64_t db = umma_desc_k128(smem_u32(sB + s * S::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                        umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {                                              // ===== epilogue: warps 2..9 =====
+        // Two warps per TMEM lane quarter (one per half of the tile's columns): every SM sub-partition has two epilogue warps to
+        // switch between.  A warp owns its 32 rows x BN / 2 columns end to end -- its own 32 x 32 staging block (4 KB) and its
+        // own TMA stores, no barrier between the warps -- and keeps the next 32 columns' tcgen05.ld in flight while it
+        // finishes the current ones.
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;
+        constexpr int NCH = BN / 64;                      // 32-column chunks per warp and tile
+        uint8_t* stage = sC + (warp - 2) * 4096;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
+            const int m0 = (tile % tiles_m) * kBM, n0 = (tile / tiles_m) * BN + half * (BN / 2);
+            const uint32_t buf = lt & 1;
+            mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+            tc_fence_after();
+            const int64_t row = (int64_t)m0 + q * 32 + lane;
+            const float* rrow = (residual && row < M) ? residual + row * (int64_t)N : nullptr;   // may alias C
+            const uint32_t t0 = tmem_acc + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
+            float v[2][32];
+            tmem_ld32_nowait(t0, v[0]);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                tmem_ld_wait();
+                if (ch + 1 < NCH) tmem_ld32_nowait(t0 + (uint32_t)(ch + 1) * 32, v[(ch + 1) & 1]);
+                if (ch + 1 == NCH) {                      // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                const int col = n0 + ch * 32;
+                if (col >= N || m0 + q * 32 >= M) continue;   // warp-uniform (ragged last tiles)
+                const bool full32 = col + 32 <= N;
+                float (&w)[32] = v[ch & 1];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (full32 || col + j + 4 <= N) {     // N % 4 == 0: whole quads are inside or outside
+                        if (bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + j));
+                            w[j] += b.x; w[j + 1] += b.y; w[j + 2] += b.z; w[j + 3] += b.w;
+                        }
+                        if (act & 1) {
+                            w[j] = gelu_erf(w[j]); w[j + 1] = gelu_erf(w[j + 1]); w[j + 2] = gelu_erf(w[j + 2]); w[j + 3] = gelu_erf(w[j + 3]);
+                        }
+                        if (rrow) {
+                            const float4 rr = *reinterpret_cast<const float4*>(rrow + col + j);
+                            w[j] += rr.x; w[j + 1] += rr.y; w[j + 2] += rr.z; w[j + 3] += rr.w;
+                        }
+                        if (act & 2) {
+                            w[j] = rna_tf32(w[j]); w[j + 1] = rna_tf32(w[j + 1]); w[j + 2] = rna_tf32(w[j + 2]); w[j + 3] = rna_tf32(w[j + 3]);
+                        }
+                    }
+                }
+                if (lane == 0) tma_store_wait_read<0>();  // this warp's previous store has read the staging block
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)           // 128-byte swizzle: 16-byte chunk j / 4 of row `lane` -> chunk (j / 4) ^ (lane & 7)
+                    *reinterpret_cast<float4*>(stage + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4)) =
+                        make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmC, stage, col, m0 + q * 32);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, 2 * BN);
+}
+
+template <int BN>
+static int launch_gemm_persist(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M,
+                               int N, int K, int act, cudaStream_t st) {
+    CUtensorMap tmA, tmB, tmC;
+    const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)K * 4};
+    const uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)K * 4};
+    const uint64_t dC[2] = {(uint64_t)N, (uint64_t)M}, sC[1] = {(uint64_t)N * 4};
+    const uint32_t bA[2] = {kBlockK, kBM}, bB[2] = {kBlockK, (uint32_t)BN}, bC[2] = {32, 32};
+    int rc = make_tmap_f32(&tmA, A, 2, dA, sA, bA);
+    if (rc) return rc;
+    rc = make_tmap_f32(&tmB, B, 2, dB, sB, bB);
+    if (rc) return rc;
+    rc = make_tmap_f32(&tmC, C, 2, dC, sC, bC);
+    if (rc) return rc;
+    auto kern = k_gemm_tf32_persist<BN>;
+    OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PGemmSmem<BN>::kBytes));
+    const int tiles_m = (int)((M + kBM - 1) / kBM);
+    const int64_t tiles = (int64_t)tiles_m * ((N + BN - 1) / BN);
+    if (tiles >= (1ll << 31)) return OESS_E_RANGE;
+    const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+    OESS_KERNEL("tc_gemm_tf32", st, kern<<<grid, kPGemmThreads, PGemmSmem<BN>::kBytes, st>>>(
+        tmA, tmB, tmC, bias, residual, M, N, K, act, tiles_m, (int)tiles));
+    return 0;
+}
+
 template <int BN, int kStages, bool MC>
 static int launch_gemm(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M, int N,
                        int K, int act, cudaStream_t st) {
@@ -252,22 +445,31 @@ OESS_API int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias
     // per SM in clusters of two with the B tile multicast (measured: no gain, see the kernel comment)
     static const int variant = [] {
         const char* e = getenv("OESS_GEMM");
-        return !e ? 1 : (e[0] == 'd' ? 0 : (e[0] == 'm' ? 2 : 1));
+        return !e ? 3 : (e[0] == 'd' ? 0 : (e[0] == 'm' ? 2 : (e[0] == 't' ? 1 : 3)));   // t: one tile per CTA, two CTAs per SM
     }();
+    if (variant == 3 && (N & 3) == 0) {
+        // persistent kernel; tile width: 256 unless that leaves most SMs without a tile (tall-skinny products)
+        const int64_t mt = (M + 127) / 128;
+        int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+        while (bn > 64 && mt * ((N + bn - 1) / bn) * 5 < (int64_t)kNumSMs * 3) bn >>= 1;
+        if (bn == 256) return tc::launch_gemm_persist<256>(A, B, bias, residual, C, M, N, K, act, st);
+        if (bn == 128) return tc::launch_gemm_persist<128>(A, B, bias, residual, C, M, N, K, act, st);
+        return tc::launch_gemm_persist<64>(A, B, bias, residual, C, M, N, K, act, st);
+    }
     // fewer tiles than SMs: a second resident CTA has nothing to overlap with, the deeper ring hides the load latency instead
     const int64_t tiles = ((M + 127) / 128) * (int64_t)((N + (N > 128 ? 255 : (N > 64 ? 127 : 63))) / (N > 128 ? 256 : (N > 64 ? 128 : 64)));
-    if (variant == 0 || (variant == 1 && tiles <= kNumSMs)) {
+    if (variant == 0 || (variant != 2 && tiles <= kNumSMs)) {
         // tall-skinny products (e.g. the InfoNCE gradient G q: M = 3 200, N = 256, K = 9 600 -> 25 tiles of 128 x 256): narrower
         // N tiles put more SMs to work; the extra A-tile reads hit L2
         const int64_t mt = (M + 127) / 128;
-        const bool few = variant == 1 && tiles * 5 < kNumSMs * 3;
+        const bool few = variant != 0 && tiles * 5 < kNumSMs * 3;
         const int bn = !few ? (N > 128 ? 256 : (N > 64 ? 128 : 64))
                             : ((N > 128 && mt * ((N + 127) / 128) * 5 >= kNumSMs * 3) ? 128 : 64);
         if (bn == 256) return tc::launch_gemm<256, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
         if (bn == 128) return tc::launch_gemm<128, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
         return tc::launch_gemm<64, 4, false>(A, B, bias, residual, C, M, N, K, act, st);
     }
-    if (variant == 1) {
+    if (variant != 2) {
         if (N > 128) return tc::launch_gemm<256, 2, false>(A, B, bias, residual, C, M, N, K, act, st);
         if (N > 64) return tc::launch_gemm<128, 3, false>(A, B, bias, residual, C, M, N, K, act, st);
         return tc::launch_gemm<64, 4, false>(A, B, bias, residual, C, M, N, K, act, st);

@@ -68,6 +68,14 @@ class ConvLayer(nn.Module):
             self._packed = (key, _tc.conv2d_pack(w), None if b is None else b.detach().float().contiguous())
         return self._packed[1], self._packed[2]
 
+    def _tc_weights_bf16(self):
+        """bf16 packing for `oess_conv2d_nhwc_bf16` (input available as bf16: the hidden state of a bf16 ConvLSTM step)."""
+        w, b = self._folded if self._folded is not None else (self.conv2d.weight, self.conv2d.bias)
+        key = (w.data_ptr(), w._version, w.device)
+        if getattr(self, "_packed_bf16", None) is None or self._packed_bf16[0] != key:
+            self._packed_bf16 = (key, _tc.conv2d_pack_bf16(w), None if b is None else b.detach().float().contiguous())
+        return self._packed_bf16[1], self._packed_bf16[2]
+
     def fold_bn(self):
         """Eval-mode BN folded into the conv: w' = w * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps)."""
         if self.norm == 'BN' and not self.training:
@@ -176,10 +184,16 @@ class RecurrentConvLayer(nn.Module):
         rb = self.recurrent_block
         if (CONVLSTM_BF16 and USE_TENSOR_CORES and self.conv._tc_ok(x) and rb.hidden_size % 64 == 0
                 and rb.input_size == rb.hidden_size and tuple(rb.Gates.kernel_size) == (3, 3)):
-            wp, b = self.conv._tc_weights()                     # the conv output goes straight to bf16: ConvLSTM operand
-            c = self.conv.conv2d
-            x = _tc.conv2d_tc_bf16out(x, wp, b, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0],
-                                      relu=self.conv.activation is not None)
+            c = self.conv.conv2d                                # the conv output goes straight to bf16: ConvLSTM operand
+            xb = getattr(x, "_oess_bf16", None)                 # bf16 copy of the previous level's hidden state
+            if xb is not None and c.in_channels % 64 == 0:
+                wp, b = self.conv._tc_weights_bf16()
+                x = _tc.conv2d_tc_bf16(xb, wp, b, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0],
+                                       relu=self.conv.activation is not None, want_f32=False)[1]
+            else:
+                wp, b = self.conv._tc_weights()
+                x = _tc.conv2d_tc_bf16out(x, wp, b, c.kernel_size[0], c.stride[0], c.padding[0], c.dilation[0],
+                                          relu=self.conv.activation is not None)
         else:
             x = self.conv(x)
         state = self.recurrent_block(x, prev_state)

@@ -19,10 +19,11 @@ class PackedConvCache:
     def __init__(self):
         self._packed = {}
 
-    def get(self, conv, bn, pad_cin=0):
-        """pad_cin: zero-pad the input channels to this count (the 3-channel stem runs on an 8-channel repack)."""
+    def get(self, conv, bn, pad_cin=0, bf16=False):
+        """pad_cin: zero-pad the input channels to this count (the 3-channel stem runs on an 8-channel repack).
+        bf16: weights packed as bfloat16 for `oess_conv2d_nhwc_bf16`."""
         fold = bn is not None and not bn.training
-        key = (id(conv), fold)
+        key = (id(conv), fold, bf16)
         ver = (conv.weight.data_ptr(), conv.weight._version, conv.weight.device,
                (bn.running_var._version, bn.weight._version, bn.bias._version) if fold else None)
         hit = self._packed.get(key)
@@ -38,7 +39,7 @@ class PackedConvCache:
                 wp = torch.zeros(w.shape[0], pad_cin, w.shape[2], w.shape[3], dtype=w.dtype, device=w.device)
                 wp[:, :w.shape[1]] = w
                 w = wp
-            hit = (ver, _tc.conv2d_pack(w), b)
+            hit = (ver, _tc.conv2d_pack_bf16(w) if bf16 else _tc.conv2d_pack(w), b)
             self._packed[key] = hit
         return hit[1], hit[2]
 
@@ -71,6 +72,38 @@ def bottleneck(cache, blk, x):
     if blk.downsample is not None:
         identity = conv_bn(cache, x, blk.downsample[0], blk.downsample[1], False)
     return conv_bn(cache, out, blk.conv3, blk.bn3, True, residual=identity)
+
+
+def conv_bn_bf16(cache, x_bf, conv, bn, relu, residual=None, want_f32=True):
+    """conv_bn with bfloat16 conv operands; returns (y fp32 or None, y bf16)."""
+    wp, b = cache.get(conv, bn, bf16=True)
+    k, s, p, d = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
+    if bn is None or not bn.training:
+        return _tc.conv2d_tc_bf16(x_bf, wp, b, k, s, p, d, relu=relu, residual=residual, want_f32=want_f32)
+    return _tc.conv_bn_train_bf16(x_bf, wp, b, k, s, p, d, bn, residual=residual, relu=relu, want_f32=want_f32)
+
+
+def bottleneck_bf16(cache, blk, x, x_bf):
+    """`bottleneck` with bf16 operands: activations inside the block exist only as bf16, the block output (the next block's
+    identity) as fp32 + bf16; every sum (accumulators, BatchNorm statistics, residual add) is fp32."""
+    _, out = conv_bn_bf16(cache, x_bf, blk.conv1, blk.bn1, True, want_f32=False)
+    _, out = conv_bn_bf16(cache, out, blk.conv2, blk.bn2, True, want_f32=False)
+    identity = x
+    if blk.downsample is not None:
+        identity, _ = conv_bn_bf16(cache, x_bf, blk.downsample[0], blk.downsample[1], False)
+    return conv_bn_bf16(cache, out, blk.conv3, blk.bn3, True, residual=identity)
+
+
+def bf16_ok(net):
+    """every block a Bottleneck whose convs the bf16 kernel takes and whose BatchNorms have C % 4 == 0"""
+    for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+        for blk in layer:
+            if not hasattr(blk, "conv3"):
+                return False
+            convs = [blk.conv1, blk.conv2, blk.conv3] + ([blk.downsample[0]] if blk.downsample is not None else [])
+            if not all(conv_supported(c) and c.in_channels % 8 == 0 and c.out_channels % 4 == 0 for c in convs):
+                return False
+    return True
 
 
 def basic_block(cache, blk, x):
@@ -109,9 +142,16 @@ def stem(cache, net, x):
     return _tc.maxpool3x3s2_nhwc(y)
 
 
-def resnet_stages(cache, net, x):
-    """Stem + layer1..4 on hand-written kernels (tcgen05 convs, fused BN, own max pool); returns layer4 channels-last."""
+def resnet_stages(cache, net, x, bf16=False):
+    """Stem + layer1..4 on hand-written kernels (tcgen05 convs, fused BN, own max pool); returns layer4 channels-last.
+    bf16 (frozen Bottleneck networks): bfloat16 conv operands after the stem, fp32 accumulation / statistics / residuals."""
     x = stem(cache, net, x)
+    if bf16 and bf16_ok(net):
+        x_bf = x.to(torch.bfloat16)
+        for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
+            for blk in layer:
+                x, x_bf = bottleneck_bf16(cache, blk, x, x_bf)
+        return x
     for layer in (net.layer1, net.layer2, net.layer3, net.layer4):
         for blk in layer:
             x = bottleneck(cache, blk, x) if hasattr(blk, "conv3") else basic_block(cache, blk, x)

@@ -409,6 +409,80 @@ def conv_bn_train(x, w_packed, bias, kernel_size, stride, padding, dilation, bn,
     return y
 
 
+def conv2d_pack_bf16(weight):
+    """[Cout, Cin, KH, KW] -> bf16 [Cout, KH * KW * Cin_p] (Cin_p = Cin rounded up to 64, zero padded), column (tap, channel):
+    the K order of oess_conv2d_nhwc_bf16."""
+    Cout, Cin, KH, KW = weight.shape
+    cin_p = (Cin + 63) // 64 * 64
+    w = torch.zeros(Cout, KH * KW, cin_p, dtype=torch.float32, device=weight.device)
+    w[:, :, :Cin] = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, KH * KW, Cin)
+    return w.reshape(Cout, KH * KW * cin_p).to(torch.bfloat16).contiguous()
+
+
+def _check_bf16_nhwc(x):
+    if x.dtype != torch.bfloat16 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise ValueError("expected a bfloat16 channels-last [B, C, H, W] tensor")
+
+
+def conv2d_tc_bf16(x_bf, w_packed_bf, bias, kernel_size, stride=1, padding=0, dilation=1, relu=False, residual=None,
+                   want_f32=True, want_bf16=True):
+    """Frozen-network convolution with bfloat16 operands (tcgen05 kind::f16, fp32 accumulate; oess_conv2d_nhwc_bf16).
+    x_bf: bf16 channels-last [B, Cin, H, W], Cin % 8 == 0; residual fp32.  Returns (y fp32 or None, y bf16 or None)."""
+    _lib.require_cuda(x_bf, w_packed_bf, bias, residual)
+    _check_bf16_nhwc(x_bf)
+    B, Cin, H, W = x_bf.shape
+    KH = KW = int(kernel_size)
+    Cout = w_packed_bf.shape[0]
+    cl = torch.channels_last
+    Ho = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
+    Wo = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+    y = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x_bf.device, memory_format=cl) if want_f32 else None
+    yb = torch.empty((B, Cout, Ho, Wo), dtype=torch.bfloat16, device=x_bf.device, memory_format=cl) if want_bf16 else None
+    rc = None if residual is None else residual.float().contiguous(memory_format=cl)
+    bc = None if bias is None else _f32c(bias)
+    with torch.cuda.device(x_bf.device):
+        check(lib().oess_conv2d_nhwc_bf16(ptr(x_bf), ptr(w_packed_bf), ptr(bc), ptr(rc), ptr(y), ptr(yb), B, H, W, Cin, Cout,
+                                          KH, KW, stride, padding, dilation, 1 if relu else 0, None, stream_ptr(x_bf.device)),
+              "oess_conv2d_nhwc_bf16")
+    return y, yb
+
+
+def conv_bn_train_bf16(x_bf, w_packed_bf, bias, kernel_size, stride, padding, dilation, bn, residual=None, relu=False,
+                       want_f32=True):
+    """conv_bn_train with bfloat16 conv operands: batch statistics from the fp32 accumulators in the conv epilogue, the
+    normalised result stored as bf16 (next conv's operand) and, when want_f32, as fp32 (a later residual / the output).
+    Returns (y fp32 or None, y bf16)."""
+    _lib.require_cuda(x_bf, w_packed_bf)
+    _check_bf16_nhwc(x_bf)
+    B, Cin, H, W = x_bf.shape
+    KH = KW = int(kernel_size)
+    Cout = w_packed_bf.shape[0]
+    cl = torch.channels_last
+    Ho = (H + 2 * padding - dilation * (KH - 1) - 1) // stride + 1
+    Wo = (W + 2 * padding - dilation * (KW - 1) - 1) // stride + 1
+    y = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x_bf.device, memory_format=cl)
+    yb = torch.empty((B, Cout, Ho, Wo), dtype=torch.bfloat16, device=x_bf.device, memory_format=cl)
+    res = None if residual is None else residual.float().contiguous(memory_format=cl)
+    bc = None if bias is None else _f32c(bias)
+    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    track = bn.track_running_stats and bn.running_mean is not None
+    nb = ctypes.c_size_t(0)
+    check(lib().oess_bn_ws_bytes(Cout, ctypes.byref(nb)), "oess_bn_ws_bytes")
+    with torch.cuda.device(x_bf.device):
+        ws = _lib.workspace(nb.value, x_bf.device)
+        st = stream_ptr(x_bf.device)
+        check(lib().oess_conv2d_nhwc_bf16(ptr(x_bf), ptr(w_packed_bf), ptr(bc), None, ptr(y), None, B, H, W, Cin, Cout, KH, KW,
+                                          stride, padding, dilation, 0, ptr(ws), st), "oess_conv2d_nhwc_bf16")
+        check(lib().oess_batchnorm_nhwc_sums_bf16(ptr(y), B * Ho * Wo, Cout, ptr(bn.weight), ptr(bn.bias),
+                                                  ptr(bn.running_mean) if track else None,
+                                                  ptr(bn.running_var) if track else None, float(bn.eps), mom, ptr(res),
+                                                  1 if relu else 0, ptr(yb), 1 if want_f32 else 0, ptr(ws), ws.numel(), st),
+              "oess_batchnorm_nhwc_sums_bf16")
+        if track and bn.num_batches_tracked is not None:
+            bn.num_batches_tracked += 1
+    return (y if want_f32 else None), yb
+
+
 def zero_insert2x_nhwc(x, skip=None):
     """[B, C, H, W] (channels-last) -> [B, C, 2H, 2W] with (x + skip) at the even positions and zeros elsewhere: the input of
     a stride-2 transposed convolution run as a stride-1 convolution (oess_zero_insert2x_nhwc)."""

@@ -165,6 +165,18 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
                 w_.wait()
         ar_ms, _ = timed(ar_only, 10)
     peak_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    # the same step with TF32 operands everywhere (the frozen E2VID encoder's bf16 tensor-core operands switched off)
+    dtypes = {"frozen_e2vid_encoder": "bf16" if e2vid_model.CONVLSTM_BF16 else "tf32",
+              "frozen_teacher": "bf16" if im.TEACHER_BF16 else "tf32", "trainable_modules": "tf32", "accumulate": "fp32"}
+    ms_tf32 = None
+    if e2vid_model.CONVLSTM_BF16 or im.TEACHER_BF16:
+        saved = (e2vid_model.CONVLSTM_BF16, im.TEACHER_BF16)
+        e2vid_model.CONVLSTM_BF16, im.TEACHER_BF16 = False, False
+        try:
+            one()
+            ms_tf32, _ = timed(one, steps)
+        finally:
+            e2vid_model.CONVLSTM_BF16, im.TEACHER_BF16 = saved
 
     base = None
     if baseline_steps > 0:
@@ -178,6 +190,7 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
     out = {"metric": "end-to-end pretrain step (frame2voxel): event-frames/s = 20 x samples/s", "n_gpus": world,
            "batch_per_gpu": B, "events_per_frame": events, "steps": steps, "ms_per_step": ms,
            "samples_per_s": world * B / ms * 1e3, "event_frames_per_s": world * B * NF / ms * 1e3, "loss": loss,
+           "operand_dtypes": dtypes, "ms_per_step_tf32_operands": ms_tf32,
            "own_kernel_launches_per_step": launches, "peak_mem_gb": peak_gb, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
            "allreduce": {"backend": "nccl" if world > 1 else None, "bytes_per_step": ar_bytes, "calls_per_step": ar_calls,
                          "ms_alone": ar_ms, "overlapped_with_backward": world > 1}}

@@ -123,3 +123,66 @@ def test_conv2d_autograd_tensor_cores_vs_torch(B, C, Cout, H, W, k, p, d):
     assert bool(((xg.grad.cpu().double() - x.grad).abs() <= bound_x).all())
     torch.testing.assert_close(bg.grad.cpu().double(), b.grad, atol=1e-4, rtol=1e-5)
     assert float((yg.detach().cpu().double() - y.detach()).abs().max()) < 1e-2
+
+
+@pytest.mark.parametrize("B,Cin,Cout,H,W,k,s,p,d,relu,res", [
+    (1, 64, 128, 22, 40, 5, 2, 2, 1, True, False),    # E2VID encoder 2 with bf16 operands
+    (2, 128, 256, 11, 20, 5, 2, 2, 1, True, False),   # encoder 3, two 64-channel chunks, odd input size
+    (1, 64, 64, 12, 20, 3, 1, 2, 2, True, False),     # dilated 3x3 (teacher layer3 / layer4)
+    (1, 256, 64, 10, 16, 1, 1, 0, 1, True, False),    # 1x1 bottleneck reduce, four chunks
+    (1, 64, 256, 9, 17, 1, 1, 0, 1, True, True),      # 1x1 expand + fp32 residual
+    (1, 32, 64, 16, 32, 5, 2, 2, 1, True, False),     # Cin = 32: half of the 64-element K block is TMA zero fill
+    (1, 24, 20, 8, 16, 3, 1, 1, 1, False, False),     # Cin % 64 != 0, Cout % 16 != 0
+])
+def test_conv2d_tc_bf16_operands(B, Cin, Cout, H, W, k, s, p, d, relu, res):
+    """oess_conv2d_nhwc_bf16 against torch's conv2d in float64 on the bf16-ROUNDED operands (products of bf16 values are exact
+    in fp32: only the accumulation order differs -> 1e-5 * conv(|x|, |w|)); the bf16 copy of the result within one bf16 ulp."""
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(Cin * 5 + k)
+    x = torch.randn(B, Cin, H, W, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(torch.bfloat16)
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = F.conv2d(x.double(), w.double(), b.double(), stride=s, padding=p, dilation=d)
+    bound = 1e-5 * F.conv2d(x.abs().double(), w.abs().double(), None, stride=s, padding=p, dilation=d) + 1e-6
+    r = None
+    if res:
+        r = torch.randn(ref.shape, generator=g)
+        ref = ref + r.double()
+    if relu:
+        ref = ref.clamp_min(0)
+    xb = x.cuda().contiguous(memory_format=torch.channels_last)
+    y, yb = ops.conv2d_tc_bf16(xb, ops.conv2d_pack_bf16(w.cuda().float()), b.cuda(), k, s, p, d, relu,
+                               None if r is None else r.cuda())
+    assert tuple(y.shape) == tuple(ref.shape) and yb.dtype == torch.bfloat16
+    err = (y.cpu().double() - ref).abs()
+    assert bool((err <= bound).all()), f"max err {float(err.max())}, bound min {float(bound.min())}"
+    assert torch.equal(yb, y.to(torch.bfloat16))
+    only_bf = ops.conv2d_tc_bf16(xb, ops.conv2d_pack_bf16(w.cuda().float()), b.cuda(), k, s, p, d, relu,
+                                 None if r is None else r.cuda(), want_f32=False)
+    assert only_bf[0] is None and torch.equal(only_bf[1], yb)
+
+
+def test_conv_bn_train_bf16_vs_torch():
+    """bf16-operand conv + train-mode BatchNorm (statistics from the fp32 accumulators) against torch on the rounded operands."""
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    C, Cout, H, W, k = 64, 256, 22, 37, 1
+    x = torch.randn(2, C, H, W, generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, C, k, k, generator=g) / C ** 0.5).to(torch.bfloat16)
+    res = torch.randn(2, Cout, H, W, generator=g)
+    bn_ref = torch.nn.BatchNorm2d(Cout).double()
+    bn = torch.nn.BatchNorm2d(Cout).cuda()
+    with torch.no_grad():
+        bn_ref.weight.copy_(torch.rand(Cout, generator=g) + 0.5)
+        bn_ref.bias.copy_(torch.randn(Cout, generator=g) * 0.1)
+        bn.weight.copy_(bn_ref.weight.float())
+        bn.bias.copy_(bn_ref.bias.float())
+        ref = (bn_ref(F.conv2d(x.double(), w.double())) + res.double()).clamp_min(0)
+    xb = x.cuda().contiguous(memory_format=torch.channels_last)
+    y, yb = ops.conv_bn_train_bf16(xb, ops.conv2d_pack_bf16(w.cuda().float()), None, k, 1, 0, 1, bn, residual=res.cuda(), relu=True)
+    assert float((y.cpu().double() - ref).abs().max()) < 2e-4
+    assert torch.equal(yb, y.to(torch.bfloat16))
+    torch.testing.assert_close(bn.running_var.cpu().double(), bn_ref.running_var, rtol=1e-4, atol=1e-5)
+    y2, yb2 = ops.conv_bn_train_bf16(xb, ops.conv2d_pack_bf16(w.cuda().float()), None, k, 1, 0, 1, bn, residual=res.cuda(),
+                                     relu=True, want_f32=False)
+    assert y2 is None and torch.equal(yb2, yb)

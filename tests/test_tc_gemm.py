@@ -33,6 +33,8 @@ def _check(M, N, K, bias, seed=0):
     (17600, 256, 2048, True),   # DilationFeatureExtractor decoder conv at 110 x 160 (image_model.py:121-124)
     (300, 64, 36, False),       # BN = 64, K < one block
     (77, 11, 512, True),        # text-embedding conv: K classes = 11 (style_networks.py:165), unaligned N
+    (40000, 520, 96, True),     # persistent kernel: 313 x 3 tiles over 148 CTAs (both TMEM accumulators, ring across tiles), ragged N
+    (19000, 72, 160, False),    # persistent, BN = 128 with a ragged last N tile (72 = 2 x 32 + 8), 149 tiles: one CTA takes two
 ])
 def test_gemm_tf32(M, N, K, bias):
     _check(M, N, K, bias)
@@ -46,6 +48,20 @@ def test_gemm_tf32_exact_on_tf32_representable_inputs():
     b = torch.randint(-8, 9, (160, 96), device="cuda", generator=g).float()
     out = ops.gemm_tf32(a, b)
     assert torch.equal(out, a @ b.t())
+
+
+def test_gemm_tf32_persistent_exact_with_residual_in_place():
+    """Many tiles per CTA, bias + residual aliasing the output (the ViT's x += proj(...)): bit-exact on small integers."""
+    from openess_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    M, N, K = 128 * 301 + 5, 256, 64
+    a = torch.randint(-4, 5, (M, K), device="cuda", generator=g).float()
+    b = torch.randint(-4, 5, (N, K), device="cuda", generator=g).float()
+    bias = torch.randint(-4, 5, (N,), device="cuda", generator=g).float()
+    c = torch.randint(-4, 5, (M, N), device="cuda", generator=g).float()
+    ref = a @ b.t() + bias + c
+    out = ops.gemm_tf32_ex(a, b, bias, residual=c, out=c)
+    assert out.data_ptr() == c.data_ptr() and torch.equal(out, ref)
 
 
 def test_gemm_tf32_argument_errors():

@@ -34,14 +34,26 @@ def test_teacher_mirror_structure_and_cpu_forward():
 
 
 @pytest.mark.gpu
-def test_teacher_tensor_core_train_mode_vs_reference_golden():
+@pytest.mark.parametrize("dtype", ["tf32", "bf16"])
+def test_teacher_tensor_core_train_mode_vs_reference_golden(dtype, monkeypatch):
+    """bf16 (opt-in, OESS_TEACHER_DTYPE=bf16): bfloat16 conv operands after the stem, fp32 accumulation / statistics /
+    residuals.  Stated tolerance against the fp32 golden: 8x the error of torch's cuDNN-TF32 run of the same network on the
+    layer4 features (measured 6x: 2 fewer mantissa bits through 52 batch-renormalised convs of a random network),
+    3e-2 mean / 5e-1 max on the unit-norm output features."""
     from openess_b200 import _lib
+    from openess_b200.models import image_model as im
+    monkeypatch.setattr(im, "TEACHER_BF16", dtype == "bf16")
     z, m = _build()
     m = m.cuda()
     x = torch.from_numpy(z["x"]).cuda()
     with _lib.profile() as prof:
         feats = m.encoder(x)
-    assert prof.kernels["tc_conv2d"][0] == 53 and "bn_stats" not in prof.kernels and prof.kernels["bn_apply"][0] == 53
+    if dtype == "bf16":
+        assert prof.kernels["tc_conv2d"][0] == 1 and prof.kernels["tc_conv2d_bf16"][0] == 52
+    else:
+        assert prof.kernels["tc_conv2d"][0] == 53
+    assert "bn_stats" not in prof.kernels and prof.kernels["bn_apply"][0] == 53
+    k = 8.0 if dtype == "bf16" else 2.0
     assert prof.kernels["maxpool3x3s2_nhwc"][0] == 1        # stem conv + pool on own kernels too
     err_f = np.abs(feats[:, ::16].cpu().numpy() - z["feats_sub"])
     # the noise class this has to stay in: torch's own default GPU arithmetic for the same network (cuDNN TF32
@@ -54,9 +66,9 @@ def test_teacher_tensor_core_train_mode_vs_reference_golden():
     finally:
         torch.backends.cudnn.allow_tf32 = False
     err_lib = np.abs(feats_lib[:, ::16].cpu().numpy() - z["feats_sub"])
-    print("teacher features (max |value| %.1f): tensor-core path max / mean |err| %.3e / %.3e; torch cuDNN-TF32 path %.3e / %.3e"
-          % (float(z["feats_absmax"]), err_f.max(), err_f.mean(), err_lib.max(), err_lib.mean()))
-    assert err_f.mean() < 2.0 * err_lib.mean() + 1e-4 and err_f.max() < 2.0 * err_lib.max() + 1e-3
+    print("teacher features (max |value| %.1f): %s tensor-core path max / mean |err| %.3e / %.3e; torch cuDNN-TF32 path %.3e / %.3e"
+          % (float(z["feats_absmax"]), dtype, err_f.max(), err_f.mean(), err_lib.max(), err_lib.mean()))
+    assert err_f.mean() < k * err_lib.mean() + 1e-4 and err_f.max() < k * err_lib.max() + 1e-3
     sd = m.state_dict()                                      # running statistics updated exactly once, like the reference
     np.testing.assert_allclose(sd["encoder.layer4.2.bn3.running_mean"].cpu().numpy(), z["rm_l4"], atol=2e-3)
     np.testing.assert_allclose(sd["encoder.layer1.0.bn1.running_var"].cpu().numpy(), z["rv_l1"], rtol=2e-3)
@@ -65,16 +77,18 @@ def test_teacher_tensor_core_train_mode_vs_reference_golden():
     m.load_state_dict({k: v.cuda() for k, v in seeded_state_dict(m, int(z["seed"])).items()}, strict=True)
     y = m(x)                                                 # full forward: encoder (tensor cores) + trainable decoder
     err_y = np.abs(y.detach()[:, ::8, ::4, ::4].cpu().numpy() - z["y_sub"])
-    print("teacher unit-norm output features: max / mean |err| %.3e / %.3e" % (err_y.max(), err_y.mean()))
-    assert err_y.mean() < 3e-3 and err_y.max() < 5e-2
+    print("teacher unit-norm output features (%s): max / mean |err| %.3e / %.3e" % (dtype, err_y.max(), err_y.mean()))
+    assert (err_y.mean() < 3e-2 and err_y.max() < 5e-1) if dtype == "bf16" else (err_y.mean() < 3e-3 and err_y.max() < 5e-2)
     y.square().mean().backward()
     assert m.decoder[0].weight.grad is not None and float(m.decoder[0].weight.grad.abs().max()) > 0
 
 
 @pytest.mark.gpu
-def test_teacher_eval_mode_folded_bn_vs_torch():
+@pytest.mark.parametrize("dtype", ["tf32", "bf16"])
+def test_teacher_eval_mode_folded_bn_vs_torch(dtype, monkeypatch):
     from openess_b200 import _lib
     from openess_b200.models import image_model as im
+    monkeypatch.setattr(im, "TEACHER_BF16", dtype == "bf16")
     z, m = _build()
     m = m.cuda().eval()
     x = torch.from_numpy(z["x"]).cuda()
@@ -82,9 +96,11 @@ def test_teacher_eval_mode_folded_bn_vs_torch():
         ref = m.encoder.forward_torch(x)                     # cuDNN fp32 (TF32 disabled in conftest)
         with _lib.profile() as prof:
             out = m.encoder(x)
-    assert prof.kernels["tc_conv2d"][0] == 53 and "bn_apply" not in prof.kernels    # BN folded: no BN pass at all
+    nconv = prof.kernels["tc_conv2d"][0] + (prof.kernels["tc_conv2d_bf16"][0] if dtype == "bf16" else 0)
+    assert nconv == 53 and "bn_apply" not in prof.kernels    # BN folded: no BN pass at all
     scale = float(ref.abs().max())
-    assert float((out - ref).abs().max()) < 2e-2 * scale
+    print("teacher eval-mode features (%s): max |err| / max |value| %.3e" % (dtype, float((out - ref).abs().max()) / scale))
+    assert float((out - ref).abs().max()) < (6e-2 if dtype == "bf16" else 2e-2) * scale
 
 
 @pytest.mark.gpu
