@@ -11,6 +11,9 @@
 // out-of-bounds zero fill is the convolution's zero padding.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "tc_common.cuh"
 
 namespace oess {
@@ -209,6 +212,264 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
     if (warp == 1) tmem_dealloc(tmem_acc, BN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant (default when Cout % 4 == 0; OESS_CONV=tile selects the kernel above): one CTA per SM walks the tiles
+// (pixel tile fastest, then Cout tile, then sample), the operand ring keeps running across tile boundaries, two TMEM
+// accumulators: epilogue group g (four warps, one per TMEM lane quarter) drains the tiles of accumulator g while the MMA warp
+// fills the other one.  fp32 output goes through a swizzled 32-pixel x 32-channel staging block per warp and a 4-D TMA store
+// (box {32 ch, 16 px, 2 rows, 1}, clipped at the ragged edges); BatchNorm / InstanceNorm statistics are reduced across the
+// warp's 32 pixels by recursive halving (lane l ends up with channel l of the chunk), kept in registers across tiles and
+// flushed with fp64 atomics only when the CTA moves to another Cout tile or sample.
+constexpr int kPConvThreads = 320;
+
+template <int BN>
+struct PConvSmem {
+    static constexpr int kBBytes = BN * kBlockK * 4;
+    static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
+    static constexpr int kBytes = 1024 + kStages * (kVABytes + kBBytes) + 8 * 4096 + 256;
+};
+
+struct PConvArgs {
+    ConvArgs a;
+    int tiles_px, n_tiles, tiles;
+};
+
+template <int BN, bool BF16>
+__global__ void __launch_bounds__(kPConvThreads, 1)
+k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+            const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, const float* __restrict__ residual,
+            const bool y_f32, __nv_bfloat16* __restrict__ ybf, double* __restrict__ bn_sums, const PConvArgs pa) {
+    extern __shared__ uint8_t smem_raw[];
+    using S = PConvSmem<BN>;
+    constexpr int kStages = S::kStages;
+    constexpr int kKE = BF16 ? 64 : kBlockK;
+    constexpr int NCH = BN / 32;
+    const ConvArgs& a = pa.a;
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;
+    uint8_t* sB = sA + kStages * kVABytes;
+    uint8_t* sC = sB + kStages * S::kBBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sC + 8 * 4096);
+    uint64_t* empty = full + kStages;
+    uint64_t* acc_full = empty + kStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = a.taps * a.chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmW);
+        if (y_f32) tma_prefetch_desc(&tmY);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN < 32 ? 32 : 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                  // ===== TMA producer =====
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < pa.tiles; tile += gridDim.x) {
+                const int px = tile % pa.tiles_px, rest = tile / pa.tiles_px;
+                const int n0 = (rest % pa.n_tiles) * BN, b = rest / pa.n_tiles;
+                const int th = px / a.tiles_w, tw = px - th * a.tiles_w;
+                const int x0 = tw * kVW * a.stride - a.pad_x, y0 = th * kVH * a.stride - a.pad;
+                int tap = 0, chunk = 0;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kStages;
+                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], kVABytes + S::kBBytes);
+                    const int ky = tap / a.KW, kx = tap - ky * a.KW;
+                    tma_load_4d(sA + s * kVABytes, &tmX, &full[s], chunk * kKE, x0 + kx * a.dil, y0 + ky * a.dil, b);
+                    tma_load_2d(sB + s * S::kBBytes, &tmW, &full[s], kb * kKE, n0);
+                    if (++chunk == a.chunks) { chunk = 0; ++tap; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                  // ===== MMA issuer =====
+            constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(128, BN) : umma_idesc_tf32(128, BN);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < pa.tiles; tile += gridDim.x, ++lt) {
+                const uint32_t buf = lt & 1;
+                mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_acc + buf * BN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kStages;
+                    mbar_wait(&full[s], (it / kStages) & 1);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k128(smem_u32(sA + s * kVABytes));
+                    const uint64_t db = umma_desc_k128(smem_u32(sB + s * S::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        if (BF16) umma_bf16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {                                              // ===== epilogue: group g = warps 2 + 4 g .. 5 + 4 g =====
+        const int q = warp & 3;                           // TMEM lane quarter this warp may access
+        const uint32_t g = (uint32_t)(warp - 2) >> 2;     // drains accumulator g = the CTA's tiles with (local index & 1) == g
+        uint8_t* stage = sC + (warp - 2) * 4096;
+        float st_s[NCH], st_q[NCH];                       // running statistics of channel n0 + 32 ch + lane over this warp's pixels
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch) st_s[ch] = st_q[ch] = 0.f;
+        int st_key = -1;                                  // (sample, Cout tile) the running statistics belong to
+        auto flush = [&](int key) {
+            if (key < 0) return;
+            const int n0 = (key % pa.n_tiles) * BN, b = key / pa.n_tiles;
+            double* sums = bn_sums + (size_t)b * a.stats_stride;
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                const int c = n0 + ch * 32 + lane;
+                if (c < a.Cout) {
+                    atomicAdd(&sums[c], (double)st_s[ch]);
+                    atomicAdd(&sums[a.Cout + c], (double)st_q[ch]);
+                }
+                st_s[ch] = st_q[ch] = 0.f;
+            }
+        };
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < pa.tiles; tile += gridDim.x, ++lt) {
+            if ((lt & 1) != g) continue;
+            const int px = tile % pa.tiles_px, rest = tile / pa.tiles_px;
+            const int n0 = (rest % pa.n_tiles) * BN, b = rest / pa.n_tiles;
+            const int th = px / a.tiles_w, tw = px - th * a.tiles_w;
+            const int h0 = th * kVH, w0 = tw * kVW;
+            if (bn_sums && rest != st_key) {
+                flush(st_key);
+                st_key = rest;
+            }
+            mbar_wait(&acc_full[g], (lt >> 1) & 1);
+            tc_fence_after();
+            const int oy = h0 + q * 2 + (lane >> 4), ox = w0 + (lane & 15);
+            const bool valid = oy < a.Ho && ox < a.Wo;
+            const int64_t pix = (((int64_t)b * a.Ho + oy) * a.Wo + ox) * a.Cout;
+            const uint32_t t0 = tmem_acc + g * BN + ((uint32_t)(q * 32) << 16);
+            float v[2][32];
+            tmem_ld32_nowait(t0, v[0]);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                tmem_ld_wait();
+                if (ch + 1 < NCH) tmem_ld32_nowait(t0 + (uint32_t)(ch + 1) * 32, v[(ch + 1) & 1]);
+                if (ch + 1 == NCH) {                      // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[g]);
+                }
+                const int col = n0 + ch * 32;
+                if (col >= a.Cout) continue;              // warp-uniform
+                float (&w)[32] = v[ch & 1];
+                const bool full32 = col + 32 <= a.Cout;
+                if (bias) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (full32 || col + j + 4 <= a.Cout) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(bias + col + j));
+                            w[j] += bb.x; w[j + 1] += bb.y; w[j + 2] += bb.z; w[j + 3] += bb.w;
+                        }
+                    }
+                }
+                if (bn_sums) {
+                    // column sums / sums of squares over the warp's 32 pixels: five exchange rounds, each halving the columns
+                    // a lane is responsible for; lane l ends with channel col + l
+                    float s_[16], q_[16];
+                    {
+                        const bool up = (lane & 16) != 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float lo = valid ? w[j] : 0.f, hi = valid ? w[j + 16] : 0.f;
+                            const float keep = up ? hi : lo, send = up ? lo : hi;
+                            s_[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                            q_[j] = keep * keep + __shfl_xor_sync(0xffffffffu, send * send, 16);
+                        }
+                    }
+#pragma unroll
+                    for (int step = 1; step < 5; ++step) {
+                        const int m = 16 >> step, hcount = 16 >> step;
+                        const bool up = (lane & m) != 0;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (j < hcount) {
+                                const float ks = up ? s_[j + hcount] : s_[j], ss = up ? s_[j] : s_[j + hcount];
+                                const float kq = up ? q_[j + hcount] : q_[j], sq = up ? q_[j] : q_[j + hcount];
+                                s_[j] = ks + __shfl_xor_sync(0xffffffffu, ss, m);
+                                q_[j] = kq + __shfl_xor_sync(0xffffffffu, sq, m);
+                            }
+                        }
+                    }
+                    st_s[ch] += s_[0];
+                    st_q[ch] += q_[0];
+                }
+                if (residual && valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (full32 || col + j + 4 <= a.Cout) {
+                            const float4 rr = *reinterpret_cast<const float4*>(residual + pix + col + j);
+                            w[j] += rr.x; w[j + 1] += rr.y; w[j + 2] += rr.z; w[j + 3] += rr.w;
+                        }
+                    }
+                }
+                if (a.relu & 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) w[j] = fmaxf(w[j], 0.f);
+                }
+                if (a.relu & 2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) w[j] = rna_tf32(w[j]);
+                }
+                if (ybf && valid) {                       // bf16 copy: operand of a kind::f16 consumer
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (full32 || col + j + 4 <= a.Cout) {
+                            const __nv_bfloat162 lo = __floats2bfloat162_rn(w[j], w[j + 1]), hi = __floats2bfloat162_rn(w[j + 2], w[j + 3]);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                            *reinterpret_cast<uint2*>(ybf + pix + col + j) = pk;
+                        }
+                    }
+                }
+                if (y_f32) {
+                    if (lane == 0) tma_store_wait_read<0>();  // this warp's previous store has read the staging block
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)       // 128-byte swizzle: 16-byte chunk j / 4 of row `lane` -> chunk (j / 4) ^ (lane & 7)
+                        *reinterpret_cast<float4*>(stage + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4)) =
+                            make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&tmY, stage, col, w0, h0 + q * 2, b);
+                        tma_store_commit();
+                    }
+                }
+            }
+        }
+        if (bn_sums) flush(st_key);
+        if (lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, 2 * BN < 32 ? 32 : 2 * BN);
+}
+
 template <int BN, bool BF16 = false>
 static int launch_conv(const CUtensorMap& tmX, const void* w_packed, int Cout, int Ktot, const float* bias,
                        const float* residual, float* y, double* bn_sums, const ConvArgs& a, int B, cudaStream_t st,
@@ -218,10 +479,32 @@ static int launch_conv(const CUtensorMap& tmX, const void* w_packed, int Cout, i
     const uint32_t bW[2] = {BF16 ? 64u : (uint32_t)kBlockK, (uint32_t)BN};
     int rc = BF16 ? make_tmap_bf16(&tmW, w_packed, 2, dW, sW, bW) : make_tmap_f32(&tmW, w_packed, 2, dW, sW, bW);
     if (rc) return rc;
+    const int tiles_h = (a.Ho + kVH - 1) / kVH;
+    const int n_tiles = (Cout + BN - 1) / BN;
+    static const bool tile_env = [] { const char* e = std::getenv("OESS_CONV"); return e && e[0] == 't'; }();
+    const int64_t tiles = (int64_t)a.tiles_w * tiles_h * n_tiles * B;
+    if (!tile_env && (Cout & 3) == 0 && tiles < (1ll << 31)) {
+        CUtensorMap tmY;
+        memset(&tmY, 0, sizeof(tmY));
+        if (y) {
+            const uint64_t dY[4] = {(uint64_t)Cout, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)B};
+            const uint64_t sY[3] = {(uint64_t)Cout * 4, (uint64_t)a.Wo * Cout * 4, (uint64_t)a.Ho * a.Wo * Cout * 4};
+            const uint32_t bY[4] = {32, (uint32_t)kVW, 2, 1};
+            rc = make_tmap_f32(&tmY, y, 4, dY, sY, bY);
+            if (rc) return rc;
+        }
+        auto kern = k_conv_tc_p<BN, BF16>;
+        OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PConvSmem<BN>::kBytes));
+        const PConvArgs pa{a, a.tiles_w * tiles_h, n_tiles, (int)tiles};
+        const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+        OESS_KERNEL(BF16 ? "tc_conv2d_bf16" : "tc_conv2d", st,
+                    kern<<<grid, kPConvThreads, PConvSmem<BN>::kBytes, st>>>(tmX, tmW, tmY, bias, residual, y != nullptr, ybf,
+                                                                             bn_sums, pa));
+        return 0;
+    }
     auto kern = k_conv_tc<BN, BF16>;
     OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<BN>::kBytes));
-    const int tiles_h = (a.Ho + kVH - 1) / kVH;
-    const dim3 grid((unsigned)(a.tiles_w * tiles_h), (unsigned)((Cout + BN - 1) / BN), (unsigned)B);
+    const dim3 grid((unsigned)(a.tiles_w * tiles_h), (unsigned)n_tiles, (unsigned)B);
     OESS_KERNEL(BF16 ? "tc_conv2d_bf16" : "tc_conv2d", st,
                 kern<<<grid, 192, ConvSmem<BN>::kBytes, st>>>(tmX, tmW, bias, residual, y, ybf, bn_sums, a));
     return 0;

@@ -14,6 +14,8 @@
 // fp32 operands are read as TF32 (torch's default cuDNN conv arithmetic on the reference's GPU run), fp32 accumulate.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace oess {
@@ -157,6 +159,170 @@ k_convlstm_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (warp == 1) tmem_dealloc(tmem_acc, kCN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant (default; OESS_CONVLSTM=tile selects the kernel above): one CTA per SM walks the tiles (pixel patch
+// fastest, then 64-channel chunk, then sample) with a 4-stage operand ring that keeps running across tile boundaries and TWO
+// TMEM accumulators (2 x 256 columns): epilogue group g (four warps, one per TMEM lane quarter) does the gate math of the tiles
+// of accumulator g while the MMA warp fills the other one.  With 18 - 72 K blocks per tile (bf16), the per-tile prologue
+// (barrier setup, TMEM allocation, pipeline fill) and the un-overlapped epilogue were ~30 % of the one-tile-per-CTA kernel.
+constexpr int kPCStages = 4;
+constexpr int kPCSmem = 1024 + kPCStages * (kCABytes + kCBBytes) + 256;
+constexpr int kPCThreads = 320;
+
+template <bool BF16>
+__global__ void __launch_bounds__(kPCThreads, 1)
+k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
+                const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias, const float* __restrict__ c_prev,
+                float* __restrict__ h_out, __nv_bfloat16* __restrict__ h_bf, float* __restrict__ c_out, int H, int W, int C,
+                int has_h, int tiles_w, int tiles_px, int tiles) {
+    constexpr int kKE = BF16 ? 64 : kBlockK;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;
+    uint8_t* sB = base + kPCStages * kCABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + kPCStages * kCBBytes);
+    uint64_t* empty = full + kPCStages;
+    uint64_t* acc_full = empty + kPCStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = C / kKE, nchunks = C / 64;
+    const int kblocks = (has_h ? 2 : 1) * 9 * chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmH);
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < kPCStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * kCN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                  // ===== TMA producer =====
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int px = tile % tiles_px, rest = tile / tiles_px;
+                const int nchunk = rest % nchunks, b = rest / nchunks;
+                const int th = px / tiles_w, tw = px - th * tiles_w;
+                const int h0 = th * kTH, w0 = tw * kTW;
+                int src = 0, tap = 0, chunk = 0;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kPCStages;
+                    mbar_wait(&empty[s], ((it / kPCStages) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], kCABytes + kCBBytes);
+                    const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
+                    tma_load_4d(sA + s * kCABytes, src ? &tmH : &tmX, &full[s], chunk * kKE, w0 + dx, h0 + dy, b);
+                    tma_load_2d(sB + s * kCBBytes, &tmW, &full[s], kb * kKE, nchunk * kCN);
+                    if (++chunk == chunks) { chunk = 0; if (++tap == 9) { tap = 0; ++src; } }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                  // ===== MMA issuer =====
+            constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(128, kCN) : umma_idesc_tf32(128, kCN);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
+                const uint32_t buf = lt & 1;
+                mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_acc + buf * kCN;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % kPCStages;
+                    mbar_wait(&full[s], (it / kPCStages) & 1);
+                    tc_fence_after();
+                    const uint64_t da = umma_desc_k128(smem_u32(sA + s * kCABytes));
+                    const uint64_t db = umma_desc_k128(smem_u32(sB + s * kCBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                        if (BF16) umma_bf16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[buf]);
+            }
+        }
+    } else {                                              // ===== epilogue: group g = warps 2 + 4 g .. 5 + 4 g =====
+        const int q = warp & 3;
+        const uint32_t g = (uint32_t)(warp - 2) >> 2;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
+            if ((lt & 1) != g) continue;
+            const int px = tile % tiles_px, rest = tile / tiles_px;
+            const int nchunk = rest % nchunks, b = rest / nchunks;
+            const int th = px / tiles_w, tw = px - th * tiles_w;
+            const int r = q * 32 + lane;                  // accumulator row = pixel of the patch (h-major, w-minor)
+            const int y = th * kTH + r / kTW, x = tw * kTW + r % kTW;
+            const bool valid = y < H && x < W;
+            const int64_t pix = (((int64_t)b * H + y) * W + x) * C + nchunk * 64;
+            const float* bn = bias + nchunk * kCN;
+            mbar_wait(&acc_full[g], (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_acc + g * kCN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int sub = 0; sub < 4; ++sub) {           // 16 hidden channels at a time
+                float gi[16], gf[16], go[16], gg[16];
+                tmem_ld16_nowait(trow + 0 * 64 + sub * 16, gi);   // submodules.py:203 chunk order: in, remember, out, cell
+                tmem_ld16_nowait(trow + 1 * 64 + sub * 16, gf);
+                tmem_ld16_nowait(trow + 2 * 64 + sub * 16, go);
+                tmem_ld16_nowait(trow + 3 * 64 + sub * 16, gg);
+                tmem_ld_wait();
+                if (sub == 3) {                           // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_empty[g]);
+                }
+                if (valid) {
+                    const int64_t e = pix + sub * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c_prev) pc = *reinterpret_cast<const float4*>(c_prev + e + j);
+                        const float4 bi = __ldg(reinterpret_cast<const float4*>(bn + 0 * 64 + sub * 16 + j));
+                        const float4 bf = __ldg(reinterpret_cast<const float4*>(bn + 1 * 64 + sub * 16 + j));
+                        const float4 bo = __ldg(reinterpret_cast<const float4*>(bn + 2 * 64 + sub * 16 + j));
+                        const float4 bg = __ldg(reinterpret_cast<const float4*>(bn + 3 * 64 + sub * 16 + j));
+                        float4 c, h;
+                        c.x = sigm(gf[j] + bf.x) * pc.x + sigm(gi[j] + bi.x) * tanhf(gg[j] + bg.x);
+                        c.y = sigm(gf[j + 1] + bf.y) * pc.y + sigm(gi[j + 1] + bi.y) * tanhf(gg[j + 1] + bg.y);
+                        c.z = sigm(gf[j + 2] + bf.z) * pc.z + sigm(gi[j + 2] + bi.z) * tanhf(gg[j + 2] + bg.z);
+                        c.w = sigm(gf[j + 3] + bf.w) * pc.w + sigm(gi[j + 3] + bi.w) * tanhf(gg[j + 3] + bg.w);
+                        h.x = sigm(go[j] + bo.x) * tanhf(c.x);
+                        h.y = sigm(go[j + 1] + bo.y) * tanhf(c.y);
+                        h.z = sigm(go[j + 2] + bo.z) * tanhf(c.z);
+                        h.w = sigm(go[j + 3] + bo.w) * tanhf(c.w);
+                        *reinterpret_cast<float4*>(c_out + e + j) = c;
+                        if (h_out) *reinterpret_cast<float4*>(h_out + e + j) = h;
+                        if (BF16) {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(h.x, h.y), hi = __floats2bfloat162_rn(h.z, h.w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                            *reinterpret_cast<uint2*>(h_bf + e + j) = pk;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_acc, 2 * kCN);
+}
+
 }  // namespace tc
 }  // namespace oess
 
@@ -193,8 +359,19 @@ static int convlstm_impl(const void* x, const void* h_prev, const float* c_prev,
     const uint32_t bW[2] = {KE, tc::kCN};
     rc = mk(&tmW, w_packed, 2, dW, sW, bW);
     if (rc) return rc;
-    OESS_CUDA(cudaFuncSetAttribute(tc::k_convlstm_tc<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kCSmem));
     const int tiles_w = (W + tc::kTW - 1) / tc::kTW, tiles_h = (H + tc::kTH - 1) / tc::kTH;
+    static const bool tile_env = [] { const char* e = std::getenv("OESS_CONVLSTM"); return e && e[0] == 't'; }();
+    const int64_t tiles = (int64_t)tiles_w * tiles_h * (C / 64) * B;
+    if (!tile_env && tiles < (1ll << 31)) {
+        OESS_CUDA(cudaFuncSetAttribute(tc::k_convlstm_tc_p<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kPCSmem));
+        const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+        OESS_KERNEL(BF16 ? "tc_convlstm_step_bf16" : "tc_convlstm_step", st,
+                    tc::k_convlstm_tc_p<BF16><<<grid, tc::kPCThreads, tc::kPCSmem, st>>>(
+                        tmX, tmH, tmW, bias_packed, c_prev, h_out, h_bf, c_out, H, W, C, h_prev ? 1 : 0, tiles_w,
+                        tiles_w * tiles_h, (int)tiles));
+        return 0;
+    }
+    OESS_CUDA(cudaFuncSetAttribute(tc::k_convlstm_tc<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kCSmem));
     const dim3 grid((unsigned)(tiles_w * tiles_h), (unsigned)(C / 64), (unsigned)B);
     OESS_KERNEL(BF16 ? "tc_convlstm_step_bf16" : "tc_convlstm_step", st, tc::k_convlstm_tc<BF16><<<grid, 192, tc::kCSmem, st>>>(
         tmX, tmH, tmW, bias_packed, c_prev, h_out, h_bf, c_out, H, W, C, h_prev ? 1 : 0, tiles_w));

@@ -127,8 +127,19 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
             dist.barrier()
             torch.cuda.synchronize()
 
+    # every step copies its whole batch from pinned host memory; the copy of step i + 1 runs on a side stream under step i
+    from .prefetch import DevicePrefetcher
+    prefetch = os.environ.get("OESS_PREFETCH", "1") != "0"
+    pf = DevicePrefetcher(dev)
+    if prefetch:
+        pf.feed(data)
+
     def one():
-        _, _, total = step.train_step(data)
+        cur = data
+        if prefetch:
+            cur = pf.take()
+            pf.feed(data)
+        _, _, total = step.train_step(cur)
         return float(total.detach())                       # D2H read of the step's loss (the trainer logs it)
 
     def timed(fn, n):
@@ -191,7 +202,8 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
            "batch_per_gpu": B, "events_per_frame": events, "steps": steps, "ms_per_step": ms,
            "samples_per_s": world * B / ms * 1e3, "event_frames_per_s": world * B * NF / ms * 1e3, "loss": loss,
            "operand_dtypes": dtypes, "ms_per_step_tf32_operands": ms_tf32,
-           "own_kernel_launches_per_step": launches, "peak_mem_gb": peak_gb, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+           "own_kernel_launches_per_step": launches, "peak_mem_gb": peak_gb, "h2d_bytes_per_step": h2d,
+           "h2d_prefetch_on_side_stream": prefetch, "d2h_bytes_per_step": 4,
            "allreduce": {"backend": "nccl" if world > 1 else None, "bytes_per_step": ar_bytes, "calls_per_step": ar_calls,
                          "ms_alone": ar_ms, "overlapped_with_backward": world > 1}}
     if base is not None:

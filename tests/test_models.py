@@ -94,7 +94,10 @@ def test_e2vid_full_width_tensor_core_convlstm_vs_reference_golden():
             # 3 levels x 3 steps of ConvLSTM and encoder convs + 3 head convs on the tensor cores, none otherwise
             assert prof.kernels.get("tc_convlstm_step", (0, 0.0))[0] == (9 if mode == "tf32" else 0)
             assert prof.kernels.get("tc_convlstm_step_bf16", (0, 0.0))[0] == (9 if mode == "bf16" else 0)
-            assert prof.kernels.get("tc_conv2d", (0, 0.0))[0] == (12 if use_tc else 0)
+            # bf16 mode: the level-2 / level-3 encoder convs read the previous level's bf16 hidden state (kind::f16 kernel)
+            nconv = prof.kernels.get("tc_conv2d", (0, 0.0))[0] + prof.kernels.get("tc_conv2d_bf16", (0, 0.0))[0]
+            assert nconv == (12 if use_tc else 0)
+            assert prof.kernels.get("tc_conv2d_bf16", (0, 0.0))[0] == (6 if mode == "bf16" else 0)
         finally:
             mm.USE_TENSOR_CORES = True
             mm.CONVLSTM_BF16 = bf16_was
@@ -130,7 +133,8 @@ def test_e2vid_online_reconstruction_on_own_kernels_vs_reference_golden():
                     worst = max(worst, float(np.abs(img.cpu().numpy() - z[f"img{i}"]).max()))
             errs[use_tc] = worst
             if use_tc:      # per step: 2 resblocks x 2 convs + 3 decoders (+ 1 head + 3 encoder convs) on the conv kernel
-                assert prof.kernels["tc_conv2d"][0] == 3 * (4 + 4 + 3) and prof.kernels["zero_insert2x_nhwc"][0] == 9
+                nconv = prof.kernels["tc_conv2d"][0] + prof.kernels.get("tc_conv2d_bf16", (0, 0.0))[0]
+                assert nconv == 3 * (4 + 4 + 3) and prof.kernels["zero_insert2x_nhwc"][0] == 9
                 assert prof.kernels["pred_sigmoid_nhwc"][0] == 3
         finally:
             mm.USE_TENSOR_CORES = True
