@@ -109,6 +109,50 @@ k_zero_insert2x(const float4* __restrict__ x, const float4* __restrict__ skip, i
     }
 }
 
+// out [B, 2H, 2W, C1 + C2] = cat(nearest-x2(x [B, H, W, C1]), skip [B, 2H, 2W, C2]) along the channels: the decoder transitions of
+// SemSegE2VID (models/style_networks.py:148-158: f.interpolate(scale_factor=2, mode='nearest') + torch.cat) in one pass.
+__global__ void __launch_bounds__(256)
+k_up2x_cat(const float4* __restrict__ x, const float4* __restrict__ skip, int B, int H, int W, int C1q, int C2q,
+           float4* __restrict__ out) {
+    const int Cq = C1q + C2q;
+    const int64_t total = (int64_t)B * 2 * H * 2 * W * Cq;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cq);
+        const int64_t pix = i / Cq;
+        if (c < C1q) {
+            const int xo = (int)(pix % (2 * W));
+            const int yo = (int)((pix / (2 * W)) % (2 * H));
+            const int b = (int)(pix / ((int64_t)4 * W * H));
+            out[i] = __ldg(x + (((int64_t)b * H + (yo >> 1)) * W + (xo >> 1)) * C1q + c);
+        } else {
+            out[i] = __ldcs(skip + pix * C2q + (c - C1q));
+        }
+    }
+}
+// backward: dx [B, H, W, C1] = 2 x 2 sums of g[..., :C1]; dskip [B, 2H, 2W, C2] = g[..., C1:] (either may be NULL)
+__global__ void __launch_bounds__(256)
+k_up2x_cat_bwd(const float4* __restrict__ g, int B, int H, int W, int C1q, int C2q, float4* __restrict__ dx,
+               float4* __restrict__ dskip) {
+    const int Cq = C1q + C2q;
+    const int64_t n1 = dx ? (int64_t)B * H * W * C1q : 0, n2 = dskip ? (int64_t)B * 4 * H * W * C2q : 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < n1) {
+            const int c = (int)(i % C1q);
+            const int xi = (int)((i / C1q) % W);
+            const int yi = (int)((i / ((int64_t)C1q * W)) % H);
+            const int b = (int)(i / ((int64_t)C1q * W * H));
+            const int64_t row = ((int64_t)b * 2 * H + 2 * yi) * (2 * W) + 2 * xi;
+            const float4 a0 = __ldcs(g + row * Cq + c), a1 = __ldcs(g + (row + 1) * Cq + c);
+            const float4 a2 = __ldcs(g + (row + 2 * W) * Cq + c), a3 = __ldcs(g + (row + 2 * W + 1) * Cq + c);
+            dx[i] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y), (a0.z + a1.z) + (a2.z + a3.z),
+                                (a0.w + a1.w) + (a2.w + a3.w));
+        } else {
+            const int64_t j = i - n1;
+            dskip[j] = __ldcs(g + (j / C2q) * Cq + C1q + (int)(j % C2q));
+        }
+    }
+}
+
 // out[p] = sigmoid(sum_c w[c] * (x[p, c] + skip[p, c]) + bias): the prediction layer (1x1 conv to one channel + sigmoid) with
 // the last skip sum fused.  One warp per 32 / (C / 4)... simple form: thread per pixel, C <= 64.
 __global__ void __launch_bounds__(256)
@@ -144,6 +188,32 @@ OESS_API int oess_zero_insert2x_nhwc(const float* x, const float* skip, int B, i
     if (g > (int64_t)kNumSMs * 16) g = (int64_t)kNumSMs * 16;
     cudaStream_t st = (cudaStream_t)stream;
     OESS_KERNEL("zero_insert2x_nhwc", st, pool::k_zero_insert2x<<<(unsigned)g, 256, 0, st>>>((const float4*)x, (const float4*)skip, B, H, W, C / 4, (float4*)z));
+    return OESS_OK;
+}
+
+OESS_API int oess_upsample2x_cat_nhwc(const float* x, const float* skip, int B, int H, int W, int C1, int C2, float* out,
+                                      oess_stream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || C1 <= 0 || C2 < 0 || (C1 & 3) || (C2 & 3)) return OESS_E_ARG;
+    if (!x || !out || (C2 > 0 && !skip) || (((uintptr_t)x | (uintptr_t)skip | (uintptr_t)out) & 15)) return OESS_E_ARG;
+    const int64_t total = (int64_t)B * 4 * H * W * ((C1 + C2) / 4);
+    int64_t g = (total + 255) / 256;
+    if (g > (int64_t)kNumSMs * 16) g = (int64_t)kNumSMs * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    OESS_KERNEL("upsample2x_cat_nhwc", st, pool::k_up2x_cat<<<(unsigned)g, 256, 0, st>>>(
+        (const float4*)x, (const float4*)skip, B, H, W, C1 / 4, C2 / 4, (float4*)out));
+    return OESS_OK;
+}
+
+OESS_API int oess_upsample2x_cat_nhwc_bwd(const float* g, int B, int H, int W, int C1, int C2, float* dx, float* dskip,
+                                          oess_stream_t stream) {
+    if (B <= 0 || H <= 0 || W <= 0 || C1 <= 0 || C2 < 0 || (C1 & 3) || (C2 & 3)) return OESS_E_ARG;
+    if (!g || (!dx && !dskip) || (dskip && C2 == 0) || (((uintptr_t)g | (uintptr_t)dx | (uintptr_t)dskip) & 15)) return OESS_E_ARG;
+    const int64_t total = (dx ? (int64_t)B * H * W * (C1 / 4) : 0) + (dskip ? (int64_t)B * 4 * H * W * (C2 / 4) : 0);
+    int64_t gr = (total + 255) / 256;
+    if (gr > (int64_t)kNumSMs * 16) gr = (int64_t)kNumSMs * 16;
+    cudaStream_t st = (cudaStream_t)stream;
+    OESS_KERNEL("upsample2x_cat_nhwc_bwd", st, pool::k_up2x_cat_bwd<<<(unsigned)gr, 256, 0, st>>>(
+        (const float4*)g, B, H, W, C1 / 4, C2 / 4, (float4*)dx, (float4*)dskip));
     return OESS_OK;
 }
 

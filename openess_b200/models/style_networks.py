@@ -178,19 +178,19 @@ class SemSegE2VID(nn.Module):
 
     def trunk_tc(self, input_dict, out, train=False):
         """`trunk` with every conv + InstanceNorm (+ residual) (+ ReLU) on the hand-written kernels; nearest x2 upsampling
-        and the skip concatenations stay (channels-last) torch ops.  train=False: forward only (no autograd graph);
+        + skip concatenation is one kernel (`ops.upsample2x_cat`).  train=False: forward only (no autograd graph);
         train=True: differentiable blocks (`ops.conv_in_autograd`)."""
         with torch.set_grad_enabled(train and torch.is_grad_enabled()):
             cl = torch.channels_last
             sz_in = input_dict[1].shape[3]
             x = self._seq_tc(self.decoder_scale_1, input_dict[8], train)
-            x = torch.cat([f.interpolate(x, scale_factor=2, mode='nearest'), input_dict[4]], dim=1).contiguous(memory_format=cl)
+            x = _ops.upsample2x_cat(x, input_dict[4])            # nearest x2 + skip concat in one pass (:148-150)
             x = self._seq_tc(self.decoder_scale_2, x, train)
             self.update_skip_dict(out, x, sz_in)
-            x = torch.cat([f.interpolate(x, scale_factor=2, mode='nearest'), input_dict[2]], dim=1).contiguous(memory_format=cl)
+            x = _ops.upsample2x_cat(x, input_dict[2])
             x = self._seq_tc(self.decoder_scale_3, x, train)
             self.update_skip_dict(out, x, sz_in)
-            x = f.interpolate(x, scale_factor=2, mode='nearest').contiguous(memory_format=cl)
+            x = _ops.upsample2x_cat(x)
             return self._seq_tc(self.decoder_scale_4, x, train)
 
     def _tc_train_ok(self, input_dict):

@@ -483,6 +483,45 @@ def conv_bn_train_bf16(x_bf, w_packed_bf, bias, kernel_size, stride, padding, di
     return (y if want_f32 else None), yb
 
 
+class _Up2xCat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, skip):
+        B, C1, H, W = x.shape
+        C2 = 0 if skip is None else skip.shape[1]
+        cl = torch.channels_last
+        xc = x.float().contiguous(memory_format=cl)
+        sc = None if skip is None else skip.float().contiguous(memory_format=cl)
+        out = torch.empty((B, C1 + C2, 2 * H, 2 * W), dtype=torch.float32, device=x.device, memory_format=cl)
+        with torch.cuda.device(x.device):
+            check(lib().oess_upsample2x_cat_nhwc(ptr(xc), ptr(sc), B, H, W, C1, C2, ptr(out), stream_ptr(x.device)),
+                  "oess_upsample2x_cat_nhwc")
+        ctx.dims = (B, H, W, C1, C2)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, H, W, C1, C2 = ctx.dims
+        cl = torch.channels_last
+        gc = g.float().contiguous(memory_format=cl)
+        need_x, need_s = ctx.needs_input_grad[0], C2 > 0 and ctx.needs_input_grad[1]
+        dx = torch.empty((B, C1, H, W), dtype=torch.float32, device=g.device, memory_format=cl) if need_x else None
+        ds = torch.empty((B, C2, 2 * H, 2 * W), dtype=torch.float32, device=g.device, memory_format=cl) if need_s else None
+        if need_x or need_s:
+            with torch.cuda.device(g.device):
+                check(lib().oess_upsample2x_cat_nhwc_bwd(ptr(gc), B, H, W, C1, C2, ptr(dx), ptr(ds), stream_ptr(g.device)),
+                      "oess_upsample2x_cat_nhwc_bwd")
+        return dx, ds
+
+
+def upsample2x_cat(x, skip=None):
+    """cat([F.interpolate(x, scale_factor=2, mode='nearest'), skip], dim=1) in one pass, channels-last, differentiable
+    (oess_upsample2x_cat_nhwc; models/style_networks.py:148-158).  skip None: plain nearest x2 upsampling."""
+    _lib.require_cuda(x, skip)
+    if x.shape[1] % 4 or (skip is not None and (skip.shape[1] % 4 or skip.shape[2:] != (2 * x.shape[2], 2 * x.shape[3]))):
+        raise ValueError("upsample2x_cat: channels % 4 == 0 and skip at twice the resolution of x")
+    return _Up2xCat.apply(x, skip)
+
+
 def zero_insert2x_nhwc(x, skip=None):
     """[B, C, H, W] (channels-last) -> [B, C, 2H, 2W] with (x + skip) at the even positions and zeros elsewhere: the input of
     a stride-2 transposed convolution run as a stride-1 convolution (oess_zero_insert2x_nhwc)."""

@@ -251,3 +251,24 @@ def test_conv_instancenorm_autograd_vs_torch(C, Cout, res, relu):
     if res:
         assert float((rg.grad.cpu().double() - r.grad).abs().max()) < 1e-6
     assert float(bg.grad.abs().max()) < 1e-2 * float(w.grad.abs().max())      # mathematically zero
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C1,C2", [(64, 128), (32, 64), (16, 0)])
+def test_upsample2x_cat_matches_torch_forward_and_backward(C1, C2):
+    """oess_upsample2x_cat_nhwc (+ _bwd) against f.interpolate(nearest, x2) + torch.cat (style_networks.py:148-158): exact."""
+    import torch.nn.functional as f
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(C1 + C2)
+    x = torch.randn(2, C1, 7, 9, generator=g).cuda().requires_grad_(True)
+    s = torch.randn(2, C2, 14, 18, generator=g).cuda().requires_grad_(True) if C2 else None
+    out = ops.upsample2x_cat(x, s)
+    up = f.interpolate(x, scale_factor=2, mode='nearest')
+    ref = torch.cat([up, s], dim=1) if C2 else up
+    assert out.is_contiguous(memory_format=torch.channels_last) and torch.equal(out, ref)
+    w = torch.randn(ref.shape, generator=g).cuda()
+    gx, *gs = torch.autograd.grad((out * w).sum(), [x] + ([s] if C2 else []))
+    rx, *rs = torch.autograd.grad((ref * w).sum(), [x] + ([s] if C2 else []))
+    torch.testing.assert_close(gx, rx, rtol=1e-6, atol=1e-6)
+    if C2:
+        assert torch.equal(gs[0], rs[0])
