@@ -20,6 +20,20 @@ constexpr uint32_t kSpinLimit = 1u << 28;   // a wedged barrier traps instead of
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of the (converged) warp: the role loops of the persistent kernels run with the WHOLE warp converged and issue their
+// TMA / tcgen05 instructions under this predicate, so the operands stay in uniform registers.  (Under `if (lane == 0)` the
+// compiler cannot prove a single active thread and wraps every UTMALDG / UTCHMMA / UTCBAR in an ELECT + BRA.U.ANY loop with
+// R2UR moves: ~90 dependent instructions per K block on one thread, ~600 cycles -- as long as the MMAs themselves.)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -278,39 +278,38 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {                                  // ===== TMA producer =====
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < pa.tiles; tile += gridDim.x) {
-                const int px = tile % pa.tiles_px, rest = tile / pa.tiles_px;
-                const int n0 = (rest % pa.n_tiles) * BN, b = rest / pa.n_tiles;
-                const int th = px / a.tiles_w, tw = px - th * a.tiles_w;
-                const int x0 = tw * kVW * a.stride - a.pad_x, y0 = th * kVH * a.stride - a.pad;
-                int tap = 0, chunk = 0;
-                for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const uint32_t s = it % kStages;
-                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+    if (warp == 0) {                                      // ===== TMA producer (whole warp converged, one lane issues) =====
+        uint32_t s = 0, ph = 1;                           // ring slot and the parity to wait for on its empty barrier
+        for (int tile = blockIdx.x; tile < pa.tiles; tile += gridDim.x) {
+            const int px = tile % pa.tiles_px, rest = tile / pa.tiles_px;
+            const int n0 = (rest % pa.n_tiles) * BN, b = rest / pa.n_tiles;
+            const int th = px / a.tiles_w, tw = px - th * a.tiles_w;
+            const int x0 = tw * kVW * a.stride - a.pad_x, y0 = th * kVH * a.stride - a.pad;
+            int ky = 0, kx = 0, chunk = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty[s], ph);
+                if (elect_one()) {
                     mbar_expect_tx(&full[s], kVABytes + S::kBBytes);
-                    const int ky = tap / a.KW, kx = tap - ky * a.KW;
                     tma_load_4d(sA + s * kVABytes, &tmX, &full[s], chunk * kKE, x0 + kx * a.dil, y0 + ky * a.dil, b);
                     tma_load_2d(sB + s * S::kBBytes, &tmW, &full[s], kb * kKE, n0);
-                    if (++chunk == a.chunks) { chunk = 0; ++tap; }
                 }
+                __syncwarp();
+                if (++chunk == a.chunks) { chunk = 0; if (++kx == a.KW) { kx = 0; ++ky; } }
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {                                  // ===== MMA issuer =====
-            constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(128, BN) : umma_idesc_tf32(128, BN);
-            uint32_t it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < pa.tiles; tile += gridDim.x, ++lt) {
-                const uint32_t buf = lt & 1;
-                mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
+    } else if (warp == 1) {                               // ===== MMA issuer (whole warp converged, one lane issues) =====
+        constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(128, BN) : umma_idesc_tf32(128, BN);
+        uint32_t s = 0, ph = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < pa.tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1;
+            mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_acc + buf * BN;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t d = tmem_acc + buf * BN;
-                for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const uint32_t s = it % kStages;
-                    mbar_wait(&full[s], (it / kStages) & 1);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint64_t da = umma_desc_k128(smem_u32(sA + s * kVABytes));
                     const uint64_t db = umma_desc_k128(smem_u32(sB + s * S::kBBytes));
 #pragma unroll
@@ -320,8 +319,11 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                     }
                     umma_commit(&empty[s]);
                 }
-                umma_commit(&acc_full[buf]);
+                __syncwarp();
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
+            if (elect_one()) umma_commit(&acc_full[buf]);
+            __syncwarp();
         }
     } else {                                              // ===== epilogue: group g = warps 2 + 4 g .. 5 + 4 g =====
         const int q = warp & 3;                           // TMEM lane quarter this warp may access
@@ -447,7 +449,7 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                     }
                 }
                 if (y_f32) {
-                    if (lane == 0) tma_store_wait_read<0>();  // this warp's previous store has read the staging block
+                    if (elect_one()) tma_store_wait_read<0>();   // this warp's previous store has read the staging block
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)       // 128-byte swizzle: 16-byte chunk j / 4 of row `lane` -> chunk (j / 4) ^ (lane & 7)
@@ -455,15 +457,17 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                             make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (elect_one()) {                    // always the same lane: bulk async-groups are per thread
                         tma_store_4d(&tmY, stage, col, w0, h0 + q * 2, b);
                         tma_store_commit();
                     }
+                    __syncwarp();
                 }
             }
         }
         if (bn_sums) flush(st_key);
-        if (lane == 0) tma_store_wait_all();
+        __syncwarp();
+        if (elect_one()) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();

@@ -210,39 +210,41 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {                                  // ===== TMA producer =====
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int px = tile % tiles_px, rest = tile / tiles_px;
-                const int nchunk = rest % nchunks, b = rest / nchunks;
-                const int th = px / tiles_w, tw = px - th * tiles_w;
-                const int h0 = th * kTH, w0 = tw * kTW;
-                int src = 0, tap = 0, chunk = 0;
-                for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const uint32_t s = it % kPCStages;
-                    mbar_wait(&empty[s], ((it / kPCStages) & 1) ^ 1);
+    if (warp == 0) {                                      // ===== TMA producer (whole warp converged, one lane issues) =====
+        uint32_t s = 0, ph = 1;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int px = tile % tiles_px, rest = tile / tiles_px;
+            const int nchunk = rest % nchunks, b = rest / nchunks;
+            const int th = px / tiles_w, tw = px - th * tiles_w;
+            const int h0 = th * kTH, w0 = tw * kTW;
+            int src = 0, dy = -1, dx = -1, chunk = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty[s], ph);
+                if (elect_one()) {
                     mbar_expect_tx(&full[s], kCABytes + kCBBytes);
-                    const int dy = tap / 3 - 1, dx = tap - (tap / 3) * 3 - 1;
                     tma_load_4d(sA + s * kCABytes, src ? &tmH : &tmX, &full[s], chunk * kKE, w0 + dx, h0 + dy, b);
                     tma_load_2d(sB + s * kCBBytes, &tmW, &full[s], kb * kKE, nchunk * kCN);
-                    if (++chunk == chunks) { chunk = 0; if (++tap == 9) { tap = 0; ++src; } }
                 }
+                __syncwarp();
+                if (++chunk == chunks) {
+                    chunk = 0;
+                    if (++dx == 2) { dx = -1; if (++dy == 2) { dy = -1; ++src; } }
+                }
+                if (++s == kPCStages) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {                                  // ===== MMA issuer =====
-            constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(128, kCN) : umma_idesc_tf32(128, kCN);
-            uint32_t it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
-                const uint32_t buf = lt & 1;
-                mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
+    } else if (warp == 1) {                               // ===== MMA issuer (whole warp converged, one lane issues) =====
+        constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(128, kCN) : umma_idesc_tf32(128, kCN);
+        uint32_t s = 0, ph = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1;
+            mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d = tmem_acc + buf * kCN;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t d = tmem_acc + buf * kCN;
-                for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const uint32_t s = it % kPCStages;
-                    mbar_wait(&full[s], (it / kPCStages) & 1);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint64_t da = umma_desc_k128(smem_u32(sA + s * kCABytes));
                     const uint64_t db = umma_desc_k128(smem_u32(sB + s * kCBBytes));
 #pragma unroll
@@ -252,8 +254,11 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     }
                     umma_commit(&empty[s]);
                 }
-                umma_commit(&acc_full[buf]);
+                __syncwarp();
+                if (++s == kPCStages) { s = 0; ph ^= 1; }
             }
+            if (elect_one()) umma_commit(&acc_full[buf]);
+            __syncwarp();
         }
     } else {                                              // ===== epilogue: group g = warps 2 + 4 g .. 5 + 4 g =====
         const int q = warp & 3;

@@ -255,33 +255,33 @@ k_gemm_tf32_persist(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 
-    if (warp == 0) {
-        if (lane == 0) {                                  // ===== TMA producer =====
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-                const int m0 = (tile % tiles_m) * kBM, n0 = (tile / tiles_m) * BN;
-                for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const uint32_t s = it % kStages;
-                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+    if (warp == 0) {                                      // ===== TMA producer (whole warp converged, one lane issues) =====
+        uint32_t s = 0, ph = 1;                           // ring slot and the parity to wait for on its empty barrier
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+            const int m0 = (tile % tiles_m) * kBM, n0 = (tile / tiles_m) * BN;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty[s], ph);
+                if (elect_one()) {
                     mbar_expect_tx(&full[s], S::kABytes + S::kBBytes);
                     tma_load_2d(sA + s * S::kABytes, &tmA, &full[s], kb * kBlockK, m0);
                     tma_load_2d(sB + s * S::kBBytes, &tmB, &full[s], kb * kBlockK, n0);
                 }
+                __syncwarp();
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {                                  // ===== MMA issuer =====
-            constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
-            uint32_t it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
-                const uint32_t buf = lt & 1;
-                mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);      // the epilogue has drained this accumulator
+    } else if (warp == 1) {                               // ===== MMA issuer (whole warp converged, one lane issues) =====
+        constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+        uint32_t s = 0, ph = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
+            const uint32_t buf = lt & 1;
+            mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d = tmem_acc + buf * BN;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint32_t d = tmem_acc + buf * BN;
-                for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const uint32_t s = it % kStages;
-                    mbar_wait(&full[s], (it / kStages) & 1);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint64_t da = umma_desc_k128(smem_u32(sA + s * S::kABytes));
                     const uint64_t db = umma_desc_k128(smem_u32(sB + s * S::kBBytes));
 #pragma unroll
@@ -289,8 +289,11 @@ k_gemm_tf32_persist(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     umma_commit(&empty[s]);
                 }
-                umma_commit(&acc_full[buf]);
+                __syncwarp();
+                if (++s == kStages) { s = 0; ph ^= 1; }
             }
+            if (elect_one()) umma_commit(&acc_full[buf]);
+            __syncwarp();
         }
     } else {                                              // ===== epilogue: warps 2..9 =====
         // Two warps per TMEM lane quarter (one per half of the tile's columns): every SM sub-partition has two epilogue warps to
@@ -344,7 +347,7 @@ k_gemm_tf32_persist(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                     }
                 }
-                if (lane == 0) tma_store_wait_read<0>();  // this warp's previous store has read the staging block
+                if (elect_one()) tma_store_wait_read<0>();   // this warp's previous store has read the staging block
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)           // 128-byte swizzle: 16-byte chunk j / 4 of row `lane` -> chunk (j / 4) ^ (lane & 7)
@@ -352,13 +355,15 @@ k_gemm_tf32_persist(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
+                if (elect_one()) {                        // always the same lane: bulk async-groups are per thread
                     tma_store_2d(&tmC, stage, col, m0 + q * 32);
                     tma_store_commit();
                 }
+                __syncwarp();
             }
         }
-        if (lane == 0) tma_store_wait_all();
+        __syncwarp();
+        if (elect_one()) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();

@@ -65,14 +65,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
     const uint32_t tmem_acc = *tmem_slot;
 
     if (kblocks > 0) {
-        if (warp == 0) {
-            if (lane == 0) {                              // ===== TMA producer =====
-                int r = r_lo, xc = 0;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    const int s = kb % kWStages;
-                    mbar_wait(&empty[s], ((kb / kWStages) & 1) ^ 1);
+        if (warp == 0) {                                  // ===== TMA producer (whole warp converged, one lane issues) =====
+            int r = r_lo, xc = 0;
+            int b = r / a.Ho, y = r - b * a.Ho;
+            uint32_t s = 0, ph = 1;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty[s], ph);
+                if (elect_one()) {
                     mbar_expect_tx(&full[s], (uint32_t)stageBytes);
-                    const int b = r / a.Ho, y = r - b * a.Ho;
                     uint8_t* st = base + s * stageBytes;
                     for (int gco = 0; gco < 4; ++gco)
                         tma_load_4d(st + gco * kWGroupBytes, &tmDY, &full[s], co0 + gco * 32, xc * kBlockK, y, b);
@@ -80,16 +80,18 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
                         for (int gci = 0; gci < ngroups; ++gci)
                             tma_load_4d(st + kWABytes + kx * bBytes + gci * kWGroupBytes, &tmX, &full[s], ci0 + gci * 32,
                                         xc * kBlockK + kx * a.dil - a.pad, y + ky * a.dil - a.pad, b);
-                    if (++xc == a.xchunks) { xc = 0; ++r; }
                 }
+                __syncwarp();
+                if (++xc == a.xchunks) { xc = 0; if (++y == a.Ho) { y = 0; ++b; } }
+                if (++s == (uint32_t)kWStages) { s = 0; ph ^= 1; }
             }
-        } else if (warp == 1) {
-            if (lane == 0) {                              // ===== MMA issuer =====
-                const uint32_t idesc = umma_idesc_tf32_mn(128, a.NT);
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    const int s = kb % kWStages;
-                    mbar_wait(&full[s], (kb / kWStages) & 1);
-                    tc_fence_after();
+        } else if (warp == 1) {                           // ===== MMA issuer (whole warp converged, one lane issues) =====
+            const uint32_t idesc = umma_idesc_tf32_mn(128, a.NT);
+            uint32_t s = 0, ph = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (elect_one()) {
                     uint8_t* st = base + s * stageBytes;
                     const uint64_t da = umma_desc_mn128(smem_u32(st), kWGroupBytes);
                     for (int kx = 0; kx < a.KW; ++kx) {
@@ -100,8 +102,11 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUt
                     }
                     umma_commit(&empty[s]);
                 }
-                umma_commit(acc_full);
+                __syncwarp();
+                if (++s == (uint32_t)kWStages) { s = 0; ph ^= 1; }
             }
+            if (elect_one()) umma_commit(acc_full);
+            __syncwarp();
         } else {                                          // ===== epilogue: warps 2..5 =====
             const int q = warp & 3;
             mbar_wait(acc_full, 0);
