@@ -110,18 +110,26 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
     const uint32_t tmem_s = *tmem_slot;                    // columns [0, 64) and [64, 128): S (double-buffered), [128, 192): O tile
     const uint32_t tmem_o = tmem_s + 128;
 
-    if (warp == 0) {
-        if (lane == 0) {                                   // ===== TMA producer =====
+    // The two single-issuer roles run with the WHOLE warp converged and issue under elect.sync (tc_common.cuh elect_one): the
+    // operands stay in uniform registers instead of an ELECT + BRA.U.ANY loop around every UTMALDG / UTCHMMA / UTCBAR.
+    if (warp == 0) {                                       // ===== TMA producer =====
+        if (elect_one()) {
             mbar_expect_tx(q_full, kQBytes);
             tma_load_3d(sQ, &tmQ, q_full, hh * kMhaD, q0, b);
             tma_load_3d(sQ + kQBytes / 2, &tmQ, q_full, hh * kMhaD + 32, q0, b);
-            for (int j = 0; j < ntiles; ++j) {
-                const int k0 = j * kMhaK;
-                if (j > 0) mbar_wait(k_empty, (j - 1) & 1);
+        }
+        __syncwarp();
+        for (int j = 0; j < ntiles; ++j) {
+            const int k0 = j * kMhaK;
+            if (j > 0) mbar_wait(k_empty, (j - 1) & 1);
+            if (elect_one()) {
                 mbar_expect_tx(k_full, kKBytes);
                 tma_load_3d(sK, &tmK, k_full, D + hh * kMhaD, k0, b);
                 tma_load_3d(sK + kKBytes / 2, &tmK, k_full, D + hh * kMhaD + 32, k0, b);
-                if (j > 0) mbar_wait(v_empty, (j - 1) & 1);
+            }
+            __syncwarp();
+            if (j > 0) mbar_wait(v_empty, (j - 1) & 1);
+            if (elect_one()) {
                 mbar_expect_tx(v_full, kVBytes);
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb)
@@ -129,17 +137,18 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
                     for (int g = 0; g < 2; ++g)
                         tma_load_3d(sV + kb * 8192 + g * 4096, &tmV, v_full, 2 * D + hh * kMhaD + g * 32, k0 + kb * 32, b);
             }
+            __syncwarp();
         }
-    } else if (warp == 1) {
-        if (lane == 0) {                                   // ===== MMA issuer =====
-            constexpr uint32_t idesc_s = umma_idesc_tf32(kMhaQ, kMhaK);
-            constexpr uint32_t idesc_o = umma_idesc_tf32_bmn(kMhaQ, kMhaD);
-            mbar_wait(q_full, 0);
-            // S of tile j + 1 is issued BEFORE the P V product of tile j (into the other S buffer), so it runs -- and its
-            // completion reaches the softmax warps -- while they are still busy with tile j
-            auto issue_s = [&](int jj) {
-                mbar_wait(k_full, jj & 1);
-                tc_fence_after();
+    } else if (warp == 1) {                                // ===== MMA issuer =====
+        constexpr uint32_t idesc_s = umma_idesc_tf32(kMhaQ, kMhaK);
+        constexpr uint32_t idesc_o = umma_idesc_tf32_bmn(kMhaQ, kMhaD);
+        mbar_wait(q_full, 0);
+        // S of tile j + 1 is issued BEFORE the P V product of tile j (into the other S buffer), so it runs -- and its
+        // completion reaches the softmax warps -- while they are still busy with tile j
+        auto issue_s = [&](int jj) {
+            mbar_wait(k_full, jj & 1);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
                     const uint64_t da = umma_desc_k128(smem_u32(sQ + kb * (kQBytes / 2)));
@@ -150,13 +159,16 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
                 }
                 umma_commit(k_empty);
                 umma_commit(s_full2[jj & 1]);
-            };
-            issue_s(0);
-            for (int j = 0; j < ntiles; ++j) {
-                if (j + 1 < ntiles) issue_s(j + 1);
-                mbar_wait(p_ready, j & 1);
-                mbar_wait(v_full, j & 1);
-                tc_fence_after();
+            }
+            __syncwarp();
+        };
+        issue_s(0);
+        for (int j = 0; j < ntiles; ++j) {
+            if (j + 1 < ntiles) issue_s(j + 1);
+            mbar_wait(p_ready, j & 1);
+            mbar_wait(v_full, j & 1);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
                 for (int kb = 0; kb < 2; ++kb) {
                     const uint64_t da = umma_desc_k128(smem_u32(sP + kb * (kPBytes / 2)));
@@ -167,6 +179,7 @@ k_mha_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtens
                 umma_commit(v_empty);
                 umma_commit(o_full);                       // arrives last: the CTA outlives every pending arrive
             }
+            __syncwarp();
         }
     } else {                                               // ===== softmax / output: warps 2 .. 2 + SW =====
         constexpr int HV = SW / 4;                         // threads per query row
