@@ -268,6 +268,13 @@ int oess_global_avgpool_nhwc(const float* x, int B, int64_t HW, int C, float* y,
  * oess_pred_sigmoid_nhwc: out[p] = sigmoid(dot(w, x[p, :] + skip[p, :]) + bias), the 1x1 prediction conv to one channel
  *   (eval BatchNorm folded into w / bias by the caller) + torch.sigmoid; C % 4 == 0, C <= 64; w 16-byte aligned. */
 int oess_zero_insert2x_nhwc(const float* x, const float* skip, int B, int H, int W, int C, float* z, oess_stream_t stream);
+/* F.interpolate(x, size=(H, W), mode='bilinear', align_corners=False) of a contiguous plane tensor x [planes = B * C, h, w] and
+ * its backward (models/deeplabv3.py:53-56 of the reference: full-resolution logits and 256-channel features).  The backward is
+ * a separable gather (no atomics): tmp = planes * H * w floats of scratch. */
+int oess_bilinear_resize_planes(const float* x, int64_t planes, int h, int w, int H, int W, float* out, oess_stream_t stream);
+int oess_bilinear_resize_planes_bwd(const float* g, int64_t planes, int h, int w, int H, int W, float* tmp, float* dx,
+                                    oess_stream_t stream);
+
 /* Decoder transition of SemSegE2VID (models/style_networks.py:148-158): out [B, 2H, 2W, C1 + C2] = cat(nearest-neighbour x2
  * upsampling of x [B, H, W, C1], skip [B, 2H, 2W, C2]) along the channels, channels-last, one pass (C2 = 0 / skip = NULL: plain
  * upsampling).  _bwd: dx = 2 x 2 sums of g[..., :C1], dskip = g[..., C1:]; either output may be NULL.  C1, C2 % 4 == 0. */

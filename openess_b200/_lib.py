@@ -64,6 +64,8 @@ SIGNATURES = {
     "oess_frame_color_aug": [_vp, _int, _i64, _vp, _vp, _vp, _vp, _vp],
     "oess_unsharp_rescale": [_vp, _vp, _int, _int, _int, _f32, _f32, _f32, _int, _vp, _vp],
     "oess_zero_insert2x_nhwc": [_vp, _vp, _int, _int, _int, _int, _vp, _vp],
+    "oess_bilinear_resize_planes": [_vp, _i64, _int, _int, _int, _int, _vp, _vp],
+    "oess_bilinear_resize_planes_bwd": [_vp, _i64, _int, _int, _int, _int, _vp, _vp, _vp],
     "oess_upsample2x_cat_nhwc": [_vp, _vp, _int, _int, _int, _int, _int, _vp, _vp],
     "oess_upsample2x_cat_nhwc_bwd": [_vp, _int, _int, _int, _int, _int, _vp, _vp, _vp],
     "oess_pred_sigmoid_nhwc": [_vp, _vp, _vp, _f32, _i64, _int, _vp, _vp],

@@ -37,6 +37,7 @@ SOURCES = {
     "vit.cu": [],
     "tc_mha.cu": [],
     "pool_nhwc.cu": [],
+    "resize.cu": [],
     "augment.cu": ["--fmad=false"],
 }
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

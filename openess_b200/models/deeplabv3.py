@@ -167,8 +167,13 @@ class deeplabv3_resnet50(nn.Module):
         input_shape = x.shape[-2:]
         features = self._backbone(x)                                                # [B, 2048, H/16, W/16]
         logist, feats = self.classifier(features)
-        logist = F.interpolate(logist, size=input_shape, mode='bilinear', align_corners=False)
-        feats = F.interpolate(feats, size=input_shape, mode='bilinear', align_corners=False)
+        if USE_TENSOR_CORES and logist.is_cuda and logist.dtype == torch.float32 and feats.dtype == torch.float32:
+            from .. import ops as _ops                                              # own resize: gather backward, no atomics
+            logist = _ops.bilinear_resize(logist, input_shape)
+            feats = _ops.bilinear_resize(feats, input_shape)
+        else:
+            logist = F.interpolate(logist, size=input_shape, mode='bilinear', align_corners=False)
+            feats = F.interpolate(feats, size=input_shape, mode='bilinear', align_corners=False)
         if self.if_linear_probing:
             logist = self.linear_probe(logist)
         return logist, feats

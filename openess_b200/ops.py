@@ -483,6 +483,38 @@ def conv_bn_train_bf16(x_bf, w_packed_bf, bias, kernel_size, stride, padding, di
     return (y if want_f32 else None), yb
 
 
+class _BilinearResize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, H, W):
+        B, C, h, w = x.shape
+        xc = x.float().contiguous()
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib().oess_bilinear_resize_planes(ptr(xc), B * C, h, w, H, W, ptr(out), stream_ptr(x.device)),
+                  "oess_bilinear_resize_planes")
+        ctx.dims = (B, C, h, w, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        B, C, h, w, H, W = ctx.dims
+        gc = g.float().contiguous()
+        tmp = torch.empty((B * C, H, w), dtype=torch.float32, device=g.device)
+        dx = torch.empty((B, C, h, w), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib().oess_bilinear_resize_planes_bwd(ptr(gc), B * C, h, w, H, W, ptr(tmp), ptr(dx), stream_ptr(g.device)),
+                  "oess_bilinear_resize_planes_bwd")
+        return dx, None, None
+
+
+def bilinear_resize(x, size):
+    """F.interpolate(x, size=size, mode='bilinear', align_corners=False) for a CUDA [B, C, h, w] tensor, differentiable: the
+    backward is a separable gather instead of torch's atomic scatter (oess_bilinear_resize_planes / _bwd)."""
+    _lib.require_cuda(x)
+    H, W = int(size[0]), int(size[1])
+    return _BilinearResize.apply(x, H, W)
+
+
 class _Up2xCat(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, skip):

@@ -137,3 +137,21 @@ def test_conv_batchnorm_autograd_vs_torch(C, Cout, k, p, d, res, relu):
     if res:
         assert float((rg.grad.cpu().double() - r.grad).abs().max()) < 1e-6
     torch.testing.assert_close(bn.running_var.cpu().double(), bn_ref.running_var, atol=1e-3, rtol=2e-3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,C,h,w,H,W", [(2, 11, 14, 20, 440, 640), (1, 5, 7, 9, 30, 23), (1, 3, 16, 16, 16, 16), (2, 4, 9, 5, 4, 3)])
+def test_bilinear_resize_matches_torch_forward_and_backward(B, C, h, w, H, W):
+    """oess_bilinear_resize_planes (+ separable gather backward) against F.interpolate(bilinear, align_corners=False) and its
+    autograd backward (deeplabv3.py:53-56): up- and down-scaling, non-integer ratios, identity."""
+    import torch.nn.functional as F
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(h * 31 + W)
+    x = torch.randn(B, C, h, w, generator=g).cuda().requires_grad_(True)
+    wgt = torch.randn(B, C, H, W, generator=g).cuda()
+    out = ops.bilinear_resize(x, (H, W))
+    ref = F.interpolate(x, size=(H, W), mode='bilinear', align_corners=False)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-6)
+    gx, = torch.autograd.grad((out * wgt).sum(), x)
+    rx, = torch.autograd.grad((ref * wgt).sum(), x)
+    torch.testing.assert_close(gx, rx, rtol=1e-4, atol=1e-4 * float(rx.abs().max()))

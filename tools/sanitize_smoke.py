@@ -118,5 +118,30 @@ if os.environ.get("OESS_INFONCE", "")[:1] == "t":
     kk = torch.nn.functional.normalize(torch.randn(133, 64, device=dev), dim=1).requires_grad_(True)
     qq = torch.nn.functional.normalize(torch.randn(133, 64, device=dev), dim=1).requires_grad_(True)
     losses.infonce(kk, qq, 0.07).backward()
+# persistent tensor-core kernels (second session of round 2) at sizes where every CTA walks SEVERAL tiles: operand ring across
+# tile boundaries, both TMEM accumulators, staging-block reuse under TMA stores, statistics flush on a Cout-tile change
+a2 = torch.randn(128 * 450 + 5, 64, device=dev)
+r2 = torch.randn(a2.shape[0], 256, device=dev)
+ops.gemm_tf32_ex(a2, torch.randn(256, 64, device=dev), torch.randn(256, device=dev), residual=r2, out=r2)
+ops.gemm_tf32(a2[:19000], torch.randn(72, 64, device=dev))                      # BN = 128, ragged last N tile
+xl = torch.randn(2, 64, 120, 160, device=dev).contiguous(memory_format=torch.channels_last)
+w1 = torch.randn(512, 64, 1, 1, device=dev) * 0.1
+bn2 = torch.nn.BatchNorm2d(512).to(dev).train()
+ops.conv_bn_train(xl, ops.conv2d_pack(w1), None, 1, 1, 0, 1, bn2, relu=True)     # 300 pixel tiles x 2 Cout tiles, fused statistics
+ops.conv2d_tc(xl, ops.conv2d_pack(torch.randn(64, 64, 3, 3, device=dev) * 0.05), None, 3, 2, 1, 1, relu=True, residual=None)
+xlb = xl.to(torch.bfloat16)
+ops.conv2d_tc_bf16(xlb, ops.conv2d_pack_bf16(w1), None, 1, 1, 0, 1, relu=True)
+ops.conv_bn_train_bf16(xlb, ops.conv2d_pack_bf16(w1), None, 1, 1, 0, 1, bn2, relu=True, want_f32=False)
+wl = torch.randn(4 * 64, 128, 3, 3, device=dev) * 0.05
+wpl, bpl = ops.convlstm_pack(wl, torch.randn(256, device=dev) * 0.1, 64)
+hl, cl_ = ops.convlstm_step(xl, None, wpl, bpl)                                  # 150 tiles x 2 samples
+ops.convlstm_step(xl, (hl, cl_), wpl, bpl)
+hb, cb = ops.convlstm_step_bf16(xlb, None, wpl.to(torch.bfloat16), bpl)
+ops.convlstm_step_bf16(xlb, (hb, cb), wpl.to(torch.bfloat16), bpl)
+xu = torch.randn(2, 32, 9, 11, device=dev, requires_grad=True)
+su = torch.randn(2, 16, 18, 22, device=dev, requires_grad=True)
+ops.upsample2x_cat(xu, su).square().sum().backward()
+xr = torch.randn(2, 5, 7, 9, device=dev, requires_grad=True)
+ops.bilinear_resize(xr, (30, 23)).square().sum().backward()
 torch.cuda.synchronize()
 print("sanitize smoke done")
