@@ -195,31 +195,14 @@ k_strip_splat(const float4* __restrict__ items, const int64_t* __restrict__ fram
               int F_, float* __restrict__ out) {
     extern __shared__ __align__(16) float s_strip[];  // [warps][C][WC]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // frame-major launch order (OESS_STRIP_ORDER=1): consecutive CTAs take the same (row, strip) of consecutive frames,
+    // so heavy (edge-clustered) and light frames interleave in time instead of forming a heavy tail
+    const bool fmajor = gridDim.z != (unsigned)F_;
+    const int s = (fmajor ? blockIdx.z : blockIdx.x) * (blockDim.x >> 5) + warp;
+    if (s >= NS) return;                               // warps are independent: no CTA-wide barrier below
+    const int Y = blockIdx.y, f = fmajor ? blockIdx.x : blockIdx.z;
     const int C = CT ? CT : g.C;
     const int H = g.H, W = g.W;
-    // persistent launch (gridDim.y == 1, gridDim.z == 1, OESS_STRIP_PERSIST=1): every warp walks tasks gw, gw + warps, ...;
-    // a task = (frame fastest, then strip, then row), so heavy and light frames interleave as in the frame-major order
-    const bool persist = gridDim.y == 1 && gridDim.z == 1 && (H > 1 || F_ > 1);
-    const int64_t ntasks = (int64_t)F_ * NS * H;
-    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    int64_t task = persist ? (int64_t)blockIdx.x * (blockDim.x >> 5) + warp : 0;
-  for (;; task += nwarps) {
-    int s, Y, f;
-    if (persist) {
-        if (task >= ntasks) return;
-        f = (int)(task % F_);
-        const int64_t rest = task / F_;
-        s = (int)(rest % NS);
-        Y = (int)(rest / NS);
-    } else {
-        // frame-major launch order (OESS_STRIP_ORDER=1): consecutive CTAs take the same (row, strip) of consecutive frames,
-        // so heavy (edge-clustered) and light frames interleave in time instead of forming a heavy tail
-        const bool fmajor = gridDim.z != (unsigned)F_;
-        s = (fmajor ? blockIdx.z : blockIdx.x) * (blockDim.x >> 5) + warp;
-        if (s >= NS) return;                           // warps are independent: no CTA-wide barrier below
-        Y = blockIdx.y;
-        f = fmajor ? blockIdx.x : blockIdx.z;
-    }
     const int xbase = s * WC;
     const int wlim = min(WC, W - xbase);
     const int KT = 2 * (NS + 1);
@@ -306,9 +289,6 @@ k_strip_splat(const float4* __restrict__ items, const int64_t* __restrict__ fram
         for (int cc = 0; cc < C; ++cc)
             for (int q = lane; q < wlim; q += 32) __stcs(o + (int64_t)cc * HW + q, acc[cc * WC + q]);
     }
-    if (!persist) return;
-    __syncwarp();                                      // accumulators are re-zeroed by the next task
-  }
 }
 
 }  // namespace tri

@@ -219,16 +219,7 @@ static int launch_strip_ct(const Plan& plan, const float4* items, const int64_t*
     static const bool fmajor_env = [] { const char* e = std::getenv("OESS_STRIP_ORDER"); return !(e && e[0] == '0'); }();
     // frame-major needs gridDim.z != F to be told apart in the kernel and gs <= 65535
     const bool fmajor = fmajor_env && gs != (unsigned)F;
-    dim3 grid = fmajor ? dim3((unsigned)F, (unsigned)g.H, gs) : dim3(gs, (unsigned)g.H, (unsigned)F);
-    static const int persist_env = [] { const char* e = std::getenv("OESS_STRIP_PERSIST"); return e ? std::atoi(e) : 0; }();
-    if (persist_env > 0 && (g.H > 1 || F > 1)) {
-        // persistent warps: persist_env CTAs per SM, each warp strides over the (frame, strip, row) tasks
-        const int64_t ntasks = (int64_t)F * plan.NS * g.H;
-        int64_t blocks = (int64_t)kNumSMs * persist_env;
-        const int64_t need = (ntasks + plan.strip_warps - 1) / plan.strip_warps;
-        if (blocks > need) blocks = need;
-        grid = dim3((unsigned)blocks, 1, 1);
-    }
+    const dim3 grid = fmajor ? dim3((unsigned)F, (unsigned)g.H, gs) : dim3(gs, (unsigned)g.H, (unsigned)F);
     OESS_KERNEL("tri_strip_splat", st, kern<<<grid, plan.strip_warps * 32, plan.strip_smem, st>>>(
         items, frame_offsets, coloff, rowflag, g, plan.NS, F, out));
     return 0;
