@@ -352,7 +352,7 @@ def run_ours(args):
     def e2e_batch(j, consumer="encoder"):
         ph = packed_host[j & 1]
         for s, f0 in enumerate(range(0, F, sub)):
-            b = s % NS_
+            b = (j * n_sub + s) % NS_                # alternate the staging buffers / streams ACROSS batches too
             with torch.cuda.stream(streams[b]):
                 raw_stage[b].copy_(ph[s], non_blocking=True)
                 grids = voxel.dsec_events_to_voxel_grid(*raw_views[b], rmap, C, frame_offsets=fo_sub, mode=mode,
@@ -478,7 +478,7 @@ def main():
     ap.add_argument("--mode", default="ordered", choices=["ordered", "atomic"])
     ap.add_argument("--frames", type=int, default=160, help="event-frames per batch per GPU")
     ap.add_argument("--inner", type=int, default=32, help="batches per bench step (so that K steps last about a second)")
-    ap.add_argument("--e2e-sub", type=int, default=80, help="frames per pipelined H2D/compute sub-batch")
+    ap.add_argument("--e2e-sub", type=int, default=160, help="frames per pipelined H2D/compute sub-batch")
     ap.add_argument("--host-output", type=int, default=1, help="also measure e2e with full D2H of the grids")
     ap.add_argument("--clustered-every", type=int, default=2, help="every k-th frame is edge-clustered (0: none, 1: all)")
     ap.add_argument("--train-steps", type=int, default=5, help="timed steps of the end-to-end pretraining step (0: skip)")
