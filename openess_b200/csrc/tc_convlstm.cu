@@ -169,7 +169,11 @@ constexpr int kPCStages = 4;
 constexpr int kPCSmem = 1024 + kPCStages * (kCABytes + kCBBytes) + 256;
 constexpr int kPCThreads = 320;
 
-template <bool BF16>
+// MC: clusters of two CTAs take two neighbouring pixel patches of the same (channel chunk, sample) in lockstep; each loads its
+// own A tile and HALF of the weight tile, which TMA multicasts into both CTAs' shared memory: 256 instead of 384 128-byte rows
+// requested per K block and SM (the L2 -> shared-memory fill, not the MMA rate, bounds this kernel: profiles/r02_convlstm_full.md).
+// A stage is released to BOTH producers: the MMA commit arrives on the empty barrier of both CTAs (count 2).
+template <bool BF16, bool MC>
 __global__ void __launch_bounds__(kPCThreads, 1)
 k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
                 const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias, const float* __restrict__ c_prev,
@@ -196,7 +200,7 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tma_prefetch_desc(&tmW);
         for (int s = 0; s < kPCStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], MC ? 2 : 1);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
@@ -206,14 +210,21 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * kCN);
     tc_fence_before();
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();      // peers' barriers exist before any multicast / remote arrive
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
+    // MC: the pair walks PAIR tiles (two neighbouring pixel patches); rank r takes patch 2 * pair_px + r (a patch index past
+    // tiles_px is a dummy: TMA zero-fills it and the epilogue's bounds test drops it)
+    const uint32_t crank = MC ? cluster_ctarank() : 0u;
+    const int tile0 = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tstep = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int px_units = MC ? (tiles_px + 1) / 2 : tiles_px;
 
     if (warp == 0) {                                      // ===== TMA producer (whole warp converged, one lane issues) =====
         uint32_t s = 0, ph = 1;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-            const int px = tile % tiles_px, rest = tile / tiles_px;
+        for (int tile = tile0; tile < tiles; tile += tstep) {
+            const int pu = tile % px_units, rest = tile / px_units;
+            const int px = MC ? 2 * pu + (int)crank : pu;
             const int nchunk = rest % nchunks, b = rest / nchunks;
             const int th = px / tiles_w, tw = px - th * tiles_w;
             const int h0 = th * kTH, w0 = tw * kTW;
@@ -223,7 +234,11 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 if (elect_one()) {
                     mbar_expect_tx(&full[s], kCABytes + kCBBytes);
                     tma_load_4d(sA + s * kCABytes, src ? &tmH : &tmX, &full[s], chunk * kKE, w0 + dx, h0 + dy, b);
-                    tma_load_2d(sB + s * kCBBytes, &tmW, &full[s], kb * kKE, nchunk * kCN);
+                    if (MC)
+                        tma_load_2d_mc(sB + s * kCBBytes + crank * (kCBBytes / 2), &tmW, &full[s], kb * kKE,
+                                       nchunk * kCN + (int)crank * (kCN / 2), (uint16_t)3);
+                    else
+                        tma_load_2d(sB + s * kCBBytes, &tmW, &full[s], kb * kKE, nchunk * kCN);
                 }
                 __syncwarp();
                 if (++chunk == chunks) {
@@ -236,7 +251,7 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     } else if (warp == 1) {                               // ===== MMA issuer (whole warp converged, one lane issues) =====
         constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(128, kCN) : umma_idesc_tf32(128, kCN);
         uint32_t s = 0, ph = 0, lt = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
+        for (int tile = tile0; tile < tiles; tile += tstep, ++lt) {
             const uint32_t buf = lt & 1;
             mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -252,7 +267,8 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                         if (BF16) umma_bf16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                         else umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty[s]);
+                    if (MC) umma_commit_mc(&empty[s], (uint16_t)3);   // frees the stage in BOTH CTAs' producers' eyes
+                    else umma_commit(&empty[s]);
                 }
                 __syncwarp();
                 if (++s == kPCStages) { s = 0; ph ^= 1; }
@@ -264,9 +280,10 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int q = warp & 3;
         const uint32_t g = (uint32_t)(warp - 2) >> 2;
         uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
+        for (int tile = tile0; tile < tiles; tile += tstep, ++lt) {
             if ((lt & 1) != g) continue;
-            const int px = tile % tiles_px, rest = tile / tiles_px;
+            const int pu = tile % px_units, rest = tile / px_units;
+            const int px = MC ? 2 * pu + (int)crank : pu;
             const int nchunk = rest % nchunks, b = rest / nchunks;
             const int th = px / tiles_w, tw = px - th * tiles_w;
             const int r = q * 32 + lane;                  // accumulator row = pixel of the patch (h-major, w-minor)
@@ -324,7 +341,7 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (MC) cluster_sync_all(); else __syncthreads();      // no CTA leaves while its peer can still write into it
     if (warp == 1) tmem_dealloc(tmem_acc, 2 * kCN);
 }
 
@@ -361,19 +378,35 @@ static int convlstm_impl(const void* x, const void* h_prev, const float* c_prev,
     rc = mk(&tmH, h_prev ? h_prev : x, 4, dims, strides, box);
     if (rc) return rc;
     const uint64_t dW[2] = {Kfull, (uint64_t)4 * C}, sW[1] = {Kfull * ES};
-    const uint32_t bW[2] = {KE, tc::kCN};
-    rc = mk(&tmW, w_packed, 2, dW, sW, bW);
-    if (rc) return rc;
     const int tiles_w = (W + tc::kTW - 1) / tc::kTW, tiles_h = (H + tc::kTH - 1) / tc::kTH;
     static const bool tile_env = [] { const char* e = std::getenv("OESS_CONVLSTM"); return e && e[0] == 't'; }();
-    const int64_t tiles = (int64_t)tiles_w * tiles_h * (C / 64) * B;
+    static const bool mc_env = [] { const char* e = std::getenv("OESS_CONVLSTM_MC"); return !(e && e[0] == '0'); }();   // default on
+    const int tiles_px = tiles_w * tiles_h;
+    const bool mc = mc_env && !tile_env && tiles_px >= 2;
+    const uint32_t bW[2] = {KE, (uint32_t)(mc ? tc::kCN / 2 : tc::kCN)};
+    rc = mk(&tmW, w_packed, 2, dW, sW, bW);
+    if (rc) return rc;
+    const int64_t tiles = (int64_t)(mc ? (tiles_px + 1) / 2 : tiles_px) * (C / 64) * B;
     if (!tile_env && tiles < (1ll << 31)) {
-        OESS_CUDA(cudaFuncSetAttribute(tc::k_convlstm_tc_p<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kPCSmem));
-        const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+        auto kern = mc ? tc::k_convlstm_tc_p<BF16, true> : tc::k_convlstm_tc_p<BF16, false>;
+        OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kPCSmem));
+        unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
+        if (mc) grid = (unsigned)(2 * (tiles < kNumSMs / 2 ? tiles : kNumSMs / 2));      // whole clusters
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(tc::kPCThreads);
+        cfg.dynamicSmemBytes = tc::kPCSmem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = mc ? 2 : 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
         OESS_KERNEL(BF16 ? "tc_convlstm_step_bf16" : "tc_convlstm_step", st,
-                    tc::k_convlstm_tc_p<BF16><<<grid, tc::kPCThreads, tc::kPCSmem, st>>>(
-                        tmX, tmH, tmW, bias_packed, c_prev, h_out, h_bf, c_out, H, W, C, h_prev ? 1 : 0, tiles_w,
-                        tiles_w * tiles_h, (int)tiles));
+                    cudaLaunchKernelEx(&cfg, kern, tmX, tmH, tmW, bias_packed, c_prev, h_out, h_bf, c_out, H, W, C,
+                                       h_prev ? 1 : 0, tiles_w, tiles_px, (int)tiles));
         return 0;
     }
     OESS_CUDA(cudaFuncSetAttribute(tc::k_convlstm_tc<BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kCSmem));
