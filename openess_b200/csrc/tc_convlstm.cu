@@ -29,6 +29,24 @@ constexpr int kCBBytes = kCN * kBlockK * 4; // 32 KB
 constexpr int kCSmem = 1024 + kCStages * (kCABytes + kCBBytes) + 256;
 
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// Gate activations of the bf16 variant: one MUFU.TANH each (tanh.approx.f32, max relative error 2^-11 -- below the bf16
+// rounding of the operands that produced the gates); sigmoid(x) = 0.5 tanh(x / 2) + 0.5.  The exact forms (ex2 + rcp, tanhf's
+// ~25-instruction sequence) made the epilogue ~120 instructions per hidden channel: at the C = 64 level, where a tile has only
+// 18 K blocks of MMA work, the eight epilogue warps were busy 90 % of the time at 0.28 IPC and the MMA warp waited for a free
+// accumulator (profiles/r02_convlstm_full.md).
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// TF32 variant: tanh(x) = 1 - 2 / (1 + e^(2x)) on ex2.approx + rcp (absolute error ~2e-7, saturates correctly at +-inf) instead
+// of tanhf's branchy ~25-instruction sequence.
+template <bool FAST> __device__ __forceinline__ float act_tanh(float x) {
+    return FAST ? tanh_fast(x) : 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x));
+}
+template <bool FAST> __device__ __forceinline__ float act_sigm(float x) {
+    return FAST ? fmaf(0.5f, tanh_fast(0.5f * x), 0.5f) : sigm(x);
+}
 
 // BF16 = false: fp32 operands read as TF32 (32 channels per 128-byte K block).  BF16 = true: bf16 operands
 // (tcgen05.mma.kind::f16, 64 channels per K block: half the operand bytes per flop, twice the MMA rate), fp32 accumulate,
@@ -133,14 +151,14 @@ k_convlstm_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                     const float4 bo = __ldg(reinterpret_cast<const float4*>(bn + 2 * 64 + sub * 16 + j));
                     const float4 bg = __ldg(reinterpret_cast<const float4*>(bn + 3 * 64 + sub * 16 + j));
                     float4 c, h;
-                    c.x = sigm(gf[j] + bf.x) * pc.x + sigm(gi[j] + bi.x) * tanhf(gg[j] + bg.x);
-                    c.y = sigm(gf[j + 1] + bf.y) * pc.y + sigm(gi[j + 1] + bi.y) * tanhf(gg[j + 1] + bg.y);
-                    c.z = sigm(gf[j + 2] + bf.z) * pc.z + sigm(gi[j + 2] + bi.z) * tanhf(gg[j + 2] + bg.z);
-                    c.w = sigm(gf[j + 3] + bf.w) * pc.w + sigm(gi[j + 3] + bi.w) * tanhf(gg[j + 3] + bg.w);
-                    h.x = sigm(go[j] + bo.x) * tanhf(c.x);
-                    h.y = sigm(go[j + 1] + bo.y) * tanhf(c.y);
-                    h.z = sigm(go[j + 2] + bo.z) * tanhf(c.z);
-                    h.w = sigm(go[j + 3] + bo.w) * tanhf(c.w);
+                    c.x = act_sigm<BF16>(gf[j] + bf.x) * pc.x + act_sigm<BF16>(gi[j] + bi.x) * act_tanh<BF16>(gg[j] + bg.x);
+                    c.y = act_sigm<BF16>(gf[j + 1] + bf.y) * pc.y + act_sigm<BF16>(gi[j + 1] + bi.y) * act_tanh<BF16>(gg[j + 1] + bg.y);
+                    c.z = act_sigm<BF16>(gf[j + 2] + bf.z) * pc.z + act_sigm<BF16>(gi[j + 2] + bi.z) * act_tanh<BF16>(gg[j + 2] + bg.z);
+                    c.w = act_sigm<BF16>(gf[j + 3] + bf.w) * pc.w + act_sigm<BF16>(gi[j + 3] + bi.w) * act_tanh<BF16>(gg[j + 3] + bg.w);
+                    h.x = act_sigm<BF16>(go[j] + bo.x) * act_tanh<BF16>(c.x);
+                    h.y = act_sigm<BF16>(go[j + 1] + bo.y) * act_tanh<BF16>(c.y);
+                    h.z = act_sigm<BF16>(go[j + 2] + bo.z) * act_tanh<BF16>(c.z);
+                    h.w = act_sigm<BF16>(go[j + 3] + bo.w) * act_tanh<BF16>(c.w);
                     *reinterpret_cast<float4*>(c_out + e + j) = c;
                     if (h_out) *reinterpret_cast<float4*>(h_out + e + j) = h;
                     if (BF16) {
@@ -318,14 +336,14 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                         const float4 bo = __ldg(reinterpret_cast<const float4*>(bn + 2 * 64 + sub * 16 + j));
                         const float4 bg = __ldg(reinterpret_cast<const float4*>(bn + 3 * 64 + sub * 16 + j));
                         float4 c, h;
-                        c.x = sigm(gf[j] + bf.x) * pc.x + sigm(gi[j] + bi.x) * tanhf(gg[j] + bg.x);
-                        c.y = sigm(gf[j + 1] + bf.y) * pc.y + sigm(gi[j + 1] + bi.y) * tanhf(gg[j + 1] + bg.y);
-                        c.z = sigm(gf[j + 2] + bf.z) * pc.z + sigm(gi[j + 2] + bi.z) * tanhf(gg[j + 2] + bg.z);
-                        c.w = sigm(gf[j + 3] + bf.w) * pc.w + sigm(gi[j + 3] + bi.w) * tanhf(gg[j + 3] + bg.w);
-                        h.x = sigm(go[j] + bo.x) * tanhf(c.x);
-                        h.y = sigm(go[j + 1] + bo.y) * tanhf(c.y);
-                        h.z = sigm(go[j + 2] + bo.z) * tanhf(c.z);
-                        h.w = sigm(go[j + 3] + bo.w) * tanhf(c.w);
+                        c.x = act_sigm<BF16>(gf[j] + bf.x) * pc.x + act_sigm<BF16>(gi[j] + bi.x) * act_tanh<BF16>(gg[j] + bg.x);
+                        c.y = act_sigm<BF16>(gf[j + 1] + bf.y) * pc.y + act_sigm<BF16>(gi[j + 1] + bi.y) * act_tanh<BF16>(gg[j + 1] + bg.y);
+                        c.z = act_sigm<BF16>(gf[j + 2] + bf.z) * pc.z + act_sigm<BF16>(gi[j + 2] + bi.z) * act_tanh<BF16>(gg[j + 2] + bg.z);
+                        c.w = act_sigm<BF16>(gf[j + 3] + bf.w) * pc.w + act_sigm<BF16>(gi[j + 3] + bi.w) * act_tanh<BF16>(gg[j + 3] + bg.w);
+                        h.x = act_sigm<BF16>(go[j] + bo.x) * act_tanh<BF16>(c.x);
+                        h.y = act_sigm<BF16>(go[j + 1] + bo.y) * act_tanh<BF16>(c.y);
+                        h.z = act_sigm<BF16>(go[j + 2] + bo.z) * act_tanh<BF16>(c.z);
+                        h.w = act_sigm<BF16>(go[j + 3] + bo.w) * act_tanh<BF16>(c.w);
                         *reinterpret_cast<float4*>(c_out + e + j) = c;
                         if (h_out) *reinterpret_cast<float4*>(h_out + e + j) = h;
                         if (BF16) {
@@ -343,6 +361,184 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tc_fence_before();
     if (MC) cluster_sync_all(); else __syncthreads();      // no CTA leaves while its peer can still write into it
     if (warp == 1) tmem_dealloc(tmem_acc, 2 * kCN);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2, OESS_CONVLSTM_2SM=1): the two CTAs of a cluster compute ONE 256-pixel x 256-column tile per
+// step -- two neighbouring pixel patches x all four gates of a channel chunk.  Each CTA stages its own A box (16 KB) and HALF of
+// the weight tile (16 KB) per K block, so the 192 KB ring holds SIX K blocks in flight instead of four (the kernel is bound by
+// operand-fill latency x ring depth: profiles/r02_convlstm_full.md); the leader issues `tcgen05.mma.cta_group::2` with M = 256
+// and commits to both CTAs' barriers; every CTA's epilogue works on its own 128 TMEM lanes as before.
+constexpr int kP2Stages = 6;
+constexpr int kP2BBytes = kCBBytes / 2;
+constexpr int kP2Smem = 1024 + kP2Stages * (kCABytes + kP2BBytes) + 256;
+
+template <bool BF16>
+__global__ void __launch_bounds__(kPCThreads, 1)
+k_convlstm_tc_p2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
+                 const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias, const float* __restrict__ c_prev,
+                 float* __restrict__ h_out, __nv_bfloat16* __restrict__ h_bf, float* __restrict__ c_out, int H, int W, int C,
+                 int has_h, int tiles_w, int tiles_px, int tiles) {
+    constexpr int kKE = BF16 ? 64 : kBlockK;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;
+    uint8_t* sB = base + kP2Stages * kCABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + kP2Stages * kP2BBytes);
+    uint64_t* empty = full + kP2Stages;
+    uint64_t* acc_full = empty + kP2Stages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = C / kKE, nchunks = C / 64;
+    const int kblocks = (has_h ? 2 : 1) * 9 * chunks;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmH);
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < kP2Stages; ++s) {
+            mbar_init(&full[s], 1);                       // the leader's own arrive.expect_tx (both CTAs' bytes)
+            mbar_init(&empty[s], 1);                      // the leader's multicast commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);                   // the leader's multicast commit
+            mbar_init(&acc_empty[b], 8);                  // four epilogue warps of each CTA (used in the leader only)
+        }
+        mbar_fence_init();
+    }
+    cluster_sync_all();                                   // barriers of both CTAs exist before TMEM allocation / any remote arrive
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * kCN);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+    const int tile0 = (int)(blockIdx.x >> 1), tstep = (int)(gridDim.x >> 1);
+    const int px_units = (tiles_px + 1) / 2;
+
+    if (warp == 0) {                                      // ===== TMA producer (both CTAs) =====
+        uint32_t s = 0, ph = 1;
+        for (int tile = tile0; tile < tiles; tile += tstep) {
+            const int pu = tile % px_units, rest = tile / px_units;
+            const int px = 2 * pu + (int)crank;           // past tiles_px: a dummy patch (TMA zero fill, epilogue drops it)
+            const int nchunk = rest % nchunks, b = rest / nchunks;
+            const int th = px / tiles_w, tw = px - th * tiles_w;
+            const int h0 = th * kTH, w0 = tw * kTW;
+            int src = 0, dy = -1, dx = -1, chunk = 0;
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty[s], ph);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(&full[s], 2 * (kCABytes + kP2BBytes));
+                    tma_load_4d_2sm(sA + s * kCABytes, src ? &tmH : &tmX, &full[s], chunk * kKE, w0 + dx, h0 + dy, b);
+                    tma_load_2d_2sm(sB + s * kP2BBytes, &tmW, &full[s], kb * kKE, nchunk * kCN + (int)crank * (kCN / 2));
+                }
+                __syncwarp();
+                if (++chunk == chunks) {
+                    chunk = 0;
+                    if (++dx == 2) { dx = -1; if (++dy == 2) { dy = -1; ++src; } }
+                }
+                if (++s == kP2Stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {                               // ===== MMA issuer (leader CTA only) =====
+        if (leader) {
+            constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(256, kCN) : umma_idesc_tf32(256, kCN);
+            uint32_t s = 0, ph = 0, lt = 0;
+            for (int tile = tile0; tile < tiles; tile += tstep, ++lt) {
+                const uint32_t buf = lt & 1;
+                mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_acc + buf * kCN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = umma_desc_k128(smem_u32(sA + s * kCABytes));
+                        const uint64_t db = umma_desc_k128(smem_u32(sB + s * kP2BBytes));
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                            if (BF16) umma_bf16_2sm(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            else umma_tf32_2sm(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        umma_commit_2sm(&empty[s], (uint16_t)3);
+                    }
+                    __syncwarp();
+                    if (++s == kP2Stages) { s = 0; ph ^= 1; }
+                }
+                if (elect_one()) umma_commit_2sm(&acc_full[buf], (uint16_t)3);
+                __syncwarp();
+            }
+        }
+    } else {                                              // ===== epilogue: group g = warps 2 + 4 g .. 5 + 4 g (both CTAs) =====
+        const int q = warp & 3;
+        const uint32_t g = (uint32_t)(warp - 2) >> 2;
+        uint32_t lt = 0;
+        for (int tile = tile0; tile < tiles; tile += tstep, ++lt) {
+            if ((lt & 1) != g) continue;
+            const int pu = tile % px_units, rest = tile / px_units;
+            const int px = 2 * pu + (int)crank;
+            const int nchunk = rest % nchunks, b = rest / nchunks;
+            const int th = px / tiles_w, tw = px - th * tiles_w;
+            const int r = q * 32 + lane;
+            const int y = th * kTH + r / kTW, x = tw * kTW + r % kTW;
+            const bool valid = y < H && x < W;
+            const int64_t pix = (((int64_t)b * H + y) * W + x) * C + nchunk * 64;
+            const float* bn = bias + nchunk * kCN;
+            mbar_wait(&acc_full[g], (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_acc + g * kCN + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int sub = 0; sub < 4; ++sub) {
+                float gi[16], gf[16], go[16], gg[16];
+                tmem_ld16_nowait(trow + 0 * 64 + sub * 16, gi);
+                tmem_ld16_nowait(trow + 1 * 64 + sub * 16, gf);
+                tmem_ld16_nowait(trow + 2 * 64 + sub * 16, go);
+                tmem_ld16_nowait(trow + 3 * 64 + sub * 16, gg);
+                tmem_ld_wait();
+                if (sub == 3) {                           // accumulator fully read: tell the LEADER's MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&acc_empty[g], 0);
+                }
+                if (valid) {
+                    const int64_t e = pix + sub * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c_prev) pc = *reinterpret_cast<const float4*>(c_prev + e + j);
+                        const float4 bi = __ldg(reinterpret_cast<const float4*>(bn + 0 * 64 + sub * 16 + j));
+                        const float4 bf = __ldg(reinterpret_cast<const float4*>(bn + 1 * 64 + sub * 16 + j));
+                        const float4 bo = __ldg(reinterpret_cast<const float4*>(bn + 2 * 64 + sub * 16 + j));
+                        const float4 bg = __ldg(reinterpret_cast<const float4*>(bn + 3 * 64 + sub * 16 + j));
+                        float4 c, h;
+                        c.x = act_sigm<BF16>(gf[j] + bf.x) * pc.x + act_sigm<BF16>(gi[j] + bi.x) * act_tanh<BF16>(gg[j] + bg.x);
+                        c.y = act_sigm<BF16>(gf[j + 1] + bf.y) * pc.y + act_sigm<BF16>(gi[j + 1] + bi.y) * act_tanh<BF16>(gg[j + 1] + bg.y);
+                        c.z = act_sigm<BF16>(gf[j + 2] + bf.z) * pc.z + act_sigm<BF16>(gi[j + 2] + bi.z) * act_tanh<BF16>(gg[j + 2] + bg.z);
+                        c.w = act_sigm<BF16>(gf[j + 3] + bf.w) * pc.w + act_sigm<BF16>(gi[j + 3] + bi.w) * act_tanh<BF16>(gg[j + 3] + bg.w);
+                        h.x = act_sigm<BF16>(go[j] + bo.x) * act_tanh<BF16>(c.x);
+                        h.y = act_sigm<BF16>(go[j + 1] + bo.y) * act_tanh<BF16>(c.y);
+                        h.z = act_sigm<BF16>(go[j + 2] + bo.z) * act_tanh<BF16>(c.z);
+                        h.w = act_sigm<BF16>(go[j + 3] + bo.w) * act_tanh<BF16>(c.w);
+                        *reinterpret_cast<float4*>(c_out + e + j) = c;
+                        if (h_out) *reinterpret_cast<float4*>(h_out + e + j) = h;
+                        if (BF16) {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(h.x, h.y), hi = __floats2bfloat162_rn(h.z, h.w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                            *reinterpret_cast<uint2*>(h_bf + e + j) = pk;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                   // no CTA leaves (or frees TMEM) while its peer still works
+    if (warp == 1) tmem_dealloc_2sm(tmem_acc, 2 * kCN);
 }
 
 }  // namespace tc
@@ -382,20 +578,23 @@ static int convlstm_impl(const void* x, const void* h_prev, const float* c_prev,
     static const bool tile_env = [] { const char* e = std::getenv("OESS_CONVLSTM"); return e && e[0] == 't'; }();
     static const bool mc_env = [] { const char* e = std::getenv("OESS_CONVLSTM_MC"); return !(e && e[0] == '0'); }();   // default on
     const int tiles_px = tiles_w * tiles_h;
-    const bool mc = mc_env && !tile_env && tiles_px >= 2;
+    static const bool sm2_env = [] { const char* e = std::getenv("OESS_CONVLSTM_2SM"); return !(e && e[0] == '0'); }();   // default on
+    const bool sm2 = sm2_env && !tile_env && tiles_px >= 2;
+    const bool mc = (mc_env || sm2) && !tile_env && tiles_px >= 2;
     const uint32_t bW[2] = {KE, (uint32_t)(mc ? tc::kCN / 2 : tc::kCN)};
     rc = mk(&tmW, w_packed, 2, dW, sW, bW);
     if (rc) return rc;
     const int64_t tiles = (int64_t)(mc ? (tiles_px + 1) / 2 : tiles_px) * (C / 64) * B;
     if (!tile_env && tiles < (1ll << 31)) {
-        auto kern = mc ? tc::k_convlstm_tc_p<BF16, true> : tc::k_convlstm_tc_p<BF16, false>;
-        OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kPCSmem));
+        auto kern = sm2 ? tc::k_convlstm_tc_p2<BF16> : (mc ? tc::k_convlstm_tc_p<BF16, true> : tc::k_convlstm_tc_p<BF16, false>);
+        const int smem_bytes = sm2 ? tc::kP2Smem : tc::kPCSmem;
+        OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);
         if (mc) grid = (unsigned)(2 * (tiles < kNumSMs / 2 ? tiles : kNumSMs / 2));      // whole clusters
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
         cfg.blockDim = dim3(tc::kPCThreads);
-        cfg.dynamicSmemBytes = tc::kPCSmem;
+        cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
