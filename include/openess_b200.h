@@ -374,13 +374,6 @@ int oess_conv2d_nhwc_bf16(const void* x_bf16, const void* w_packed_bf16, const f
 int oess_batchnorm_nhwc_sums_bf16(float* x, int64_t R, int C, const float* gamma, const float* beta, float* running_mean,
                                   float* running_var, float eps, float momentum, const float* residual, int relu, void* y_bf16,
                                   int write_f32, void* ws, size_t ws_bytes, oess_stream_t stream);
-/* bf16 form of the thin-input head convolution (oess_planes_to_nhwc_padded_w + oess_conv2d_nhwc_tf32_rowunfold): the padded
- * channels-last input is written as bfloat16 (Cp % 8 == 0) and one 64-element K block covers a kernel row of up to 64 / Cp
- * taps; w_packed_bf16 [Cout, KH * ceil(KW * Cin / 64) * 64], column (ky, kx * Cin + c); fp32 accumulation and result. */
-int oess_planes_to_nhwc_padded_w_bf16(const float* x, int B, int C, int H, int W, const double* stats, int Cp, int pad_w,
-                                      void* y_bf16, oess_stream_t stream);
-int oess_conv2d_nhwc_bf16_rowunfold(const void* x_bf16, const void* w_packed_bf16, const float* bias, float* y, int B, int H,
-                                    int W, int Cin, int Cout, int KH, int KW, int relu, oess_stream_t stream);
 
 /* Conv + InstanceNorm2d(affine=False) (+ residual) (+ ReLU) of the SemSegE2VID task decoder (models/style_networks.py:
  * 252-289 ReLUINSConv2d / INSResBlock) for its forward-only uses (validation, linear probing, test.py): the conv

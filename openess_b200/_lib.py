@@ -89,8 +89,6 @@ SIGNATURES = {
     "oess_batchnorm_nhwc_sums_bf16": [_vp, _i64, _int, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _int, _vp, _int, _vp, _sz, _vp],
     "oess_planes_to_nhwc_padded": [_vp, _int, _int, _i64, _vp, _int, _vp, _vp],
     "oess_planes_to_nhwc_padded_w": [_vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _vp],
-    "oess_planes_to_nhwc_padded_w_bf16": [_vp, _int, _int, _int, _int, _vp, _int, _int, _vp, _vp],
-    "oess_conv2d_nhwc_bf16_rowunfold": [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp],
     "oess_conv2d_nhwc_tf32_rowunfold": [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _vp],
     "oess_conv2d_nhwc_tf32_instats": [_vp, _vp, _vp, _vp, _int, _int, _int, _int, _int, _int, _int, _int, _int, _int, _vp, _vp],
     "oess_instancenorm_nhwc_sums": [_vp, _int, _i64, _int, _vp, _f32, _vp, _int, _vp],

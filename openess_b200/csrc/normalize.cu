@@ -5,8 +5,6 @@
 // Algorithmic bytes: 2 reads + 1 write of the tensor = 12 B / element.
 // Sums are accumulated in float64 (per-thread -> warp shuffle -> one atomicAdd(double) per CTA), so
 // the statistics are at least as accurate as torch's float32 reductions; parity is tolerance-based.
-#include <cuda_bf16.h>
-
 #include "normalize.cuh"
 
 namespace oess {
@@ -91,22 +89,9 @@ k_apply(float* __restrict__ x, int64_t group_numel, const double* __restrict__ s
 // applying the EventPreprocessor normalisation (biased, inference_utils.py:77-85) from precomputed stats on the way:
 // the input transform in front of the tensor-core head convolution of E2VID (a 5-channel plane tensor is too thin for
 // a 16-byte-aligned TMA row).
-__device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) {
-    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
-}
-__device__ __forceinline__ void store4(__nv_bfloat16* p, float a, float b, float c, float d) {
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
-    uint2 pk;
-    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(p) = pk;
-}
-
-// T = float, or __nv_bfloat16 (the operand of the bf16 head convolution, oess_conv2d_nhwc_bf16_rowunfold)
-template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_to_nhwc_padded(const float* __restrict__ x, int C, int64_t HW, int64_t total, const double* __restrict__ stats, int Cp,
-                 T* __restrict__ y, int W, int pad_w) {
+                 float* __restrict__ y, int W, int pad_w) {
     bool norm = false;
     float mean = 0.f, sd = 1.f;
     if (stats) {
@@ -124,7 +109,7 @@ k_to_nhwc_padded(const float* __restrict__ x, int C, int64_t HW, int64_t total, 
         const float* xp = x + b * C * HW + px;
         // pad_w > 0: the output rows are W + 2 pad_w pixels wide with zero borders (written by k_zero_borders)
         const int64_t row = (b * HW + px) / W;
-        T* yp = y + (pad_w ? (i + (2 * row + 1) * (int64_t)pad_w) : i) * Cp;
+        float* yp = y + (pad_w ? (i + (2 * row + 1) * (int64_t)pad_w) : i) * Cp;
         for (int c0 = 0; c0 < Cp; c0 += 4) {
             float v[4];
 #pragma unroll
@@ -134,21 +119,20 @@ k_to_nhwc_padded(const float* __restrict__ x, int C, int64_t HW, int64_t total, 
                 if (norm && c < C) t = __fdiv_rn(__fmul_rn((t != 0.0f) ? 1.0f : 0.0f, __fsub_rn(t, mean)), sd);
                 v[j] = t;
             }
-            store4(yp + c0, v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(yp + c0) = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
 }
 
 // zero the pad_w border pixels at both ends of every row of y [rows, W + 2 pad_w, Cp]
-template <typename T>
-__global__ void k_zero_borders(T* __restrict__ y, int64_t rows, int W, int pad_w, int Cp) {
+__global__ void k_zero_borders(float* __restrict__ y, int64_t rows, int W, int pad_w, int Cp) {
     const int64_t n = rows * 2 * pad_w * Cp;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = i / (2 * pad_w * Cp);
         const int j = (int)(i - r * 2 * pad_w * Cp);
         const int px = j / Cp, c = j - px * Cp;
         const int col = px < pad_w ? px : W + px;          // left border, then right border
-        y[(r * (W + 2 * pad_w) + col) * Cp + c] = T(0.0f);
+        y[(r * (W + 2 * pad_w) + col) * Cp + c] = 0.0f;
     }
 }
 
@@ -159,30 +143,17 @@ using namespace oess;
 
 // Same as oess_planes_to_nhwc_padded with the rows additionally zero-padded by pad_w pixels at both ends:
 // y [B, H, W + 2 pad_w, Cp] (the input layout of oess_conv2d_nhwc_tf32_rowunfold).
-template <typename T>
-static int planes_to_nhwc_padded_w_impl(const float* x, int B, int C, int H, int W, const double* stats, int Cp, int pad_w,
-                                        T* y, oess_stream_t stream) {
+OESS_API int oess_planes_to_nhwc_padded_w(const float* x, int B, int C, int H, int W, const double* stats, int Cp, int pad_w,
+                                          float* y, oess_stream_t stream) {
     if (!x || !y || B <= 0 || C <= 0 || H <= 0 || W <= 0 || Cp < C || (Cp & 3) || pad_w <= 0 || ((uintptr_t)y & 15)) return OESS_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t HW = (int64_t)H * W, total = (int64_t)B * HW;
     int64_t blocks = (total + norm::kThreads - 1) / norm::kThreads;
     if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
-    OESS_KERNEL("k_zero_borders", st, norm::k_zero_borders<T><<<kNumSMs, 256, 0, st>>>(y, (int64_t)B * H, W, pad_w, Cp));
-    OESS_KERNEL("k_to_nhwc_padded", st, norm::k_to_nhwc_padded<T><<<(unsigned)blocks, norm::kThreads, 0, st>>>(
+    OESS_KERNEL("k_zero_borders", st, norm::k_zero_borders<<<kNumSMs, 256, 0, st>>>(y, (int64_t)B * H, W, pad_w, Cp));
+    OESS_KERNEL("k_to_nhwc_padded", st, norm::k_to_nhwc_padded<<<(unsigned)blocks, norm::kThreads, 0, st>>>(
         x, C, HW, total, stats, Cp, y, W, pad_w));
     return OESS_OK;
-}
-
-OESS_API int oess_planes_to_nhwc_padded_w(const float* x, int B, int C, int H, int W, const double* stats, int Cp, int pad_w,
-                                          float* y, oess_stream_t stream) {
-    return planes_to_nhwc_padded_w_impl<float>(x, B, C, H, W, stats, Cp, pad_w, y, stream);
-}
-
-// Same with a bfloat16 result (Cp % 8 == 0): the input of oess_conv2d_nhwc_bf16_rowunfold.
-OESS_API int oess_planes_to_nhwc_padded_w_bf16(const float* x, int B, int C, int H, int W, const double* stats, int Cp, int pad_w,
-                                               void* y_bf16, oess_stream_t stream) {
-    if (Cp & 7) return OESS_E_ARG;
-    return planes_to_nhwc_padded_w_impl<__nv_bfloat16>(x, B, C, H, W, stats, Cp, pad_w, (__nv_bfloat16*)y_bf16, stream);
 }
 
 OESS_API int oess_planes_to_nhwc_padded(const float* x, int B, int C, int64_t HW, const double* stats, int Cp, float* y,
@@ -192,7 +163,7 @@ OESS_API int oess_planes_to_nhwc_padded(const float* x, int B, int C, int64_t HW
     const int64_t total = (int64_t)B * HW;
     int64_t blocks = (total + norm::kThreads - 1) / norm::kThreads;
     if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
-    OESS_KERNEL("k_to_nhwc_padded", st, norm::k_to_nhwc_padded<float><<<(unsigned)blocks, norm::kThreads, 0, st>>>(
+    OESS_KERNEL("k_to_nhwc_padded", st, norm::k_to_nhwc_padded<<<(unsigned)blocks, norm::kThreads, 0, st>>>(
         x, C, HW, total, stats, Cp, y, 1, 0));
     return OESS_OK;
 }

@@ -613,34 +613,6 @@ OESS_API int oess_conv2d_nhwc_tf32_rowunfold(const float* x, const float* w_pack
     return tc::launch_conv<32>(tmX, w_packed, Cout, Ktot, bias, nullptr, y, nullptr, a, B, st);
 }
 
-// oess_conv2d_nhwc_tf32_rowunfold with bfloat16 operands (frozen E2VID head): x [B, H, W + KW - 1, Cin] bf16 (Cin % 8 == 0,
-// oess_planes_to_nhwc_padded_w_bf16), w_packed [Cout, KH * chunks * 64] bf16 with chunks = ceil(KW * Cin / 64), fp32 result.
-// The 5 x 5 head on 8-channel pixels is ONE 64-element K block per kernel row (40 used) = 5 K blocks per tile instead of 10:
-// a 32-wide tile is bound by the per-K-block issue loop, not by the MMAs.
-OESS_API int oess_conv2d_nhwc_bf16_rowunfold(const void* x_bf16, const void* w_packed_bf16, const float* bias, float* y, int B,
-                                             int H, int W, int Cin, int Cout, int KH, int KW, int relu, oess_stream_t stream) {
-    if (B <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0 || KH <= 0 || KW <= 0 || !(KH & 1) || !(KW & 1)) return OESS_E_ARG;
-    if (!x_bf16 || !w_packed_bf16 || !y || (Cin & 7) || KW * Cin > 256 || KH > 64) return OESS_E_ARG;
-    if (((uintptr_t)x_bf16 | (uintptr_t)w_packed_bf16 | (uintptr_t)bias | (uintptr_t)y) & 15) return OESS_E_ARG;
-    if (B > 65535) return OESS_E_RANGE;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int Wp = W + KW - 1, Cv = KW * Cin;
-    const int chunks = (Cv + 63) / 64;
-    const int Ktot = KH * chunks * 64;
-    CUtensorMap tmX;
-    const uint64_t dims[4] = {(uint64_t)Cv, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    const uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Wp * Cin * 2, (uint64_t)H * Wp * Cin * 2};
-    const uint32_t box[4] = {64, (uint32_t)tc::kVW, (uint32_t)tc::kVH, 1};
-    const uint32_t estr[4] = {1, 1, 1, 1};
-    int rc = tc::make_tmap_f32_strided(&tmX, x_bf16, 4, dims, strides, box, estr, true);
-    if (rc) return rc;
-    tc::ConvArgs a{H, W, Cout, 1, KH, chunks, 1, (KH - 1) / 2, 0, 1, relu & 3, (W + tc::kVW - 1) / tc::kVW, 0};
-    if (Cout > 128) return tc::launch_conv<256, true>(tmX, w_packed_bf16, Cout, Ktot, bias, nullptr, y, nullptr, a, B, st);
-    if (Cout > 64) return tc::launch_conv<128, true>(tmX, w_packed_bf16, Cout, Ktot, bias, nullptr, y, nullptr, a, B, st);
-    if (Cout > 32) return tc::launch_conv<64, true>(tmX, w_packed_bf16, Cout, Ktot, bias, nullptr, y, nullptr, a, B, st);
-    return tc::launch_conv<32, true>(tmX, w_packed_bf16, Cout, Ktot, bias, nullptr, y, nullptr, a, B, st);
-}
-
 OESS_API int oess_conv2d_nhwc_tf32(const float* x, const float* w_packed, const float* bias, const float* residual, float* y,
                                    int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dil,
                                    int relu, oess_stream_t stream) {

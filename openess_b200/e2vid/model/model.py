@@ -276,15 +276,13 @@ class UNetRecurrent(nn.Module):
         # K = 5 x 64 instead of 25 x 32 for the 5 x 5 head of E2VID)
         unfold = (conv.kernel_size[0] == conv.kernel_size[1] and k % 2 == 1 and conv.stride[0] == 1 and conv.dilation[0] == 1
                   and conv.padding[0] == k // 2 and k * 8 <= 256)
-        bf16 = unfold and CONVLSTM_BF16                         # frozen-encoder bf16 operands: one 64-element K block per kernel row
-        key = key + (bf16,)
         if getattr(self, "_head_packed", None) is None or self._head_packed[0] != key:
             wpad = torch.zeros(w.shape[0], 8, w.shape[2], w.shape[3], dtype=torch.float32, device=w.device)
             wpad[:, :w.shape[1]] = w.detach()
-            self._head_packed = (key, _tc.conv2d_pack_rowunfold(wpad, bf16=bf16) if unfold else _tc.conv2d_pack(wpad),
+            self._head_packed = (key, _tc.conv2d_pack_rowunfold(wpad) if unfold else _tc.conv2d_pack(wpad),
                                  None if b is None else b.detach().float().contiguous())
         if unfold:
-            x8 = _tc.planes_to_nhwc_padded_w(x, 8, k // 2, bf16=bf16)
+            x8 = _tc.planes_to_nhwc_padded_w(x, 8, k // 2)
             return _tc.conv2d_rowunfold(x8, self._head_packed[1], self._head_packed[2], k, k, x.shape[3],
                                         relu=self.head.activation is not None)
         x8 = _tc.planes_to_nhwc_padded(x, 8)

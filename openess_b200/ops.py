@@ -627,31 +627,28 @@ def planes_to_nhwc_padded(x, cp, stats=None):
     return y
 
 
-def planes_to_nhwc_padded_w(x, cp, pad_w, stats=None, bf16=False):
+def planes_to_nhwc_padded_w(x, cp, pad_w, stats=None):
     """planes_to_nhwc_padded with the rows zero-padded by pad_w pixels at both ends: returns the raw [B, H, W + 2 pad_w, cp]
-    channels-last buffer (input of conv2d_rowunfold), float32 or (bf16=True, cp % 8 == 0) bfloat16."""
+    channels-last buffer (input of conv2d_rowunfold)."""
     _lib.require_cuda(x)
     x = _f32c(x)
     B, C, H, W = x.shape
-    y = torch.empty((B, H, W + 2 * pad_w, cp), dtype=torch.bfloat16 if bf16 else torch.float32, device=x.device)
-    fn = lib().oess_planes_to_nhwc_padded_w_bf16 if bf16 else lib().oess_planes_to_nhwc_padded_w
+    y = torch.empty((B, H, W + 2 * pad_w, cp), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(fn(ptr(x), B, C, H, W, ptr(stats), cp, pad_w, ptr(y), stream_ptr(x.device)), "oess_planes_to_nhwc_padded_w")
+        check(lib().oess_planes_to_nhwc_padded_w(ptr(x), B, C, H, W, ptr(stats), cp, pad_w, ptr(y), stream_ptr(x.device)),
+              "oess_planes_to_nhwc_padded_w")
     return y
 
 
-def conv2d_pack_rowunfold(weight, bf16=False):
+def conv2d_pack_rowunfold(weight):
     """[Cout, Cin, KH, KW] -> [Cout, KH * roundup(KW * Cin, 32)], column (ky, kx * Cin + c): the K order of
-    oess_conv2d_nhwc_tf32_rowunfold (thin-input convolution: the taps of a kernel row folded into the channel dimension).
-    bf16: bfloat16, rows rounded up to 64 (oess_conv2d_nhwc_bf16_rowunfold)."""
+    oess_conv2d_nhwc_tf32_rowunfold (thin-input convolution: the taps of a kernel row folded into the channel dimension)."""
     Cout, Cin, KH, KW = weight.shape
     cv = KW * Cin
-    blk = 64 if bf16 else 32
-    cvp = (cv + blk - 1) // blk * blk
+    cvp = (cv + 31) // 32 * 32
     w = torch.zeros(Cout, KH, cvp, dtype=torch.float32, device=weight.device)
     w[:, :, :cv] = weight.detach().float().permute(0, 2, 3, 1).reshape(Cout, KH, cv)
-    w = w.reshape(Cout, KH * cvp).contiguous()
-    return w.to(torch.bfloat16) if bf16 else round_tf32(w)
+    return round_tf32(w.reshape(Cout, KH * cvp).contiguous())
 
 
 def conv2d_rowunfold(x_padded, w_packed, bias, KH, KW, W, relu=False, round_out=False):
@@ -664,14 +661,6 @@ def conv2d_rowunfold(x_padded, w_packed, bias, KH, KW, W, relu=False, round_out=
     Cout = w_packed.shape[0]
     y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x_padded.device, memory_format=torch.channels_last)
     bc = None if bias is None else _f32c(bias)
-    if x_padded.dtype == torch.bfloat16:
-        if w_packed.dtype != torch.bfloat16:
-            raise ValueError("conv2d_rowunfold: bf16 input needs conv2d_pack_rowunfold(..., bf16=True) weights")
-        with torch.cuda.device(x_padded.device):
-            check(lib().oess_conv2d_nhwc_bf16_rowunfold(ptr(x_padded), ptr(w_packed), ptr(bc), ptr(y), B, H, W, Cin, Cout, KH, KW,
-                                                        1 if relu else 0, stream_ptr(x_padded.device)),
-                  "oess_conv2d_nhwc_bf16_rowunfold")
-        return y
     with torch.cuda.device(x_padded.device):
         check(lib().oess_conv2d_nhwc_tf32_rowunfold(ptr(x_padded), ptr(w_packed), ptr(bc), ptr(y), B, H, W, Cin, Cout, KH, KW,
                                                     (1 if relu else 0) | (2 if round_out else 0), stream_ptr(x_padded.device)),

@@ -97,8 +97,7 @@ def test_e2vid_full_width_tensor_core_convlstm_vs_reference_golden():
             # bf16 mode: the level-2 / level-3 encoder convs read the previous level's bf16 hidden state (kind::f16 kernel)
             nconv = prof.kernels.get("tc_conv2d", (0, 0.0))[0] + prof.kernels.get("tc_conv2d_bf16", (0, 0.0))[0]
             assert nconv == (12 if use_tc else 0)
-            # ... and the head conv takes bf16 input planes (one 64-element K block per kernel row): 3 + 6 launches
-            assert prof.kernels.get("tc_conv2d_bf16", (0, 0.0))[0] == (9 if mode == "bf16" else 0)
+            assert prof.kernels.get("tc_conv2d_bf16", (0, 0.0))[0] == (6 if mode == "bf16" else 0)
         finally:
             mm.USE_TENSOR_CORES = True
             mm.CONVLSTM_BF16 = bf16_was

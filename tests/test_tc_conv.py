@@ -188,24 +188,21 @@ def test_conv_bn_train_bf16_vs_torch():
     assert y2 is None and torch.equal(yb2, yb)
 
 
-@pytest.mark.parametrize("bf16", [False, True])
 @pytest.mark.parametrize("B,C,Cout,H,W,k", [(2, 5, 32, 21, 37, 5), (1, 3, 64, 16, 48, 3), (1, 8, 32, 9, 16, 7)])
-def test_conv2d_rowunfold_thin_input(B, C, Cout, H, W, k, bf16):
+def test_conv2d_rowunfold_thin_input(B, C, Cout, H, W, k):
     """Thin-input 'same' convolution with the taps of a kernel row folded into the channel dimension (E2VID head, unet.py:126-127)
-    against torch's conv2d in float64; bf16: on the bf16-rounded operands (products exact in fp32)."""
+    against torch's conv2d in float64."""
     from openess_b200 import ops
     g = torch.Generator().manual_seed(C * 11 + k)
     x = torch.randn(B, C, H, W, generator=g)
     w = torch.randn(Cout, C, k, k, generator=g) / (C * k * k) ** 0.5
     b = torch.randn(Cout, generator=g) * 0.1
-    if bf16:
-        x, w = x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float()
     ref = F.conv2d(x.double(), w.double(), b.double(), padding=k // 2).clamp_min(0)
-    bound = (1e-5 if bf16 else 2e-3) * F.conv2d(x.abs().double(), w.abs().double(), None, padding=k // 2) + 1e-6
+    bound = 2e-3 * F.conv2d(x.abs().double(), w.abs().double(), None, padding=k // 2) + 1e-6
     wpad = torch.zeros(Cout, 8, k, k)
     wpad[:, :C] = w
-    x8 = ops.planes_to_nhwc_padded_w(x.cuda(), 8, k // 2, bf16=bf16)
-    assert x8.dtype == (torch.bfloat16 if bf16 else torch.float32) and tuple(x8.shape) == (B, H, W + k - 1, 8)
-    y = ops.conv2d_rowunfold(x8, ops.conv2d_pack_rowunfold(wpad.cuda(), bf16=bf16), b.cuda(), k, k, W, relu=True)
+    x8 = ops.planes_to_nhwc_padded_w(x.cuda(), 8, k // 2)
+    assert tuple(x8.shape) == (B, H, W + k - 1, 8)
+    y = ops.conv2d_rowunfold(x8, ops.conv2d_pack_rowunfold(wpad.cuda()), b.cuda(), k, k, W, relu=True)
     err = (y.cpu().double() - ref).abs()
     assert bool((err <= bound).all()), f"max err {float(err.max())}"

@@ -11,10 +11,9 @@ B, H, W = int(os.environ.get("B", 4)), 440, 640
 x = torch.randn(B, 5, H, W, device="cuda")
 w = torch.zeros(32, 8, 5, 5, device="cuda")
 w[:, :5] = torch.randn(32, 5, 5, 5, device="cuda") * 0.1
-BF16 = os.environ.get("BF16", "0") == "1"
-wp = ops.conv2d_pack_rowunfold(w, bf16=BF16)
+wp = ops.conv2d_pack_rowunfold(w)
 b = torch.zeros(32, device="cuda")
-x8 = ops.planes_to_nhwc_padded_w(x, 8, 2, bf16=BF16)
+x8 = ops.planes_to_nhwc_padded_w(x, 8, 2)
 for _ in range(3):
     y = ops.conv2d_rowunfold(x8, wp, b, 5, 5, W, relu=True)
 torch.cuda.synchronize()
@@ -25,4 +24,4 @@ for _ in range(20):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 20
-print(f"head conv B={B} bf16={BF16}: {ms:.4f} ms, output {y.numel() * 4 / ms / 1e6:.0f} GB/s")
+print(f"head conv B={B}: {ms:.4f} ms, output {y.numel() * 4 / ms / 1e6:.0f} GB/s")
