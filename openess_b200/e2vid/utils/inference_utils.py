@@ -33,7 +33,10 @@ class EventPreprocessor:
         if self.flip:
             events = torch.flip(events, dims=[2, 3])
         if not self.no_normalize:
-            x = events.to(torch.float32).contiguous().clone()   # the reference returns a new tensor
+            # the reference returns a new tensor: ONE copy (a strided [B, 5, H, W] slice of the [B, 100, H, W] sample tensor is
+            # already copied by .contiguous(); only a contiguous float32 input still needs the clone)
+            x = events.to(torch.float32)
+            x = x.clone() if (x.is_contiguous() and x.data_ptr() == events.data_ptr()) else x.contiguous()
             if self.reduce_stats is None:
                 _voxel.nonzero_standardize(x, n_groups=1, unbiased=False, phase=0)
             else:
