@@ -217,9 +217,9 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
 // (pixel tile fastest, then Cout tile, then sample), the operand ring keeps running across tile boundaries, two TMEM
 // accumulators: epilogue group g (four warps, one per TMEM lane quarter) drains the tiles of accumulator g while the MMA warp
 // fills the other one.  fp32 output goes through a swizzled 32-pixel x 32-channel staging block per warp and a 4-D TMA store
-// (box {32 ch, 16 px, 2 rows, 1}, clipped at the ragged edges); BatchNorm / InstanceNorm statistics are column sums of the
-// staged block (lane l reads channel l down the warp's 32 pixels), kept in registers across tiles and flushed with fp64
-// atomics only when the CTA moves to another Cout tile or sample.
+// (box {32 ch, 16 px, 2 rows, 1}, clipped at the ragged edges); BatchNorm / InstanceNorm statistics are reduced across the
+// warp's 32 pixels by recursive halving (lane l ends up with channel l of the chunk), kept in registers across tiles and
+// flushed with fp64 atomics only when the CTA moves to another Cout tile or sample.
 constexpr int kPConvThreads = 320;
 
 template <int BN>
@@ -388,8 +388,7 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                         }
                     }
                 }
-                if (bn_sums && !y_f32) {
-                    // (no staged fp32 output to read back: shuffle reduction)
+                if (bn_sums) {
                     // column sums / sums of squares over the warp's 32 pixels: five exchange rounds, each halving the columns
                     // a lane is responsible for; lane l ends with channel col + l
                     float s_[16], q_[16];
@@ -463,24 +462,6 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                         tma_store_commit();
                     }
                     __syncwarp();
-                    if (bn_sums) {
-                        // statistics from the staged block: lane l sums channel col + l down the 32 staged pixels -- one 128-byte
-                        // row per load instruction, conflict-free under the swizzle -- instead of 124 shuffles per chunk (the
-                        // epilogue, not the MMAs, bounds the short-K 1 x 1 convs of the teacher)
-                        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-                        const uint8_t* colp = stage + ((lane & 3) << 2);
-                        float cs = 0.f, cq = 0.f;
-#pragma unroll 8
-                        for (int r = 0; r < 32; ++r) {
-                            const float v = *reinterpret_cast<const float*>(colp + r * 128 + (((lane >> 2) ^ (r & 7)) << 4));
-                            if ((vmask >> r) & 1u) {
-                                cs += v;
-                                cq = fmaf(v, v, cq);
-                            }
-                        }
-                        st_s[ch] += cs;
-                        st_q[ch] += cq;
-                    }
                 }
             }
         }
