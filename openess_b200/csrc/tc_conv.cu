@@ -225,8 +225,13 @@ constexpr int kPConvThreads = 320;
 template <int BN>
 struct PConvSmem {
     static constexpr int kBBytes = BN * kBlockK * 4;
-    static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : 8);
-    static constexpr int kBytes = 1024 + kStages * (kVABytes + kBBytes) + 8 * 4096 + 256;
+    // narrow tiles: TWO K blocks per ring stage.  Their four MMAs take 4 x BN / 2 cycles, far less than one trip of the
+    // single-lane issue loops (~430 cycles: wait, elect, descriptors, commit), so the loops -- not the tensor pipe -- set the
+    // pace; eight MMAs and four TMA boxes per trip halve that overhead.
+    static constexpr int kKbPerStage = BN <= 64 ? 2 : 1;
+    static constexpr int kStageBytes = kKbPerStage * (kVABytes + kBBytes);
+    static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : (BN >= 64 ? 4 : 4));
+    static constexpr int kBytes = 1024 + kStages * kStageBytes + 8 * 4096 + 256;
 };
 
 struct PConvArgs {
@@ -246,9 +251,10 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
     constexpr int NCH = BN / 32;
     const ConvArgs& a = pa.a;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sA = base;
-    uint8_t* sB = sA + kStages * kVABytes;
-    uint8_t* sC = sB + kStages * S::kBBytes;
+    constexpr int KPS = S::kKbPerStage;
+    uint8_t* sA = base;                                   // [kStages][KPS] A boxes
+    uint8_t* sB = sA + kStages * KPS * kVABytes;          // [kStages][KPS] B boxes
+    uint8_t* sC = sB + kStages * KPS * S::kBBytes;
     uint64_t* full = reinterpret_cast<uint64_t*>(sC + 8 * 4096);
     uint64_t* empty = full + kStages;
     uint64_t* acc_full = empty + kStages;
@@ -286,15 +292,28 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             const int th = px / a.tiles_w, tw = px - th * a.tiles_w;
             const int x0 = tw * kVW * a.stride - a.pad_x, y0 = th * kVH * a.stride - a.pad;
             int ky = 0, kx = 0, chunk = 0;
-            for (int kb = 0; kb < kblocks; ++kb) {
+            for (int kb = 0; kb < kblocks; kb += KPS) {
                 mbar_wait(&empty[s], ph);
+                const int nk = (KPS == 1 || kb + 1 < kblocks) ? KPS : 1;      // K blocks in this stage (odd tail: one)
+                int cc[KPS], cx[KPS], cy[KPS];                                // the tap walk, by every lane alike
+#pragma unroll
+                for (int u = 0; u < KPS; ++u) {
+                    cc[u] = chunk * kKE;
+                    cx[u] = x0 + kx * a.dil;
+                    cy[u] = y0 + ky * a.dil;
+                    if (u < nk && ++chunk == a.chunks) { chunk = 0; if (++kx == a.KW) { kx = 0; ++ky; } }
+                }
                 if (elect_one()) {
-                    mbar_expect_tx(&full[s], kVABytes + S::kBBytes);
-                    tma_load_4d(sA + s * kVABytes, &tmX, &full[s], chunk * kKE, x0 + kx * a.dil, y0 + ky * a.dil, b);
-                    tma_load_2d(sB + s * S::kBBytes, &tmW, &full[s], kb * kKE, n0);
+                    mbar_expect_tx(&full[s], nk * (kVABytes + S::kBBytes));
+#pragma unroll
+                    for (int u = 0; u < KPS; ++u) {
+                        if (u < nk) {
+                            tma_load_4d(sA + (s * KPS + u) * kVABytes, &tmX, &full[s], cc[u], cx[u], cy[u], b);
+                            tma_load_2d(sB + (s * KPS + u) * S::kBBytes, &tmW, &full[s], (kb + u) * kKE, n0);
+                        }
+                    }
                 }
                 __syncwarp();
-                if (++chunk == a.chunks) { chunk = 0; if (++kx == a.KW) { kx = 0; ++ky; } }
                 if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
@@ -306,16 +325,22 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d = tmem_acc + buf * BN;
-            for (int kb = 0; kb < kblocks; ++kb) {
+            for (int kb = 0; kb < kblocks; kb += KPS) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
+                const int nk = (KPS == 1 || kb + 1 < kblocks) ? KPS : 1;
                 if (elect_one()) {
-                    const uint64_t da = umma_desc_k128(smem_u32(sA + s * kVABytes));
-                    const uint64_t db = umma_desc_k128(smem_u32(sB + s * S::kBBytes));
 #pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        if (BF16) umma_bf16(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-                        else umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int u = 0; u < KPS; ++u) {
+                        if (u < nk) {
+                            const uint64_t da = umma_desc_k128(smem_u32(sA + (s * KPS + u) * kVABytes));
+                            const uint64_t db = umma_desc_k128(smem_u32(sB + (s * KPS + u) * S::kBBytes));
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                if (BF16) umma_bf16(d, da + 2 * k, db + 2 * k, idesc, (kb | u | k) != 0);
+                                else umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | u | k) != 0);
+                            }
+                        }
                     }
                     umma_commit(&empty[s]);
                 }
