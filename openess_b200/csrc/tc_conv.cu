@@ -228,9 +228,9 @@ struct PConvSmem {
     // narrow tiles: TWO K blocks per ring stage.  Their four MMAs take 4 x BN / 2 cycles, far less than one trip of the
     // single-lane issue loops (~430 cycles: wait, elect, descriptors, commit), so the loops -- not the tensor pipe -- set the
     // pace; eight MMAs and four TMA boxes per trip halve that overhead.
-    static constexpr int kKbPerStage = BN <= 64 ? 2 : 1;
+    static constexpr int kKbPerStage = BN <= 128 ? 2 : 1;
     static constexpr int kStageBytes = kKbPerStage * (kVABytes + kBBytes);
-    static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 6 : (BN >= 64 ? 4 : 4));
+    static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);
     static constexpr int kBytes = 1024 + kStages * kStageBytes + 8 * 4096 + 256;
 };
 
