@@ -254,3 +254,34 @@ def test_pretrain_step_matches_reference_trainer_golden():
         torch.backends.cudnn.allow_tf32 = tf32_was
         im.USE_TENSOR_CORES = True
         sn.TRAIN_ON_TENSOR_CORES = True
+
+
+@pytest.mark.gpu
+def test_device_prefetcher_moves_nested_batches_on_a_side_stream():
+    """training/prefetch.py: the batch fed last comes back on the device with equal contents (RawEvents slab, dense tensors, None
+    and nested tuples kept), ordered after the copies; take() without a feed raises."""
+    import numpy as np
+    from openess_b200.training.prefetch import DevicePrefetcher
+    from openess_b200.training.pretrain_step import RawEvents
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    n = 50_000
+    ev = RawEvents(torch.randint(0, 640, (n,), generator=g).to(torch.uint16).pin_memory(),
+                   torch.randint(0, 480, (n,), generator=g).to(torch.uint16).pin_memory(),
+                   torch.arange(n, dtype=torch.int64).to(torch.uint32).pin_memory(),
+                   torch.randint(0, 2, (n,), generator=g).to(torch.uint8).pin_memory(),
+                   torch.tensor([0, n // 2, n], dtype=torch.int64), torch.rand(480, 640, 2, generator=g), (480, 640), 440)
+    frame = torch.rand(2, 3, 8, 8, generator=g).pin_memory()
+    batch = (ev, None, frame, (torch.arange(6).pin_memory(), "keep"))
+    pf = DevicePrefetcher(dev)
+    with pytest.raises(RuntimeError):
+        pf.take()
+    for _ in range(3):                                       # re-feeding recycles the buffers of the batch taken before
+        pf.feed(batch)
+        cur = pf.take()
+        assert isinstance(cur[0], RawEvents) and cur[1] is None and cur[3][1] == "keep"
+        assert cur[0].x.is_cuda and cur[2].is_cuda and cur[3][0].is_cuda and cur[0].sensor_hw == (480, 640) and cur[0].crop_h == 440
+        torch.cuda.synchronize()
+        for a, b in ((cur[0].x, ev.x), (cur[0].y, ev.y), (cur[0].t, ev.t), (cur[0].p, ev.p), (cur[0].frame_offsets, ev.frame_offsets),
+                     (cur[0].rectify_map, ev.rectify_map), (cur[2], frame), (cur[3][0], batch[3][0])):
+            assert np.array_equal(a.cpu().numpy(), b.numpy())
