@@ -12,6 +12,8 @@ python tools/bench_tc.py --teacher >> gpurun_out/${R}_tc_bench.jsonl 2>/dev/null
 python tools/bench_tc.py --config2 >> gpurun_out/${R}_tc_bench.jsonl 2>/dev/null
 python tools/bench_infonce.py > gpurun_out/${R}_infonce.jsonl 2>/dev/null
 python tools/bench_headconv.py >> gpurun_out/${R}_tc_bench.jsonl 2>/dev/null
+python tools/bench_conv_shapes.py > gpurun_out/${R}_conv_shapes.jsonl 2>/dev/null
+python tools/bench_wgrad.py > gpurun_out/${R}_wgrad.jsonl 2>/dev/null
 python tools/bench_configs.py --config1 --gpu > gpurun_out/${R}_configs.jsonl 2>/dev/null
 python tools/bench_configs.py --config4 >> gpurun_out/${R}_configs.jsonl 2>/dev/null
 python tools/bench_configs.py --config5 >> gpurun_out/${R}_configs.jsonl 2>/dev/null

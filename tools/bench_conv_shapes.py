@@ -17,6 +17,8 @@ shapes = [  # (Cin, Cout, H, W, k, stride, pad, dil)
     (1024, 256, 55, 80, 1, 1, 0, 1), (1024, 512, 55, 80, 1, 1, 0, 1), (512, 512, 55, 80, 3, 1, 4, 4), (512, 2048, 55, 80, 1, 1, 0, 1),
     (2048, 512, 55, 80, 1, 1, 0, 1),
 ]
+if os.environ.get("SHAPE"):                                   # e.g. SHAPE=11 : one shape only (for an ncu capture)
+    shapes = [shapes[int(os.environ["SHAPE"])]]
 dev = torch.device("cuda")
 for (ci, co, H, W, k, s, p, d) in shapes:
     x = torch.randn(B, ci, H, W, device=dev).contiguous(memory_format=torch.channels_last)
