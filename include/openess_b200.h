@@ -162,8 +162,10 @@ int oess_infonce(const float* k, const float* q, int64_t M, int D, float tempera
 
 /* Replaces utils/loss_functions.py:6-24 TaskLoss (= :96-135 DiceLoss + CrossEntropyLoss(ignore_index)).
  * logits [B, K, H, W] f32, target [B, H, W] int64.
- * partials: device float64 [2K+2] = {inter[K], denom[K], ce_sum, n_valid}; exposed so that ranks can
- * all-reduce them for exact global-batch semantics.
+ * partials: device float64 [2K+3] = {inter[K], denom[K], ce_sum, n_valid, n_bad}; exposed so that ranks can
+ * all-reduce them for exact global-batch semantics.  n_bad counts targets that are neither a class in
+ * [0, K) nor ignore_index (the reference raises on them in scatter_ / CrossEntropyLoss; the host checks the count).
+ * A class equal to ignore_index contributes no Dice term but the sum is still divided by K (:127, :135).
  *   oess_dice_ce_partials: one pass over logits -> partials (accumulates into zeroed partials)
  *   oess_dice_ce_finish  : partials -> losses[3] = {dice, ce, w_dice*dice + w_ce*ce} (device f32)
  *   oess_dice_ce_bwd     : d(w_dice*dice + w_ce*ce)/d logits * grad_scale[0] -> d_logits            */
@@ -171,6 +173,8 @@ int oess_dice_ce_partials(const float* logits, const int64_t* target, int B, int
                           int64_t ignore_index, double* partials, oess_stream_t stream);
 int oess_dice_ce_finish(const double* partials, int K, float w_dice, float w_ce, float* losses,
                         oess_stream_t stream);
+int oess_dice_ce_finish_ex(const double* partials, int K, int64_t ignore_index, float w_dice, float w_ce, float* losses,
+                           oess_stream_t stream);
 int oess_dice_ce_bwd(const float* logits, const int64_t* target, int B, int K, int H, int W,
                      int64_t ignore_index, const double* partials, float w_dice, float w_ce,
                      const float* grad_scale, float* d_logits, oess_stream_t stream);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "oess_infonce": [_vp, _vp, _i64, _int, _f32, _vp, _vp, _vp, _vp, _sz, _vp],
     "oess_dice_ce_partials": [_vp, _vp, _int, _int, _int, _int, _i64, _vp, _vp],
     "oess_dice_ce_finish": [_vp, _int, _f32, _f32, _vp, _vp],
+    "oess_dice_ce_finish_ex": [_vp, _int, _i64, _f32, _f32, _vp, _vp],
     "oess_dice_ce_bwd": [_vp, _vp, _int, _int, _int, _int, _i64, _vp, _f32, _f32, _vp, _vp, _vp],
     "oess_confusion": [_vp, _vp, _i64, _int, _i64, _vp, _vp, _vp],
     "oess_argmax_confusion": [_vp, _vp, _int, _int, _int, _int, _i64, _vp, _vp, _vp],

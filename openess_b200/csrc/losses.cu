@@ -93,7 +93,10 @@ k_dice_ce_partials(const float* __restrict__ logits, const int64_t* __restrict__
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int64_t tg = __ldcs(target + i);
         if (tg == ignore) continue;                           // mask = target != ignore_index (:115)
-        if (tg < 0 || tg >= K) { if (bad) *bad = 1; continue; }
+        if (tg < 0 || tg >= K) {                              // neither a class nor the ignore label: counted (the reference raises)
+            atomicAdd(&partials[2 * K + 2], 1.0);
+            continue;
+        }
         const int64_t b = i / HW, px = i - b * HW;
         const float* lp = logits + (b * K) * HW + px;
         float v[KMAX];
@@ -148,12 +151,14 @@ k_dice_ce_partials(const float* __restrict__ logits, const int64_t* __restrict__
     }
 }
 
-__global__ void k_dice_ce_finish(const double* __restrict__ partials, int K, float w_dice, float w_ce,
+__global__ void k_dice_ce_finish(const double* __restrict__ partials, int K, int64_t ignore, float w_dice, float w_ce,
                                  float* __restrict__ losses) {
     if (threadIdx.x || blockIdx.x) return;
     double dice = 0.0;
-    for (int c = 0; c < K; ++c)                              // BinaryDiceLoss, smooth = 1, p = 2 (:80-90)
+    for (int c = 0; c < K; ++c) {                            // BinaryDiceLoss, smooth = 1, p = 2 (:80-90)
+        if ((int64_t)c == ignore) continue;                  // `if i != self.ignore_index` (:127) -- still divided by K below
         dice += 1.0 - (2.0 * partials[c] + 1.0) / (partials[K + c] + 1.0);
+    }
     dice /= (double)K;                                       // total_loss / target.shape[1] (:135)
     const double ce = partials[2 * K] / partials[2 * K + 1]; // CrossEntropyLoss mean over valid (0/0 -> NaN)
     losses[0] = (float)dice;
@@ -172,8 +177,9 @@ k_dice_ce_bwd(const float* __restrict__ logits, const int64_t* __restrict__ targ
         const int c = threadIdx.x;
         if (c < K) {
             const double D1 = partials[K + c] + 1.0, N1 = 2.0 * partials[c] + 1.0;
-            s_a[c] = (float)(-2.0 / D1 / (double)K);
-            s_b[c] = (float)(2.0 * N1 / (D1 * D1) / (double)K);
+            const bool skip = (int64_t)c == ignore;          // the Dice term of class `ignore_index` is not part of the loss
+            s_a[c] = skip ? 0.f : (float)(-2.0 / D1 / (double)K);
+            s_b[c] = skip ? 0.f : (float)(2.0 * N1 / (D1 * D1) / (double)K);
         } else {
             s_a[c] = 0.f; s_b[c] = 0.f;
         }
@@ -401,7 +407,7 @@ OESS_API int oess_dice_ce_partials(const float* logits, const int64_t* target, i
     if (B <= 0 || K <= 0 || K > 64 || H <= 0 || W <= 0 || !logits || !target || !partials) return OESS_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t HW = (int64_t)H * W;
-    OESS_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (2 * K + 2), st));
+    OESS_CUDA(cudaMemsetAsync(partials, 0, sizeof(double) * (2 * K + 3), st));
     const unsigned g = loss_grid((int64_t)B * HW);
     OESS_KERNEL("k_dice_ce_partials", st, if (K <= 8) k_dice_ce_partials<8><<<g, 256, 0, st>>>(logits, target, B, K, HW, ignore_index, partials, nullptr);
     else if (K <= 16) k_dice_ce_partials<16><<<g, 256, 0, st>>>(logits, target, B, K, HW, ignore_index, partials, nullptr);
@@ -410,12 +416,17 @@ OESS_API int oess_dice_ce_partials(const float* logits, const int64_t* target, i
     return OESS_OK;
 }
 
-OESS_API int oess_dice_ce_finish(const double* partials, int K, float w_dice, float w_ce, float* losses,
-                                 oess_stream_t stream) {
+OESS_API int oess_dice_ce_finish_ex(const double* partials, int K, int64_t ignore_index, float w_dice, float w_ce,
+                                    float* losses, oess_stream_t stream) {
     if (!partials || !losses || K <= 0) return OESS_E_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    OESS_KERNEL("k_dice_ce_finish", st, k_dice_ce_finish<<<1, 32, 0, st>>>(partials, K, w_dice, w_ce, losses));
+    OESS_KERNEL("k_dice_ce_finish", st, k_dice_ce_finish<<<1, 32, 0, st>>>(partials, K, ignore_index, w_dice, w_ce, losses));
     return OESS_OK;
+}
+
+OESS_API int oess_dice_ce_finish(const double* partials, int K, float w_dice, float w_ce, float* losses,
+                                 oess_stream_t stream) {
+    return oess_dice_ce_finish_ex(partials, K, -(1ll << 62), w_dice, w_ce, losses, stream);
 }
 
 OESS_API int oess_dice_ce_bwd(const float* logits, const int64_t* target, int B, int K, int H, int W,

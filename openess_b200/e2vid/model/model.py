@@ -76,15 +76,32 @@ class ConvLayer(nn.Module):
             self._packed_bf16 = (key, _tc.conv2d_pack_bf16(w), None if b is None else b.detach().float().contiguous())
         return self._packed_bf16[1], self._packed_bf16[2]
 
+    def _fold_key(self):
+        bn, w = self.norm_layer, self.conv2d.weight
+        return (w.data_ptr(), w._version, w.device, bn.weight._version, bn.bias._version, bn.running_mean._version,
+                bn.running_var._version, bn.running_var.data_ptr())
+
     def fold_bn(self):
-        """Eval-mode BN folded into the conv: w' = w * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps)."""
+        """Eval-mode BN folded into the conv: w' = w * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps).
+        The fold is keyed on the versions / storage / device of its sources and redone lazily (`_refresh_fold`, called at the
+        top of forward), so a later `load_state_dict`, `.to(device)` or in-place parameter update cannot leave stale folded
+        weights behind."""
         if self.norm == 'BN' and not self.training:
             bn = self.norm_layer
             scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
             self._folded = ((self.conv2d.weight * scale[:, None, None, None]).detach(),
                             (bn.bias - bn.running_mean * scale).detach())
+            self._folded_key = self._fold_key()
+
+    def _refresh_fold(self):
+        if self._folded is not None and getattr(self, "_folded_key", None) != self._fold_key():
+            if self.training:
+                self._folded = None
+            else:
+                self.fold_bn()
 
     def forward(self, x):
+        self._refresh_fold()
         if self._tc_ok(x):
             wp, b = self._tc_weights()
             c = self.conv2d
@@ -182,6 +199,7 @@ class RecurrentConvLayer(nn.Module):
 
     def forward(self, x, prev_state):
         rb = self.recurrent_block
+        self.conv._refresh_fold()
         if (CONVLSTM_BF16 and USE_TENSOR_CORES and self.conv._tc_ok(x) and rb.hidden_size % 64 == 0
                 and rb.input_size == rb.hidden_size and tuple(rb.Gates.kernel_size) == (3, 3)):
             c = self.conv.conv2d                                # the conv output goes straight to bf16: ConvLSTM operand

@@ -110,12 +110,13 @@ def infonce(k, q, temperature):
 
 # ------------------------------------------------------------------------------------------ Dice + CE
 def dice_ce_partials(logits, target, ignore_index):
-    """One pass over the logits -> float64 [2K+2] = {inter[K], denom[K], ce_sum, n_valid} (all-reducible)."""
+    """One pass over the logits -> float64 [2K+3] = {inter[K], denom[K], ce_sum, n_valid, n_bad} (all-reducible); n_bad counts
+    targets that are neither a class nor `ignore_index`."""
     require_cuda(logits, target)
     logits = _f32c(logits)
     target = target.to(torch.int64).contiguous()
     B, K, H, W = logits.shape
-    partials = torch.empty(2 * K + 2, dtype=torch.float64, device=logits.device)
+    partials = torch.empty(2 * K + 3, dtype=torch.float64, device=logits.device)
     ig = -(1 << 62) if ignore_index is None else int(ignore_index)
     with torch.cuda.device(logits.device):
         check(lib().oess_dice_ce_partials(ptr(logits), ptr(target), B, K, H, W, ig, ptr(partials),
@@ -123,12 +124,45 @@ def dice_ce_partials(logits, target, ignore_index):
     return partials
 
 
-def dice_ce_finish(partials, K, w_dice, w_ce):
+def dice_ce_finish(partials, K, w_dice, w_ce, ignore_index=None):
     losses = torch.empty(3, dtype=torch.float32, device=partials.device)
+    ig = -(1 << 62) if ignore_index is None else int(ignore_index)
     with torch.cuda.device(partials.device):
-        check(lib().oess_dice_ce_finish(ptr(partials), K, float(w_dice), float(w_ce), ptr(losses),
-                                        stream_ptr(partials.device)), "oess_dice_ce_finish")
+        check(lib().oess_dice_ce_finish_ex(ptr(partials), K, ig, float(w_dice), float(w_ce), ptr(losses),
+                                           stream_ptr(partials.device)), "oess_dice_ce_finish_ex")
     return losses
+
+
+class _LabelCheck:
+    """Out-of-range labels (neither a class nor ignore_index) make the reference raise (scatter_ / CrossEntropyLoss).  The fused
+    kernel counts them; the count of call i is copied to pinned host memory without a synchronisation and inspected at call
+    i + 1 (or by `flush()`), so corrupt labels stop the run one step late instead of training silently."""
+
+    def __init__(self):
+        self._pending = None            # (pinned host tensor, event)
+
+    def submit(self, partials, K):
+        self.check(wait=False)
+        host = torch.empty(1, dtype=torch.float64).pin_memory()
+        host.copy_(partials[2 * K + 2:2 * K + 3], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(partials.device))
+        self._pending = (host, ev)
+
+    def check(self, wait=True):
+        if self._pending is None:
+            return
+        host, ev = self._pending
+        if not wait and not ev.query():
+            return                      # not there yet: looked at again on the next call
+        ev.synchronize()
+        self._pending = None
+        if float(host[0]) != 0.0:
+            raise ValueError(f"dice_ce: {int(host[0])} target value(s) outside [0, K) that are not ignore_index "
+                             "(utils/loss_functions.py:43-57 make_one_hot / CrossEntropyLoss raise on these)")
+
+
+label_check = _LabelCheck()
 
 
 class _DiceCE(torch.autograd.Function):
@@ -140,7 +174,8 @@ class _DiceCE(torch.autograd.Function):
         if reduce_partials is not None:          # exact global-batch semantics across ranks
             reduce_partials(partials)
         K = logits.shape[1]
-        losses = dice_ce_finish(partials, K, w_dice, w_ce)
+        losses = dice_ce_finish(partials, K, w_dice, w_ce, ignore_index)
+        label_check.submit(partials, K)
         ctx.save_for_backward(logits, target, partials)
         ctx.cfg = (ignore_index, w_dice, w_ce)
         # With all-reduced partial sums every rank differentiates the GLOBAL loss w.r.t. its LOCAL logits, so the true

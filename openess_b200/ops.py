@@ -310,6 +310,15 @@ def conv2d_tc(x, w_packed, bias, kernel_size, stride=1, padding=0, dilation=1, r
     return y
 
 
+def _bn_momentum(bn):
+    """exponential_average_factor of torch.nn.BatchNorm2d: `momentum`, or the cumulative moving average 1 / num_batches_tracked
+    (counted AFTER this batch) when momentum is None (torch/nn/modules/batchnorm.py)."""
+    if bn.momentum is not None:
+        return float(bn.momentum)
+    nbt = bn.num_batches_tracked
+    return 1.0 / (float(nbt) + 1.0) if nbt is not None else 0.0
+
+
 def batchnorm_nhwc_(x, bn, residual=None, relu=False):
     """In-place torch.nn.BatchNorm2d (module `bn`: batch statistics + running-stat update when bn.training, running
     statistics otherwise) on a channels-last [B, C, H, W] tensor, with optional residual add and ReLU fused."""
@@ -319,7 +328,7 @@ def batchnorm_nhwc_(x, bn, residual=None, relu=False):
         raise ValueError("batchnorm_nhwc_: x must be a float32 channels-last tensor")
     res = None if residual is None else residual.float().contiguous(memory_format=torch.channels_last)
     training = bn.training or bn.running_mean is None
-    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    mom = _bn_momentum(bn)
     nb = ctypes.c_size_t(0)
     check(lib().oess_bn_ws_bytes(C, ctypes.byref(nb)), "oess_bn_ws_bytes")
     track = training and bn.track_running_stats and bn.running_mean is not None
@@ -391,7 +400,7 @@ def conv_bn_train(x, w_packed, bias, kernel_size, stride, padding, dilation, bn,
     y = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=cl)
     res = None if residual is None else residual.float().contiguous(memory_format=cl)
     bc = None if bias is None else _f32c(bias)
-    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    mom = _bn_momentum(bn)
     track = bn.track_running_stats and bn.running_mean is not None
     nb = ctypes.c_size_t(0)
     check(lib().oess_bn_ws_bytes(Cout, ctypes.byref(nb)), "oess_bn_ws_bytes")
@@ -464,7 +473,7 @@ def conv_bn_train_bf16(x_bf, w_packed_bf, bias, kernel_size, stride, padding, di
     yb = torch.empty((B, Cout, Ho, Wo), dtype=torch.bfloat16, device=x_bf.device, memory_format=cl)
     res = None if residual is None else residual.float().contiguous(memory_format=cl)
     bc = None if bias is None else _f32c(bias)
-    mom = 0.1 if bn.momentum is None else float(bn.momentum)
+    mom = _bn_momentum(bn)
     track = bn.track_running_stats and bn.running_mean is not None
     nb = ctypes.c_size_t(0)
     check(lib().oess_bn_ws_bytes(Cout, ctypes.byref(nb)), "oess_bn_ws_bytes")
@@ -825,7 +834,7 @@ class _ConvBNAct(torch.autograd.Function):
         z = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device, memory_format=cl)
         y = torch.empty_like(z)
         res = None if residual is None else residual.float().contiguous(memory_format=cl)
-        mom = 0.1 if bn.momentum is None else float(bn.momentum)
+        mom = _bn_momentum(bn)
         track = bn.track_running_stats and bn.running_mean is not None
         nb = ctypes.c_size_t(0)
         check(lib().oess_bn_ws_bytes(Cout, ctypes.byref(nb)), "oess_bn_ws_bytes")

@@ -244,3 +244,72 @@ def test_task_loss_global_partials_gradient_scaling(dev, monkeypatch):
     # the data-parallel step AVERAGES gradients over ranks; the parameter gradient is linear in d(loss)/d(logits)
     got = torch.cat([l.grad for l in logits]) / world
     torch.testing.assert_close(got, full_logits.grad, rtol=2e-4, atol=1e-9)
+
+
+def _reference_task_loss(logits, target, ignore, K):
+    """utils/loss_functions.py:96-135 DiceLoss (class `ignore_index` skipped, sum / K) + CrossEntropyLoss(ignore_index), torch."""
+    import torch.nn.functional as F
+    mask = (target != ignore)
+    t = target.clone()
+    t[~mask] = 0
+    onehot = F.one_hot(t, K).permute(0, 3, 1, 2).double() * mask[:, None].double()
+    p = torch.softmax(logits.double(), 1) * mask[:, None].double()
+    total = 0.0
+    for c in range(K):
+        if c != ignore:
+            num = 2.0 * (p[:, c] * onehot[:, c]).sum() + 1.0
+            den = (p[:, c] ** 2 + onehot[:, c] ** 2).sum() + 1.0
+            total = total + (1.0 - num / den)
+    ce = F.cross_entropy(logits.double(), target, ignore_index=ignore)
+    return total / K + ce
+
+
+def test_dice_ce_ignore_index_inside_class_range(dev):
+    """with ignore_index in [0, K) the reference skips that CLASS's Dice term (still dividing by K) and ignores
+    those pixels; loss and gradient against a float64 torch statement of loss_functions.py:96-135."""
+    from openess_b200 import losses
+    g = torch.Generator().manual_seed(3)
+    B, K, H, W, ig = 2, 7, 19, 23, 2
+    logits = (torch.randn(B, K, H, W, generator=g) * 2).to(dev).requires_grad_(True)
+    target = torch.randint(0, K, (B, H, W), generator=g).to(dev)
+    loss = losses.dice_ce(logits, target, ig)
+    ref_in = logits.detach().clone().requires_grad_(True)
+    ref = _reference_task_loss(ref_in, target, ig, K)
+    assert float(loss) == pytest.approx(float(ref), rel=2e-5)
+    loss.backward()
+    ref.backward()
+    np.testing.assert_allclose(logits.grad.cpu().numpy(), ref_in.grad.cpu().numpy(), rtol=3e-4, atol=2e-8)
+    losses.label_check.check()
+
+
+def test_dice_ce_out_of_range_labels_are_reported(dev):
+    """a target that is neither a class nor ignore_index makes the reference raise; the fused kernel counts it and the
+    host raises at the next call (or on `label_check.check()`), without a synchronisation in the step itself."""
+    from openess_b200 import losses
+    g = torch.Generator().manual_seed(4)
+    logits = torch.randn(1, 5, 8, 8, generator=g).to(dev)
+    target = torch.randint(0, 5, (1, 8, 8), generator=g).to(dev)
+    losses.label_check.check()
+    losses.dice_ce(logits, target, 255)
+    losses.label_check.check()                               # clean labels: nothing raised
+    target[0, 3, 3] = 77
+    losses.dice_ce(logits, target, 255)
+    with pytest.raises(ValueError, match="outside"):
+        losses.label_check.check()
+    losses.label_check.check()                               # reported once
+
+
+def test_batchnorm_momentum_none_is_cumulative_average(dev):
+    """torch.nn.BatchNorm2d(momentum=None) uses the cumulative moving average 1 / num_batches_tracked."""
+    from openess_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    bn = torch.nn.BatchNorm2d(16, momentum=None).to(dev).train()
+    ref = torch.nn.BatchNorm2d(16, momentum=None).to(dev).train()
+    for i in range(3):
+        x = (torch.randn(2, 16, 9, 11, generator=g) * (i + 1) + i).to(dev).contiguous(memory_format=torch.channels_last)
+        want = ref(x)
+        got = ops.batchnorm_nhwc_(x.clone(memory_format=torch.channels_last), bn)
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(bn.running_mean, ref.running_mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(bn.running_var, ref.running_var, rtol=1e-4, atol=1e-6)
+    assert int(bn.num_batches_tracked) == 3

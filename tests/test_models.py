@@ -282,3 +282,22 @@ def test_post_processor_matches_reference_golden():
     post = PostProcessor(dev, opts)                      # running median of the clipped per-image bounds over three images
     for i in range(3):
         check(post.process(torch.from_numpy(z[f"img{i}"])), z[f"post_hdr_img{i}"])
+
+
+@pytest.mark.gpu
+def test_conv_layer_bn_fold_follows_later_weight_loads():
+    """`ConvLayer.fold_bn()` before `load_state_dict` / `.to(device)` must not leave stale folded weights: the fold is
+    keyed on its sources and redone lazily."""
+    from openess_b200.e2vid.model import model as mm
+    g = torch.Generator().manual_seed(2)
+    layer = mm.ConvLayer(32, 64, 5, stride=2, padding=2, norm='BN').eval()
+    layer.fold_bn()                                          # folded on the CPU, with the initial weights
+    sd = {k: torch.randn(v.shape, generator=g) * 0.1 if v.dtype.is_floating_point else v for k, v in layer.state_dict().items()}
+    sd["norm_layer.running_var"] = sd["norm_layer.running_var"].abs() + 0.5
+    layer.load_state_dict(sd)
+    layer = layer.cuda()
+    x = torch.randn(2, 32, 24, 40, generator=g).cuda()
+    with torch.no_grad():
+        got = layer(x)
+        ref = torch.relu(layer.norm_layer(layer.conv2d(x)))
+    assert float((got - ref).abs().max()) < 2e-2 * float(ref.abs().max())
