@@ -140,10 +140,16 @@ class _LabelCheck:
 
     def __init__(self):
         self._pending = None            # (pinned host tensor, event)
+        self._bufs, self._turn = None, 0
 
     def submit(self, partials, K):
         self.check(wait=False)
-        host = torch.empty(1, dtype=torch.float64).pin_memory()
+        if self._bufs is None:          # two pinned doubles, reused in turn (no cudaHostAlloc per step)
+            self._bufs = [torch.empty(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+        if self._pending is not None:   # the previous count has not arrived yet: wait for it rather than overwrite its buffer
+            self.check(wait=True)
+        host = self._bufs[self._turn]
+        self._turn ^= 1
         host.copy_(partials[2 * K + 2:2 * K + 3], non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(partials.device))
