@@ -372,9 +372,10 @@ k_convlstm_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 constexpr int kP2Stages = 6;
 constexpr int kP2BBytes = kCBBytes / 2;
 constexpr int kP2Smem = 1024 + kP2Stages * (kCABytes + kP2BBytes) + 256;
+constexpr int kP2Threads = 64 + 16 * 32;     // TMA warp, MMA warp, SIXTEEN epilogue warps (two per TMEM lane quarter and accumulator)
 
 template <bool BF16>
-__global__ void __launch_bounds__(kPCThreads, 1)
+__global__ void __launch_bounds__(kP2Threads, 1)
 k_convlstm_tc_p2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
                  const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias, const float* __restrict__ c_prev,
                  float* __restrict__ h_out, __nv_bfloat16* __restrict__ h_bf, float* __restrict__ c_out, int H, int W, int C,
@@ -406,7 +407,7 @@ k_convlstm_tc_p2(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);                   // the leader's multicast commit
-            mbar_init(&acc_empty[b], 8);                  // four epilogue warps of each CTA (used in the leader only)
+            mbar_init(&acc_empty[b], 16);                 // eight epilogue warps per accumulator in each CTA (used in the leader only)
         }
         mbar_fence_init();
     }
@@ -472,9 +473,13 @@ k_convlstm_tc_p2(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                 __syncwarp();
             }
         }
-    } else {                                              // ===== epilogue: group g = warps 2 + 4 g .. 5 + 4 g (both CTAs) =====
-        const int q = warp & 3;
-        const uint32_t g = (uint32_t)(warp - 2) >> 2;
+    } else {                                              // ===== epilogue: 16 warps (both CTAs) =====
+        // warp e = warp - 2: TMEM lane quarter q = warp & 3, channel half hs = (e >> 2) & 1 (hidden channels 32 hs .. 32 hs + 31 of the
+        // chunk), accumulator g = e >> 3.  Four epilogue warps per SM sub-partition instead of two: at the C = 64 level the MMA
+        // warp still waited 36 % of its time for a drained accumulator (profiles/r02_convlstm2sm_full.md).
+        const int e = warp - 2;
+        const int q = warp & 3, hs = (e >> 2) & 1;       // a warp may only touch the TMEM lanes of quarter warp % 4
+        const uint32_t g = (uint32_t)e >> 3;
         uint32_t lt = 0;
         for (int tile = tile0; tile < tiles; tile += tstep, ++lt) {
             if ((lt & 1) != g) continue;
@@ -485,34 +490,34 @@ k_convlstm_tc_p2(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const int r = q * 32 + lane;
             const int y = th * kTH + r / kTW, x = tw * kTW + r % kTW;
             const bool valid = y < H && x < W;
-            const int64_t pix = (((int64_t)b * H + y) * W + x) * C + nchunk * 64;
-            const float* bn = bias + nchunk * kCN;
+            const int64_t pix = (((int64_t)b * H + y) * W + x) * C + nchunk * 64 + hs * 32;
+            const float* bn = bias + nchunk * kCN + hs * 32;
             mbar_wait(&acc_full[g], (lt >> 1) & 1);
             tc_fence_after();
-            const uint32_t trow = tmem_acc + g * kCN + ((uint32_t)(q * 32) << 16);
+            const uint32_t trow = tmem_acc + g * kCN + ((uint32_t)(q * 32) << 16) + (uint32_t)(hs * 32);
 #pragma unroll 1
-            for (int sub = 0; sub < 4; ++sub) {
-                float gi[16], gf[16], go[16], gg[16];
-                tmem_ld16_nowait(trow + 0 * 64 + sub * 16, gi);
-                tmem_ld16_nowait(trow + 1 * 64 + sub * 16, gf);
-                tmem_ld16_nowait(trow + 2 * 64 + sub * 16, go);
-                tmem_ld16_nowait(trow + 3 * 64 + sub * 16, gg);
+            for (int sub = 0; sub < 4; ++sub) {           // 8 hidden channels at a time
+                float gi[8], gf[8], go[8], gg[8];
+                tmem_ld8_nowait(trow + 0 * 64 + sub * 8, gi);     // submodules.py:203 chunk order: in, remember, out, cell
+                tmem_ld8_nowait(trow + 1 * 64 + sub * 8, gf);
+                tmem_ld8_nowait(trow + 2 * 64 + sub * 8, go);
+                tmem_ld8_nowait(trow + 3 * 64 + sub * 8, gg);
                 tmem_ld_wait();
-                if (sub == 3) {                           // accumulator fully read: tell the LEADER's MMA warp
+                if (sub == 3) {                           // this warp's part of the accumulator is read: tell the LEADER's MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(&acc_empty[g], 0);
                 }
                 if (valid) {
-                    const int64_t e = pix + sub * 16;
+                    const int64_t e0 = pix + sub * 8;
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
+                    for (int j = 0; j < 8; j += 4) {
                         float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (c_prev) pc = *reinterpret_cast<const float4*>(c_prev + e + j);
-                        const float4 bi = __ldg(reinterpret_cast<const float4*>(bn + 0 * 64 + sub * 16 + j));
-                        const float4 bf = __ldg(reinterpret_cast<const float4*>(bn + 1 * 64 + sub * 16 + j));
-                        const float4 bo = __ldg(reinterpret_cast<const float4*>(bn + 2 * 64 + sub * 16 + j));
-                        const float4 bg = __ldg(reinterpret_cast<const float4*>(bn + 3 * 64 + sub * 16 + j));
+                        if (c_prev) pc = *reinterpret_cast<const float4*>(c_prev + e0 + j);
+                        const float4 bi = __ldg(reinterpret_cast<const float4*>(bn + 0 * 64 + sub * 8 + j));
+                        const float4 bf = __ldg(reinterpret_cast<const float4*>(bn + 1 * 64 + sub * 8 + j));
+                        const float4 bo = __ldg(reinterpret_cast<const float4*>(bn + 2 * 64 + sub * 8 + j));
+                        const float4 bg = __ldg(reinterpret_cast<const float4*>(bn + 3 * 64 + sub * 8 + j));
                         float4 c, h;
                         c.x = act_sigm<BF16>(gf[j] + bf.x) * pc.x + act_sigm<BF16>(gi[j] + bi.x) * act_tanh<BF16>(gg[j] + bg.x);
                         c.y = act_sigm<BF16>(gf[j + 1] + bf.y) * pc.y + act_sigm<BF16>(gi[j + 1] + bi.y) * act_tanh<BF16>(gg[j + 1] + bg.y);
@@ -522,14 +527,14 @@ k_convlstm_tc_p2(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                         h.y = act_sigm<BF16>(go[j + 1] + bo.y) * act_tanh<BF16>(c.y);
                         h.z = act_sigm<BF16>(go[j + 2] + bo.z) * act_tanh<BF16>(c.z);
                         h.w = act_sigm<BF16>(go[j + 3] + bo.w) * act_tanh<BF16>(c.w);
-                        *reinterpret_cast<float4*>(c_out + e + j) = c;
-                        if (h_out) *reinterpret_cast<float4*>(h_out + e + j) = h;
+                        *reinterpret_cast<float4*>(c_out + e0 + j) = c;
+                        if (h_out) *reinterpret_cast<float4*>(h_out + e0 + j) = h;
                         if (BF16) {
                             __nv_bfloat162 lo = __floats2bfloat162_rn(h.x, h.y), hi = __floats2bfloat162_rn(h.z, h.w);
                             uint2 pk;
                             pk.x = *reinterpret_cast<uint32_t*>(&lo);
                             pk.y = *reinterpret_cast<uint32_t*>(&hi);
-                            *reinterpret_cast<uint2*>(h_bf + e + j) = pk;
+                            *reinterpret_cast<uint2*>(h_bf + e0 + j) = pk;
                         }
                     }
                 }
@@ -593,7 +598,7 @@ static int convlstm_impl(const void* x, const void* h_prev, const float* c_prev,
         if (mc) grid = (unsigned)(2 * (tiles < kNumSMs / 2 ? tiles : kNumSMs / 2));      // whole clusters
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(tc::kPCThreads);
+        cfg.blockDim = dim3(sm2 ? tc::kP2Threads : tc::kPCThreads);
         cfg.dynamicSmemBytes = smem_bytes;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
