@@ -76,29 +76,37 @@ class ConvLayer(nn.Module):
             self._packed_bf16 = (key, _tc.conv2d_pack_bf16(w), None if b is None else b.detach().float().contiguous())
         return self._packed_bf16[1], self._packed_bf16[2]
 
-    def _fold_key(self):
-        bn, w = self.norm_layer, self.conv2d.weight
-        return (w.data_ptr(), w._version, w.device, bn.weight._version, bn.bias._version, bn.running_mean._version,
-                bn.running_var._version, bn.running_var.data_ptr())
-
     def fold_bn(self):
         """Eval-mode BN folded into the conv: w' = w * g / sqrt(var + eps), b' = beta - mean * g / sqrt(var + eps).
-        The fold is keyed on the versions / storage / device of its sources and redone lazily (`_refresh_fold`, called at the
-        top of forward), so a later `load_state_dict`, `.to(device)` or in-place parameter update cannot leave stale folded
-        weights behind."""
+        A later `load_state_dict`, `.to(device)` / `.cuda()` / `.float()` or `train()` marks the fold stale (`_apply`,
+        `_load_from_state_dict`, `train` below) and it is redone lazily at the next forward, so the order of fold / load / move does
+        not matter; no per-forward key comparison: the E2VID step is launch-bound on the host side."""
         if self.norm == 'BN' and not self.training:
             bn = self.norm_layer
             scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
             self._folded = ((self.conv2d.weight * scale[:, None, None, None]).detach(),
                             (bn.bias - bn.running_mean * scale).detach())
-            self._folded_key = self._fold_key()
+            self._fold_stale = False
 
     def _refresh_fold(self):
-        if self._folded is not None and getattr(self, "_folded_key", None) != self._fold_key():
+        if self._folded is not None and getattr(self, "_fold_stale", False):
             if self.training:
                 self._folded = None
             else:
                 self.fold_bn()
+
+    def _apply(self, fn, *args, **kwargs):
+        self._fold_stale = True
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._fold_stale = True
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def train(self, mode=True):
+        if mode != self.training:
+            self._fold_stale = True
+        return super().train(mode)
 
     def forward(self, x):
         self._refresh_fold()

@@ -158,8 +158,9 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
             ms = float(tt)
         return ms, last
 
-    for _ in range(max(warmup, 2)):                        # step 1 learns the gradient set, step 2 builds the overlap hooks
+    for _ in range(max(warmup, 3)):                        # step 1 learns the gradient set, step 2 builds the overlap hooks, step 3 captures the encoder graph
         one()
+    graphed = bool(step._graph_loop is not None and step._graph_loop.graph is not None)
     n0 = _lib.launch_count()
     ms, loss = timed(one, steps)
     launches = (_lib.launch_count() - n0) / steps
@@ -183,11 +184,16 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
     if e2vid_model.CONVLSTM_BF16 or im.TEACHER_BF16:
         saved = (e2vid_model.CONVLSTM_BF16, im.TEACHER_BF16)
         e2vid_model.CONVLSTM_BF16, im.TEACHER_BF16 = False, False
+        if step._graph_loop is not None:
+            step._graph_loop.reset()                       # the captured encoder loop holds the bf16 kernels
         try:
-            one()
+            for _ in range(3):                             # two eager calls + the capture
+                one()
             ms_tf32, _ = timed(one, steps)
         finally:
             e2vid_model.CONVLSTM_BF16, im.TEACHER_BF16 = saved
+            if step._graph_loop is not None:
+                step._graph_loop.reset()
 
     base = None
     if baseline_steps > 0:
@@ -203,7 +209,8 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
            "samples_per_s": world * B / ms * 1e3, "event_frames_per_s": world * B * NF / ms * 1e3, "loss": loss,
            "operand_dtypes": dtypes, "ms_per_step_tf32_operands": ms_tf32,
            "own_kernel_launches_per_step": launches, "peak_mem_gb": peak_gb, "h2d_bytes_per_step": h2d,
-           "h2d_prefetch_on_side_stream": prefetch, "d2h_bytes_per_step": 4,
+           "h2d_prefetch_on_side_stream": prefetch,
+           "encoder_loop_cuda_graph": graphed, "d2h_bytes_per_step": 4,
            "allreduce": {"backend": "nccl" if world > 1 else None, "bytes_per_step": ar_bytes, "calls_per_step": ar_calls,
                          "ms_alone": ar_ms, "overlapped_with_backward": world > 1}}
     if base is not None:

@@ -17,6 +17,7 @@ What changes on the B200:
     of the two trainable modules over NCCL in buckets that are all-reduced WHILE backward is still running (the
     reference is single-GPU, README.md:303).
 """
+import os
 from collections import namedtuple
 
 import torch
@@ -31,7 +32,7 @@ from ..losses import superpixel_pool
 RawEvents = namedtuple("RawEvents", "x y t p frame_offsets rectify_map sensor_hw crop_h flip", defaults=(None,))
 
 
-def assemble_event_tensor(ev, device, nr_events_data=20, C=5):
+def assemble_event_tensor(ev, device, nr_events_data=20, C=5, out=None):
     """batch[0] of a trainer step -> dense [B, nr_events_data * C, crop_h, W] on `device`: a `RawEvents` slab is rectified,
     time-normalised and voxelised there in one batched call (F = B * nr_events_data frames; sequence_ov.py:282-307); the
     reference's dense tensor is just moved."""
@@ -40,9 +41,11 @@ def assemble_event_tensor(ev, device, nr_events_data=20, C=5):
     Hs, Ws = ev.sensor_hw
     x, y, t, p = (a.to(device, non_blocking=True) for a in (ev.x, ev.y, ev.t, ev.p))
     fo = ev.frame_offsets.to(device, non_blocking=True)
-    grids = _voxel.dsec_events_to_voxel_grid(x, y, t, p, ev.rectify_map.to(device), C, frame_offsets=fo,
-                                             mode="ordered")                        # [F, C, Hs, Ws]
     F = fo.numel() - 1
+    if out is not None and (tuple(out.shape) != (F, C, Hs, Ws) or out.device != x.device):
+        out = None                                             # `out`: a persistent [F, C, Hs, Ws] buffer (stable address for a CUDA graph)
+    grids = _voxel.dsec_events_to_voxel_grid(x, y, t, p, ev.rectify_map.to(device), C, frame_offsets=fo,
+                                             mode="ordered", out=out)               # [F, C, Hs, Ws]
     B = F // nr_events_data
     dense = grids.view(B, nr_events_data * C, Hs, Ws)
     if ev.flip is not None:                                    # sequence_ov.py:387-389 torch.flip(event_tensor, [2]) per sample
@@ -77,10 +80,25 @@ class OpenESSPretrainStep:
                                     "optimizer_frame": torch.optim.AdamW(params_frame, lr=lr_frame, fused=fused)}
         self._trainable = params_voxel + params_frame
         self._reducer = _parallel.GradientReducer(self._trainable) if data_parallel else None
+        # the frozen recurrent encoder loop as one CUDA graph (OESS_E2VID_GRAPH=0: eager); only when the encoder is frozen
+        self._grids = None
+        self._graph_loop = None
+        e2vid = reconstructor.model
+        frozen = not any(p.requires_grad for p in e2vid.parameters())
+        if os.environ.get("OESS_E2VID_GRAPH", "1") != "0" and self.device.type == "cuda" and frozen:
+            from .graphs import GraphedEncoderLoop
+            self._graph_loop = GraphedEncoderLoop(reconstructor, nr_events_data_b, input_channels_b)
 
     # ---- sample assembly on the device (replaces Sequence.__getitem__'s voxel branch, sequence_ov.py:282-307) ----
     def event_tensor(self, ev):
-        return assemble_event_tensor(ev, self.device, self.nr_events_data_b, self.input_channels_b)
+        if not (getattr(self, "_graph_loop", None) is not None and isinstance(ev, RawEvents)):
+            return assemble_event_tensor(ev, self.device, self.nr_events_data_b, self.input_channels_b)
+        # CUDA-graph mode: the voxeliser writes into a persistent buffer, so the captured encoder loop reads a stable address
+        F = ev.frame_offsets.numel() - 1
+        shape = (F, self.input_channels_b) + tuple(ev.sensor_hw)
+        if self._grids is None or tuple(self._grids.shape) != shape:
+            self._grids = torch.empty(shape, dtype=torch.float32, device=self.device)
+        return assemble_event_tensor(ev, self.device, self.nr_events_data_b, self.input_channels_b, out=self._grids)
 
     # ---- pretrain_trainer.py:550-562 ----
     def trainTaskStepPretrain(self, content_features, pl, superpixels, losses):
@@ -108,10 +126,13 @@ class OpenESSPretrainStep:
         model_frame = self.models_dict["model_frame"]
         fused_q = self.if_spatial_contrastive and frame.is_cuda and hasattr(model_frame, "forward_pooled")
         feat_frame = None if fused_q else model_frame(frame)                                 # :434
-        self.reconstructor.last_states_for_each_channel = {"grayscale": None}
         C = self.input_channels_b
-        for i in range(self.nr_events_data_b):
-            _, _, latent_real = self.reconstructor.update_reconstruction(event[:, i * C:(i + 1) * C])
+        if getattr(self, "_graph_loop", None) is not None and event.is_cuda:
+            latent_real = self._graph_loop(event)              # the frozen 20-step encoder loop as one CUDA graph (training/graphs.py)
+        else:
+            self.reconstructor.last_states_for_each_channel = {"grayscale": None}
+            for i in range(self.nr_events_data_b):
+                _, _, latent_real = self.reconstructor.update_reconstruction(event[:, i * C:(i + 1) * C])
         loss_dense, pred, k = self.trainTaskStepPretrain(latent_real, pl, superpixels, losses)
         if self.if_spatial_contrastive:
             M = k.shape[0]

@@ -285,3 +285,32 @@ def test_device_prefetcher_moves_nested_batches_on_a_side_stream():
         for a, b in ((cur[0].x, ev.x), (cur[0].y, ev.y), (cur[0].t, ev.t), (cur[0].p, ev.p), (cur[0].frame_offsets, ev.frame_offsets),
                      (cur[0].rectify_map, ev.rectify_map), (cur[2], frame), (cur[3][0], batch[3][0])):
             assert np.array_equal(a.cpu().numpy(), b.numpy())
+
+
+@pytest.mark.gpu
+def test_encoder_loop_cuda_graph_equals_eager():
+    """training/graphs.py: the frozen recurrent encoder loop captured as one CUDA graph (third call on) gives the same latents as
+    the eager loop, for changing inputs in the persistent event buffer, and is re-captured after reset()."""
+    from openess_b200.e2vid.image_reconstructor import ImageReconstructor
+    from openess_b200.training.graphs import GraphedEncoderLoop
+    dev = torch.device("cuda:0")
+    e2vid, _, _, opts, _ = _models(dev)
+    Bn, H, W, steps, C = 2, 32, 48, 3, 5
+    rec = ImageReconstructor(e2vid, H, W, C, dev, opts)
+    loop = GraphedEncoderLoop(rec, steps, C)
+    ref = GraphedEncoderLoop(ImageReconstructor(e2vid, H, W, C, dev, opts), steps, C)
+    ref.disabled = True                                      # always eager
+    g = torch.Generator().manual_seed(21)
+    buf = torch.empty(Bn, C * steps, H, W, device=dev)       # persistent input buffer (what the voxeliser writes into)
+    for it in range(8):
+        ev = torch.randn(Bn, C * steps, H, W, generator=g)
+        ev[torch.rand(ev.shape, generator=g) < 0.6] = 0
+        buf.copy_(ev.to(dev))
+        got = loop(buf)
+        want = ref(buf.clone())
+        assert (loop.graph is not None) == (it in (2, 3, 6, 7))      # two eager calls, capture on the third; again after reset()
+        for k in want:
+            assert torch.equal(got[k], want[k]), (it, k)
+        if it == 3:
+            loop.reset()
+            assert loop.graph is None
