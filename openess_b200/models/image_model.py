@@ -32,6 +32,7 @@ USE_TENSOR_CORES = os.environ.get("OESS_TEACHER_TC", "1") != "0"
 # (B = 8: 24.8 -> 21.0 ms; the 1 x 1 convs are bound by their fp32 output + BatchNorm passes, not by the MMA rate) for 6x the
 # feature error of TF32 on the seeded network of tests/test_teacher.py (52 convs, each re-normalised by batch statistics).
 TEACHER_BF16 = os.environ.get("OESS_TEACHER_DTYPE", "tf32") == "bf16"
+TEACHER_GRAPH = os.environ.get("OESS_TEACHER_GRAPH", "1") != "0"
 
 
 class ResNetEncoder(ResNet):
@@ -44,6 +45,8 @@ class ResNetEncoder(ResNet):
         self._cache = _tcr.PackedConvCache()
 
     def load_state_dict(self, state_dict, **kwargs):
+        if "_graph_call" in self.__dict__:
+            self.__dict__["_graph_call"].reset()
         state_dict.pop("fc.bias", None)
         state_dict.pop("fc.weight", None)
         return super().load_state_dict(state_dict, **kwargs)
@@ -58,10 +61,33 @@ class ResNetEncoder(ResNet):
     def forward_tc(self, x):
         return _tcr.resnet_stages(self._cache, self, x, bf16=TEACHER_BF16)
 
+    def _graphed(self):
+        """The frozen tensor-core forward (53 conv + BatchNorm blocks = ~210 launches issued from Python, ~11 ms of host time at
+        any batch size) as a CUDA graph (training/graphs.py GraphedCall; OESS_TEACHER_GRAPH=0: eager).  Dropped whenever the
+        module's mode, dtype switch, device or parameters change."""
+        g = self.__dict__.get("_graph_call")
+        if g is None:
+            from ..training.graphs import GraphedCall
+
+            def run(x):
+                with torch.no_grad():
+                    return self.forward_tc(x)
+            g = GraphedCall(run, state=lambda: (self.training, TEACHER_BF16, self.conv1.weight._version,
+                                                 self.layer4[-1].conv3.weight._version))
+            self.__dict__["_graph_call"] = g
+        return g
+
+    def _apply(self, fn, *args, **kwargs):
+        if "_graph_call" in self.__dict__:
+            self.__dict__["_graph_call"].reset()
+        return super()._apply(fn, *args, **kwargs)
+
     def forward(self, x):
         tc_ok = (USE_TENSOR_CORES and x.is_cuda and not x.requires_grad and x.dtype == torch.float32
                  and _tcr.frozen(self))
         if tc_ok:
+            if TEACHER_GRAPH:
+                return self._graphed()(x)
             with torch.no_grad():
                 return self.forward_tc(x)
         return self.forward_torch(x)

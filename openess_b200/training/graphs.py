@@ -52,3 +52,49 @@ class GraphedEncoderLoop:
             self.disabled, self.graph, self.out = True, None, None
             torch.cuda.synchronize(event.device)
             return self._loop(event)
+
+
+class GraphedCall:
+    """`fn(x)` (a frozen, no-grad, static-shape CUDA computation returning a tensor) as a CUDA graph: two eager calls, capture on
+    the third, then `static_in.copy_(x)` + replay.  `state()` (optional) returns anything whose change must drop the graph (module
+    mode flags, parameter versions); `reset()` drops it explicitly."""
+
+    def __init__(self, fn, state=None, eager_calls=2):
+        self.fn, self.state, self.eager_calls = fn, state, int(eager_calls)
+        self.disabled = False
+        self.reset()
+
+    def reset(self):
+        self.graph, self.out, self.key, self.calls, self.static_in = None, None, None, 0, None
+
+    def __call__(self, x):
+        if self.disabled or not x.is_cuda or torch.cuda.is_current_stream_capturing():
+            return self.fn(x)
+        key = (tuple(x.shape), x.dtype, x.device, x.is_contiguous(memory_format=torch.channels_last),
+               self.state() if self.state is not None else None)
+        if self.graph is not None and key == self.key:
+            self.static_in.copy_(x)
+            self.graph.replay()
+            return self.out
+        if key != self.key:
+            self.reset()
+            self.key = key
+        self.calls += 1
+        if self.calls <= self.eager_calls:
+            return self.fn(x)
+        try:
+            torch.cuda.synchronize(x.device)
+            self.static_in = x.clone()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.fn(self.static_in)
+            self.graph, self.out = g, out
+            g.replay()
+            return out
+        except Exception as exc:
+            import warnings
+            warnings.warn(f"GraphedCall: CUDA-graph capture failed ({exc}); running eagerly")
+            self.disabled = True
+            self.reset()
+            torch.cuda.synchronize(x.device)
+            return self.fn(x)

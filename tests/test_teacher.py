@@ -160,3 +160,33 @@ def test_upnorm_pool_fused_vs_torch_formulation(B, h, w, S):
     (qr * wgt.double()).sum().backward()
     torch.testing.assert_close(q.double(), qr, atol=2e-5, rtol=2e-5)
     torch.testing.assert_close(d.grad.double(), dd.grad, atol=2e-4 * float(dd.grad.abs().max()), rtol=1e-3)
+
+
+@pytest.mark.gpu
+def test_teacher_encoder_cuda_graph_equals_eager(monkeypatch):
+    """The frozen tensor-core encoder forward as a CUDA graph (third call on): same features as the eager path for changing inputs,
+    running statistics advance alike, and the graph is dropped when the weights are reloaded."""
+    from openess_b200.models import image_model as im
+    z, m = _build()
+    m = m.cuda()
+    _, ref = _build()
+    ref = ref.cuda()
+    g = torch.Generator().manual_seed(9)
+    for it in range(5):
+        x = torch.rand(1, 3, 64, 96, generator=g).cuda()
+        monkeypatch.setattr(im, "TEACHER_GRAPH", True)
+        got = m.encoder(x).clone()
+        monkeypatch.setattr(im, "TEACHER_GRAPH", False)
+        want = ref.encoder(x)
+        assert torch.equal(got, want), it
+        assert (m.encoder._graphed().graph is not None) == (it >= 2)
+    torch.testing.assert_close(m.encoder.layer4[2].bn3.running_mean, ref.encoder.layer4[2].bn3.running_mean)
+    assert int(m.encoder.bn1.num_batches_tracked) == int(ref.encoder.bn1.num_batches_tracked) == 5
+    m.load_state_dict({k: v.cuda() for k, v in seeded_state_dict(m, int(z["seed"]) + 1).items()}, strict=True)
+    monkeypatch.setattr(im, "TEACHER_GRAPH", True)
+    x = torch.rand(1, 3, 64, 96, generator=g).cuda()
+    y1 = m.encoder(x).clone()
+    assert m.encoder._graphed().graph is None                # new weights: eager again until re-captured
+    monkeypatch.setattr(im, "TEACHER_GRAPH", False)
+    ref.load_state_dict({k: v.cuda() for k, v in seeded_state_dict(ref, int(z["seed"]) + 1).items()}, strict=True)
+    assert torch.equal(y1, ref.encoder(x))

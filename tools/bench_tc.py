@@ -119,7 +119,7 @@ def teacher():
             for use_tc in (True, False):
                 im.USE_TENSOR_CORES = use_tc
                 with torch.no_grad():
-                    res[use_tc] = timeit(lambda: m.encoder(x), iters=5, warm=2)
+                    res[use_tc] = timeit(lambda: m.encoder(x), iters=8, warm=4)   # warm >= 3: the third call captures the CUDA graph
             im.USE_TENSOR_CORES = True
             fl = 845.1e9 * B
             print(json.dumps({"op": "teacher_r50_dilated_encoder_fwd", "B": B, "bn": mode, "ms_tensor_core_path": res[True],
