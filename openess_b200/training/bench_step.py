@@ -158,8 +158,12 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
             ms = float(tt)
         return ms, last
 
-    for _ in range(max(warmup, 3)):                        # step 1 learns the gradient set, step 2 builds the overlap hooks, step 3 captures the encoder graph
+    launches_eager = None
+    for w_ in range(max(warmup, 3)):                       # step 1 learns the gradient set, step 2 builds the overlap hooks, step 3 captures the encoder graph
+        n_before = _lib.launch_count()
         one()
+        if w_ == 1:
+            launches_eager = _lib.launch_count() - n_before    # every kernel of the step launched eagerly (before any graph exists)
     graphed = bool(step._graph_loop is not None and step._graph_loop.graph is not None)
     n0 = _lib.launch_count()
     ms, loss = timed(one, steps)
@@ -208,7 +212,8 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
            "batch_per_gpu": B, "events_per_frame": events, "steps": steps, "ms_per_step": ms,
            "samples_per_s": world * B / ms * 1e3, "event_frames_per_s": world * B * NF / ms * 1e3, "loss": loss,
            "operand_dtypes": dtypes, "ms_per_step_tf32_operands": ms_tf32,
-           "own_kernel_launches_per_step": launches, "peak_mem_gb": peak_gb, "h2d_bytes_per_step": h2d,
+           "own_kernel_launches_per_step": launches_eager if launches_eager is not None else launches,
+           "own_kernel_launches_per_step_outside_cuda_graphs": launches, "peak_mem_gb": peak_gb, "h2d_bytes_per_step": h2d,
            "h2d_prefetch_on_side_stream": prefetch,
            "encoder_loop_cuda_graph": graphed, "d2h_bytes_per_step": 4,
            "allreduce": {"backend": "nccl" if world > 1 else None, "bytes_per_step": ar_bytes, "calls_per_step": ar_calls,
