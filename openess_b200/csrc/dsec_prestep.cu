@@ -19,8 +19,23 @@ k_dsec_rectify_tnorm(const uint16_t* __restrict__ x, const uint16_t* __restrict_
                      float* __restrict__ xo, float* __restrict__ yo, float* __restrict__ po,
                      float* __restrict__ to, int32_t* __restrict__ status) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // frame of event i: frame_offsets[lo] <= i < frame_offsets[lo + 1].  Almost every block of 256 consecutive events lies inside
+    // one frame (100 000 events per frame): two threads search for the block's first and last event, the others search only the
+    // (usually empty) range between the two answers instead of walking log2(F) dependent loads each.
+    __shared__ int s_f[2];
+    if (threadIdx.x < 2) {
+        int64_t q = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x ? blockDim.x - 1 : 0);
+        if (q > n - 1) q = n - 1;
+        int lo = 0, hi = F;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (frame_offsets[mid] <= q) lo = mid; else hi = mid;
+        }
+        s_f[threadIdx.x] = lo;
+    }
+    __syncthreads();
     if (i >= n) return;
-    int lo = 0, hi = F;  // frame_offsets[lo] <= i < frame_offsets[hi]
+    int lo = s_f[0], hi = s_f[1] + 1;
     while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (frame_offsets[mid] <= i) lo = mid; else hi = mid;
