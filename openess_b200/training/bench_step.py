@@ -199,6 +199,17 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
             if step._graph_loop is not None:
                 step._graph_loop.reset()
 
+    # ... and with bf16 operands in the frozen teacher as well (opt-in, OESS_TEACHER_DTYPE=bf16: informational)
+    ms_all_bf16 = None
+    if e2vid_model.CONVLSTM_BF16 and not im.TEACHER_BF16:
+        im.TEACHER_BF16 = True
+        try:
+            for _ in range(3):                             # the teacher's CUDA graph is re-captured (its state key changed)
+                one()
+            ms_all_bf16, _ = timed(one, steps)
+        finally:
+            im.TEACHER_BF16 = False
+
     base = None
     if baseline_steps > 0:
         if rank == 0:
@@ -212,6 +223,7 @@ def run(batch=4, steps=5, warmup=2, events=100_000, baseline_steps=0, rank=0, lo
            "batch_per_gpu": B, "events_per_frame": events, "steps": steps, "ms_per_step": ms,
            "samples_per_s": world * B / ms * 1e3, "event_frames_per_s": world * B * NF / ms * 1e3, "loss": loss,
            "operand_dtypes": dtypes, "ms_per_step_tf32_operands": ms_tf32,
+           "ms_per_step_with_bf16_teacher_optin": ms_all_bf16,
            "own_kernel_launches_per_step": launches_eager if launches_eager is not None else launches,
            "own_kernel_launches_per_step_outside_cuda_graphs": launches, "peak_mem_gb": peak_gb, "h2d_bytes_per_step": h2d,
            "h2d_prefetch_on_side_stream": prefetch,
