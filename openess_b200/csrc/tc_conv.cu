@@ -222,15 +222,15 @@ k_conv_tc(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUten
 // flushed with fp64 atomics only when the CTA moves to another Cout tile or sample.
 constexpr int kPConvThreads = 320;
 
-template <int BN>
+template <int BN, bool PAIR = false>
 struct PConvSmem {
-    static constexpr int kBBytes = BN * kBlockK * 4;
+    static constexpr int kBBytes = (PAIR ? BN / 2 : BN) * kBlockK * 4;   // CTA pair: this CTA's half of the weight tile
     // narrow tiles: TWO K blocks per ring stage.  Their four MMAs take 4 x BN / 2 cycles, far less than one trip of the
     // single-lane issue loops (~430 cycles: wait, elect, descriptors, commit), so the loops -- not the tensor pipe -- set the
     // pace; eight MMAs and four TMA boxes per trip halve that overhead.
     static constexpr int kKbPerStage = BN <= 128 ? 2 : 1;
     static constexpr int kStageBytes = kKbPerStage * (kVABytes + kBBytes);
-    static constexpr int kStages = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);
+    static constexpr int kStages = PAIR ? (BN >= 256 ? 6 : 4) : (BN >= 256 ? 4 : (BN >= 128 ? 3 : 4));
     static constexpr int kBytes = 1024 + kStages * kStageBytes + 8 * 4096 + 256;
 };
 
@@ -239,17 +239,26 @@ struct PConvArgs {
     int tiles_px, n_tiles, tiles;
 };
 
-template <int BN, bool BF16>
+// PAIR (cta_group::2, default when there is enough work; OESS_CONV_2SM=0: off): the two CTAs of a cluster compute two neighbouring
+// pixel tiles x the same Cout tile as ONE M = 256 MMA.  Each CTA stages its own A box and HALF of the weight tile, so the ring is
+// 6 (BN = 256) / 4 x 2 (BN = 128) K blocks deep instead of 4 / 3 x 2 and every SM reads a third less shared memory per MMA; the
+// leader issues the MMAs and commits to both CTAs' barriers, every CTA's epilogue drains its own 128 TMEM lanes.
+template <int BN, bool BF16, bool PAIR>
 __global__ void __launch_bounds__(kPConvThreads, 1)
 k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
             const __grid_constant__ CUtensorMap tmY, const float* __restrict__ bias, const float* __restrict__ residual,
             const bool y_f32, __nv_bfloat16* __restrict__ ybf, double* __restrict__ bn_sums, const PConvArgs pa) {
     extern __shared__ uint8_t smem_raw[];
-    using S = PConvSmem<BN>;
+    using S = PConvSmem<BN, PAIR>;
     constexpr int kStages = S::kStages;
     constexpr int kKE = BF16 ? 64 : kBlockK;
     constexpr int NCH = BN / 32;
     const ConvArgs& a = pa.a;
+    const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0;
+    // PAIR: `tile` counts pixel-tile PAIRS (pixel tiles 2 pu + rank; one past the end = a dummy tile: zero-filled loads, clipped stores)
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int px_units = PAIR ? (pa.tiles_px + 1) / 2 : pa.tiles_px;
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int KPS = S::kKbPerStage;
     uint8_t* sA = base;                                   // [kStages][KPS] A boxes
@@ -274,21 +283,28 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&acc_full[b], 1);
-            mbar_init(&acc_empty[b], 4);
+            mbar_init(&acc_empty[b], PAIR ? 8 : 4);       // PAIR: both CTAs' epilogue warps arrive on the leader's barrier
         }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN < 32 ? 32 : 2 * BN);
-    tc_fence_before();
-    __syncthreads();
+    if (PAIR) {
+        cluster_sync_all();                               // barriers of both CTAs exist before TMEM allocation / any remote arrive
+        if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * BN < 32 ? 32 : 2 * BN);
+        tc_fence_before();
+        cluster_sync_all();
+    } else {
+        if (warp == 1) tmem_alloc(tmem_slot, 2 * BN < 32 ? 32 : 2 * BN);
+        tc_fence_before();
+        __syncthreads();
+    }
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 
     if (warp == 0) {                                      // ===== TMA producer (whole warp converged, one lane issues) =====
         uint32_t s = 0, ph = 1;                           // ring slot and the parity to wait for on its empty barrier
-        for (int tile = blockIdx.x; tile < pa.tiles; tile += gridDim.x) {
-            const int px = tile % pa.tiles_px, rest = tile / pa.tiles_px;
-            const int n0 = (rest % pa.n_tiles) * BN, b = rest / pa.n_tiles;
+        for (int tile = tile0; tile < pa.tiles; tile += tstep) {
+            const int px = PAIR ? 2 * (tile % px_units) + (int)crank : tile % px_units, rest = tile / px_units;
+            const int n0 = (rest % pa.n_tiles) * BN + (PAIR ? (int)crank * (BN / 2) : 0), b = rest / pa.n_tiles;
             const int th = px / a.tiles_w, tw = px - th * a.tiles_w;
             const int x0 = tw * kVW * a.stride - a.pad_x, y0 = th * kVH * a.stride - a.pad;
             int ky = 0, kx = 0, chunk = 0;
@@ -304,12 +320,18 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                     if (u < nk && ++chunk == a.chunks) { chunk = 0; if (++kx == a.KW) { kx = 0; ++ky; } }
                 }
                 if (elect_one()) {
-                    mbar_expect_tx(&full[s], nk * (kVABytes + S::kBBytes));
+                    if (!PAIR) mbar_expect_tx(&full[s], nk * (kVABytes + S::kBBytes));
+                    else if (leader) mbar_expect_tx(&full[s], 2 * nk * (kVABytes + S::kBBytes));      // both CTAs' bytes
 #pragma unroll
                     for (int u = 0; u < KPS; ++u) {
                         if (u < nk) {
-                            tma_load_4d(sA + (s * KPS + u) * kVABytes, &tmX, &full[s], cc[u], cx[u], cy[u], b);
-                            tma_load_2d(sB + (s * KPS + u) * S::kBBytes, &tmW, &full[s], (kb + u) * kKE, n0);
+                            if (PAIR) {
+                                tma_load_4d_2sm(sA + (s * KPS + u) * kVABytes, &tmX, &full[s], cc[u], cx[u], cy[u], b);
+                                tma_load_2d_2sm(sB + (s * KPS + u) * S::kBBytes, &tmW, &full[s], (kb + u) * kKE, n0);
+                            } else {
+                                tma_load_4d(sA + (s * KPS + u) * kVABytes, &tmX, &full[s], cc[u], cx[u], cy[u], b);
+                                tma_load_2d(sB + (s * KPS + u) * S::kBBytes, &tmW, &full[s], (kb + u) * kKE, n0);
+                            }
                         }
                     }
                 }
@@ -317,10 +339,11 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                 if (++s == kStages) { s = 0; ph ^= 1; }
             }
         }
-    } else if (warp == 1) {                               // ===== MMA issuer (whole warp converged, one lane issues) =====
-        constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(128, BN) : umma_idesc_tf32(128, BN);
+    } else if (warp == 1) {                               // ===== MMA issuer (whole warp converged, one lane issues; PAIR: leader only) =====
+        constexpr int kMmaM = PAIR ? 256 : 128;
+        constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(kMmaM, BN) : umma_idesc_tf32(kMmaM, BN);
         uint32_t s = 0, ph = 0, lt = 0;
-        for (int tile = blockIdx.x; tile < pa.tiles; tile += gridDim.x, ++lt) {
+        for (int tile = tile0; leader && tile < pa.tiles; tile += tstep, ++lt) {
             const uint32_t buf = lt & 1;
             mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -337,17 +360,26 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                             const uint64_t db = umma_desc_k128(smem_u32(sB + (s * KPS + u) * S::kBBytes));
 #pragma unroll
                             for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                                if (BF16) umma_bf16(d, da + 2 * k, db + 2 * k, idesc, (kb | u | k) != 0);
-                                else umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | u | k) != 0);
+                                if (PAIR) {
+                                    if (BF16) umma_bf16_2sm(d, da + 2 * k, db + 2 * k, idesc, (kb | u | k) != 0);
+                                    else umma_tf32_2sm(d, da + 2 * k, db + 2 * k, idesc, (kb | u | k) != 0);
+                                } else {
+                                    if (BF16) umma_bf16(d, da + 2 * k, db + 2 * k, idesc, (kb | u | k) != 0);
+                                    else umma_tf32(d, da + 2 * k, db + 2 * k, idesc, (kb | u | k) != 0);
+                                }
                             }
                         }
                     }
-                    umma_commit(&empty[s]);
+                    if (PAIR) umma_commit_2sm(&empty[s], (uint16_t)3);
+                    else umma_commit(&empty[s]);
                 }
                 __syncwarp();
                 if (++s == kStages) { s = 0; ph ^= 1; }
             }
-            if (elect_one()) umma_commit(&acc_full[buf]);
+            if (elect_one()) {
+                if (PAIR) umma_commit_2sm(&acc_full[buf], (uint16_t)3);
+                else umma_commit(&acc_full[buf]);
+            }
             __syncwarp();
         }
     } else {                                              // ===== epilogue: group g = warps 2 + 4 g .. 5 + 4 g =====
@@ -373,9 +405,9 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
             }
         };
         uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < pa.tiles; tile += gridDim.x, ++lt) {
+        for (int tile = tile0; tile < pa.tiles; tile += tstep, ++lt) {
             if ((lt & 1) != g) continue;
-            const int px = tile % pa.tiles_px, rest = tile / pa.tiles_px;
+            const int px = PAIR ? 2 * (tile % px_units) + (int)crank : tile % px_units, rest = tile / px_units;
             const int n0 = (rest % pa.n_tiles) * BN, b = rest / pa.n_tiles;
             const int th = px / a.tiles_w, tw = px - th * a.tiles_w;
             const int h0 = th * kVH, w0 = tw * kVW;
@@ -398,7 +430,10 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
                 if (ch + 1 == NCH) {                      // accumulator fully read: hand it back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_empty[g]);
+                    if (lane == 0) {
+                        if (PAIR) mbar_arrive_cluster(&acc_empty[g], 0);
+                        else mbar_arrive(&acc_empty[g]);
+                    }
                 }
                 const int col = n0 + ch * 32;
                 if (col >= a.Cout) continue;              // warp-uniform
@@ -495,8 +530,13 @@ k_conv_tc_p(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUt
         if (elect_one()) tma_store_wait_all();
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_acc, 2 * BN < 32 ? 32 : 2 * BN);
+    if (PAIR) {
+        cluster_sync_all();                               // no CTA leaves (or frees TMEM) while its peer still works
+        if (warp == 1) tmem_dealloc_2sm(tmem_acc, 2 * BN < 32 ? 32 : 2 * BN);
+    } else {
+        __syncthreads();
+        if (warp == 1) tmem_dealloc(tmem_acc, 2 * BN < 32 ? 32 : 2 * BN);
+    }
 }
 
 template <int BN, bool BF16 = false>
@@ -522,7 +562,38 @@ static int launch_conv(const CUtensorMap& tmX, const void* w_packed, int Cout, i
             rc = make_tmap_f32(&tmY, y, 4, dY, sY, bY);
             if (rc) return rc;
         }
-        auto kern = k_conv_tc_p<BN, BF16>;
+        // CTA pairs: 256-wide tiles with K >= 1024 and at least one pair tile per pair of SMs.  Measured (profiles/r02_conv_pair.log):
+        // 2048 -> 512 1 x 1 +14 %, 512 -> 512 3 x 3 +5 %, 1024 -> 256 +4 %; narrower tiles and K <= 512 lose 2 - 13 % (half as many
+        // schedulable units, cluster-wide barriers per K block), so they stay on single CTAs.
+        static const bool sm2_env = [] { const char* e = std::getenv("OESS_CONV_2SM"); return !e || e[0] != '0'; }();
+        const int tiles_px = a.tiles_w * tiles_h;
+        const int64_t pair_tiles = (int64_t)((tiles_px + 1) / 2) * n_tiles * B;
+        if constexpr (BN == 256) if (sm2_env && a.taps * a.chunks * (BF16 ? 64 : kBlockK) >= 1024 && pair_tiles >= kNumSMs / 2) {
+            CUtensorMap tmW2;                             // this CTA's half of the weight tile per box
+            const uint32_t bW2[2] = {BF16 ? 64u : (uint32_t)kBlockK, (uint32_t)(BN / 2)};
+            rc = BF16 ? make_tmap_bf16(&tmW2, w_packed, 2, dW, sW, bW2) : make_tmap_f32(&tmW2, w_packed, 2, dW, sW, bW2);
+            if (rc) return rc;
+            auto kern2 = k_conv_tc_p<BN, BF16, true>;
+            OESS_CUDA(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, PConvSmem<BN, true>::kBytes));
+            const PConvArgs pa2{a, tiles_px, n_tiles, (int)pair_tiles};
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(kNumSMs & ~1));
+            cfg.blockDim = dim3(kPConvThreads);
+            cfg.dynamicSmemBytes = PConvSmem<BN, true>::kBytes;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            const bool y_f32 = y != nullptr;
+            OESS_KERNEL(BF16 ? "tc_conv2d_bf16" : "tc_conv2d", st,
+                        cudaLaunchKernelEx(&cfg, kern2, tmX, tmW2, tmY, bias, residual, y_f32, ybf, bn_sums, pa2));
+            return 0;
+        }
+        auto kern = k_conv_tc_p<BN, BF16, false>;
         OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PConvSmem<BN>::kBytes));
         const PConvArgs pa{a, a.tiles_w * tiles_h, n_tiles, (int)tiles};
         const unsigned grid = (unsigned)(tiles < kNumSMs ? tiles : kNumSMs);

@@ -395,6 +395,210 @@ static int launch_gemm_persist(const float* A, const float* B, const float* bias
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant of the persistent kernel for 256-wide tiles (cta_group::2; default for N > 128 when there are at least as many
+// 256 x 256 tiles as CTA pairs, OESS_GEMM_2SM=0: off).  The two CTAs of a cluster compute ONE 256 x 256 tile per step: each stages
+// its own 128 rows of A (16 KB) and HALF of the B tile (16 KB) per K block, so the ring holds SIX K blocks instead of four and
+// every SM reads 8 KB instead of 12 KB of shared memory per K = 8 MMA (the TF32 product at BN = 256 otherwise reads + fills
+// 192 B / clk of shared memory per SM); the leader issues `tcgen05.mma.cta_group::2` with M = 256 and commits to both CTAs'
+// barriers; every CTA's epilogue drains its own 128 TMEM lanes exactly as in k_gemm_tf32_persist.
+constexpr int kG2BN = 256;
+constexpr int kG2Stages = 6;
+constexpr int kG2ABytes = kBM * kBlockK * 4;                // 16 KB
+constexpr int kG2BBytes = (kG2BN / 2) * kBlockK * 4;        // 16 KB: this CTA's half of the B tile
+constexpr int kG2CBytes = kBM * 32 * 4;
+constexpr int kG2Smem = 1024 + kG2Stages * (kG2ABytes + kG2BBytes) + 2 * kG2CBytes + 256;
+
+__global__ void __launch_bounds__(kPGemmThreads, 1)
+k_gemm_tf32_p2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int64_t M, int N,
+               int K, int act, int tiles_m, int tiles) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int BN = kG2BN;
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;
+    uint8_t* sB = sA + kG2Stages * kG2ABytes;
+    uint8_t* sC = sB + kG2Stages * kG2BBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sC + 2 * kG2CBytes);
+    uint64_t* empty = full + kG2Stages;
+    uint64_t* acc_full = empty + kG2Stages;                // [2]
+    uint64_t* acc_empty = acc_full + 2;                    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = (K + kBlockK - 1) / kBlockK;
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmC);
+        for (int s = 0; s < kG2Stages; ++s) {
+            mbar_init(&full[s], 1);                        // the leader's own arrive.expect_tx (both CTAs' bytes)
+            mbar_init(&empty[s], 1);                       // the leader's multicast commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);                    // the leader's multicast commit
+            mbar_init(&acc_empty[b], 16);                  // eight epilogue warps in each CTA (used in the leader only)
+        }
+        mbar_fence_init();
+    }
+    cluster_sync_all();                                    // barriers of both CTAs exist before TMEM allocation / any remote arrive
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * BN);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+    const int tile0 = (int)(blockIdx.x >> 1), tstep = (int)(gridDim.x >> 1);
+
+    if (warp == 0) {                                       // ===== TMA producer (both CTAs) =====
+        uint32_t s = 0, ph = 1;
+        for (int tile = tile0; tile < tiles; tile += tstep) {
+            const int m0 = (tile % tiles_m) * 256 + (int)crank * kBM, n0 = (tile / tiles_m) * BN + (int)crank * (BN / 2);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty[s], ph);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(&full[s], 2 * (kG2ABytes + kG2BBytes));
+                    tma_load_2d_2sm(sA + s * kG2ABytes, &tmA, &full[s], kb * kBlockK, m0);
+                    tma_load_2d_2sm(sB + s * kG2BBytes, &tmB, &full[s], kb * kBlockK, n0);
+                }
+                __syncwarp();
+                if (++s == kG2Stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {                                // ===== MMA issuer (leader CTA only) =====
+        if (leader) {
+            constexpr uint32_t idesc = umma_idesc_tf32(256, BN);
+            uint32_t s = 0, ph = 0, lt = 0;
+            for (int tile = tile0; tile < tiles; tile += tstep, ++lt) {
+                const uint32_t buf = lt & 1;
+                mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_acc + buf * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t da = umma_desc_k128(smem_u32(sA + s * kG2ABytes));
+                        const uint64_t db = umma_desc_k128(smem_u32(sB + s * kG2BBytes));
+#pragma unroll
+                        for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                            umma_tf32_2sm(d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit_2sm(&empty[s], (uint16_t)3);
+                    }
+                    __syncwarp();
+                    if (++s == kG2Stages) { s = 0; ph ^= 1; }
+                }
+                if (elect_one()) umma_commit_2sm(&acc_full[buf], (uint16_t)3);
+                __syncwarp();
+            }
+        }
+    } else {                                               // ===== epilogue: warps 2..9 of both CTAs, own 128 rows each =====
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;
+        constexpr int NCH = BN / 64;
+        uint8_t* stage = sC + (warp - 2) * 4096;
+        uint32_t lt = 0;
+        for (int tile = tile0; tile < tiles; tile += tstep, ++lt) {
+            const int m0 = (tile % tiles_m) * 256 + (int)crank * kBM, n0 = (tile / tiles_m) * BN + half * (BN / 2);
+            const uint32_t buf = lt & 1;
+            mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+            tc_fence_after();
+            const int64_t row = (int64_t)m0 + q * 32 + lane;
+            const float* rrow = (residual && row < M) ? residual + row * (int64_t)N : nullptr;   // may alias C
+            const uint32_t t0 = tmem_acc + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
+            float v[2][32];
+            tmem_ld32_nowait(t0, v[0]);
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                tmem_ld_wait();
+                if (ch + 1 < NCH) tmem_ld32_nowait(t0 + (uint32_t)(ch + 1) * 32, v[(ch + 1) & 1]);
+                if (ch + 1 == NCH) {                       // accumulator fully read: tell the LEADER's MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&acc_empty[buf], 0);
+                }
+                const int col = n0 + ch * 32;
+                if (col >= N || m0 + q * 32 >= M) continue;   // warp-uniform (ragged last tiles)
+                const bool full32 = col + 32 <= N;
+                float (&w)[32] = v[ch & 1];
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (full32 || col + j + 4 <= N) {
+                        if (bias) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + j));
+                            w[j] += b.x; w[j + 1] += b.y; w[j + 2] += b.z; w[j + 3] += b.w;
+                        }
+                        if (act & 1) {
+                            w[j] = gelu_erf(w[j]); w[j + 1] = gelu_erf(w[j + 1]); w[j + 2] = gelu_erf(w[j + 2]); w[j + 3] = gelu_erf(w[j + 3]);
+                        }
+                        if (rrow) {
+                            const float4 rr = *reinterpret_cast<const float4*>(rrow + col + j);
+                            w[j] += rr.x; w[j + 1] += rr.y; w[j + 2] += rr.z; w[j + 3] += rr.w;
+                        }
+                        if (act & 2) {
+                            w[j] = rna_tf32(w[j]); w[j + 1] = rna_tf32(w[j + 1]); w[j + 2] = rna_tf32(w[j + 2]); w[j + 3] = rna_tf32(w[j + 3]);
+                        }
+                    }
+                }
+                if (elect_one()) tma_store_wait_read<0>();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(stage + lane * 128 + ((((j >> 2) ^ (lane & 7))) << 4)) =
+                        make_float4(w[j], w[j + 1], w[j + 2], w[j + 3]);
+                fence_proxy_async();
+                __syncwarp();
+                if (elect_one()) {
+                    tma_store_2d(&tmC, stage, col, m0 + q * 32);
+                    tma_store_commit();
+                }
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+        if (elect_one()) tma_store_wait_all();
+    }
+    tc_fence_before();
+    cluster_sync_all();                                    // no CTA leaves (or frees TMEM) while its peer still works
+    if (warp == 1) tmem_dealloc_2sm(tmem_acc, 2 * BN);
+}
+
+static int launch_gemm_p2(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M, int N,
+                          int K, int act, cudaStream_t st) {
+    CUtensorMap tmA, tmB, tmC;
+    const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)K * 4};
+    const uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)K * 4};
+    const uint64_t dC[2] = {(uint64_t)N, (uint64_t)M}, sC[1] = {(uint64_t)N * 4};
+    const uint32_t bA[2] = {kBlockK, kBM}, bB[2] = {kBlockK, (uint32_t)(kG2BN / 2)}, bC[2] = {32, 32};
+    int rc = make_tmap_f32(&tmA, A, 2, dA, sA, bA);
+    if (rc) return rc;
+    rc = make_tmap_f32(&tmB, B, 2, dB, sB, bB);
+    if (rc) return rc;
+    rc = make_tmap_f32(&tmC, C, 2, dC, sC, bC);
+    if (rc) return rc;
+    auto kern = k_gemm_tf32_p2;
+    OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem));
+    const int tiles_m = (int)((M + 255) / 256);
+    const int64_t tiles = (int64_t)tiles_m * ((N + kG2BN - 1) / kG2BN);
+    if (tiles >= (1ll << 30)) return OESS_E_RANGE;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * tiles < kNumSMs ? 2 * tiles : (kNumSMs & ~1)));
+    cfg.blockDim = dim3(kPGemmThreads);
+    cfg.dynamicSmemBytes = kG2Smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    OESS_KERNEL("tc_gemm_tf32", st, cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, bias, residual, M, N, K, act, tiles_m, (int)tiles));
+    return 0;
+}
+
 template <int BN, int kStages, bool MC>
 static int launch_gemm(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M, int N,
                        int K, int act, cudaStream_t st) {
@@ -457,6 +661,9 @@ OESS_API int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias
         const int64_t mt = (M + 127) / 128;
         int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
         while (bn > 64 && mt * ((N + bn - 1) / bn) * 5 < (int64_t)kNumSMs * 3) bn >>= 1;
+        static const bool sm2 = [] { const char* e = getenv("OESS_GEMM_2SM"); return !e || e[0] != '0'; }();
+        if (bn == 256 && sm2 && K > 2 * tc::kBlockK && ((M + 255) / 256) * ((N + 255) / 256) >= kNumSMs / 2)   // K <= 64: store-bound, the pair only adds cluster latency (measured)
+            return tc::launch_gemm_p2(A, B, bias, residual, C, M, N, K, act, st);
         if (bn == 256) return tc::launch_gemm_persist<256>(A, B, bias, residual, C, M, N, K, act, st);
         if (bn == 128) return tc::launch_gemm_persist<128>(A, B, bias, residual, C, M, N, K, act, st);
         return tc::launch_gemm_persist<64>(A, B, bias, residual, C, M, N, K, act, st);

@@ -16,6 +16,8 @@ pytestmark = pytest.mark.gpu
     (1, 256, 64, 10, 16, 1, 1, 0, 1, True, False),    # 1x1 bottleneck reduce
     (1, 20, 24, 8, 16, 3, 1, 1, 1, False, False),     # Cin not a multiple of 32 (zero-filled chunk), Cout % 16 != 0
     (1, 8, 10, 8, 16, 3, 2, 1, 1, True, False),       # scalar store path (Cout % 4 != 0)
+    (3, 128, 320, 40, 72, 3, 1, 1, 1, True, True),    # CTA pairs (cta_group::2; BN = 256, K = 1152): 25 pixel tiles (odd: a dummy peer tile), ragged second Cout tile
+    (6, 32, 96, 40, 72, 3, 1, 1, 1, False, True),     # many tiles per CTA, BN = 128, two K blocks per stage with an odd tail (9 blocks), ragged Cout
 ])
 def test_conv2d_tc(B, Cin, Cout, H, W, k, s, p, d, relu, res):
     from openess_b200 import ops
@@ -49,7 +51,8 @@ def test_conv2d_tc_exact_on_tf32_representable_inputs():
     assert torch.equal(y.cpu(), ref)
 
 
-@pytest.mark.parametrize("C,Cout,H,W,k,s,p,d", [(64, 256, 22, 37, 1, 1, 0, 1), (64, 64, 19, 30, 3, 1, 2, 2), (128, 32, 17, 20, 3, 2, 1, 1)])
+@pytest.mark.parametrize("C,Cout,H,W,k,s,p,d", [(64, 256, 22, 37, 1, 1, 0, 1), (64, 64, 19, 30, 3, 1, 2, 2), (128, 32, 17, 20, 3, 2, 1, 1),
+                                                 (128, 256, 104, 136, 3, 1, 1, 1)])     # CTA pairs: 2 x 59 pair tiles (117 pixel tiles per sample: a dummy peer tile), K = 1152
 def test_conv_bn_train_fused_stats_vs_torch(C, Cout, H, W, k, s, p, d):
     """conv + train-mode BatchNorm with the batch statistics accumulated in the conv's TMEM epilogue, against torch
     (fp64 conv on the CPU, then torch.nn.BatchNorm2d in train mode)."""
@@ -133,6 +136,7 @@ def test_conv2d_autograd_tensor_cores_vs_torch(B, C, Cout, H, W, k, p, d):
     (1, 64, 256, 9, 17, 1, 1, 0, 1, True, True),      # 1x1 expand + fp32 residual
     (1, 32, 64, 16, 32, 5, 2, 2, 1, True, False),     # Cin = 32: half of the 64-element K block is TMA zero fill
     (1, 24, 20, 8, 16, 3, 1, 1, 1, False, False),     # Cin % 64 != 0, Cout % 16 != 0
+    (3, 128, 320, 40, 72, 3, 1, 1, 1, True, True),    # CTA pairs with bf16 operands, ragged second Cout tile, dummy peer tile
 ])
 def test_conv2d_tc_bf16_operands(B, Cin, Cout, H, W, k, s, p, d, relu, res):
     """oess_conv2d_nhwc_bf16 against torch's conv2d in float64 on the bf16-ROUNDED operands (products of bf16 values are exact

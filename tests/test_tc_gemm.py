@@ -64,6 +64,18 @@ def test_gemm_tf32_persistent_exact_with_residual_in_place():
     assert out.data_ptr() == c.data_ptr() and torch.equal(out, ref)
 
 
+def test_gemm_tf32_cta_pair_exact_with_an_empty_peer_tile():
+    """CTA-pair kernel (256 x 256 tiles, cta_group::2): the last pair's second CTA has no rows at all (M = 256 * 80 + 100), N has
+    a ragged last tile, K is not a multiple of the 32-wide block; bit-exact on small integers, with GELU off and a bias."""
+    from openess_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, N, K = 256 * 80 + 100, 520, 72
+    a = torch.randint(-4, 5, (M, K), device="cuda", generator=g).float()
+    b = torch.randint(-4, 5, (N, K), device="cuda", generator=g).float()
+    bias = torch.randint(-4, 5, (N,), device="cuda", generator=g).float()
+    assert torch.equal(ops.gemm_tf32_ex(a, b, bias), a @ b.t() + bias)
+
+
 def test_gemm_tf32_argument_errors():
     from openess_b200 import ops
     from openess_b200._lib import OpenESSB200Error
