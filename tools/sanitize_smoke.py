@@ -138,6 +138,14 @@ hl, cl_ = ops.convlstm_step(xl, None, wpl, bpl)                                 
 ops.convlstm_step(xl, (hl, cl_), wpl, bpl)
 hb, cb = ops.convlstm_step_bf16(xlb, None, wpl.to(torch.bfloat16), bpl)
 ops.convlstm_step_bf16(xlb, (hb, cb), wpl.to(torch.bfloat16), bpl)
+# CTA-pair kernels (cta_group::2): remote barrier arrives, 2-SM TMA loads and commits, a dummy peer tile, ragged N / Cout tiles
+a3 = torch.randn(256 * 80 + 100, 96, device=dev)
+ops.gemm_tf32_ex(a3, torch.randn(520, 96, device=dev), torch.randn(520, device=dev))
+xp = torch.randn(3, 128, 40, 72, device=dev).contiguous(memory_format=torch.channels_last)
+wp3 = torch.randn(320, 128, 3, 3, device=dev) * 0.03
+bn3 = torch.nn.BatchNorm2d(320).to(dev).train()
+ops.conv_bn_train(xp, ops.conv2d_pack(wp3), None, 3, 1, 1, 1, bn3, relu=True)
+ops.conv2d_tc_bf16(xp.to(torch.bfloat16), ops.conv2d_pack_bf16(wp3), None, 3, 1, 1, 1, relu=True)
 xu = torch.randn(2, 32, 9, 11, device=dev, requires_grad=True)
 su = torch.randn(2, 16, 18, 22, device=dev, requires_grad=True)
 ops.upsample2x_cat(xu, su).square().sum().backward()
