@@ -17,7 +17,7 @@ python tools/bench_wgrad.py > gpurun_out/${R}_wgrad.jsonl 2>/dev/null
 python tools/bench_configs.py --config1 --gpu > gpurun_out/${R}_configs.jsonl 2>/dev/null
 python tools/bench_configs.py --config4 >> gpurun_out/${R}_configs.jsonl 2>/dev/null
 python tools/bench_configs.py --config5 >> gpurun_out/${R}_configs.jsonl 2>/dev/null
-ncu --set full --clock-control none --import-source on -k regex:k_gemm_tf32_persist -s 6 -c 1 -o gpurun_out/${R}_gemm -f python tools/bench_tc.py > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_gemm_tf32_p -s 6 -c 1 -o gpurun_out/${R}_gemm -f python tools/bench_tc.py > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_convlstm_tc_p -s 30 -c 1 -o gpurun_out/${R}_convlstm -f python tools/bench_tc.py > /dev/null 2>&1
 OESS_INFONCE=tc compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > gpurun_out/${R}_sanitizer_memcheck.log 2>&1; tail -3 gpurun_out/${R}_sanitizer_memcheck.log
 OESS_INFONCE=tc compute-sanitizer --tool racecheck python tools/sanitize_smoke.py > gpurun_out/${R}_sanitizer_racecheck.log 2>&1; tail -3 gpurun_out/${R}_sanitizer_racecheck.log

@@ -143,8 +143,9 @@ a3 = torch.randn(256 * 80 + 100, 96, device=dev)
 ops.gemm_tf32_ex(a3, torch.randn(520, 96, device=dev), torch.randn(520, device=dev))
 xp = torch.randn(3, 128, 40, 72, device=dev).contiguous(memory_format=torch.channels_last)
 wp3 = torch.randn(320, 128, 3, 3, device=dev) * 0.03
-bn3 = torch.nn.BatchNorm2d(320).to(dev).train()
-ops.conv_bn_train(xp, ops.conv2d_pack(wp3), None, 3, 1, 1, 1, bn3, relu=True)
+bn3 = torch.nn.BatchNorm2d(256).to(dev).train()
+ops.conv_bn_train(xp, ops.conv2d_pack(wp3[:256].contiguous()), None, 3, 1, 1, 1, bn3, relu=True)   # fused statistics, one Cout tile
+ops.conv2d_tc(xp, ops.conv2d_pack(wp3), torch.randn(320, device=dev), 3, 1, 1, 1, relu=True)       # ragged second Cout tile
 ops.conv2d_tc_bf16(xp.to(torch.bfloat16), ops.conv2d_pack_bf16(wp3), None, 3, 1, 1, 1, relu=True)
 xu = torch.randn(2, 32, 9, 11, device=dev, requires_grad=True)
 su = torch.randn(2, 16, 18, 22, device=dev, requires_grad=True)
