@@ -402,19 +402,25 @@ static int launch_gemm_persist(const float* A, const float* B, const float* bias
 // every SM reads 8 KB instead of 12 KB of shared memory per K = 8 MMA (the TF32 product at BN = 256 otherwise reads + fills
 // 192 B / clk of shared memory per SM); the leader issues `tcgen05.mma.cta_group::2` with M = 256 and commits to both CTAs'
 // barriers; every CTA's epilogue drains its own 128 TMEM lanes exactly as in k_gemm_tf32_persist.
-constexpr int kG2BN = 256;
+// BN = 192 as well as 256: the tile width is chosen per product so that the last wave of pair tiles is as full as possible
+// (N = 768 on M = 8 968: 108 tiles of 256 x 256 are 1.46 waves of 74 pairs, 144 tiles of 256 x 192 are 1.95).
 constexpr int kG2Stages = 6;
 constexpr int kG2ABytes = kBM * kBlockK * 4;                // 16 KB
-constexpr int kG2BBytes = (kG2BN / 2) * kBlockK * 4;        // 16 KB: this CTA's half of the B tile
 constexpr int kG2CBytes = kBM * 32 * 4;
-constexpr int kG2Smem = 1024 + kG2Stages * (kG2ABytes + kG2BBytes) + 2 * kG2CBytes + 256;
+template <int BN>
+struct G2Smem {
+    static constexpr int kBBytes = (BN / 2) * kBlockK * 4;  // 16 / 12 KB: this CTA's half of the B tile
+    static constexpr int kBytes = 1024 + kG2Stages * (kG2ABytes + kBBytes) + 2 * kG2CBytes + 256;
+};
 
+template <int BN>
 __global__ void __launch_bounds__(kPGemmThreads, 1)
 k_gemm_tf32_p2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias, const float* residual, int64_t M, int N,
                int K, int act, int tiles_m, int tiles) {
     extern __shared__ uint8_t smem_raw[];
-    constexpr int BN = kG2BN;
+    constexpr int kG2BBytes = G2Smem<BN>::kBBytes;
+    constexpr uint32_t kAccStride = 256;                   // TMEM columns between the two accumulators (512 allocated)
     uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = base;
     uint8_t* sB = sA + kG2Stages * kG2ABytes;
@@ -445,7 +451,7 @@ k_gemm_tf32_p2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_fence_init();
     }
     cluster_sync_all();                                    // barriers of both CTAs exist before TMEM allocation / any remote arrive
-    if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * BN);
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -475,7 +481,7 @@ k_gemm_tf32_p2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t buf = lt & 1;
                 mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t d = tmem_acc + buf * BN;
+                const uint32_t d = tmem_acc + buf * kAccStride;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
@@ -507,7 +513,7 @@ k_gemm_tf32_p2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const int64_t row = (int64_t)m0 + q * 32 + lane;
             const float* rrow = (residual && row < M) ? residual + row * (int64_t)N : nullptr;   // may alias C
-            const uint32_t t0 = tmem_acc + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
+            const uint32_t t0 = tmem_acc + buf * kAccStride + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2));
             float v[2][32];
             tmem_ld32_nowait(t0, v[0]);
 #pragma unroll
@@ -562,26 +568,28 @@ k_gemm_tf32_p2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     cluster_sync_all();                                    // no CTA leaves (or frees TMEM) while its peer still works
-    if (warp == 1) tmem_dealloc_2sm(tmem_acc, 2 * BN);
+    if (warp == 1) tmem_dealloc_2sm(tmem_acc, 512);
 }
 
+template <int BN>
 static int launch_gemm_p2(const float* A, const float* B, const float* bias, const float* residual, float* C, int64_t M, int N,
                           int K, int act, cudaStream_t st) {
     CUtensorMap tmA, tmB, tmC;
     const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[1] = {(uint64_t)K * 4};
     const uint64_t dB[2] = {(uint64_t)K, (uint64_t)N}, sB[1] = {(uint64_t)K * 4};
     const uint64_t dC[2] = {(uint64_t)N, (uint64_t)M}, sC[1] = {(uint64_t)N * 4};
-    const uint32_t bA[2] = {kBlockK, kBM}, bB[2] = {kBlockK, (uint32_t)(kG2BN / 2)}, bC[2] = {32, 32};
+    const uint32_t bA[2] = {kBlockK, kBM}, bB[2] = {kBlockK, (uint32_t)(BN / 2)}, bC[2] = {32, 32};
     int rc = make_tmap_f32(&tmA, A, 2, dA, sA, bA);
     if (rc) return rc;
     rc = make_tmap_f32(&tmB, B, 2, dB, sB, bB);
     if (rc) return rc;
     rc = make_tmap_f32(&tmC, C, 2, dC, sC, bC);
     if (rc) return rc;
-    auto kern = k_gemm_tf32_p2;
+    auto kern = k_gemm_tf32_p2<BN>;
+    constexpr int kG2Smem = G2Smem<BN>::kBytes;
     OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2Smem));
     const int tiles_m = (int)((M + 255) / 256);
-    const int64_t tiles = (int64_t)tiles_m * ((N + kG2BN - 1) / kG2BN);
+    const int64_t tiles = (int64_t)tiles_m * ((N + BN - 1) / BN);
     if (tiles >= (1ll << 30)) return OESS_E_RANGE;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * tiles < kNumSMs ? 2 * tiles : (kNumSMs & ~1)));
@@ -662,8 +670,16 @@ OESS_API int oess_gemm_tf32_ex(const float* A, const float* B, const float* bias
         int bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
         while (bn > 64 && mt * ((N + bn - 1) / bn) * 5 < (int64_t)kNumSMs * 3) bn >>= 1;
         static const bool sm2 = [] { const char* e = getenv("OESS_GEMM_2SM"); return !e || e[0] != '0'; }();
-        if (bn == 256 && sm2 && K > 2 * tc::kBlockK && ((M + 255) / 256) * ((N + 255) / 256) >= kNumSMs / 2)   // K <= 64: store-bound, the pair only adds cluster latency (measured)
-            return tc::launch_gemm_p2(A, B, bias, residual, C, M, N, K, act, st);
+        if (bn == 256 && sm2 && K > 2 * tc::kBlockK && ((M + 255) / 256) * ((N + 255) / 256) >= kNumSMs / 2) {   // K <= 64: store-bound, the pair only adds cluster latency (measured)
+            // tile width 256 or 192: whichever needs fewer (waves of 74 pair tiles) x (columns per tile)
+            static const bool w192 = [] { const char* e = getenv("OESS_GEMM_192"); return !e || e[0] != '0'; }();
+            const int64_t pairs = kNumSMs / 2, tm2 = (M + 255) / 256;
+            const int64_t c256 = ((tm2 * ((N + 255) / 256) + pairs - 1) / pairs) * 256;
+            const int64_t c192 = ((tm2 * ((N + 191) / 192) + pairs - 1) / pairs) * 192;
+            // (a 192-wide tile costs more per column -- the A fill per K block is the same -- so it has to save an eighth: measured)
+            if (w192 && c192 * 8 < c256 * 7) return tc::launch_gemm_p2<192>(A, B, bias, residual, C, M, N, K, act, st);
+            return tc::launch_gemm_p2<256>(A, B, bias, residual, C, M, N, K, act, st);
+        }
         if (bn == 256) return tc::launch_gemm_persist<256>(A, B, bias, residual, C, M, N, K, act, st);
         if (bn == 128) return tc::launch_gemm_persist<128>(A, B, bias, residual, C, M, N, K, act, st);
         return tc::launch_gemm_persist<64>(A, B, bias, residual, C, M, N, K, act, st);
