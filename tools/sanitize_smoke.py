@@ -140,7 +140,8 @@ hb, cb = ops.convlstm_step_bf16(xlb, None, wpl.to(torch.bfloat16), bpl)
 ops.convlstm_step_bf16(xlb, (hb, cb), wpl.to(torch.bfloat16), bpl)
 # CTA-pair kernels (cta_group::2): remote barrier arrives, 2-SM TMA loads and commits, a dummy peer tile, ragged N / Cout tiles
 a3 = torch.randn(256 * 80 + 100, 96, device=dev)
-ops.gemm_tf32_ex(a3, torch.randn(520, 96, device=dev), torch.randn(520, device=dev))
+ops.gemm_tf32_ex(a3, torch.randn(520, 96, device=dev), torch.randn(520, device=dev))    # 192-wide pair tiles, ragged last N tile
+ops.gemm_tf32_ex(a3, torch.randn(256, 96, device=dev), torch.randn(256, device=dev))    # 256-wide pair tiles
 xp = torch.randn(3, 128, 40, 72, device=dev).contiguous(memory_format=torch.channels_last)
 wp3 = torch.randn(320, 128, 3, 3, device=dev) * 0.03
 bn3 = torch.nn.BatchNorm2d(256).to(dev).train()
