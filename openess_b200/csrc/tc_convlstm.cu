@@ -546,6 +546,213 @@ k_convlstm_tc_p2(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (warp == 1) tmem_dealloc_2sm(tmem_acc, 2 * kCN);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Haloed CTA-pair variant (default where its patches tile the image as well; OESS_CONVLSTM_HALO=0 / 1): the nine taps of a (source, channel chunk) read ONE 18-row x 10-pixel halo
+// box (23 KB) instead of nine 16 KB boxes.  The pixel patch of a CTA is 8 wide x 16 high, so every 8-row core-matrix group of
+// the A operand is one patch row and a tap's shifted window is the halo tile read from row ky * 10 + kx on with 8-row groups
+// 10 rows (1 280 B = the descriptor's stride byte offset) apart; the 128-byte swizzle is a function of the shared-memory
+// address, so a start address that is not a multiple of 8 rows reads what TMA wrote (tools/probe_umma_window.cu checks exactly
+// this on the device).  Fill per tile and CTA at C = 64: 2 x 23 KB of A + 18 x 16 KB of B = 334 KB instead of 576 KB (the pair
+// kernel above sits on the L2 -> shared-memory fill bound).  A halos and B boxes run in separate rings.
+constexpr int kHW = 8, kHH = 16;                          // pixel patch of one CTA = the 128 rows of M
+constexpr int kHaloW = kHW + 2, kHaloH = kHH + 2;
+constexpr int kHaloBytes = kHaloW * kHaloH * 128;          // 23 040
+constexpr int kHaloSlot = 23 * 1024;
+constexpr int kH2AStages = 3, kH2BStages = 9;
+constexpr int kH2Smem = 1024 + kH2AStages * kHaloSlot + kH2BStages * kP2BBytes + 256;
+
+template <bool BF16>
+__global__ void __launch_bounds__(kP2Threads, 1)
+k_convlstm_tc_h2(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmH,
+                 const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias, const float* __restrict__ c_prev,
+                 float* __restrict__ h_out, __nv_bfloat16* __restrict__ h_bf, float* __restrict__ c_out, int H, int W, int C,
+                 int has_h, int tiles_w, int tiles_px, int tiles) {
+    constexpr int kKE = BF16 ? 64 : kBlockK;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = base;
+    uint8_t* sB = base + kH2AStages * kHaloSlot;
+    uint64_t* fullA = reinterpret_cast<uint64_t*>(sB + kH2BStages * kP2BBytes);
+    uint64_t* emptyA = fullA + kH2AStages;
+    uint64_t* fullB = emptyA + kH2AStages;
+    uint64_t* emptyB = fullB + kH2BStages;
+    uint64_t* acc_full = emptyB + kH2BStages;
+    uint64_t* acc_empty = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = C / kKE, nchunks = C / 64;
+    const int groups = (has_h ? 2 : 1) * chunks;          // (source, channel chunk) pairs per tile
+    const uint32_t crank = cluster_ctarank();
+    const bool leader = crank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmH);
+        tma_prefetch_desc(&tmW);
+        for (int s = 0; s < kH2AStages; ++s) {
+            mbar_init(&fullA[s], 1);
+            mbar_init(&emptyA[s], 1);
+        }
+        for (int s = 0; s < kH2BStages; ++s) {
+            mbar_init(&fullB[s], 1);
+            mbar_init(&emptyB[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&acc_full[b], 1);
+            mbar_init(&acc_empty[b], 16);
+        }
+        mbar_fence_init();
+    }
+    cluster_sync_all();
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * kCN);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+    const int tile0 = (int)(blockIdx.x >> 1), tstep = (int)(gridDim.x >> 1);
+    const int px_units = (tiles_px + 1) / 2;
+
+    if (warp == 0) {                                      // ===== TMA producer (both CTAs) =====
+        uint32_t sa = 0, pha = 1, sb = 0, phb = 1;
+        for (int tile = tile0; tile < tiles; tile += tstep) {
+            const int pu = tile % px_units, rest = tile / px_units;
+            const int px = 2 * pu + (int)crank;           // past tiles_px: a dummy patch (TMA zero fill, epilogue drops it)
+            const int nchunk = rest % nchunks, b = rest / nchunks;
+            const int th = px / tiles_w, tw = px - th * tiles_w;
+            const int h0 = th * kHH, w0 = tw * kHW;
+            for (int g = 0; g < groups; ++g) {
+                const int src = g / chunks, chunk = g - src * chunks;
+                mbar_wait(&emptyA[sa], pha);
+                if (elect_one()) {
+                    if (leader) mbar_expect_tx(&fullA[sa], 2 * kHaloBytes);
+                    tma_load_4d_2sm(sA + sa * kHaloSlot, src ? &tmH : &tmX, &fullA[sa], chunk * kKE, w0 - 1, h0 - 1, b);
+                }
+                __syncwarp();
+                if (++sa == kH2AStages) { sa = 0; pha ^= 1; }
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait(&emptyB[sb], phb);
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(&fullB[sb], 2 * kP2BBytes);
+                        tma_load_2d_2sm(sB + sb * kP2BBytes, &tmW, &fullB[sb], ((src * 9 + tap) * chunks + chunk) * kKE,
+                                        nchunk * kCN + (int)crank * (kCN / 2));
+                    }
+                    __syncwarp();
+                    if (++sb == kH2BStages) { sb = 0; phb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {                               // ===== MMA issuer (leader CTA only) =====
+        if (leader) {
+            constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(256, kCN) : umma_idesc_tf32(256, kCN);
+            uint32_t sa = 0, pha = 0, sb = 0, phb = 0, lt = 0;
+            for (int tile = tile0; tile < tiles; tile += tstep, ++lt) {
+                const uint32_t buf = lt & 1;
+                mbar_wait(&acc_empty[buf], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d = tmem_acc + buf * kCN;
+                for (int g = 0; g < groups; ++g) {
+                    mbar_wait(&fullA[sa], pha);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + sa * kHaloSlot);
+                    int ky = 0, kx = 0;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&fullB[sb], phb);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            // window of tap (ky, kx): halo rows (r + ky) * 10 + kx + c, r = patch row = 8-row group, c = 0..7
+                            const uint32_t a_addr = a0 + (uint32_t)(ky * kHaloW + kx) * 128u;
+                            const uint64_t da = (uint64_t)((a_addr >> 4) & 0x3FFFu) | (1ull << 16) |
+                                                ((uint64_t)((kHaloW * 128) >> 4) << 32) | (1ull << 46) | (2ull << 61);
+                            const uint64_t db = umma_desc_k128(smem_u32(sB + sb * kP2BBytes));
+#pragma unroll
+                            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                                if (BF16) umma_bf16_2sm(d, da + 2 * k, db + 2 * k, idesc, (g | tap | k) != 0);
+                                else umma_tf32_2sm(d, da + 2 * k, db + 2 * k, idesc, (g | tap | k) != 0);
+                            }
+                            umma_commit_2sm(&emptyB[sb], (uint16_t)3);
+                            if (tap == 8) umma_commit_2sm(&emptyA[sa], (uint16_t)3);
+                        }
+                        __syncwarp();
+                        if (++kx == 3) { kx = 0; ++ky; }
+                        if (++sb == kH2BStages) { sb = 0; phb ^= 1; }
+                    }
+                    if (++sa == kH2AStages) { sa = 0; pha ^= 1; }
+                }
+                if (elect_one()) umma_commit_2sm(&acc_full[buf], (uint16_t)3);
+                __syncwarp();
+            }
+        }
+    } else {                                              // ===== epilogue: 16 warps (both CTAs), as in k_convlstm_tc_p2 =====
+        const int e = warp - 2;
+        const int q = warp & 3, hs = (e >> 2) & 1;
+        const uint32_t g = (uint32_t)e >> 3;
+        uint32_t lt = 0;
+        for (int tile = tile0; tile < tiles; tile += tstep, ++lt) {
+            if ((lt & 1) != g) continue;
+            const int pu = tile % px_units, rest = tile / px_units;
+            const int px = 2 * pu + (int)crank;
+            const int nchunk = rest % nchunks, b = rest / nchunks;
+            const int th = px / tiles_w, tw = px - th * tiles_w;
+            const int r = q * 32 + lane;
+            const int y = th * kHH + r / kHW, x = tw * kHW + r % kHW;
+            const bool valid = y < H && x < W;
+            const int64_t pix = (((int64_t)b * H + y) * W + x) * C + nchunk * 64 + hs * 32;
+            const float* bn = bias + nchunk * kCN + hs * 32;
+            mbar_wait(&acc_full[g], (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_acc + g * kCN + ((uint32_t)(q * 32) << 16) + (uint32_t)(hs * 32);
+#pragma unroll 1
+            for (int sub = 0; sub < 4; ++sub) {
+                float gi[8], gf[8], go[8], gg[8];
+                tmem_ld8_nowait(trow + 0 * 64 + sub * 8, gi);
+                tmem_ld8_nowait(trow + 1 * 64 + sub * 8, gf);
+                tmem_ld8_nowait(trow + 2 * 64 + sub * 8, go);
+                tmem_ld8_nowait(trow + 3 * 64 + sub * 8, gg);
+                tmem_ld_wait();
+                if (sub == 3) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&acc_empty[g], 0);
+                }
+                if (valid) {
+                    const int64_t e0 = pix + sub * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; j += 4) {
+                        float4 pc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (c_prev) pc = *reinterpret_cast<const float4*>(c_prev + e0 + j);
+                        const float4 bi = __ldg(reinterpret_cast<const float4*>(bn + 0 * 64 + sub * 8 + j));
+                        const float4 bf = __ldg(reinterpret_cast<const float4*>(bn + 1 * 64 + sub * 8 + j));
+                        const float4 bo = __ldg(reinterpret_cast<const float4*>(bn + 2 * 64 + sub * 8 + j));
+                        const float4 bg = __ldg(reinterpret_cast<const float4*>(bn + 3 * 64 + sub * 8 + j));
+                        float4 c, h;
+                        c.x = act_sigm<BF16>(gf[j] + bf.x) * pc.x + act_sigm<BF16>(gi[j] + bi.x) * act_tanh<BF16>(gg[j] + bg.x);
+                        c.y = act_sigm<BF16>(gf[j + 1] + bf.y) * pc.y + act_sigm<BF16>(gi[j + 1] + bi.y) * act_tanh<BF16>(gg[j + 1] + bg.y);
+                        c.z = act_sigm<BF16>(gf[j + 2] + bf.z) * pc.z + act_sigm<BF16>(gi[j + 2] + bi.z) * act_tanh<BF16>(gg[j + 2] + bg.z);
+                        c.w = act_sigm<BF16>(gf[j + 3] + bf.w) * pc.w + act_sigm<BF16>(gi[j + 3] + bi.w) * act_tanh<BF16>(gg[j + 3] + bg.w);
+                        h.x = act_sigm<BF16>(go[j] + bo.x) * act_tanh<BF16>(c.x);
+                        h.y = act_sigm<BF16>(go[j + 1] + bo.y) * act_tanh<BF16>(c.y);
+                        h.z = act_sigm<BF16>(go[j + 2] + bo.z) * act_tanh<BF16>(c.z);
+                        h.w = act_sigm<BF16>(go[j + 3] + bo.w) * act_tanh<BF16>(c.w);
+                        *reinterpret_cast<float4*>(c_out + e0 + j) = c;
+                        if (h_out) *reinterpret_cast<float4*>(h_out + e0 + j) = h;
+                        if (BF16) {
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(h.x, h.y), hi = __floats2bfloat162_rn(h.z, h.w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                            *reinterpret_cast<uint2*>(h_bf + e0 + j) = pk;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm(tmem_acc, 2 * kCN);
+}
+
 }  // namespace tc
 }  // namespace oess
 
@@ -579,6 +786,45 @@ static int convlstm_impl(const void* x, const void* h_prev, const float* c_prev,
     rc = mk(&tmH, h_prev ? h_prev : x, 4, dims, strides, box);
     if (rc) return rc;
     const uint64_t dW[2] = {Kfull, (uint64_t)4 * C}, sW[1] = {Kfull * ES};
+    // haloed pair kernel: default where its 8 x 16 patches tile the image with no more patches than the 16 x 8 ones of the other
+    // kernels (55 x 80: 40 against 35 -- slower there); OESS_CONVLSTM_HALO=0 never, =1 always
+    static const int halo_env = [] { const char* e = std::getenv("OESS_CONVLSTM_HALO"); return !e ? -1 : (e[0] == '1' ? 1 : 0); }();
+    const int64_t halo_px = (int64_t)((W + tc::kHW - 1) / tc::kHW) * ((H + tc::kHH - 1) / tc::kHH);
+    const int64_t tile_px = (int64_t)((W + tc::kTW - 1) / tc::kTW) * ((H + tc::kTH - 1) / tc::kTH);
+    if (halo_px >= 2 && (halo_env == 1 || (halo_env < 0 && halo_px <= tile_px))) {
+        CUtensorMap tmXh, tmHh, tmWh;
+        const uint32_t hbox[4] = {KE, (uint32_t)tc::kHaloW, (uint32_t)tc::kHaloH, 1};
+        rc = mk(&tmXh, x, 4, dims, strides, hbox);
+        if (rc) return rc;
+        rc = mk(&tmHh, h_prev ? h_prev : x, 4, dims, strides, hbox);
+        if (rc) return rc;
+        const uint32_t bWh[2] = {KE, (uint32_t)(tc::kCN / 2)};
+        rc = mk(&tmWh, w_packed, 2, dW, sW, bWh);
+        if (rc) return rc;
+        const int htw = (W + tc::kHW - 1) / tc::kHW, hth = (H + tc::kHH - 1) / tc::kHH;
+        const int hpx = htw * hth;
+        const int64_t htiles = (int64_t)((hpx + 1) / 2) * (C / 64) * B;
+        if (htiles < (1ll << 31)) {
+            auto kern = tc::k_convlstm_tc_h2<BF16>;
+            OESS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kH2Smem));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(2 * (htiles < kNumSMs / 2 ? htiles : kNumSMs / 2)));
+            cfg.blockDim = dim3(tc::kP2Threads);
+            cfg.dynamicSmemBytes = tc::kH2Smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            OESS_KERNEL(BF16 ? "tc_convlstm_step_bf16" : "tc_convlstm_step", st,
+                        cudaLaunchKernelEx(&cfg, kern, tmXh, tmHh, tmWh, bias_packed, c_prev, h_out, h_bf, c_out, H, W, C,
+                                           h_prev ? 1 : 0, htw, hpx, (int)htiles));
+            return 0;
+        }
+    }
     const int tiles_w = (W + tc::kTW - 1) / tc::kTW, tiles_h = (H + tc::kTH - 1) / tc::kTH;
     static const bool tile_env = [] { const char* e = std::getenv("OESS_CONVLSTM"); return e && e[0] == 't'; }();
     static const bool mc_env = [] { const char* e = std::getenv("OESS_CONVLSTM_MC"); return !(e && e[0] == '0'); }();   // default on
